@@ -1,0 +1,166 @@
+/*
+ * qspectra_b200 -- C ABI of the B200-native Liouville-space propagation engine.
+ *
+ * The reference (whaley-group-berkeley/qspectra) is pure Python and has no FFI;
+ * its boundary for this path is the DynamicalModel plugin protocol.  Each entry
+ * point below names the reference call site it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - complex128 is passed as interleaved (re, im) doubles ("double2").
+ *   - a density operator is vectorised column-major (liouville_space.py:46-50)
+ *     and restricted to a Liouville subspace index list (:9-29) on the host.
+ *   - state batches are row-major [column][state_dim]; trajectories are
+ *     [column][time][saved_dim].
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).
+ *   - every function returns 0 on success or a negative qsx_status; the message
+ *     is available from qsx_last_error() (thread local).
+ *   - pointers named *_dev are device pointers owned by the caller (torch
+ *     tensors on the Python side); handles own their staged generators/tables.
+ */
+#ifndef QSPECTRA_B200_H
+#define QSPECTRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QSX_OK = 0,
+    QSX_ERR_INVALID = -1,      /* bad argument                           -> ValueError       */
+    QSX_ERR_CUDA = -2,         /* CUDA runtime failure                   -> RuntimeError     */
+    QSX_ERR_INTEGRATOR = -3,   /* step-size underflow / non-finite state -> IntegratorError  */
+    QSX_ERR_UNSUPPORTED = -4   /* configuration outside the kernel limits-> NotImplementedError */
+} qsx_status;
+
+typedef enum {
+    QSX_METHOD_TAYLOR = 0,     /* adaptive-order Taylor of exp(hL), LTI generators only */
+    QSX_METHOD_RK4 = 1,        /* classic RK4, fixed sub-steps per output interval      */
+    QSX_METHOD_DOPRI5 = 2      /* Dormand-Prince 5(4), on-device step-size control      */
+} qsx_method;
+
+typedef enum {
+    QSX_SAVE_STATE = 0,        /* save_func = identity                                  */
+    QSX_SAVE_MATRIX = 1,       /* save_func = S . y  (commutator / left / right / expectation) */
+    QSX_SAVE_ADO0 = 2          /* HEOM: state_vector_to_density_matrix, first M entries */
+} qsx_save_mode;
+
+#define QSX_MAX_PULSES 4
+
+/* A Gaussian pulse in the rotating frame (pulse.py:110-114):
+ *   E(t) = scale * exp(i*detuning*(t - t_peak) - (t - t_peak)^2 * inv_two_sigma_sq)
+ * The RHS adds (-i*E) * C.y, with E conjugated when `conjugate` != 0 (eom.py:87-94). */
+typedef struct {
+    double scale, detuning, t_peak, inv_two_sigma_sq;
+    int32_t conjugate;
+    int32_t _pad;
+} qsx_pulse;
+
+/* Arguments of a propagation = one call of simulate/utils.py:53-109 `integrate`
+ * for a batch of initial states that share one output grid. */
+typedef struct {
+    int32_t n_columns;            /* number of initial states (leading axis of y0)   */
+    int32_t n_times;              /* len(t)                                          */
+    const double *t_host;         /* output times, host pointer, increasing          */
+    double t0;                    /* start time (utils.py:17-18)                     */
+    const void *y0_dev;           /* [n_columns][D] complex128                       */
+    const int32_t *generator_of_column_host; /* [n_columns] or NULL (all use 0)      */
+    int32_t method;               /* qsx_method                                      */
+    double rtol, atol;            /* tolerances (Taylor: rtol = per-step truncation) */
+    int32_t rk4_substeps;         /* RK4 sub-steps per output interval               */
+    int32_t save_mode;            /* qsx_save_mode                                   */
+    int32_t save_rows;            /* rows of S when save_mode == QSX_SAVE_MATRIX     */
+    const void *save_dev;         /* S: [n_save][save_rows][M_from] complex128       */
+    int32_t n_save;               /* 1 (shared) or n_generators (per member)         */
+    int32_t n_pulses;             /* time-dependent terms, <= QSX_MAX_PULSES         */
+    qsx_pulse pulses[QSX_MAX_PULSES];
+    const void *pulse_ops_dev;    /* C_p: [n_pulse_sets][n_pulses][D][D] (dense) or
+                                     [n_pulse_sets][n_pulses][M][M] per-ADO (HEOM)   */
+    int32_t n_pulse_sets;         /* 1 (shared) or n_generators                      */
+    void *out_dev;                /* [n_columns][n_times][saved_dim] complex128      */
+    /* results */
+    uint64_t rhs_evaluations;     /* RHS applications summed over columns            */
+    uint64_t accepted_steps;      /* integrator steps summed over columns            */
+    double kernel_ms;             /* device time of the propagation kernel (CUDA events) */
+} qsx_propagate_args;
+
+const char *qsx_last_error(void);
+int qsx_version(void);
+/* number of kernels this library has launched since load (bench.py: gpu_launches) */
+uint64_t qsx_kernel_launches(void);
+/* device properties the host side needs: SM count, L2 bytes, max smem per block */
+int qsx_device_info(int32_t *sm_count, int64_t *l2_bytes, int32_t *smem_per_block);
+
+/* ------------------------------------------------------------------------
+ * Dense Liouvillians (RedfieldModel / UnitaryModel).
+ * Replaces `evolve_matrix.dot(rho)` of LiouvilleSpaceModel.equation_of_motion
+ * (dynamics/liouville_space.py:316-341) and the ZVODE loop around it
+ * (simulate/utils.py:45-49).
+ * ---------------------------------------------------------------------- */
+typedef struct qsx_dense_s *qsx_dense_t;
+
+/* L: [n_generators][M][M] complex128 row-major, already restricted to the
+ * subspace (np.ix_(index, index)) and scaled by unit_convert.  `on_device` says
+ * whether L is a device pointer.  `transpose` != 0 stores L^T: the Heisenberg
+ * picture of liouville_space.py:325-330. */
+int qsx_dense_create(qsx_dense_t *out, int32_t M, int32_t n_generators,
+                     const void *L, int32_t on_device, int32_t transpose,
+                     void *stream);
+/* dy[c] = L[gen(c)] . y[c] for a batch of columns: the function returned by
+ * equation_of_motion.  y/dy: [n_columns][M] device. */
+int qsx_dense_apply(qsx_dense_t h, const void *y_dev, void *dy_dev,
+                    int32_t n_columns, const int32_t *generator_of_column_host,
+                    void *stream);
+int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void *stream);
+void qsx_dense_destroy(qsx_dense_t h);
+
+/* ------------------------------------------------------------------------
+ * HEOM hierarchy (HEOMModel).  Replaces HEOM_tensor + csr_matrix.dot
+ * (dynamics/heom.py:228-244, 298-443) with an index-map driven structured
+ * apply; no CSR matrix is ever built.
+ * ---------------------------------------------------------------------- */
+typedef struct qsx_heom_s *qsx_heom_t;
+
+typedef struct {
+    int32_t n_sites;              /* independent baths (heom.py:221)                 */
+    int32_t K;                    /* Matsubara terms beyond the Drude pole           */
+    int32_t level_cutoff;         /* ADOs with sum(n) < level_cutoff (heom.py:92-152)*/
+    int32_t n_hilbert;            /* N = states of the Hilbert subspace              */
+    int32_t M;                    /* size of the Liouville subspace                  */
+    const int64_t *subspace_index;/* [M] flat column-major positions (host)          */
+    int32_t n_members;            /* distinct Hamiltonians (disorder ensemble), >= 1 */
+    const void *H;                /* [n_members][N][N] complex128 row-major (host), rotating frame */
+    const double *coupling_diag;  /* [n_sites][N]: diagonal of V_j (hamiltonian.py:593-608) */
+    const double *nu;             /* [K+1] Matsubara frequencies (heom.py:61-67)     */
+    const void *c;                /* [K+1] complex coefficients (heom.py:69-89)      */
+    double temp_corr;             /* sum_{k>K} c_k/nu_k, 0 if low_temp_corr is off (heom.py:387-393) */
+    double unit_convert;
+    int32_t modified;             /* modified_HEOM scaling (heom.py:423-437)         */
+    int32_t heisenberg;           /* generator transposed (heom.py:236-237)          */
+} qsx_heom_config;
+
+int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void *stream);
+int64_t qsx_heom_ado_count(qsx_heom_t h);
+/* integer artefacts for bit-exact comparison with ADO_mappings (heom.py:92-152):
+ * ado_index [n_ado][n_sites*(K+1)], up/down [n_ado][bins] (-1 = absent). Host buffers. */
+int qsx_heom_index_maps(qsx_heom_t h, int64_t *ado_index, int32_t *up,
+                        int32_t *down);
+/* dy = L_heom . y for [n_columns][n_ado*M] states; member_of_column selects H. */
+int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev,
+                   int32_t n_columns, const int32_t *member_of_column_host,
+                   void *stream);
+int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *stream);
+void qsx_heom_destroy(qsx_heom_t h);
+
+/* Closed-form ADO enumeration without a handle (host only; used by the
+ * bit-exact index-map tests and by HEOMModel.ado_indices). */
+int64_t qsx_ado_count(int32_t bins, int32_t level_cutoff);
+int qsx_ado_enumerate(int32_t bins, int32_t level_cutoff, int64_t *ado_index,
+                      int32_t *up, int32_t *down);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSPECTRA_B200_H */

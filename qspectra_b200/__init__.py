@@ -15,3 +15,16 @@ from .polarization import (polarization_vector, check_polarizations,
                            invariant_polarizations, FOURTH_ORDER_INVARIANTS,
                            MAGIC_ANGLE)
 from .pulse import CustomPulse, GaussianPulse
+from .dynamics.liouville_space import (matrix_to_ket_vec, ket_vec_to_matrix,
+                                       matrix_to_bra_vec)
+from .dynamics.redfield import RedfieldModel
+from .dynamics.unitary import UnitaryModel
+from .dynamics.heom import HEOMModel
+from .simulate.eom import (simulate_dynamics, simulate_with_fields,
+                           simulate_pump)
+from .simulate.response import (linear_response, absorption_spectra,
+                                impulsive_probe, third_order_response,
+                                two_dimensional_spectra, PUMP_PROBE_PATHWAYS,
+                                THIRD_ORDER_PATHWAYS)
+from .simulate.utils import (fourier_transform, integrate, bound_signal,
+                             IntegratorError)

@@ -1,0 +1,183 @@
+"""
+ctypes binding of ``libqsx.so`` (the C ABI declared in
+``include/qspectra_b200.h``).  The library is built in-tree by
+``__graft_entry__.build()`` / ``make -C qspectra_b200/csrc``.  There is no CPU
+fallback: if the library or a CUDA device is missing, every compute entry point
+raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libqsx.so')
+
+QSX_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_INTEGRATOR, ERR_UNSUPPORTED = -1, -2, -3, -4
+METHOD_TAYLOR, METHOD_RK4, METHOD_DOPRI5 = 0, 1, 2
+SAVE_STATE, SAVE_MATRIX, SAVE_ADO0 = 0, 1, 2
+MAX_PULSES = 4
+METHODS = {'taylor': METHOD_TAYLOR, 'rk4': METHOD_RK4, 'dopri5': METHOD_DOPRI5}
+
+
+class IntegratorError(Exception):
+    """Same role as reference simulate/utils.py:12-13."""
+
+
+class QsxPulse(C.Structure):
+    _fields_ = [('scale', C.c_double), ('detuning', C.c_double),
+                ('t_peak', C.c_double), ('inv_two_sigma_sq', C.c_double),
+                ('conjugate', C.c_int32), ('_pad', C.c_int32)]
+
+
+class QsxPropagateArgs(C.Structure):
+    _fields_ = [('n_columns', C.c_int32), ('n_times', C.c_int32),
+                ('t_host', C.POINTER(C.c_double)), ('t0', C.c_double),
+                ('y0_dev', C.c_void_p),
+                ('generator_of_column_host', C.POINTER(C.c_int32)),
+                ('method', C.c_int32), ('rtol', C.c_double), ('atol', C.c_double),
+                ('rk4_substeps', C.c_int32), ('save_mode', C.c_int32),
+                ('save_rows', C.c_int32), ('save_dev', C.c_void_p),
+                ('n_save', C.c_int32), ('n_pulses', C.c_int32),
+                ('pulses', QsxPulse * MAX_PULSES),
+                ('pulse_ops_dev', C.c_void_p), ('n_pulse_sets', C.c_int32),
+                ('out_dev', C.c_void_p),
+                ('rhs_evaluations', C.c_uint64), ('accepted_steps', C.c_uint64),
+                ('kernel_ms', C.c_double)]
+
+
+class QsxHeomConfig(C.Structure):
+    _fields_ = [('n_sites', C.c_int32), ('K', C.c_int32),
+                ('level_cutoff', C.c_int32), ('n_hilbert', C.c_int32),
+                ('M', C.c_int32), ('subspace_index', C.POINTER(C.c_int64)),
+                ('n_members', C.c_int32), ('H', C.c_void_p),
+                ('coupling_diag', C.POINTER(C.c_double)),
+                ('nu', C.POINTER(C.c_double)), ('c', C.c_void_p),
+                ('temp_corr', C.c_double), ('unit_convert', C.c_double),
+                ('modified', C.c_int32), ('heisenberg', C.c_int32)]
+
+
+#: every symbol include/qspectra_b200.h declares (checked by the CPU tests)
+EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches',
+           'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
+           'qsx_dense_propagate', 'qsx_dense_destroy', 'qsx_heom_create',
+           'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
+           'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
+           'qsx_ado_enumerate']
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'qspectra_b200: %s is missing -- build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` or '
+            '`make -C qspectra_b200/csrc`; there is no CPU fallback'
+            % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.qsx_last_error.restype = C.c_char_p
+    L.qsx_kernel_launches.restype = C.c_uint64
+    L.qsx_ado_count.restype = C.c_int64
+    L.qsx_ado_count.argtypes = [C.c_int32, C.c_int32]
+    L.qsx_heom_ado_count.restype = C.c_int64
+    L.qsx_heom_ado_count.argtypes = [C.c_void_p]
+    L.qsx_ado_enumerate.argtypes = [C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    L.qsx_device_info.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int32)]
+    L.qsx_dense_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.qsx_dense_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.POINTER(C.c_int32), C.c_void_p]
+    L.qsx_dense_propagate.argtypes = [C.c_void_p, C.POINTER(QsxPropagateArgs),
+                                      C.c_void_p]
+    L.qsx_dense_destroy.argtypes = [C.c_void_p]
+    L.qsx_dense_destroy.restype = None
+    L.qsx_heom_create.argtypes = [C.POINTER(C.c_void_p),
+                                  C.POINTER(QsxHeomConfig), C.c_void_p]
+    L.qsx_heom_index_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
+    L.qsx_heom_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.POINTER(C.c_int32), C.c_void_p]
+    L.qsx_heom_propagate.argtypes = [C.c_void_p, C.POINTER(QsxPropagateArgs),
+                                     C.c_void_p]
+    L.qsx_heom_destroy.argtypes = [C.c_void_p]
+    L.qsx_heom_destroy.restype = None
+    _lib = L
+    return L
+
+
+def check(status):
+    """Map a qsx_status to the reference's exception types."""
+    if status == QSX_OK:
+        return
+    msg = lib().qsx_last_error().decode('utf-8', 'replace')
+    if status == ERR_INVALID:
+        raise ValueError(msg)
+    if status == ERR_INTEGRATOR:
+        raise IntegratorError(msg)
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError('qspectra_b200 CUDA failure: ' + msg)
+
+
+def kernel_launches():
+    return int(lib().qsx_kernel_launches())
+
+
+def ado_enumerate(bins, level_cutoff):
+    """(ado_index int64 [n, bins], up int32, down int32) from the closed-form
+    enumeration -- host only, no GPU needed."""
+    L = lib()
+    n = int(L.qsx_ado_count(bins, level_cutoff))
+    if n < 0:
+        raise ValueError('bad ADO enumeration arguments')
+    idx = np.empty((n, bins), dtype=np.int64)
+    up = np.empty((n, bins), dtype=np.int32)
+    down = np.empty((n, bins), dtype=np.int32)
+    check(L.qsx_ado_enumerate(bins, level_cutoff, idx.ctypes.data,
+                              up.ctypes.data, down.ctypes.data))
+    return idx, up, down
+
+
+# ----------------------------------------------------------------- torch glue
+def torch_cuda():
+    """torch, after checking that a CUDA device is usable (fail loudly)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('qspectra_b200 needs a CUDA device (B200); there is '
+                           'no CPU fallback')
+    return torch
+
+
+def current_stream_ptr():
+    torch = torch_cuda()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_device(array, dtype=None):
+    """numpy / torch -> contiguous CUDA tensor (complex128 by default)."""
+    torch = torch_cuda()
+    if isinstance(array, torch.Tensor):
+        t = array
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.cuda().contiguous()
+    a = np.ascontiguousarray(array, dtype=np.complex128 if dtype is None else None)
+    t = torch.from_numpy(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def int32_ptr(values):
+    if values is None:
+        return None, None
+    arr = np.ascontiguousarray(values, dtype=np.int32)
+    return arr, arr.ctypes.data_as(C.POINTER(C.c_int32))

@@ -1,0 +1,437 @@
+// K1 + K4: batched dense Liouvillian application and fused propagation for
+// RedfieldModel / UnitaryModel drop-ins.
+//
+// Replaces `evolve_matrix.dot(rho)` (reference dynamics/liouville_space.py:339-340)
+// and the ZVODE loop around it (simulate/utils.py:45-49).  One thread block owns
+// one generator (ensemble member) and up to NB state columns that share it; the
+// M x M generator is staged once in shared memory (stored transposed so the
+// per-row threads read it conflict-free) and the whole trajectory -- all
+// integrator stages, the time-dependent pulse terms and the save_func epilogue
+// -- runs inside the kernel.
+#include "cta_integrator.cuh"
+#include <algorithm>
+#include <mutex>
+
+struct qsx_dense_s {
+    int M = 0;
+    int n_gen = 0;
+    DevBuf<cplx> Lt;        // [n_gen][c][r] = L[r][c]   (transposed storage)
+    DevBuf<double> lnorm;   // [n_gen] inf-norm of L
+};
+
+// ------------------------------------------------------------------ kernels
+// Lt[g][c][r] <- L[g][r][c] (or L[g][c][r] when the Heisenberg transpose is requested)
+__global__ void dense_stage_kernel(const cplx *__restrict__ L, cplx *__restrict__ Lt, int M,
+                                   int transpose) {
+    const cplx *Lg = L + (size_t)blockIdx.x * M * M;
+    cplx *Ltg = Lt + (size_t)blockIdx.x * M * M;
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+        int c = i / M, r = i % M;
+        Ltg[i] = transpose ? Lg[c * M + r] : Lg[r * M + c];
+    }
+}
+
+__global__ void dense_norm_kernel(const cplx *__restrict__ Lt, double *__restrict__ lnorm, int M) {
+    __shared__ double scratch[32];
+    const cplx *Ltg = Lt + (size_t)blockIdx.x * M * M;
+    double best = 0.0;
+    for (int r = threadIdx.x; r < M; r += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < M; ++c) s += sqrt(cabs2(Ltg[c * M + r]));
+        best = fmax(best, s);
+    }
+    best = block_max(best, scratch);
+    if (threadIdx.x == 0) lnorm[blockIdx.x] = best;
+}
+
+// dy[col] = L[gen(col)] y[col]
+__global__ void dense_apply_kernel(const cplx *__restrict__ Lt, const int *__restrict__ gen_of,
+                                   const cplx *__restrict__ y, cplx *__restrict__ dy, int M) {
+    extern __shared__ cplx xs[];
+    const int col = blockIdx.x;
+    const int g = gen_of ? gen_of[col] : 0;
+    const cplx *Ltg = Lt + (size_t)g * M * M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) xs[i] = y[(size_t)col * M + i];
+    __syncthreads();
+    for (int r = threadIdx.x; r < M; r += blockDim.x) {
+        cplx acc = cmake(0, 0);
+        for (int c = 0; c < M; ++c) cfma(acc, __ldg(&Ltg[c * M + r]), xs[c]);
+        dy[(size_t)col * M + r] = acc;
+    }
+}
+
+struct DenseKernelArgs {
+    int M, nt;
+    const cplx *Lt;
+    const double *lnorm;
+    const cplx *y0;
+    const double *t;
+    double t0;
+    const int *grp_col0, *grp_ncol, *grp_gen;
+    int method;
+    double rtol, atol;
+    int rk4_sub, kmax;
+    double theta;
+    int save_mode, save_rows;
+    const cplx *S;
+    long long S_stride;
+    int n_pulse;
+    qsx_pulse pulses[QSX_MAX_PULSES];
+    const cplx *C;          // [set][p][r][c] row-major
+    long long C_stride;     // elements between pulse sets (0: shared)
+    cplx *out;
+    int saved_dim;
+    unsigned long long *stats;   // [0] rhs, [1] steps, [2] status (non-zero = failure)
+    int L_in_smem, C_in_smem, n_vec;
+};
+
+template <int NB>
+struct DenseRhs {
+    int M;
+    const cplx *L;      // transposed [c*M + r], shared or global
+    int n_pulse;
+    const qsx_pulse *pulses;
+    const cplx *C[QSX_MAX_PULSES];   // transposed [c*M + r] when in shared memory, else row-major global
+    int C_transposed;
+
+    template <class Epi>
+    __device__ __forceinline__ void apply(const cplx *x, double t, Epi epi) {
+        cplx g[QSX_MAX_PULSES];
+        for (int p = 0; p < n_pulse; ++p) g[p] = pulse_coefficient(pulses[p], t);
+        for (int r = threadIdx.x; r < M; r += blockDim.x) {
+            cplx acc[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[j] = cmake(0, 0);
+            for (int c = 0; c < M; ++c) {
+                cplx l = L[c * M + r];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) cfma(acc[j], l, x[c * NB + j]);
+            }
+            for (int p = 0; p < n_pulse; ++p) {
+                cplx tmp[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) tmp[j] = cmake(0, 0);
+                const cplx *Cp = C[p];
+                for (int c = 0; c < M; ++c) {
+                    cplx l = C_transposed ? Cp[c * M + r] : __ldg(&Cp[r * M + c]);
+                    if (l.x == 0.0 && l.y == 0.0) continue;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) cfma(tmp[j], l, x[c * NB + j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) cfma(acc[j], g[p], tmp[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) epi(r * NB + j, acc[j]);
+        }
+    }
+};
+
+template <int NB>
+struct DenseSaver {
+    int M, ncol, nt, mode, save_rows, saved_dim;
+    const cplx *S;
+    cplx *out;          // already offset to the group's first column
+    __device__ __forceinline__ void operator()(int it, const cplx *Y) {
+        if (mode == QSX_SAVE_MATRIX) {
+            for (int i = threadIdx.x; i < save_rows * ncol; i += blockDim.x) {
+                int m = i / ncol, j = i % ncol;
+                cplx acc = cmake(0, 0);
+                for (int r = 0; r < M; ++r) cfma(acc, __ldg(&S[(size_t)m * M + r]), Y[r * NB + j]);
+                out[((size_t)j * nt + it) * saved_dim + m] = acc;
+            }
+        } else {
+            for (int i = threadIdx.x; i < M * ncol; i += blockDim.x) {
+                int j = i / M, r = i % M;
+                out[((size_t)j * nt + it) * saved_dim + r] = Y[r * NB + j];
+            }
+        }
+    }
+};
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+dense_propagate_kernel(DenseKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = a.M;
+    const int g = blockIdx.x;
+    const int col0 = a.grp_col0[g], ncol = a.grp_ncol[g], gen = a.grp_gen[g];
+
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    double *scratch = reinterpret_cast<double *>(sm);           // 32*NB doubles
+    sm += 16 * NB;
+    const int n = M * NB;
+    cplx *vec = sm;
+    sm += (size_t)a.n_vec * n;
+
+    DenseRhs<NB> rhs;
+    rhs.M = M;
+    rhs.n_pulse = a.n_pulse;
+    rhs.pulses = a.pulses;
+    const cplx *Lg = a.Lt + (size_t)gen * M * M;
+    if (a.L_in_smem) {
+        cplx *Ls = sm;
+        sm += (size_t)M * M;
+        for (int i = threadIdx.x; i < M * M; i += blockDim.x) Ls[i] = Lg[i];
+        rhs.L = Ls;
+    } else {
+        rhs.L = Lg;
+    }
+    rhs.C_transposed = a.C_in_smem;
+    for (int p = 0; p < a.n_pulse; ++p) {
+        const cplx *Cg = a.C + (size_t)gen * a.C_stride + (size_t)p * M * M;
+        if (a.C_in_smem) {
+            cplx *Cs = sm;
+            sm += (size_t)M * M;
+            for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+                int c = i / M, r = i % M;
+                Cs[i] = Cg[r * M + c];
+            }
+            rhs.C[p] = Cs;
+        } else {
+            rhs.C[p] = Cg;
+        }
+    }
+    // initial state, zero padding for unused columns
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int r = i / NB, j = i % NB;
+        vec[i] = (j < ncol) ? a.y0[(size_t)(col0 + j) * M + r] : cmake(0, 0);
+    }
+    __syncthreads();
+
+    DenseSaver<NB> saver;
+    saver.M = M; saver.ncol = ncol; saver.nt = a.nt; saver.mode = a.save_mode;
+    saver.save_rows = a.save_rows; saver.saved_dim = a.saved_dim;
+    saver.S = a.S ? a.S + (size_t)gen * a.S_stride : nullptr;
+    saver.out = a.out + (size_t)col0 * a.nt * a.saved_dim;
+
+    CtaProp P;
+    P.n = n; P.method = a.method; P.rtol = a.rtol; P.atol = a.atol;
+    P.rk4_sub = a.rk4_sub; P.kmax = a.kmax; P.theta = a.theta;
+    P.lnorm = a.lnorm[gen]; P.nt = a.nt; P.t = a.t; P.t0 = a.t0;
+    CtaStats st;
+    cta_propagate<NB>(rhs, saver, P, vec, scratch, st);
+    if (threadIdx.x == 0) {
+        atomicAdd(&a.stats[0], st.rhs * (unsigned long long)ncol);
+        atomicAdd(&a.stats[1], st.steps * (unsigned long long)ncol);
+        if (st.status != 0) atomicAdd(&a.stats[2], 1ULL);
+    }
+}
+
+// --------------------------------------------------------------------- host
+static int n_vectors_for(int method) {
+    return method == QSX_METHOD_TAYLOR ? 3 : method == QSX_METHOD_RK4 ? 4 : 10;
+}
+
+extern "C" int qsx_dense_create(qsx_dense_t *out, int32_t M, int32_t n_generators, const void *L,
+                                int32_t on_device, int32_t transpose, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(out && L && M > 0 && n_generators > 0, "qsx_dense_create: bad arguments");
+    qsx_dense_s *h = new qsx_dense_s();
+    h->M = M;
+    h->n_gen = n_generators;
+    size_t count = (size_t)n_generators * M * M;
+    DevBuf<cplx> staging;
+    const cplx *src = (const cplx *)L;
+    cudaError_t e = h->Lt.alloc(count);
+    if (e == cudaSuccess) e = h->lnorm.alloc(n_generators);
+    if (e == cudaSuccess && !on_device) {
+        e = staging.upload((const cplx *)L, count, stream);
+        src = staging.p;
+    }
+    if (e != cudaSuccess) {
+        delete h;
+        qsx_set_error("qsx_dense_create: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    dense_stage_kernel<<<n_generators, 256, 0, stream>>>(src, h->Lt.p, M, transpose);
+    dense_norm_kernel<<<n_generators, 64, 0, stream>>>(h->Lt.p, h->lnorm.p, M);
+    qsx_launch_counter += 2;
+    e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        delete h;
+        qsx_set_error("qsx_dense_create: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    *out = h;
+    return QSX_OK;
+}
+
+extern "C" void qsx_dense_destroy(qsx_dense_t h) { delete h; }
+
+static int upload_ints(DevBuf<int> &buf, const std::vector<int> &v, cudaStream_t s) {
+    cudaError_t e = buf.upload(v, s);
+    if (e != cudaSuccess) {
+        qsx_set_error("upload: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    return QSX_OK;
+}
+
+extern "C" int qsx_dense_apply(qsx_dense_t h, const void *y_dev, void *dy_dev, int32_t n_columns,
+                               const int32_t *gen_host, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(h && y_dev && dy_dev && n_columns > 0, "qsx_dense_apply: bad arguments");
+    DevBuf<int> gen;
+    if (gen_host) {
+        std::vector<int> g(gen_host, gen_host + n_columns);
+        for (int v : g) QSX_REQUIRE(v >= 0 && v < h->n_gen, "qsx_dense_apply: generator index out of range");
+        int rc = upload_ints(gen, g, stream);
+        if (rc) return rc;
+    }
+    int threads = std::min(256, std::max(64, (h->M + 31) / 32 * 32));
+    dense_apply_kernel<<<n_columns, threads, h->M * sizeof(cplx), stream>>>(
+        h->Lt.p, gen_host ? gen.p : nullptr, (const cplx *)y_dev, (cplx *)dy_dev, h->M);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    QSX_CUDA(cudaStreamSynchronize(stream));
+    return QSX_OK;
+}
+
+template <int NB>
+static cudaError_t launch_dense(const DenseKernelArgs &a, int groups, int threads, size_t smem,
+                                cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(dense_propagate_kernel<NB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dense_propagate_kernel<NB><<<groups, threads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(h && args, "qsx_dense_propagate: null argument");
+    const int M = h->M, B = args->n_columns, nt = args->n_times;
+    QSX_REQUIRE(B > 0 && nt > 0 && args->t_host && args->y0_dev && args->out_dev,
+                "qsx_dense_propagate: empty batch or missing buffers");
+    QSX_REQUIRE(args->method >= QSX_METHOD_TAYLOR && args->method <= QSX_METHOD_DOPRI5,
+                "qsx_dense_propagate: unknown method %d", args->method);
+    QSX_REQUIRE(args->n_pulses >= 0 && args->n_pulses <= QSX_MAX_PULSES, "too many pulses");
+    QSX_REQUIRE(!(args->n_pulses > 0 && args->method == QSX_METHOD_TAYLOR),
+                "Taylor propagation needs a time-independent generator");
+    QSX_REQUIRE(args->save_mode == QSX_SAVE_STATE || args->save_mode == QSX_SAVE_MATRIX,
+                "qsx_dense_propagate: bad save_mode");
+    for (int i = 1; i < nt; ++i)
+        QSX_REQUIRE(args->t_host[i] >= args->t_host[i - 1], "output times must be non-decreasing");
+    QSX_REQUIRE(args->t_host[0] >= args->t0, "first output time precedes t0");
+
+    // groups: runs of consecutive columns sharing a generator, at most NB wide
+    int max_run = 1, run = 0, prev = -1;
+    for (int c = 0; c < B; ++c) {
+        int g = args->generator_of_column_host ? args->generator_of_column_host[c] : 0;
+        QSX_REQUIRE(g >= 0 && g < h->n_gen, "generator index %d out of range", g);
+        run = (g == prev) ? run + 1 : 1;
+        prev = g;
+        max_run = std::max(max_run, run);
+    }
+    int NB = max_run >= 8 ? 8 : max_run >= 4 ? 4 : max_run >= 2 ? 2 : 1;
+    const int n_vec = n_vectors_for(args->method);
+
+    int dev = 0, smem_limit = 0;
+    QSX_CUDA(cudaGetDevice(&dev));
+    QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    auto smem_need = [&](int nb, bool Ls, bool Cs) {
+        size_t s = (size_t)16 * nb + (size_t)n_vec * M * nb;
+        if (Ls) s += (size_t)M * M;
+        if (Cs) s += (size_t)args->n_pulses * M * M;
+        return s * sizeof(cplx);
+    };
+    bool L_in = true, C_in = args->n_pulses > 0;
+    while (smem_need(NB, L_in, C_in) > (size_t)smem_limit) {
+        if (C_in) C_in = false;
+        else if (NB > 1) NB /= 2;
+        else if (L_in) L_in = false;
+        else {
+            qsx_set_error("state dimension %d too large for the CTA-resident integrator", M);
+            return QSX_ERR_UNSUPPORTED;
+        }
+    }
+    std::vector<int> col0, ncol, gens;
+    prev = -1;
+    for (int c = 0; c < B; ++c) {
+        int g = args->generator_of_column_host ? args->generator_of_column_host[c] : 0;
+        if (g == prev && ncol.back() < NB) {
+            ncol.back() += 1;
+        } else {
+            col0.push_back(c); ncol.push_back(1); gens.push_back(g);
+        }
+        prev = g;
+    }
+    const int groups = (int)col0.size();
+    DevBuf<int> d_col0, d_ncol, d_gen;
+    DevBuf<double> d_t;
+    DevBuf<unsigned long long> d_stats;
+    int rc;
+    if ((rc = upload_ints(d_col0, col0, stream)) || (rc = upload_ints(d_ncol, ncol, stream)) ||
+        (rc = upload_ints(d_gen, gens, stream)))
+        return rc;
+    QSX_CUDA(d_t.upload(args->t_host, nt, stream));
+    QSX_CUDA(d_stats.alloc(3));
+    QSX_CUDA(cudaMemsetAsync(d_stats.p, 0, 3 * sizeof(unsigned long long), stream));
+
+    DenseKernelArgs a;
+    a.M = M; a.nt = nt; a.Lt = h->Lt.p; a.lnorm = h->lnorm.p;
+    a.y0 = (const cplx *)args->y0_dev; a.t = d_t.p; a.t0 = args->t0;
+    a.grp_col0 = d_col0.p; a.grp_ncol = d_ncol.p; a.grp_gen = d_gen.p;
+    a.method = args->method;
+    a.rtol = args->rtol > 0 ? args->rtol : (args->method == QSX_METHOD_TAYLOR ? 1e-13 : 1e-10);
+    a.atol = args->atol > 0 ? args->atol : 1e-12;
+    a.rk4_sub = args->rk4_substeps > 0 ? args->rk4_substeps : 16;
+    a.kmax = 40; a.theta = 2.0;
+    a.save_mode = args->save_mode; a.save_rows = args->save_rows;
+    a.S = (const cplx *)args->save_dev;
+    a.S_stride = (args->n_save > 1) ? (long long)args->save_rows * M : 0;
+    if (a.save_mode == QSX_SAVE_MATRIX) {
+        QSX_REQUIRE(a.S && a.save_rows > 0, "save matrix missing");
+        QSX_REQUIRE(args->n_save == 1 || args->n_save == h->n_gen, "n_save must be 1 or n_generators");
+    }
+    a.saved_dim = a.save_mode == QSX_SAVE_MATRIX ? a.save_rows : M;
+    a.n_pulse = args->n_pulses;
+    for (int p = 0; p < QSX_MAX_PULSES; ++p) a.pulses[p] = args->pulses[p];
+    a.C = (const cplx *)args->pulse_ops_dev;
+    a.C_stride = (args->n_pulse_sets > 1) ? (long long)args->n_pulses * M * M : 0;
+    if (a.n_pulse > 0) {
+        QSX_REQUIRE(a.C, "pulse operators missing");
+        QSX_REQUIRE(args->n_pulse_sets == 1 || args->n_pulse_sets == h->n_gen,
+                    "n_pulse_sets must be 1 or n_generators");
+    }
+    a.out = (cplx *)args->out_dev;
+    a.stats = d_stats.p;
+    a.L_in_smem = L_in; a.C_in_smem = C_in; a.n_vec = n_vec;
+
+    const int threads = std::min(256, std::max(64, (M + 31) / 32 * 32));
+    const size_t smem = smem_need(NB, L_in, C_in);
+    cudaEvent_t e0, e1;
+    QSX_CUDA(cudaEventCreate(&e0));
+    QSX_CUDA(cudaEventCreate(&e1));
+    QSX_CUDA(cudaEventRecord(e0, stream));
+    cudaError_t e;
+    switch (NB) {
+        case 8: e = launch_dense<8>(a, groups, threads, smem, stream); break;
+        case 4: e = launch_dense<4>(a, groups, threads, smem, stream); break;
+        case 2: e = launch_dense<2>(a, groups, threads, smem, stream); break;
+        default: e = launch_dense<1>(a, groups, threads, smem, stream); break;
+    }
+    qsx_launch_counter += 1;
+    if (e != cudaSuccess) {
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        qsx_set_error("dense_propagate launch: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    QSX_CUDA(cudaEventRecord(e1, stream));
+    unsigned long long stats[3] = {0, 0, 0};
+    QSX_CUDA(cudaMemcpyAsync(stats, d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, stream));
+    QSX_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    args->rhs_evaluations = stats[0];
+    args->accepted_steps = stats[1];
+    args->kernel_ms = ms;
+    if (stats[2] != 0) {
+        qsx_set_error("integration failed in %llu column group(s) (method %d)", stats[2], args->method);
+        return QSX_ERR_INTEGRATOR;
+    }
+    return QSX_OK;
+}

@@ -1,0 +1,321 @@
+"""
+Device equations of motion: thin Python objects around the C-ABI handles.
+
+A ``DeviceEOM`` is what ``DynamicalModel.equation_of_motion`` returns.  It is a
+callable ``f(t, y)`` like the reference's closures
+(dynamics/liouville_space.py:339-341, heom.py:241-244) *and* it knows how to
+run the whole ``integrate`` loop (simulate/utils.py:53-109) on the GPU for a
+batch of initial states.  PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import IntegratorError  # noqa: F401  (re-export)
+
+
+class PropagationStats(object):
+    """Counters of the most recent propagations (bench.py reads these)."""
+    rhs_evaluations = 0
+    accepted_steps = 0
+    kernel_ms = 0.0
+    propagations = 0
+
+    @classmethod
+    def reset(cls):
+        cls.rhs_evaluations = 0
+        cls.accepted_steps = 0
+        cls.kernel_ms = 0.0
+        cls.propagations = 0
+
+
+class LinearMap(object):
+    """A linear save_func: ``state -> matrix . state`` (the reference's
+    ``SystemOperator.commutator`` etc. are exactly such maps,
+    liouville_space.py:183-209).  ``per_ado`` marks HEOM block-diagonal maps."""
+
+    def __init__(self, matrix, n_ado=1, ado0_only=False):
+        self.matrix = np.asarray(matrix)
+        self.n_ado = n_ado
+        self.ado0_only = ado0_only
+
+    def __call__(self, state):
+        state = np.asarray(state)
+        m = self.matrix
+        k = m.shape[-1]
+        if self.ado0_only:
+            return np.tensordot(state[..., :k], m, axes=(-1, -1))
+        if self.n_ado == 1:
+            return np.tensordot(state, m, axes=(-1, -1))
+        blocks = state.reshape(state.shape[:-1] + (self.n_ado, k))
+        out = np.tensordot(blocks, m, axes=(-1, -1))
+        return out.reshape(state.shape[:-1] + (-1,))
+
+    #: reference code calls ``V.commutator(state)`` and also passes
+    #: ``V.commutator`` as save_func; both work with this object.
+    dot = __call__
+
+
+def resolve_method(method_name, lti):
+    """Map the reference's ``method_name`` to a device integrator.  'zvode'
+    (the reference default, simulate/utils.py:53) selects the engine's default:
+    adaptive Taylor for constant generators, DOPRI5 otherwise."""
+    name = (method_name or 'zvode').lower()
+    if name in ('zvode', 'vode', 'auto', 'lsoda'):
+        return 'taylor' if lti else 'dopri5'
+    if name in ('dop853',):
+        return 'dopri5'
+    if name not in _capi.METHODS:
+        raise ValueError('unknown integration method %r (device methods: '
+                         'taylor, rk4, dopri5)' % method_name)
+    if name == 'taylor' and not lti:
+        raise ValueError('taylor needs a time-independent linear generator')
+    return name
+
+
+class DeviceEOM(object):
+    """Base class: a generator resident on the GPU."""
+    lti = True
+    n_generators = 1
+    dim = 0
+
+    def __call__(self, t, y):
+        y = np.asarray(y, dtype=complex)
+        out = self.apply(y.reshape(1, -1) if y.ndim == 1 else y)
+        return out.reshape(y.shape)
+
+    # subclasses: _apply_dev(y_dev, dy_dev, n, gens) and _propagate(args)
+    def apply(self, y, generators=None):
+        torch = _capi.torch_cuda()
+        y_dev = _capi.to_device(y).reshape(-1, self.dim)
+        dy = torch.empty_like(y_dev)
+        _, gptr = _capi.int32_ptr(generators)
+        self._apply_dev(y_dev, dy, y_dev.shape[0], gptr)
+        return dy.cpu().numpy()
+
+    def propagate(self, y0, t, t0=None, method='zvode', save=None,
+                  generators=None, pulses=None, pulse_ops=None, rtol=None,
+                  atol=None, rk4_substeps=None, return_device=False, **ignored):
+        """Integrate a batch: y0 (B, dim) -> (B, len(t), saved_dim).
+
+        save      : None | LinearMap | ('ado0',) | ndarray (rows, dim[/n_ado])
+                    or stack (n_generators, rows, dim)
+        generators: int array (B,) choosing the generator of each column
+        pulses    : list of (scale, detuning, t_peak, inv_two_sigma_sq, conj)
+        pulse_ops : (n_sets, n_pulses, d, d) complex
+        """
+        torch = _capi.torch_cuda()
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        if t.ndim != 1 or t.size == 0:
+            raise ValueError('t must be a non-empty 1D array')
+        y0_dev = _capi.to_device(y0).reshape(-1, self.dim)
+        B = y0_dev.shape[0]
+        lti = self.lti and not pulses
+        method = resolve_method(method, lti)
+
+        args = _capi.QsxPropagateArgs()
+        args.n_columns = B
+        args.n_times = t.size
+        args.t_host = t.ctypes.data_as(C.POINTER(C.c_double))
+        args.t0 = float(t[0] if t0 is None else t0)
+        args.y0_dev = y0_dev.data_ptr()
+        garr, gptr = _capi.int32_ptr(generators)
+        if garr is not None and garr.shape != (B,):
+            raise ValueError('generators must have one entry per column')
+        args.generator_of_column_host = gptr
+        args.method = _capi.METHODS[method]
+        args.rtol = float(rtol) if rtol else 0.0
+        args.atol = float(atol) if atol else 0.0
+        args.rk4_substeps = int(rk4_substeps) if rk4_substeps else 0
+
+        keep = []
+        saved_dim = self._configure_save(args, save, keep)
+        n_p = len(pulses) if pulses else 0
+        if n_p > _capi.MAX_PULSES:
+            raise ValueError('at most %d pulses' % _capi.MAX_PULSES)
+        args.n_pulses = n_p
+        if n_p:
+            ops = _capi.to_device(pulse_ops)
+            if ops.dim() == 3:
+                ops = ops.unsqueeze(0)
+            args.pulse_ops_dev = ops.data_ptr()
+            args.n_pulse_sets = ops.shape[0]
+            keep.append(ops)
+            for i, p in enumerate(pulses):
+                (args.pulses[i].scale, args.pulses[i].detuning,
+                 args.pulses[i].t_peak, args.pulses[i].inv_two_sigma_sq) = p[:4]
+                args.pulses[i].conjugate = int(bool(p[4]))
+        out = torch.empty((B, t.size, saved_dim), dtype=torch.complex128,
+                          device=y0_dev.device)
+        args.out_dev = out.data_ptr()
+        self._propagate(args)
+        PropagationStats.rhs_evaluations += int(args.rhs_evaluations)
+        PropagationStats.accepted_steps += int(args.accepted_steps)
+        PropagationStats.kernel_ms += float(args.kernel_ms)
+        PropagationStats.propagations += 1
+        self.last = dict(rhs=int(args.rhs_evaluations),
+                         steps=int(args.accepted_steps),
+                         kernel_ms=float(args.kernel_ms), method=method)
+        return out if return_device else out.cpu().numpy()
+
+    def _configure_save(self, args, save, keep):
+        if save is None:
+            args.save_mode = _capi.SAVE_STATE
+            return self.dim
+        if isinstance(save, tuple) and save and save[0] == 'ado0':
+            return self._configure_ado0(args)
+        matrix = save.matrix if isinstance(save, LinearMap) else save
+        return self._configure_matrix(args, matrix, save, keep)
+
+    def _configure_ado0(self, args):
+        raise ValueError('ado0 save is only defined for HEOM generators')
+
+    def _configure_matrix(self, args, matrix, save, keep):
+        S = _capi.to_device(matrix)
+        if S.dim() == 1:
+            S = S.unsqueeze(0)
+        if S.dim() == 2:
+            S = S.unsqueeze(0)
+        if S.shape[-1] != self.dim:
+            raise ValueError('save matrix has %d columns, state has %d'
+                             % (S.shape[-1], self.dim))
+        keep.append(S)
+        args.save_mode = _capi.SAVE_MATRIX
+        args.save_rows = S.shape[1]
+        args.save_dev = S.data_ptr()
+        args.n_save = S.shape[0]
+        return S.shape[1]
+
+
+class DenseEOM(DeviceEOM):
+    """Batched dense Liouvillians L[g] (n_generators, M, M) staged on the GPU
+    (kernel K1/K4, csrc/dense.cu)."""
+
+    def __init__(self, L, heisenberg_picture=False):
+        torch = _capi.torch_cuda()
+        lib = _capi.lib()
+        on_device = isinstance(L, torch.Tensor)
+        if on_device:
+            Ld = L.to(torch.complex128).cuda().contiguous()
+            if Ld.dim() == 2:
+                Ld = Ld.unsqueeze(0)
+            shape, ptr = tuple(Ld.shape), Ld.data_ptr()
+        else:
+            Lh = np.ascontiguousarray(L, dtype=np.complex128)
+            if Lh.ndim == 2:
+                Lh = Lh[None]
+            shape, ptr = Lh.shape, Lh.ctypes.data
+        if len(shape) != 3 or shape[1] != shape[2]:
+            raise ValueError('generators must have shape (n, M, M)')
+        self.n_generators, self.dim = int(shape[0]), int(shape[1])
+        self.heisenberg_picture = bool(heisenberg_picture)
+        self._h = C.c_void_p()
+        _capi.check(lib.qsx_dense_create(C.byref(self._h), self.dim,
+                                         self.n_generators, ptr, int(on_device),
+                                         int(self.heisenberg_picture),
+                                         _capi.current_stream_ptr()))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            _capi.lib().qsx_dense_destroy(h)
+            self._h = None
+
+    def _apply_dev(self, y, dy, n, gptr):
+        _capi.check(_capi.lib().qsx_dense_apply(
+            self._h, y.data_ptr(), dy.data_ptr(), n, gptr,
+            _capi.current_stream_ptr()))
+
+    def _propagate(self, args):
+        _capi.check(_capi.lib().qsx_dense_propagate(
+            self._h, C.byref(args), _capi.current_stream_ptr()))
+
+
+class HeomEOM(DeviceEOM):
+    """HEOM hierarchy generator (kernel K2/K4, csrc/heom.cu)."""
+
+    def __init__(self, n_sites, K, level_cutoff, subspace_index, H,
+                 coupling_diag, nu, c, temp_corr, unit_convert, modified=False,
+                 heisenberg_picture=False):
+        lib = _capi.lib()
+        _capi.torch_cuda()
+        H = np.ascontiguousarray(H, dtype=np.complex128)
+        if H.ndim == 2:
+            H = H[None]
+        idx = np.ascontiguousarray(subspace_index, dtype=np.int64)
+        v = np.ascontiguousarray(coupling_diag, dtype=np.float64)
+        nu = np.ascontiguousarray(nu, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.complex128)
+        cfg = _capi.QsxHeomConfig()
+        cfg.n_sites, cfg.K, cfg.level_cutoff = int(n_sites), int(K), int(level_cutoff)
+        cfg.n_hilbert, cfg.M = H.shape[-1], idx.size
+        cfg.subspace_index = idx.ctypes.data_as(C.POINTER(C.c_int64))
+        cfg.n_members = H.shape[0]
+        cfg.H = H.ctypes.data
+        cfg.coupling_diag = v.ctypes.data_as(C.POINTER(C.c_double))
+        cfg.nu = nu.ctypes.data_as(C.POINTER(C.c_double))
+        cfg.c = c.ctypes.data
+        cfg.temp_corr = float(np.real(temp_corr))
+        cfg.unit_convert = float(unit_convert)
+        cfg.modified = int(bool(modified))
+        cfg.heisenberg = int(bool(heisenberg_picture))
+        if v.shape != (n_sites, H.shape[-1]):
+            raise ValueError('coupling_diag must have shape (n_sites, N)')
+        self._h = C.c_void_p()
+        _capi.check(lib.qsx_heom_create(C.byref(self._h), C.byref(cfg),
+                                        _capi.current_stream_ptr()))
+        self.n_generators = H.shape[0]
+        self.M = idx.size
+        self.n_ado = int(lib.qsx_heom_ado_count(self._h))
+        self.dim = self.n_ado * self.M
+        self.bins = n_sites * (K + 1)
+        self.heisenberg_picture = bool(heisenberg_picture)
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            _capi.lib().qsx_heom_destroy(h)
+            self._h = None
+
+    def index_maps(self):
+        idx = np.empty((self.n_ado, self.bins), dtype=np.int64)
+        up = np.empty((self.n_ado, self.bins), dtype=np.int32)
+        down = np.empty((self.n_ado, self.bins), dtype=np.int32)
+        _capi.check(_capi.lib().qsx_heom_index_maps(
+            self._h, idx.ctypes.data, up.ctypes.data, down.ctypes.data))
+        return idx, up, down
+
+    def _apply_dev(self, y, dy, n, gptr):
+        _capi.check(_capi.lib().qsx_heom_apply(
+            self._h, y.data_ptr(), dy.data_ptr(), n, gptr,
+            _capi.current_stream_ptr()))
+
+    def _propagate(self, args):
+        _capi.check(_capi.lib().qsx_heom_propagate(
+            self._h, C.byref(args), _capi.current_stream_ptr()))
+
+    def _configure_ado0(self, args):
+        args.save_mode = _capi.SAVE_ADO0
+        return self.M
+
+    def _configure_matrix(self, args, matrix, save, keep):
+        S = np.asarray(matrix)
+        if S.ndim == 1:
+            S = S[None]
+        if isinstance(save, LinearMap) and save.ado0_only:
+            # expectation values read ADO 0 only (heom.py:55-58): embed the row
+            # vector in a block that is applied to every ADO and keep block 0
+            raise ValueError('use save=("ado0",) and contract on the host, or '
+                             'the Heisenberg picture, for HEOM expectation '
+                             'values')
+        if S.shape[-1] != self.M:
+            raise ValueError('HEOM save matrix must act on one ADO '
+                             '(%d columns), got %d' % (self.M, S.shape[-1]))
+        Sd = _capi.to_device(S)
+        keep.append(Sd)
+        args.save_mode = _capi.SAVE_MATRIX
+        args.save_rows = S.shape[0]
+        args.save_dev = Sd.data_ptr()
+        args.n_save = 1
+        return self.n_ado * S.shape[0]

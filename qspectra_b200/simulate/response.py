@@ -1,0 +1,212 @@
+"""
+Response-function spectroscopy on the device integrators.
+
+Contract: reference ``qspectra/simulate/response.py`` -- ``linear_response``
+:13-100, ``absorption_spectra`` :103-154, ``impulsive_probe`` :174-244,
+Liouville pathway tables :157-159 / :252-264, ``third_order_response``
+:267-427, ``two_dimensional_spectra`` :430-455.
+
+Each ``integrate`` call below is one fused device propagation of a batch of
+columns: e.g. the t2 stage of the third-order response propagates all n_t1
+columns of V_rho1 under one generator in a single kernel, where the reference
+runs n_t1 serial ZVODE solves (utils.py:103-109).
+"""
+import numpy as np
+
+from .decorators import (optional_ensemble_average,
+                         optional_2nd_order_isotropic_average,
+                         optional_4th_order_isotropic_average)
+from .utils import integrate, fourier_transform
+from ..utils import ZeroArray
+
+
+@optional_ensemble_average
+@optional_2nd_order_isotropic_average
+def _linear_response(dynamical_model, liouv_space_path, time_max,
+                     initial_state=None, polarization='xx', **integrate_kwargs):
+    subspaces = liouv_space_path.split('->')
+    if initial_state is None:
+        initial_state = dynamical_model.thermal_state(subspaces[0])
+    initial_state = np.asarray(initial_state)
+    t = np.arange(0, time_max, dynamical_model.time_step)
+    signal = ZeroArray()
+    for sim_subspace in subspaces[1].split(','):
+        V = [dynamical_model.dipole_operator('{}->{}'.format(a, b), polar, trans)
+             for a, b, polar, trans in zip(subspaces[:-1], subspaces[1:],
+                                           polarization, '+-')]
+        V_rho0 = V[0].commutator(initial_state)
+        try:
+            # Heisenberg picture: one propagation of the detection operator
+            # serves every initial state
+            eom = dynamical_model.equation_of_motion(sim_subspace,
+                                                     heisenberg_picture=True)
+        except NotImplementedError:
+            eom = dynamical_model.equation_of_motion(sim_subspace)
+            signal -= integrate(eom, V_rho0, t,
+                                save_func=V[1].expectation_value,
+                                **integrate_kwargs)
+        else:
+            V_Gt = integrate(eom, -V[1].bra_vector, t, **integrate_kwargs)
+            signal += np.tensordot(V_rho0, V_Gt, (-1, -1))
+    return (t, signal)
+
+
+def linear_response(dynamical_model, liouv_space_path, time_max,
+                    initial_state=None, polarization='xx', ensemble_size=None,
+                    ensemble_random_orientations=False,
+                    exact_isotropic_average=False, **integrate_kwargs):
+    """Linear response function along a Liouville path 'ab->cd->ef'."""
+    return _linear_response(
+        dynamical_model, liouv_space_path, time_max, initial_state,
+        polarization, ensemble_size=ensemble_size,
+        ensemble_random_orientations=ensemble_random_orientations,
+        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+
+
+def absorption_spectra(dynamical_model, time_max, correlation_decay_time=None,
+                       polarization='xx', ensemble_size=None,
+                       ensemble_random_orientations=False,
+                       exact_isotropic_average=False, **integrate_kwargs):
+    """(frequencies, real absorption signal)."""
+    (t, x) = linear_response(
+        dynamical_model, 'gg->eg->gg', time_max, polarization=polarization,
+        ensemble_size=ensemble_size,
+        ensemble_random_orientations=ensemble_random_orientations,
+        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+    if correlation_decay_time is not None:
+        x = x * np.exp(-t / correlation_decay_time)
+    (f, X) = fourier_transform(t, -x, rw_freq=dynamical_model.rw_freq,
+                               unit_convert=dynamical_model.unit_convert)
+    return (f, X.real)
+
+
+PUMP_PROBE_PATHWAYS = {'GSB': 'gg->eg->gg',
+                       'ESE': 'ee->eg->gg',
+                       'ESA': 'ee->fe->ee'}
+
+
+def _parse_pathways(possible_pathways, include_signal):
+    selected = [path for name, path in possible_pathways.items()
+                if include_signal is None or name in include_signal]
+    if not selected:
+        raise ValueError('at least one Liouville space pathway must be '
+                         'selected, i.e., include_signal must include at least '
+                         'one of %r' % list(possible_pathways.keys()))
+    return selected
+
+
+def impulsive_probe(dynamical_model, state, time_max, polarization='xx',
+                    initial_liouv_subspace='gg,ge,eg,ee',
+                    include_signal='GSB,ESE,ESA', ensemble_size=None,
+                    ensemble_random_orientations=False,
+                    exact_isotropic_average=False, **integrate_kwargs):
+    """Probe the 2nd-order part of ``state`` with an impulsive probe pulse;
+    returns (frequencies, complex signal field)."""
+    state = np.asarray(state)
+    initial_state = state - dynamical_model.thermal_state(initial_liouv_subspace)
+    total_signal = ZeroArray()
+    for path in _parse_pathways(PUMP_PROBE_PATHWAYS, include_signal):
+        first = path.split('->')[0]
+        portion = np.apply_along_axis(
+            lambda s: dynamical_model.map_between_subspaces(
+                s, initial_liouv_subspace, first), -1, initial_state)
+        (t, signal) = linear_response(
+            dynamical_model, path, time_max, portion, polarization,
+            ensemble_size=ensemble_size,
+            ensemble_random_orientations=ensemble_random_orientations,
+            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+        total_signal += signal
+    return fourier_transform(t, total_signal, rw_freq=dynamical_model.rw_freq,
+                             unit_convert=dynamical_model.unit_convert)
+
+
+# Liouville-space pathways of Abramavicius et al., Chem. Rev. 109, 2350 (2009),
+# figs. 4-6 (same tables as the reference)
+THIRD_ORDER_PATHWAYS = {
+    '-++': {'ESE': 'gg->ge->ee->eg->gg',      # photon echo
+            'GSB': 'gg->ge->gg->eg->gg',
+            'ESA': 'gg->ge->ee->fe->ee'},
+    '+-+': {'ESE': 'gg->eg->ee->eg->gg',      # non-rephasing
+            'GSB': 'gg->eg->gg->eg->gg',
+            'ESA': 'gg->eg->ee->fe->ee'},
+    '++-': {'ESA1': 'gg->eg->fg->fe->ee',     # double-quantum coherence
+            'ESA2': 'gg->eg->fg->eg->gg'},
+}
+
+
+@optional_ensemble_average
+@optional_4th_order_isotropic_average
+def _third_order_response(dynamical_model, coherence_time_max,
+                          population_time_max, population_times, geometry,
+                          polarization, include_signal, **integrate_kwargs):
+    t1 = np.arange(0, coherence_time_max, dynamical_model.time_step)
+    t2 = (np.arange(0, population_time_max, dynamical_model.time_step)
+          if population_times is None
+          else np.asarray(population_times, dtype=float))
+    t3 = np.arange(0, coherence_time_max, dynamical_model.time_step)
+
+    initial_state = dynamical_model.thermal_state('gg')
+    total_signal = ZeroArray()
+    for path in _parse_pathways(THIRD_ORDER_PATHWAYS[geometry], include_signal):
+        subspaces = path.split('->')
+        V = [dynamical_model.dipole_operator('{}->{}'.format(a, b), polar, trans)
+             for a, b, polar, trans in zip(subspaces[:-1], subspaces[1:],
+                                           polarization, geometry + '-')]
+        eom = [dynamical_model.equation_of_motion(s) for s in subspaces[1:-1]]
+        V_rho0 = V[0].commutator(initial_state)
+        # t1: one column; t2: n_t1 columns under one generator (batched)
+        V_rho1 = integrate(eom[0], V_rho0, t1, save_func=V[1].commutator,
+                           **integrate_kwargs)
+        V_rho2 = integrate(eom[1], V_rho1, t2, t0=0, save_func=V[2].commutator,
+                           **integrate_kwargs)
+        try:
+            eom_heisen = dynamical_model.equation_of_motion(
+                subspaces[3], heisenberg_picture=True)
+        except NotImplementedError:
+            total_signal += integrate(eom[2], V_rho2, t3,
+                                      save_func=V[3].expectation_value,
+                                      **integrate_kwargs)
+        else:
+            V_Gt3 = integrate(eom_heisen, V[3].bra_vector, t3,
+                              **integrate_kwargs)
+            total_signal += np.einsum('ci,abi', V_Gt3, V_rho2)
+    return (t1, t2, t3), total_signal
+
+
+def third_order_response(dynamical_model, coherence_time_max,
+                         population_time_max=None, population_times=None,
+                         geometry='-++', polarization='xxxx',
+                         include_signal=None, ensemble_size=None,
+                         ensemble_random_orientations=False,
+                         exact_isotropic_average=False, **integrate_kwargs):
+    """Third-order response ((t1, t2, t3), signal[t1, t2, t3]) in the rotating
+    wave approximation, summed over the selected Liouville pathways."""
+    return _third_order_response(
+        dynamical_model, coherence_time_max, population_time_max,
+        population_times, geometry, polarization, include_signal,
+        ensemble_size=ensemble_size,
+        ensemble_random_orientations=ensemble_random_orientations,
+        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+
+
+def two_dimensional_spectra(dynamical_model, coherence_time_max,
+                            population_time_max=None, population_times=None,
+                            geometry='-++', polarization='xxxx',
+                            include_signal=None, ensemble_size=None,
+                            ensemble_random_orientations=False,
+                            exact_isotropic_average=False,
+                            **integrate_kwargs):
+    """2D spectrum: Fourier transform of the third-order response over t1
+    (sign -1) and t3."""
+    (t1, t2, t3), X = third_order_response(
+        dynamical_model, coherence_time_max, population_time_max,
+        population_times, geometry, polarization, include_signal,
+        ensemble_size, ensemble_random_orientations, exact_isotropic_average,
+        **integrate_kwargs)
+    rw_freq = dynamical_model.rw_freq
+    unit_convert = dynamical_model.unit_convert
+    f1, X_ftt = fourier_transform(t1, X, 0, rw_freq=rw_freq, sign=-1,
+                                  unit_convert=unit_convert)
+    f3, X_ftf = fourier_transform(t3, X_ftt, 2, rw_freq=rw_freq,
+                                  unit_convert=unit_convert)
+    return (f1, t2, f3), X_ftf

@@ -1,0 +1,304 @@
+"""
+GPU parity tests (B200): the CUDA path, called through the C ABI, against the
+golden fixtures recorded from the real reference and against the CPU oracle on
+the same seeded inputs.  Tolerance: 1e-8 relative L2 (BASELINE.json north_star)
+for trajectories/spectra; integer maps bit-exact.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import qspectra_b200 as qb
+from qspectra_b200 import systems, engine
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+CM_FS = qb.CM_FS
+TOL = 1e-8
+TIGHT = oracle.TIGHT
+
+
+@pytest.fixture(scope='module')
+def fmo_model():
+    return qb.RedfieldModel(systems.fmo(), hilbert_subspace='e',
+                            unit_convert=CM_FS, secular=False)
+
+
+# ------------------------------------------------------------------ K1 dense
+def test_dense_apply_matches_generator(fmo_model, golden):
+    L = golden('redfield')['fmo_L_ee']
+    rng = np.random.RandomState(0)
+    y = rng.randn(5, 49) + 1j * rng.randn(5, 49)
+    eom = fmo_model.equation_of_motion('ee')
+    assert rel_l2(eom.apply(y), y @ L.T) < 1e-14
+    assert rel_l2(eom(0.0, y[0]), L @ y[0]) < 1e-14
+    eom_h = fmo_model.equation_of_motion('ee', heisenberg_picture=True)
+    assert rel_l2(eom_h.apply(y), y @ L) < 1e-14
+
+
+@pytest.mark.parametrize('method,kw', [('taylor', {}), ('zvode', {}),
+                                       ('rk4', dict(rk4_substeps=24)),
+                                       ('dopri5', dict(rtol=1e-11, atol=1e-13))])
+def test_fmo_redfield_trajectory(fmo_model, golden, method, kw):
+    g = golden('redfield')
+    t, rho = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 1000,
+                                  method_name=method, **kw)
+    assert np.array_equal(t, g['fmo_t'])
+    assert rel_l2(rho, g['fmo_rho_1ps']) < TOL
+
+
+def test_fmo_redfield_ensemble(fmo_model, golden):
+    t, rho = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 300, ensemble_size=4)
+    assert rel_l2(rho, golden('redfield')['fmo_ens4_rho_300fs']) < TOL
+
+
+def test_batched_columns_share_generator(fmo_model):
+    """columns of one generator are propagated NB at a time: each must equal
+    its own single-column run (linearity / batching invariance)."""
+    rng = np.random.RandomState(3)
+    y0 = rng.randn(11, 49) + 1j * rng.randn(11, 49)
+    eom = fmo_model.equation_of_motion('ee')
+    t = np.arange(0, 100, fmo_model.time_step)
+    batch = eom.propagate(y0, t)
+    for j in (0, 7, 10):
+        single = eom.propagate(y0[j:j + 1], t)
+        assert rel_l2(batch[j], single[0]) < 1e-12
+    lin = eom.propagate((2 * y0[0] - 1j * y0[1])[None], t)
+    assert rel_l2(lin[0], 2 * batch[0] - 1j * batch[1]) < 1e-11
+
+
+def test_trace_preservation_100ps(fmo_model):
+    """size-independent property at BASELINE length: tr rho(t) == 1 over the
+    full 19 601-point, 100 ps grid."""
+    t, rho = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 100000)
+    assert len(t) == 19601
+    tr = np.einsum('tii->t', rho)
+    assert np.abs(tr - 1).max() < 1e-9
+
+
+def test_dimer_absorption(golden):
+    g = golden('redfield')
+    m = qb.RedfieldModel(systems.dimer(), hilbert_subspace='gef',
+                         unit_convert=CM_FS, discard_imag_corr=True)
+    f, X = qb.absorption_spectra(m, 10000)
+    assert np.array_equal(f, g['dimer_abs_f'])
+    assert rel_l2(X, g['dimer_abs_X']) < TOL
+    t, x = qb.linear_response(m, 'gg->eg->gg', 2000, polarization='xy',
+                              exact_isotropic_average=True)
+    assert rel_l2(x, g['dimer_lin_iso_xy']) < TOL
+
+
+def test_fmo_absorption_variants(golden):
+    g = golden('redfield')
+    ms = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef',
+                          unit_convert=CM_FS)
+    f, X = qb.absorption_spectra(ms, 2000, exact_isotropic_average=True)
+    assert rel_l2(X, g['fmo_abs_iso_X']) < TOL
+    f, X = qb.absorption_spectra(ms, 2000, ensemble_size=3,
+                                 ensemble_random_orientations=True)
+    assert rel_l2(X, g['fmo_abs_ens3_ro_X']) < TOL
+
+
+def test_eigenbasis_model(golden):
+    m = qb.RedfieldModel(systems.dimer(), hilbert_subspace='gef',
+                         unit_convert=CM_FS, evolve_basis='eigen',
+                         sparse_matrix=True)
+    rho0 = m.hamiltonian.transform_operator_to_eigenbasis(np.diag([1., 0]), 'e')
+    t, rho = qb.simulate_dynamics(m, rho0, 500)
+    assert rel_l2(rho, golden('redfield')['dimer_eigen_dyn']) < TOL
+
+
+# ------------------------------------------------------------------- K2 HEOM
+def test_heom_index_maps_bit_exact(golden):
+    g = golden('maps')
+    for i, (N, K, Lc) in enumerate(g['ado_cases']):
+        ham = systems.fmo(n_sites=int(N))
+        m = qb.HEOMModel(ham, hilbert_subspace='e', unit_convert=CM_FS,
+                         level_cutoff=int(Lc), K=int(K))
+        idx, up, down = m.equation_of_motion('ee').index_maps()
+        assert np.array_equal(idx, g['ado_%d' % i])
+        assert np.array_equal(up, g['up_%d' % i])
+        assert np.array_equal(down, g['down_%d' % i])
+
+
+def test_heom_apply_vs_reference_rhs(golden):
+    g = golden('heom')
+    for tag, kw in [('k2', dict(level_cutoff=3, K=2)),
+                    ('mod', dict(level_cutoff=4, K=1, modified_HEOM=True))]:
+        m = qb.HEOMModel(systems.dimer(), hilbert_subspace='ge',
+                         unit_convert=CM_FS, **kw)
+        for ss in ('ee', 'eg'):
+            y = g['dimer_%s_%s_y' % (tag, ss)]
+            assert rel_l2(m.equation_of_motion(ss)(0, y),
+                          g['dimer_%s_%s_Ly' % (tag, ss)]) < 1e-13
+            assert rel_l2(m.equation_of_motion(ss, True)(0, y),
+                          g['dimer_%s_%s_LTy' % (tag, ss)]) < 1e-13
+    mv = qb.HEOMModel(systems.jonas_dimer(), hilbert_subspace='ge',
+                      unit_convert=CM_FS, level_cutoff=3, K=1)
+    for ss in ('ee', 'eg'):
+        assert rel_l2(mv.equation_of_motion(ss)(0, g['vib_%s_y' % ss]),
+                      g['vib_%s_Ly' % ss]) < 1e-13
+    for depth in (3, 4):
+        mf = qb.HEOMModel(systems.fmo(), hilbert_subspace='e',
+                          unit_convert=CM_FS, level_cutoff=depth, K=1)
+        D = mf.ado_count * 49
+        y = (np.random.RandomState(depth).randn(D)
+             + 1j * np.random.RandomState(depth + 10).randn(D))
+        assert rel_l2(mf.equation_of_motion('ee')(0, y),
+                      g['fmo_d%d_Ly' % depth]) < 1e-13
+
+
+def test_heom_apply_vs_oracle_csr_subspaces():
+    """every Liouville subspace the response functions use, both pictures"""
+    ham = systems.fmo(n_sites=3)
+    m = qb.HEOMModel(ham, hilbert_subspace='gef', unit_convert=CM_FS,
+                     level_cutoff=3, K=1)
+    o = oracle.OracleHEOM(ham, hilbert_subspace='gef', unit_convert=CM_FS,
+                          level_cutoff=3, K=1)
+    rng = np.random.RandomState(5)
+    for ss in ('gg', 'eg', 'ge', 'ee', 'fe', 'fg', 'gg,ge,eg,ee'):
+        for heis in (False, True):
+            A = o.generator(ss, heis)
+            y = rng.randn(A.shape[0]) + 1j * rng.randn(A.shape[0])
+            got = m.equation_of_motion(ss, heis)(0, y)
+            assert rel_l2(got, A @ y) < 1e-13, (ss, heis)
+
+
+@pytest.mark.parametrize('method,kw', [('taylor', {}), ('rk4', dict(rk4_substeps=40))])
+def test_heom_trajectories(golden, method, kw):
+    g = golden('heom')
+    m = qb.HEOMModel(systems.dimer(), hilbert_subspace='gef', unit_convert=CM_FS,
+                     level_cutoff=3, low_temp_corr=False)
+    y0 = m.density_matrix_to_state_vector(np.diag([1., 0]).astype(complex), 'ee')
+    traj = qb.integrate(m.equation_of_motion('ee'), y0, g['dimer_dyn_t'],
+                        method_name=method, **kw)
+    assert rel_l2(traj, g['dimer_dyn']) < TOL
+    mf = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
+                      level_cutoff=3, K=1)
+    t, rho = qb.simulate_dynamics(mf, np.eye(7)[0], 1000, method_name=method, **kw)
+    assert np.array_equal(t, g['fmo_d3_t'])
+    assert rel_l2(rho.reshape(len(t), -1), g['fmo_d3_rho']) < TOL
+
+
+def test_heom_depth4_and_trace(golden):
+    g = golden('heom')
+    mf = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
+                      level_cutoff=4, K=1)
+    t, rho = qb.simulate_dynamics(mf, np.eye(7)[0], 200)
+    assert rel_l2(rho.reshape(len(t), -1), g['fmo_d4_rho']) < TOL
+    assert np.abs(np.einsum('tii->t', rho) - 1).max() < 1e-10
+
+
+def test_heom_absorption(golden):
+    g = golden('heom')
+    m = qb.HEOMModel(systems.dimer(), hilbert_subspace='gef', unit_convert=CM_FS,
+                     level_cutoff=3, low_temp_corr=False)
+    f, X = qb.absorption_spectra(m, 10000)
+    assert rel_l2(X, g['dimer_abs_X']) < TOL
+    mg = qb.HEOMModel(systems.fmo(), hilbert_subspace='ge', unit_convert=CM_FS,
+                      level_cutoff=2, K=1)
+    f, X = qb.absorption_spectra(mg, 1000)
+    assert rel_l2(X, g['fmo_d2_abs_X']) < TOL
+
+
+def test_heom_ensemble_members_match_single_runs():
+    ham = systems.fmo(n_sites=4)
+    m = qb.HEOMModel(ham, hilbert_subspace='e', unit_convert=CM_FS,
+                     level_cutoff=3, K=1)
+    t, avg = qb.simulate_dynamics(m, np.eye(4)[0], 150, ensemble_size=3)
+    singles = [qb.simulate_dynamics(mm, np.eye(4)[0], 150)[1]
+               for mm in m.sample_ensemble(3)]
+    assert rel_l2(avg, np.mean(singles, axis=0)) < 1e-12
+
+
+# ------------------------------------------------------------------ response
+def test_third_order_response_redfield(golden):
+    g = golden('response')
+    red = qb.RedfieldModel(systems.dimer(), hilbert_subspace='gef',
+                           unit_convert=CM_FS, discard_imag_corr=True)
+    t2 = np.linspace(0, 200, 3)
+    for geom in ('-++', '+-+', '++-'):
+        (t1, _, _), S = qb.third_order_response(red, 300, population_times=t2,
+                                                geometry=geom)
+        assert np.array_equal(t1, g['t1'])
+        assert rel_l2(S, g['red_%s' % geom]) < TOL
+    _, S = qb.third_order_response(red, 300, population_times=t2,
+                                   polarization='xxyy',
+                                   exact_isotropic_average=True)
+    assert rel_l2(S, g['red_iso_xxyy']) < TOL
+    dred = qb.RedfieldModel(systems.dimer(disorder=80), hilbert_subspace='gef',
+                            unit_convert=CM_FS, discard_imag_corr=True)
+    _, S = qb.third_order_response(dred, 300, population_times=t2,
+                                   ensemble_size=3, include_signal='GSB,ESE')
+    assert rel_l2(S, g['red_ens3_gsb_ese']) < TOL
+    (f1, _, f3), X = qb.two_dimensional_spectra(red, 300, population_times=t2)
+    assert np.allclose(f1, g['red_2d_f1']) and np.allclose(f3, g['red_2d_f3'])
+    assert rel_l2(X, g['red_2d']) < TOL
+
+
+def test_third_order_response_heom(golden):
+    g = golden('response')
+    hm = qb.HEOMModel(systems.dimer(), hilbert_subspace='gef', unit_convert=CM_FS,
+                      level_cutoff=3, low_temp_corr=False)
+    _, S = qb.third_order_response(hm, 200, population_times=np.linspace(0, 200, 3)[:2])
+    assert rel_l2(S, g['heom_-++']) < TOL
+
+
+def test_pump_probe(golden):
+    g = golden('response')
+    red = qb.RedfieldModel(systems.dimer(), hilbert_subspace='gef',
+                           unit_convert=CM_FS, discard_imag_corr=True)
+    pump = qb.GaussianPulse(12800, 40, scale=1e-3, freq_convert=CM_FS)
+    t, st = qb.simulate_pump(red, pump, 'x', time_extra=200, rtol=1e-11, atol=1e-14)
+    assert np.array_equal(t, g['pump_t'])
+    assert rel_l2(st, g['pump_states']) < TOL
+    t, st = qb.simulate_pump(red, pump, 'x', time_extra=100,
+                             exact_isotropic_average=True, rtol=1e-11, atol=1e-14)
+    assert rel_l2(st, g['pump_iso_states']) < TOL
+    f, X = qb.impulsive_probe(red, g['pump_iso_states'], 500,
+                              exact_isotropic_average=True)
+    assert rel_l2(X, g['probe_X']) < TOL
+
+
+def test_vibronic_systems(golden):
+    g = golden('response')
+    jd = qb.RedfieldModel(systems.jonas_dimer(), hilbert_subspace='gef',
+                          unit_convert=CM_FS, discard_imag_corr=True)
+    t, rho = qb.simulate_dynamics(jd, qb.unit_vec(0, 8), 300)
+    assert rel_l2(rho, g['jonas_dyn']) < TOL
+    f, X = qb.absorption_spectra(jd, 2000)
+    assert rel_l2(X, g['jonas_abs_X']) < TOL
+    mono = qb.UnitaryModel(systems.vibronic_monomer(), hilbert_subspace='ge',
+                           unit_convert=CM_FS)
+    t, rho = qb.simulate_dynamics(mono, qb.unit_vec(0, 5), 300)
+    assert rel_l2(rho, g['mono_dyn']) < TOL
+    f, X = qb.absorption_spectra(mono, 3000, correlation_decay_time=1000)
+    assert rel_l2(X, g['mono_abs_X']) < TOL
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases(fmo_model):
+    eom = fmo_model.equation_of_motion('ee')
+    y0 = np.zeros(49, complex)
+    y0[0] = 1
+    # single output point equal to t0: result is save(y0)
+    out = qb.integrate(eom, y0, np.array([0.0]))
+    assert out.shape == (1, 49) and np.array_equal(out[0], y0)
+    # t0 before the first output time (utils.py:39-44)
+    a = qb.integrate(eom, y0, np.array([10.0, 20.0]), t0=0.0)
+    b = qb.integrate(eom, y0, np.array([0.0, 10.0, 20.0]))
+    assert rel_l2(a, b[1:]) < 1e-12
+    # ragged (non-uniform) grid and repeated times
+    c = qb.integrate(eom, y0, np.array([0.0, 3.0, 3.0, 47.5]))
+    assert np.array_equal(c[1], c[2])
+    # zero state stays zero
+    z = qb.integrate(eom, np.zeros(49, complex), np.array([0.0, 5.0]))
+    assert np.all(z == 0)
+    with pytest.raises(TypeError):
+        qb.integrate(lambda t, y: y, y0, np.array([0.0, 1.0]))
+    with pytest.raises(ValueError):
+        qb.integrate(eom, y0, np.array([1.0, 0.5]))
+    with pytest.raises(NotImplementedError):
+        qb.HEOMModel(systems.dimer(), aki_temp_corr=True)
+    with pytest.raises(qb.operator_tools.SubspaceError):
+        fmo_model.equation_of_motion('eg')
