@@ -27,4 +27,7 @@ def golden():
 
 def rel_l2(a, b):
     a, b = np.asarray(a), np.asarray(b)
-    return np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+    assert a.shape == b.shape, (a.shape, b.shape)
+    ref = np.linalg.norm(b.ravel())
+    err = np.linalg.norm((a - b).ravel())
+    return err / ref if ref > 0 else err

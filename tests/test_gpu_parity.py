@@ -177,7 +177,7 @@ def test_heom_trajectories(golden, method, kw):
                       level_cutoff=3, K=1)
     t, rho = qb.simulate_dynamics(mf, np.eye(7)[0], 1000, method_name=method, **kw)
     assert np.array_equal(t, g['fmo_d3_t'])
-    assert rel_l2(rho.reshape(len(t), -1), g['fmo_d3_rho']) < TOL
+    assert rel_l2(rho, g['fmo_d3_rho'].reshape(-1, 7, 7).transpose(0, 2, 1)) < TOL
 
 
 def test_heom_depth4_and_trace(golden):
@@ -185,7 +185,7 @@ def test_heom_depth4_and_trace(golden):
     mf = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
                       level_cutoff=4, K=1)
     t, rho = qb.simulate_dynamics(mf, np.eye(7)[0], 200)
-    assert rel_l2(rho.reshape(len(t), -1), g['fmo_d4_rho']) < TOL
+    assert rel_l2(rho, g['fmo_d4_rho'].reshape(-1, 7, 7).transpose(0, 2, 1)) < TOL
     assert np.abs(np.einsum('tii->t', rho) - 1).max() < 1e-10
 
 
