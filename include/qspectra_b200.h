@@ -160,6 +160,59 @@ int64_t qsx_ado_count(int32_t bins, int32_t level_cutoff);
 int qsx_ado_enumerate(int32_t bins, int32_t level_cutoff, int64_t *ado_index,
                       int32_t *up, int32_t *down);
 
+
+/* ------------------------------------------------------------------------
+ * Batched Redfield generator construction for disorder ensembles (K5).
+ * Replaces redfield_evolve / redfield_tensor (dynamics/redfield.py:9-104) and
+ * DebyeBath.corr_func_complex / Bath.corr_func_real (bath.py:17-31, 84-102),
+ * which the reference re-runs for every ensemble member (base.py:120-128).
+ * ---------------------------------------------------------------------- */
+typedef enum {
+    QSX_BATH_DEBYE_COMPLEX = 0,  /* DebyeBath.corr_func_complex, Matsubara sum   */
+    QSX_BATH_DEBYE_REAL = 1      /* Bath.corr_func_real (discard_imag_corr=True) */
+} qsx_bath_kind;
+
+typedef struct {
+    int32_t kind;                /* qsx_bath_kind                                */
+    int32_t matsubara_cutoff;    /* 1000 in the reference (bath.py:84)           */
+    double temperature, reorg_energy, cutoff_freq;
+} qsx_bath;
+
+/* E_dev [n_members][N] (float64) and U_dev [n_members][N][N] (complex128,
+ * U[x][a] = <site x | eigenstate a>) are the members' eigen-systems in the
+ * rotating frame (hamiltonian.py:310-328); coupling_diag_host [n_baths][N] the
+ * diagonals of the system-bath operators; subspace_index_host [M] the Liouville
+ * subspace.  Writes unit_convert * L[idx, idx] to L_out_dev [n_members][M][M]. */
+int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_dev,
+                       const void *U_dev, int32_t n_baths,
+                       const double *coupling_diag_host, const qsx_bath *bath,
+                       int32_t secular, int32_t eigen_basis, double unit_convert,
+                       int32_t M, const int64_t *subspace_index_host,
+                       void *L_out_dev, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K6 (single-GPU part): weighted sum over ensemble members / columns,
+ *   out[i] = scale * sum_m in[m][i]   (complex128, i < n)
+ * Replaces `total_signal += signal; total_signal /= ensemble_size`
+ * (simulate/decorators.py:55-61).  The cross-GPU part is one NCCL reduce issued
+ * from the host side (torch.distributed).
+ * ---------------------------------------------------------------------- */
+int qsx_reduce_members(const void *in_dev, int32_t n_members, int64_t n,
+                       double scale, void *out_dev, void *stream);
+
+
+/* ------------------------------------------------------------------------
+ * Seeded disorder streams (host only).  Bit-exact replay of
+ *   rng = numpy.random.RandomState(list(seed) + [n]); rng.randn(n_gauss); rng.rand(n_uniform)
+ * for members n = member0 .. member0+n_members-1: the draws of
+ * ElectronicHamiltonian._sample (hamiltonian.py:458-461, 552-578) and
+ * random_rotation_matrix (polarization.py:96).  gauss_out [n_members][n_gauss],
+ * uniform_out [n_members][n_uniform].
+ * ---------------------------------------------------------------------- */
+int qsx_sample_streams(const uint32_t *seed_prefix, int32_t n_prefix,
+                       int64_t member0, int32_t n_members, int32_t n_gauss,
+                       int32_t n_uniform, double *gauss_out, double *uniform_out);
+
 #ifdef __cplusplus
 }
 #endif

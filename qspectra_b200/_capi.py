@@ -58,13 +58,22 @@ class QsxHeomConfig(C.Structure):
                 ('modified', C.c_int32), ('heisenberg', C.c_int32)]
 
 
+class QsxBath(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('matsubara_cutoff', C.c_int32),
+                ('temperature', C.c_double), ('reorg_energy', C.c_double),
+                ('cutoff_freq', C.c_double)]
+
+
+BATH_DEBYE_COMPLEX, BATH_DEBYE_REAL = 0, 1
+
 #: every symbol include/qspectra_b200.h declares (checked by the CPU tests)
 EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches',
            'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
            'qsx_dense_propagate', 'qsx_dense_destroy', 'qsx_heom_create',
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
-           'qsx_ado_enumerate']
+           'qsx_ado_enumerate', 'qsx_redfield_build', 'qsx_reduce_members',
+           'qsx_sample_streams']
 
 _lib = None
 
@@ -109,6 +118,15 @@ def lib():
                                      C.c_void_p]
     L.qsx_heom_destroy.argtypes = [C.c_void_p]
     L.qsx_heom_destroy.restype = None
+    L.qsx_redfield_build.argtypes = [
+        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+        C.POINTER(C.c_double), C.POINTER(QsxBath), C.c_int32, C.c_int32,
+        C.c_double, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+    L.qsx_reduce_members.argtypes = [C.c_void_p, C.c_int32, C.c_int64,
+                                     C.c_double, C.c_void_p, C.c_void_p]
+    L.qsx_sample_streams.argtypes = [C.POINTER(C.c_uint32), C.c_int32, C.c_int64,
+                                     C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -173,6 +191,9 @@ def to_device(array, dtype=None):
     t = torch.from_numpy(a)
     if dtype is not None:
         t = t.to(dtype)
+    # pinned staging makes a large H2D copy a real DMA transfer
+    if t.numel() > (1 << 16):
+        return t.pin_memory().cuda(non_blocking=True)
     return t.cuda()
 
 
@@ -181,3 +202,19 @@ def int32_ptr(values):
         return None, None
     arr = np.ascontiguousarray(values, dtype=np.int32)
     return arr, arr.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def sample_streams(seed, member0, n_members, n_gauss, n_uniform=0):
+    """(gauss [n_members, n_gauss], uniform [n_members, n_uniform]): exactly the
+    draws of RandomState(list(seed) + [n]).randn(n_gauss) then .rand(n_uniform)."""
+    prefix = np.ascontiguousarray(np.atleast_1d(seed), dtype=np.int64)
+    if ((prefix < 0) | (prefix > 2 ** 32 - 1)).any():
+        raise ValueError('seed entries must fit in uint32')
+    prefix = prefix.astype(np.uint32)
+    gauss = np.empty((n_members, n_gauss), dtype=np.float64)
+    uni = np.empty((n_members, n_uniform), dtype=np.float64)
+    check(lib().qsx_sample_streams(
+        prefix.ctypes.data_as(C.POINTER(C.c_uint32)), prefix.size, int(member0),
+        int(n_members), int(n_gauss), int(n_uniform), gauss.ctypes.data,
+        uni.ctypes.data))
+    return gauss, uni

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "ado.h"
 #include <string.h>
+#include <math.h>
+#include <algorithm>
 
 static thread_local char g_error[1024] = "";
 std::atomic<uint64_t> qsx_launch_counter{0};
@@ -127,5 +129,131 @@ extern "C" int qsx_ado_enumerate(int32_t bins, int32_t level_cutoff, int64_t *ad
     if (ado_index) for (size_t i = 0; i < total; ++i) ado_index[i] = t.index[i];
     if (up) memcpy(up, t.up.data(), total * sizeof(int32_t));
     if (down) memcpy(down, t.down.data(), total * sizeof(int32_t));
+    return QSX_OK;
+}
+
+// ------------------------------------------------------------ K6: member sum
+__global__ void reduce_members_kernel(const cplx *__restrict__ in, int n_members, long long n,
+                                      int members_per_block, double scale, cplx *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int m0 = blockIdx.y * members_per_block;
+    int m1 = min(n_members, m0 + members_per_block);
+    double sr = 0.0, si = 0.0;
+    for (int m = m0; m < m1; ++m) {
+        cplx v = __ldg(&in[(size_t)m * n + i]);
+        sr += v.x;
+        si += v.y;
+    }
+    atomicAdd(&out[i].x, scale * sr);
+    atomicAdd(&out[i].y, scale * si);
+}
+
+extern "C" int qsx_reduce_members(const void *in_dev, int32_t n_members, int64_t n, double scale,
+                                  void *out_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(in_dev && out_dev && n_members > 0 && n > 0, "qsx_reduce_members: bad arguments");
+    QSX_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(cplx), stream));
+    const int threads = 128;
+    long long bx = (n + threads - 1) / threads;
+    // enough blocks to fill the machine, at most one per 8 members
+    int by = (int)std::max<long long>(1, std::min<long long>((n_members + 7) / 8, (148 * 16 + bx - 1) / bx));
+    int per = (n_members + by - 1) / by;
+    by = (n_members + per - 1) / per;
+    reduce_members_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, stream>>>(
+        (const cplx *)in_dev, n_members, n, per, scale, (cplx *)out_dev);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+// ------------------------------------------------- seeded disorder streams (host)
+// Bit-exact replay of numpy's legacy generator for ensemble member n:
+//   rng = np.random.RandomState(list(seed) + [n]); rng.randn(n_gauss); rng.rand(n_uniform)
+// (reference hamiltonian.py:458-461, 566-573).  MT19937 init_by_array + the
+// legacy polar Box-Muller with its one-value cache, as in numpy's
+// _legacy/mt19937 sources; ~100x faster than constructing RandomState objects.
+namespace {
+struct MT19937 {
+    uint32_t mt[624];
+    int pos;
+    void init_genrand(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253U * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        pos = 624;
+    }
+    void init_by_array(const uint32_t *key, int len) {
+        init_genrand(19650218U);
+        int i = 1, j = 0;
+        for (int k = (624 > len ? 624 : len); k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525U)) + key[j] + (uint32_t)j;
+            if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+            if (++j >= len) j = 0;
+        }
+        for (int k = 623; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941U)) - (uint32_t)i;
+            if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+        }
+        mt[0] = 0x80000000U;
+        pos = 624;
+    }
+    void twist() {
+        for (int k = 0; k < 624; ++k) {
+            uint32_t y = (mt[k] & 0x80000000U) | (mt[(k + 1) % 624] & 0x7fffffffU);
+            mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+        }
+        pos = 0;
+    }
+    uint32_t next32() {
+        if (pos >= 624) twist();
+        uint32_t y = mt[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680U;
+        y ^= (y << 15) & 0xefc60000U;
+        y ^= (y >> 18);
+        return y;
+    }
+    double next_double() {
+        uint32_t a = next32() >> 5, b = next32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+};
+}  // namespace
+
+extern "C" int qsx_sample_streams(const uint32_t *seed_prefix, int32_t n_prefix, int64_t member0,
+                                  int32_t n_members, int32_t n_gauss, int32_t n_uniform,
+                                  double *gauss_out, double *uniform_out) {
+    QSX_REQUIRE(n_prefix >= 0 && n_prefix < 15 && n_members >= 0 && n_gauss >= 0 && n_uniform >= 0,
+                "qsx_sample_streams: bad arguments");
+    QSX_REQUIRE(member0 >= 0 && member0 + n_members <= (int64_t)0xffffffffLL, "member index out of range");
+    uint32_t key[16];
+    for (int i = 0; i < n_prefix; ++i) key[i] = seed_prefix[i];
+    MT19937 g;
+    for (int m = 0; m < n_members; ++m) {
+        key[n_prefix] = (uint32_t)(member0 + m);
+        g.init_by_array(key, n_prefix + 1);
+        bool has = false;
+        double cached = 0.0;
+        for (int i = 0; i < n_gauss; ++i) {
+            double val;
+            if (has) {
+                val = cached;
+                has = false;
+            } else {
+                double x1, x2, r2;
+                do {
+                    x1 = 2.0 * g.next_double() - 1.0;
+                    x2 = 2.0 * g.next_double() - 1.0;
+                    r2 = x1 * x1 + x2 * x2;
+                } while (r2 >= 1.0 || r2 == 0.0);
+                double f = sqrt(-2.0 * log(r2) / r2);
+                cached = f * x1;
+                has = true;
+                val = f * x2;
+            }
+            gauss_out[(size_t)m * n_gauss + i] = val;
+        }
+        for (int i = 0; i < n_uniform; ++i) uniform_out[(size_t)m * n_uniform + i] = g.next_double();
+    }
     return QSX_OK;
 }

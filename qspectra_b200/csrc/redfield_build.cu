@@ -1,0 +1,227 @@
+// K5: batched construction of Redfield Liouvillians for a disorder ensemble.
+//
+// Replaces, per ensemble member, the reference chain
+//   redfield_evolve -> redfield_dissipator -> redfield_tensor
+// (dynamics/redfield.py:9-104) including the 1000-term Matsubara sum of
+// DebyeBath.corr_func_complex (bath.py:84-102) -- 95 % of the reference's
+// disorder-ensemble wall time.  One thread block builds one
+// member:
+//   C[i,j]   = corr(E_i - E_j)                                  (bath.py)
+//   K_n      = U^+ V_n U            (V_n diagonal, hamiltonian.py:593-608)
+//   Gs[a,c]  = sum_{b,n} K_n[a,b] K_n[b,c] C[c,b]
+//   R[abcd]  = conj(d_ac Gs[b,d]) + d_bd Gs[a,c] - conj(G[c,a,b,d]) - G[d,b,a,c],
+//              G[a,b,c,d] = sum_n K_n[a,b] K_n[c,d] C[d,c]      (redfield.py:61-69)
+//   L        = -i (E_a - E_b) d_ac d_bd - R (.) secular mask    (redfield.py:71-98)
+//   L_site   = W^+ L W, W = kron(U^+, U^+)                      (redfield.py:99-100)
+// and writes unit_convert * L[idx, idx] for the requested Liouville subspace.
+#include "common.cuh"
+#include <algorithm>
+
+struct RedfieldBuildArgs {
+    int m, N, nb, M;
+    const double *E;        // [m][N]
+    const cplx *U;          // [m][N][N] row-major, U[x][a] = <x|a>
+    const double *v;        // [nb][N] coupling diagonals
+    const int *idx;         // [M] flat column-major positions
+    qsx_bath bath;
+    int secular, eigen_basis;
+    double unit_convert;
+    cplx *L;                // [m][M][M]
+    cplx *scratch;          // [gridDim][2][N^4] when the tensors do not fit in shared memory
+    int tensors_in_smem;
+};
+
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+    double d = b.x * b.x + b.y * b.y;
+    return cmake((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+// one-sided correlation spectrum evaluated by a full warp (all lanes get the value)
+__device__ cplx warp_corr(const qsx_bath &b, double x) {
+    const double T = b.temperature, lam = b.reorg_energy, g = b.cutoff_freq;
+    if (b.kind == QSX_BATH_DEBYE_REAL) {
+        // (n(x)+1) J_anti(x);  T J'(0) at x == 0        (bath.py:17-31, 79-82)
+        if (x == 0.0) return cmake(T * 2.0 * lam / g, 0.0);
+        double ax = fabs(x);
+        double J = 2.0 * lam * g * ax / (g * g + ax * ax);
+        if (x < 0) J = -J;
+        return cmake((1.0 / expm1(x / T) + 1.0) * J, 0.0);
+    }
+    if (x == 0.0) return cmake(lam * 2.0 * T / g, -lam);
+    const int lane = threadIdx.x & 31;
+    double sr = 0.0, si = 0.0;
+    for (int mth = lane; mth < b.matsubara_cutoff; mth += 32) {
+        double nu = 2.0 * M_PI * mth * T;
+        // nu / ((nu^2 - g^2) (nu - i x))
+        double pre = nu / (nu * nu - g * g);
+        double den = nu * nu + x * x;
+        sr += pre * nu / den;
+        si += pre * x / den;
+    }
+    sr = warp_sum(sr);
+    si = warp_sum(si);
+    cplx drude = cdiv(cmake(1.0 / tan(g / (2.0 * T)), -1.0), cmake(g, -x));
+    return cmake(lam * g * (drude.x + 4.0 * T * sr), lam * g * (drude.y + 4.0 * T * si));
+}
+
+__global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.N, nb = a.nb, N2 = N * N;
+    const size_t N4 = (size_t)N2 * N2;
+    cplx *Us = reinterpret_cast<cplx *>(smem_raw);       // [N][N]
+    cplx *Cs = Us + N2;                                  // [N][N]
+    cplx *Gs = Cs + N2;                                  // [N][N]
+    cplx *Ks = Gs + N2;                                  // [nb][N][N]
+    double *Es = reinterpret_cast<double *>(Ks + (size_t)nb * N2);   // [N]
+    cplx *TA, *TB;
+    if (a.tensors_in_smem) {
+        TA = reinterpret_cast<cplx *>(Es + ((N + 1) & ~1));
+        TB = TA + N4;
+    } else {
+        TA = a.scratch + (size_t)blockIdx.x * 2 * N4;
+        TB = TA + N4;
+    }
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, nwarp = nthr >> 5;
+
+    for (int mem = blockIdx.x; mem < a.m; mem += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < N2; i += nthr) Us[i] = a.U[(size_t)mem * N2 + i];
+        for (int i = tid; i < N; i += nthr) Es[i] = a.E[(size_t)mem * N + i];
+        __syncthreads();
+        // correlation matrix, one warp per entry
+        for (int p = warp; p < N2; p += nwarp) {
+            int i = p / N, j = p % N;
+            cplx c = warp_corr(a.bath, Es[i] - Es[j]);
+            if ((tid & 31) == 0) Cs[p] = c;
+        }
+        // couplings in the eigenbasis: K_n[a][b] = sum_x conj(U[x][a]) v_n[x] U[x][b]
+        for (int p = tid; p < nb * N2; p += nthr) {
+            int n = p / N2, ab = p % N2, aa = ab / N, bb = ab % N;
+            cplx acc = cmake(0, 0);
+            for (int x = 0; x < N; ++x) {
+                cplx ua = Us[x * N + aa];
+                ua.y = -ua.y;
+                cfma(acc, cscale(a.v[n * N + x], ua), Us[x * N + bb]);
+            }
+            Ks[p] = acc;
+        }
+        __syncthreads();
+        // Gs[a][c] = sum_b sum_n K_n[a][b] K_n[b][c] C[c][b]
+        for (int p = tid; p < N2; p += nthr) {
+            int aa = p / N, cc = p % N;
+            cplx acc = cmake(0, 0);
+            for (int bb = 0; bb < N; ++bb) {
+                cplx kk = cmake(0, 0);
+                for (int n = 0; n < nb; ++n) cfma(kk, Ks[n * N2 + aa * N + bb], Ks[n * N2 + bb * N + cc]);
+                cfma(acc, kk, Cs[cc * N + bb]);
+            }
+            Gs[p] = acc;
+        }
+        __syncthreads();
+        // eigenbasis generator as a 4-index tensor T[a][b][c][d] = L[a + N b, c + N d]
+        for (size_t p = tid; p < N4; p += nthr) {
+            int dd = (int)(p % N), cc = (int)((p / N) % N), bb = (int)((p / N2) % N), aa = (int)(p / ((size_t)N2 * N));
+            cplx g1 = cmake(0, 0), g2 = cmake(0, 0);       // G[c,a,b,d], G[d,b,a,c]
+            for (int n = 0; n < nb; ++n) {
+                cfma(g1, Ks[n * N2 + cc * N + aa], Ks[n * N2 + bb * N + dd]);
+                cfma(g2, Ks[n * N2 + dd * N + bb], Ks[n * N2 + aa * N + cc]);
+            }
+            g1 = cmul(g1, Cs[dd * N + bb]);
+            g2 = cmul(g2, Cs[cc * N + aa]);
+            cplx R = cmake(-g1.x - g2.x, g1.y - g2.y);     // - conj(g1) - g2
+            if (aa == cc) { cplx s = Gs[bb * N + dd]; R.x += s.x; R.y -= s.y; }
+            if (bb == dd) { cplx s = Gs[aa * N + cc]; R.x += s.x; R.y += s.y; }
+            if (a.secular && !((aa == bb && cc == dd) || (aa == cc && bb == dd))) R = cmake(0, 0);
+            cplx L = cmake(-R.x, -R.y);
+            if (aa == cc && bb == dd) L.y -= (Es[aa] - Es[bb]);
+            TA[p] = L;
+        }
+        __syncthreads();
+        cplx *src = TA, *dst = TB;
+        if (!a.eigen_basis) {
+            // L_site[i,j,k,l] = sum U[i,p] U[j,q] T[p,q,r,s] conj(U[k,r]) conj(U[l,s])
+            for (int pos = 0; pos < 4; ++pos) {
+                size_t stride = pos == 0 ? (size_t)N2 * N : pos == 1 ? (size_t)N2 : pos == 2 ? (size_t)N : 1;
+                for (size_t p = tid; p < N4; p += nthr) {
+                    int i = (int)((p / stride) % N);
+                    size_t base = p - (size_t)i * stride;
+                    cplx acc = cmake(0, 0);
+                    for (int q = 0; q < N; ++q) {
+                        cplx u = Us[i * N + q];
+                        if (pos >= 2) u.y = -u.y;
+                        cfma(acc, u, src[base + (size_t)q * stride]);
+                    }
+                    dst[p] = acc;
+                }
+                __syncthreads();
+                cplx *tmp = src; src = dst; dst = tmp;
+            }
+        }
+        // restricted, scaled output
+        cplx *Lout = a.L + (size_t)mem * a.M * a.M;
+        for (int p = tid; p < a.M * a.M; p += nthr) {
+            int r = p / a.M, c = p % a.M;
+            int fr = a.idx[r], fc = a.idx[c];
+            int i = fr % N, j = fr / N, k = fc % N, l = fc / N;
+            cplx val = src[(((size_t)i * N + j) * N + k) * N + l];
+            Lout[p] = cscale(a.unit_convert, val);
+        }
+    }
+}
+
+extern "C" int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_dev, const void *U_dev,
+                                  int32_t n_baths, const double *coupling_diag_host,
+                                  const qsx_bath *bath, int32_t secular, int32_t eigen_basis,
+                                  double unit_convert, int32_t M, const int64_t *subspace_index_host,
+                                  void *L_out_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(n_members > 0 && N > 0 && n_baths > 0 && M > 0 && E_dev && U_dev && bath &&
+                coupling_diag_host && subspace_index_host && L_out_dev,
+                "qsx_redfield_build: bad arguments");
+    QSX_REQUIRE(bath->kind == QSX_BATH_DEBYE_COMPLEX || bath->kind == QSX_BATH_DEBYE_REAL,
+                "qsx_redfield_build: unknown bath kind %d", bath->kind);
+    QSX_REQUIRE(N <= 64, "qsx_redfield_build: Hilbert dimension %d too large", N);
+    std::vector<int> idx(M);
+    for (int i = 0; i < M; ++i) {
+        QSX_REQUIRE(subspace_index_host[i] >= 0 && subspace_index_host[i] < (int64_t)N * N,
+                    "subspace index out of range");
+        idx[i] = (int)subspace_index_host[i];
+    }
+    DevBuf<int> d_idx;
+    DevBuf<double> d_v;
+    DevBuf<cplx> scratch;
+    QSX_CUDA(d_idx.upload(idx, stream));
+    QSX_CUDA(d_v.upload(coupling_diag_host, (size_t)n_baths * N, stream));
+
+    int dev = 0, smem_limit = 0, sms = 0;
+    QSX_CUDA(cudaGetDevice(&dev));
+    QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t N2 = (size_t)N * N, N4 = N2 * N2;
+    size_t base = (3 * N2 + (size_t)n_baths * N2) * sizeof(cplx) + (size_t)((N + 1) & ~1) * sizeof(double);
+    size_t with_t = base + 2 * N4 * sizeof(cplx);
+    QSX_REQUIRE(base <= (size_t)smem_limit, "qsx_redfield_build: too many baths/states for shared memory");
+    int tensors_in_smem = with_t <= (size_t)smem_limit;
+    size_t smem = tensors_in_smem ? with_t : base;
+    int grid;
+    if (tensors_in_smem) {
+        grid = std::min(n_members, sms * std::max(1, (int)((size_t)smem_limit / smem)));
+    } else {
+        grid = std::min(n_members, sms * 2);
+        QSX_CUDA(scratch.alloc((size_t)grid * 2 * N4));
+    }
+    RedfieldBuildArgs a;
+    a.m = n_members; a.N = N; a.nb = n_baths; a.M = M;
+    a.E = (const double *)E_dev; a.U = (const cplx *)U_dev; a.v = d_v.p; a.idx = d_idx.p;
+    a.bath = *bath;
+    if (a.bath.matsubara_cutoff <= 0) a.bath.matsubara_cutoff = 1000;
+    a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;
+    a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem;
+    QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    redfield_build_kernel<<<grid, 256, smem, stream>>>(a);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    QSX_CUDA(cudaStreamSynchronize(stream));
+    return QSX_OK;
+}

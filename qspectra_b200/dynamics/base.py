@@ -96,6 +96,22 @@ class DynamicalModel(metaclass=ABCMeta):
         raise NotImplementedError('%s does not batch ensembles'
                                   % type(self).__name__)
 
+    def ensemble_eom(self, ensemble_size, random_orientations,
+                     liouville_subspace, heisenberg_picture=False, member0=0):
+        """DeviceEOM whose generator g belongs to ensemble member member0 + g.
+        Generic form: materialise the member models; subclasses override this
+        with device-side construction."""
+        members = [self.sample(member0 + n, random_orientations)
+                   for n in range(ensemble_size)]
+        return self.ensemble_equation_of_motion(members, liouville_subspace,
+                                                heisenberg_picture)
+
+    def sample(self, n, random_orientations=False):
+        """n-th ensemble member of this model (reference base.py:120-128)."""
+        member = copy_with_new_cache(self)
+        member.hamiltonian = self.hamiltonian.sample(n, random_orientations)
+        return member
+
 
 class SystemOperator(metaclass=ABCMeta):
     """Reference dynamics/base.py:143-181.  Implementations return LinearMap

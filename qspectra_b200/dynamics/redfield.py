@@ -11,6 +11,9 @@ Liouvillians runs on the GPU (csrc/dense.cu).
 import numpy as np
 
 from .liouville_space import LiouvilleSpaceModel, tensor_to_super
+from .. import engine, _capi
+from ..bath import DebyeBath
+from ..hamiltonian import ElectronicHamiltonian
 from ..utils import memoized_property
 
 
@@ -142,3 +145,48 @@ class RedfieldModel(LiouvilleSpaceModel):
             out[lo:lo + chunk] = self.unit_convert * L[:, index[:, None],
                                                        index[None, :]]
         return out
+
+    # -- device-side ensemble construction (kernel K5) ---------------------------
+    def _device_buildable(self):
+        ham = self.hamiltonian
+        return (isinstance(ham, ElectronicHamiltonian)
+                and type(ham.bath) is DebyeBath
+                and not np.iscomplexobj(ham.H_1exc))
+
+    def ensemble_eigensystems(self, ensemble_size, member0=0):
+        """(E, U) of the members in the rotating frame, computed from the
+        lab-frame matrices like Hamiltonian.eig (hamiltonian.py:310-328), with
+        one batched LAPACK call instead of one eigh per member."""
+        ham, ss = self.hamiltonian, self.hilbert_subspace
+        shifts = ham.sampled_site_shifts(ensemble_size, member0)
+        if shifts is None:
+            return None
+        lab = ham._not_sampled._not_rotating
+        H0 = np.asarray(lab.H(ss), dtype=float)
+        number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
+        diag = np.arange(H0.shape[0])
+        H = np.broadcast_to(H0, (ensemble_size,) + H0.shape).copy()
+        H[:, diag, diag] += shifts @ number
+        E, U = np.linalg.eigh(H)
+        for letter, quanta in (('e', 1), ('f', 2)):
+            if letter in ss:
+                E[:, ham.hilbert_subspace_index(letter, ss)] -= quanta * ham.rw_freq
+        return E, U
+
+    def ensemble_eom(self, ensemble_size, random_orientations,
+                     liouville_subspace, heisenberg_picture=False, member0=0):
+        eig = self.ensemble_eigensystems(ensemble_size, member0) \
+            if self._device_buildable() else None
+        if eig is None:
+            return super(RedfieldModel, self).ensemble_eom(
+                ensemble_size, random_orientations, liouville_subspace,
+                heisenberg_picture, member0)
+        ham, ss, bath = self.hamiltonian, self.hilbert_subspace, self.hamiltonian.bath
+        number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
+        kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
+                else _capi.BATH_DEBYE_COMPLEX)
+        L = engine.redfield_build(
+            eig[0], eig[1], number, kind, bath.temperature, bath.reorg_energy,
+            bath.cutoff_freq, self.secular, self.evolve_basis == 'eigen',
+            self.unit_convert, self.liouville_subspace_index(liouville_subspace))
+        return engine.DenseEOM(L, heisenberg_picture)

@@ -319,3 +319,43 @@ class HeomEOM(DeviceEOM):
         args.save_dev = Sd.data_ptr()
         args.n_save = 1
         return self.n_ado * S.shape[0]
+
+
+def reduce_members(batch_dev, scale=1.0):
+    """out[...] = scale * sum_m batch[m, ...] on the device (kernel K6)."""
+    torch = _capi.torch_cuda()
+    batch_dev = batch_dev.contiguous()
+    out = torch.empty(batch_dev.shape[1:], dtype=torch.complex128,
+                      device=batch_dev.device)
+    _capi.check(_capi.lib().qsx_reduce_members(
+        batch_dev.data_ptr(), batch_dev.shape[0], out.numel(), float(scale),
+        out.data_ptr(), _capi.current_stream_ptr()))
+    return out
+
+
+def redfield_build(E, U, coupling_diag, bath_kind, temperature, reorg_energy,
+                   cutoff_freq, secular, eigen_basis, unit_convert,
+                   subspace_index, matsubara_cutoff=1000):
+    """Batched Redfield generators on the device (kernel K5).
+
+    E (m, N) float, U (m, N, N): eigen-systems of the members in the rotating
+    frame.  Returns a CUDA tensor (m, M, M) = unit_convert * L[idx, idx]."""
+    torch = _capi.torch_cuda()
+    E_dev = _capi.to_device(np.ascontiguousarray(E, dtype=np.float64),
+                            dtype=torch.float64)
+    U_dev = _capi.to_device(np.ascontiguousarray(U, dtype=np.complex128))
+    m, N = E_dev.shape
+    v = np.ascontiguousarray(coupling_diag, dtype=np.float64)
+    idx = np.ascontiguousarray(subspace_index, dtype=np.int64)
+    bath = _capi.QsxBath(int(bath_kind), int(matsubara_cutoff),
+                         float(temperature), float(reorg_energy),
+                         float(cutoff_freq))
+    out = torch.empty((m, idx.size, idx.size), dtype=torch.complex128,
+                      device=E_dev.device)
+    _capi.check(_capi.lib().qsx_redfield_build(
+        m, N, E_dev.data_ptr(), U_dev.data_ptr(), v.shape[0],
+        v.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bath),
+        int(bool(secular)), int(bool(eigen_basis)), float(unit_convert),
+        idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), out.data_ptr(),
+        _capi.current_stream_ptr()))
+    return out

@@ -266,6 +266,22 @@ class ElectronicHamiltonian(Hamiltonian):
         """The seeded generator of ensemble member ``n``."""
         return check_random_state(list(np.atleast_1d(self.random_seed)) + [n])
 
+    def sampled_site_shifts(self, ensemble_size, member0=0):
+        """(ensemble_size, n_sites) diagonal static-disorder shifts of members
+        member0 .. member0+ensemble_size-1 -- bit-identical to what
+        ``sample(n)`` adds -- or None when ``disorder`` is a user callable.
+        Uses the C replay of numpy's seeded streams (qsx_sample_streams), so no
+        Hamiltonian object is created per member."""
+        base = self._not_sampled
+        if base.disorder is None:
+            return np.zeros((ensemble_size, base.n_sites))
+        if not isinstance(base.disorder, Number):
+            return None
+        from ._capi import sample_streams
+        gauss, _ = sample_streams(base.random_seed, member0, ensemble_size,
+                                  base.n_sites)
+        return (base.disorder * GAUSSIAN_SD_FWHM) * gauss
+
     def _sample(self, n, random_orientations):
         rng = self.disorder_stream(n)
         if self.disorder is None:

@@ -12,16 +12,8 @@ import numpy as np
 from .decorators import (optional_ensemble_average,
                          optional_2nd_order_isotropic_average)
 from .utils import integrate, DrivenEOM
-from .. import _capi
-
-
-def ensemble_members(dynamical_model, ensemble_size, random_orientations):
-    """[model] or the list of sampled member models (reference
-    decorators.py:55-57 order: member n = sample n)."""
-    if ensemble_size is None:
-        return [dynamical_model], False
-    return list(dynamical_model.sample_ensemble(ensemble_size,
-                                                random_orientations)), True
+from .. import _capi, engine
+from ..engine import LinearMap
 
 
 def simulate_dynamics(dynamical_model, initial_state, duration=None, times=None,
@@ -29,9 +21,11 @@ def simulate_dynamics(dynamical_model, initial_state, duration=None, times=None,
                       ensemble_size=None, ensemble_random_orientations=False,
                       **integrate_kwargs):
     """Free evolution; returns (t, density matrices) -- ensemble-averaged when
-    ``ensemble_size`` is given.  Same arguments as the reference."""
-    members, averaged = ensemble_members(dynamical_model, ensemble_size,
-                                         ensemble_random_orientations)
+    ``ensemble_size`` is given.  Same arguments as the reference.  The whole
+    ensemble is one batched device propagation followed by a device-side mean
+    (kernels K5 -> K1/K4 -> K6); ``member_offset`` (extension) shifts the
+    member numbers for multi-GPU sharding."""
+    member0 = integrate_kwargs.pop('member_offset', 0)
     initial_state = np.asarray(initial_state)
     if initial_state.ndim == 1:
         # wavefunction -> density matrix; np.outer(psi*, psi) as in the reference
@@ -39,22 +33,46 @@ def simulate_dynamics(dynamical_model, initial_state, duration=None, times=None,
         initial_state = np.outer(initial_state.conj(), initial_state)
     t = (np.arange(0, duration, dynamical_model.time_step)
          if times is None else np.asarray(times, dtype=float))
-    eom = dynamical_model.ensemble_equation_of_motion(members,
-                                                      liouville_subspace)
-    y0 = members[0].density_matrix_to_state_vector(initial_state,
-                                                   liouville_subspace)
+    y0 = dynamical_model.density_matrix_to_state_vector(initial_state,
+                                                        liouville_subspace)
     save = save_func if save_func is not None else dynamical_model.dynamics_save
-    if not averaged:
+    if ensemble_size is None:
+        eom = dynamical_model.equation_of_motion(liouville_subspace)
         states = integrate(eom, y0, t, save_func=save, **integrate_kwargs)
     else:
-        E = len(members)
-        states = integrate(eom, np.broadcast_to(y0, (E,) + y0.shape), t,
-                           save_func=save, generators=np.arange(E),
-                           **integrate_kwargs)
-        states = states.sum(axis=0) / E
+        eom = dynamical_model.ensemble_eom(
+            ensemble_size, ensemble_random_orientations, liouville_subspace,
+            member0=member0)
+        states = ensemble_mean(eom, y0, t, ensemble_size, save,
+                               **integrate_kwargs)
     if save_func is None:
         states = dynamical_model.saved_states_to_density_matrix(states)
     return (t, states)
+
+
+def ensemble_mean(eom, y0, t, ensemble_size, save, return_device=False,
+                  scale=None, **integrate_kwargs):
+    """mean over members of save(y_m(t)): batched propagation + device sum."""
+    opts = {k: integrate_kwargs[k] for k in ('rtol', 'atol', 'rk4_substeps')
+            if k in integrate_kwargs}
+    if save is not None and not isinstance(save, (LinearMap, tuple)):
+        # arbitrary host callable: save full states, post-process on the host
+        states = integrate(eom, np.broadcast_to(y0, (ensemble_size,) + y0.shape),
+                           t, save_func=save, generators=np.arange(ensemble_size),
+                           **integrate_kwargs)
+        return states.sum(axis=0) / ensemble_size
+    torch = _capi.torch_cuda()
+    y0_dev = _capi.to_device(y0).reshape(1, -1).expand(ensemble_size, -1).contiguous()
+    out = eom.propagate(y0_dev, t, method=integrate_kwargs.get('method_name', 'zvode'),
+                        save=save, generators=np.arange(ensemble_size),
+                        return_device=True, **opts)
+    mean = engine.reduce_members(out, (1.0 / ensemble_size) if scale is None else scale)
+    if return_device:
+        return mean
+    res = mean.cpu().numpy()
+    if isinstance(save, LinearMap) and save.matrix.ndim == 1:
+        res = res[..., 0]
+    return res
 
 
 def _field_terms(dynamical_model, pulses, geometry, polarization,
