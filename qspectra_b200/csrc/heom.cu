@@ -4,19 +4,30 @@
 // Replaces HEOMModel.HEOM_tensor + scipy csr_matrix.dot (reference
 // dynamics/heom.py:228-244, 298-443).  No sparse matrix is materialised: with
 // diagonal system-bath operators V_j (hamiltonian.py:593-608) every inter-ADO
-// block of the reference generator is a *diagonal* matrix, so
+// block of the reference generator is a *diagonal* matrix, so for an ADO n with
+// occupation vector n_jk and a rectangular Liouville block (rows R, cols C)
 //
-//   d rho_n[e]/dt = sum_e' A[e,e'] rho_n[e']                 (commutator + temperature
-//                   - shift_n rho_n[e]                         correction, ELL rows)
-//                   + sum_links su(n_jk) gu[e] rho_{n+e_jk}[e] (index-map gather, up)
-//                   + sum_links sd(n_jk) gd[e] rho_{n-e_jk}[e] (index-map gather, down)
+//   d rho_n/dt = Hs_R rho_n - rho_n Hs_C                      Hs = -i u H  (two small GEMMs)
+//              - (shift_n + u tc dbl[e]) rho_n[e]              Matsubara shift, temperature corr.
+//              + sum_links su(n_jk) gu[e] rho_{n+e_jk}[e]      index-map gather, one level up
+//              + sum_links sd(n_jk) gd[e] rho_{n-e_jk}[e]      index-map gather, one level down
 //
-// where the neighbour indices come from the closed-form ADO rank (ado.h).  The
-// Heisenberg picture (generator transposed, heom.py:236-237) only swaps the
-// link tables and transposes H.
+// with neighbour indices from the closed-form ADO rank (ado.h).  The Heisenberg
+// picture (generator transposed, heom.py:236-237) swaps the link tables and
+// transposes H.
+//
+// Device layout ("tile-SoA"): ADOs are grouped in tiles of 32; a column's state
+// is stored as [tile][element e][32 ADOs].  A warp lane is an ADO, so
+//   * the own-tile load is one contiguous, fully coalesced block;
+//   * hierarchy gathers for a fixed element read runs of consecutive ADOs
+//     (measured on the depth-8 FMO tables: 0.53-0.61 32-byte sectors per
+//     gathered element, ideal 0.5, against 1.0 for an ADO-major layout);
+//   * all shared-memory accesses of the small GEMMs are conflict free and the
+//     H coefficients are warp-uniform broadcasts.
+// The reference ordering [ADO][element] is restored at the API boundary.
 //
 // Propagation runs as ONE cooperative kernel for the whole trajectory: CTAs own
-// tiles of ADOs, every integrator stage is "tile apply + element-local epilogue"
+// tiles, every integrator stage is "tile apply + element-local epilogue"
 // followed by a grid-wide barrier; order/convergence control lives in device
 // memory, so there is no per-step host round trip.
 #include "common.cuh"
@@ -27,18 +38,23 @@
 #include <memory>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 typedef std::complex<double> zc;
 
+#define TL 32            // ADOs per tile = warp lanes
+#define REG_DIM 8        // small-GEMM register path for block dimensions <= REG_DIM
+
 struct HeomDev {
-    int M, bins, K1, Lc, R, Lk, n_members;
-    long long n_ado;
-    const uint8_t *index;     // [n_ado][bins]
-    const int *up, *down;     // [n_ado][bins]
-    const double *shift;      // [n_ado]
-    const int *ccol;          // [M][R]   (-1 padded)
-    const cplx *cval;         // [n_members][M][R]
+    int nr, nc, M, bins, K1, Lc, Lk, n_members;
+    long long n_ado, n_tiles;
+    const double *shift;      // [n_tiles*32]
+    const double *scale;      // [n_tiles*32] similarity scale s_n of the balanced hierarchy (error norm)
+    const int *up, *down;     // [n_tiles][bins][32]
+    const uint8_t *occ;       // [n_tiles][bins][32]
+    const cplx *HR, *HC;      // [n_members][nr][nr], [n_members][nc][nc]  (pre-scaled by -i u)
+    const double *dterm;      // [M]  u * tc * dbl[e]
     const int *lbin;          // [M][Lk]  (-1 padded)
     const cplx *gu, *gd;      // [M][Lk]
     const double *su, *sd;    // [K1][Lc]
@@ -49,186 +65,535 @@ struct qsx_heom_s {
     int n_sites = 0, K = 0, N = 0, heisenberg = 0;
     double lnorm = 0;         // inf-norm bound of the generator
     std::unique_ptr<AdoTables> tabs;
-    DevBuf<uint8_t> index;
-    DevBuf<int> up, down, ccol, lbin;
-    DevBuf<double> shift, su, sd;
-    DevBuf<cplx> cval, gu, gd;
+    DevBuf<uint8_t> occ;
+    DevBuf<int> up, down, lbin;
+    DevBuf<double> shift, scale, su, sd, dterm;
+    DevBuf<cplx> HR, HC, gu, gd;
 };
 
 // ------------------------------------------------------------- tile machinery
 struct TileSmem {
-    cplx *ys;          // [T][M] own states of the tile
-    int *t_up, *t_dn;  // [T][bins]
-    uint8_t *t_n;      // [T][bins]
-    double *t_shift;   // [T]
-    // tables (shared or global)
-    const int *ccol;
-    const cplx *cval;
-    const int *lbin;
-    const cplx *gu, *gd;
-    const double *su, *sd;
+    cplx *ys;            // [M][32] source tile
+    cplx *os;            // [M][32] commutator result
+    int *t_up, *t_dn;    // [bins][32]
+    uint8_t *t_n;        // [bins][32]
+    double *t_shift;     // [32]
+    cplx *HR, *HC;       // [nr][nr], [nc][nc] of the current member
+    double *dterm;       // [M]
+    int *lbin;           // [M][Lk]
+    cplx *gu, *gd;       // [M][Lk]
+    double *su, *sd;     // [K1][Lc]
     int cur_member;
-    cplx *cval_s;      // shared staging area for cval (or null)
 };
 
-__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// carve the dynamic shared memory; returns bytes used
-__device__ __forceinline__ void tile_smem_setup(const HeomDev &H, unsigned char *base, int T,
-                                                int tables_in_smem, TileSmem &s) {
+__host__ __device__ inline size_t tile_smem_layout(const HeomDev &H, size_t *offs) {
     size_t off = 0;
-    s.ys = reinterpret_cast<cplx *>(base + off); off = align16(off + (size_t)T * H.M * sizeof(cplx));
-    s.t_up = reinterpret_cast<int *>(base + off); off = align16(off + (size_t)T * H.bins * sizeof(int));
-    s.t_dn = reinterpret_cast<int *>(base + off); off = align16(off + (size_t)T * H.bins * sizeof(int));
-    s.t_shift = reinterpret_cast<double *>(base + off); off = align16(off + (size_t)T * sizeof(double));
-    s.t_n = reinterpret_cast<uint8_t *>(base + off); off = align16(off + (size_t)T * H.bins);
-    s.cur_member = -1;
-    if (tables_in_smem) {
-        cplx *cv = reinterpret_cast<cplx *>(base + off); off = align16(off + (size_t)H.M * H.R * sizeof(cplx));
-        cplx *gu = reinterpret_cast<cplx *>(base + off); off = align16(off + (size_t)H.M * H.Lk * sizeof(cplx));
-        cplx *gd = reinterpret_cast<cplx *>(base + off); off = align16(off + (size_t)H.M * H.Lk * sizeof(cplx));
-        double *su = reinterpret_cast<double *>(base + off); off = align16(off + (size_t)H.K1 * H.Lc * sizeof(double));
-        double *sd = reinterpret_cast<double *>(base + off); off = align16(off + (size_t)H.K1 * H.Lc * sizeof(double));
-        int *cc = reinterpret_cast<int *>(base + off); off = align16(off + (size_t)H.M * H.R * sizeof(int));
-        int *lb = reinterpret_cast<int *>(base + off); off = align16(off + (size_t)H.M * H.Lk * sizeof(int));
-        for (int i = threadIdx.x; i < H.M * H.Lk; i += blockDim.x) { gu[i] = H.gu[i]; gd[i] = H.gd[i]; lb[i] = H.lbin[i]; }
-        for (int i = threadIdx.x; i < H.K1 * H.Lc; i += blockDim.x) { su[i] = H.su[i]; sd[i] = H.sd[i]; }
-        for (int i = threadIdx.x; i < H.M * H.R; i += blockDim.x) cc[i] = H.ccol[i];
-        s.cval_s = cv; s.cval = cv; s.gu = gu; s.gd = gd; s.su = su; s.sd = sd; s.ccol = cc; s.lbin = lb;
-    } else {
-        s.cval_s = nullptr; s.cval = H.cval; s.gu = H.gu; s.gd = H.gd; s.su = H.su; s.sd = H.sd;
-        s.ccol = H.ccol; s.lbin = H.lbin;
-    }
-}
-
-static size_t tile_smem_bytes(const HeomDev &H, int T, int tables_in_smem) {
-    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    size_t off = 0;
-    off = al(off + (size_t)T * H.M * sizeof(cplx));
-    off = al(off + (size_t)T * H.bins * sizeof(int));
-    off = al(off + (size_t)T * H.bins * sizeof(int));
-    off = al(off + (size_t)T * sizeof(double));
-    off = al(off + (size_t)T * H.bins);
-    if (tables_in_smem) {
-        off = al(off + (size_t)H.M * H.R * sizeof(cplx));
-        off = al(off + (size_t)H.M * H.Lk * sizeof(cplx));
-        off = al(off + (size_t)H.M * H.Lk * sizeof(cplx));
-        off = al(off + (size_t)H.K1 * H.Lc * sizeof(double));
-        off = al(off + (size_t)H.K1 * H.Lc * sizeof(double));
-        off = al(off + (size_t)H.M * H.R * sizeof(int));
-        off = al(off + (size_t)H.M * H.Lk * sizeof(int));
-    }
+    offs[0] = off; off = al16(off + (size_t)H.M * TL * sizeof(cplx));        // ys
+    offs[1] = off; off = al16(off + (size_t)H.M * TL * sizeof(cplx));        // os
+    offs[2] = off; off = al16(off + (size_t)H.bins * TL * sizeof(int));      // t_up
+    offs[3] = off; off = al16(off + (size_t)H.bins * TL * sizeof(int));      // t_dn
+    offs[4] = off; off = al16(off + (size_t)H.bins * TL);                    // t_n
+    offs[5] = off; off = al16(off + (size_t)2 * TL * sizeof(double));        // t_shift, t_scale
+    offs[6] = off; off = al16(off + (size_t)H.nr * H.nr * sizeof(cplx));     // HR
+    offs[7] = off; off = al16(off + (size_t)H.nc * H.nc * sizeof(cplx));     // HC
+    offs[8] = off; off = al16(off + (size_t)H.M * sizeof(double));           // dterm
+    offs[9] = off; off = al16(off + (size_t)H.M * H.Lk * sizeof(int));       // lbin
+    offs[10] = off; off = al16(off + (size_t)H.M * H.Lk * sizeof(cplx));     // gu
+    offs[11] = off; off = al16(off + (size_t)H.M * H.Lk * sizeof(cplx));     // gd
+    offs[12] = off; off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));  // su
+    offs[13] = off; off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));  // sd
     return off;
 }
 
-// Apply the hierarchy generator to ADOs [n0, n0+T) of one column.
-//   x    : the column's full state [n_ado][M] (global, read through L2)
-//   epi  : epi(i, value, own) with i = n*M + e inside the column, value = (L x)[i],
-//          own = x[i]; called once per element by its owner thread.
-// Contains barriers; must be called by all threads of the CTA.
-template <class Epi>
-__device__ __forceinline__ void heom_tile(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
-                                          long long n0, int T, int member, Epi epi) {
-    const int M = H.M, bins = H.bins, R = H.R, Lk = H.Lk;
-    __syncthreads();          // previous tile fully consumed before its staging area is reused
-    if (s.cval_s && member != s.cur_member) {
-        const cplx *src = H.cval + (size_t)member * M * R;
-        for (int i = threadIdx.x; i < M * R; i += blockDim.x) s.cval_s[i] = src[i];
+__device__ __forceinline__ void tile_smem_setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
+    size_t o[14];
+    tile_smem_layout(H, o);
+    s.ys = reinterpret_cast<cplx *>(base + o[0]);
+    s.os = reinterpret_cast<cplx *>(base + o[1]);
+    s.t_up = reinterpret_cast<int *>(base + o[2]);
+    s.t_dn = reinterpret_cast<int *>(base + o[3]);
+    s.t_n = reinterpret_cast<uint8_t *>(base + o[4]);
+    s.t_shift = reinterpret_cast<double *>(base + o[5]);
+    s.HR = reinterpret_cast<cplx *>(base + o[6]);
+    s.HC = reinterpret_cast<cplx *>(base + o[7]);
+    s.dterm = reinterpret_cast<double *>(base + o[8]);
+    s.lbin = reinterpret_cast<int *>(base + o[9]);
+    s.gu = reinterpret_cast<cplx *>(base + o[10]);
+    s.gd = reinterpret_cast<cplx *>(base + o[11]);
+    s.su = reinterpret_cast<double *>(base + o[12]);
+    s.sd = reinterpret_cast<double *>(base + o[13]);
+    s.cur_member = -1;
+    for (int i = threadIdx.x; i < H.M; i += blockDim.x) s.dterm[i] = H.dterm[i];
+    for (int i = threadIdx.x; i < H.M * H.Lk; i += blockDim.x) {
+        s.lbin[i] = H.lbin[i]; s.gu[i] = H.gu[i]; s.gd[i] = H.gd[i];
     }
-    s.cur_member = member;
-    const cplx *cval = s.cval_s ? s.cval_s : H.cval + (size_t)member * M * R;
-    {
-        const cplx *xs = x + (size_t)n0 * M;
-        for (int i = threadIdx.x; i < T * M; i += blockDim.x) s.ys[i] = __ldcg(&xs[i]);
-        const size_t tb = (size_t)n0 * bins;
-        for (int i = threadIdx.x; i < T * bins; i += blockDim.x) {
-            s.t_up[i] = H.up[tb + i];
-            s.t_dn[i] = H.down[tb + i];
-            s.t_n[i] = H.index[tb + i];
+    for (int i = threadIdx.x; i < H.K1 * H.Lc; i += blockDim.x) { s.su[i] = H.su[i]; s.sd[i] = H.sd[i]; }
+}
+
+// out[a] = sum_c A[a][c] in[c]  (A: n x n in shared memory, warp-uniform reads);
+// the result is handed to `put(a, value)`.  Inputs are fetched with get(c).
+template <class Get, class Put>
+__device__ __forceinline__ void small_gemv(const cplx *A, int n, Get get, Put put) {
+    if (n <= REG_DIM) {
+        cplx in[REG_DIM];
+#pragma unroll
+        for (int c = 0; c < REG_DIM; ++c) in[c] = (c < n) ? get(c) : cmake(0, 0);
+        for (int a = 0; a < n; ++a) {
+            cplx acc = cmake(0, 0);
+            const cplx *row = A + a * n;
+#pragma unroll
+            for (int c = 0; c < REG_DIM; ++c)
+                if (c < n) cfma(acc, row[c], in[c]);
+            put(a, acc);
         }
-        for (int i = threadIdx.x; i < T; i += blockDim.x) s.t_shift[i] = H.shift[n0 + i];
+    } else {
+        for (int a = 0; a < n; ++a) {
+            cplx acc = cmake(0, 0);
+            const cplx *row = A + a * n;
+            for (int c = 0; c < n; ++c) cfma(acc, row[c], get(c));
+            put(a, acc);
+        }
+    }
+}
+
+// Apply the hierarchy generator to one tile (32 ADOs) of one column.
+//   x    : the column's state in tile-SoA layout (global, read through L2)
+//   pre  : p = pre(i) is called early for every owned element (prefetch of
+//          integrator data, e.g. the accumulator Y[i]);
+//   post : post(i, value, own, p) with i the tile-SoA index inside the column,
+//          value = (L x)[i], own = x[i]; called once per element by its owner.
+// Contains barriers; must be called by all threads of the CTA.
+__device__ __forceinline__ void tile_stage(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
+                                           long long tile, int member) {
+    const int M = H.M, bins = H.bins, nr = H.nr, nc = H.nc;
+    __syncthreads();          // previous tile fully consumed before the staging areas are reused
+    if (member != s.cur_member) {
+        const cplx *hr = H.HR + (size_t)member * nr * nr, *hc = H.HC + (size_t)member * nc * nc;
+        for (int i = threadIdx.x; i < nr * nr; i += blockDim.x) s.HR[i] = hr[i];
+        for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) s.HC[i] = hc[i];
+        s.cur_member = member;
+    }
+    const cplx *xs = x + (size_t)tile * M * TL;
+    for (int i = threadIdx.x; i < M * TL; i += blockDim.x) s.ys[i] = __ldcg(&xs[i]);
+    const size_t tb = (size_t)tile * bins * TL;
+    for (int i = threadIdx.x; i < bins * TL; i += blockDim.x) {
+        s.t_up[i] = __ldg(&H.up[tb + i]);
+        s.t_dn[i] = __ldg(&H.down[tb + i]);
+        s.t_n[i] = __ldg(&H.occ[tb + i]);
+    }
+    if (threadIdx.x < TL) {
+        s.t_shift[threadIdx.x] = __ldg(&H.shift[tile * TL + threadIdx.x]);
+        s.t_shift[TL + threadIdx.x] = __ldg(&H.scale[tile * TL + threadIdx.x]);
     }
     __syncthreads();
-    int lanes, la, e0, estride;
-    if (M <= (int)blockDim.x) {
-        lanes = blockDim.x / M; la = threadIdx.x / M; e0 = threadIdx.x % M; estride = M;
-        if (la >= lanes) return;
-    } else {
-        lanes = 1; la = 0; e0 = threadIdx.x; estride = blockDim.x;
+}
+
+struct TileGeneric {
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 3;
+    static constexpr int UNITS = 1;          // tiles a CTA works on concurrently
+    static size_t smem_bytes(const HeomDev &H) { size_t o[14]; return tile_smem_layout(H, o); }
+    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
+        tile_smem_setup(H, base, s);
     }
-    for (int e = e0; e < M; e += estride) {
-        const int *crow = s.ccol + e * R;
-        const cplx *vrow = cval + e * R;
-        const int *lrow = s.lbin + e * Lk;
-        for (int nl = la; nl < T; nl += lanes) {
-            const cplx *yn = s.ys + nl * M;
-            const cplx own = yn[e];
-            cplx acc = cmake(-s.t_shift[nl] * own.x, -s.t_shift[nl] * own.y);
-            for (int l = 0; l < R; ++l) {
-                int c = crow[l];
-                if (c < 0) break;
-                cfma(acc, vrow[l], yn[c]);
-            }
+    template <class Pre, class Post>
+    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
+                                               long long tile, int member, Pre pre, Post post) {
+        const int M = H.M, nr = H.nr, nc = H.nc, Lk = H.Lk;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        tile_stage(H, s, x, tile, member);
+        // (Hs_R rho)[:, b]: one task per column b, lane = ADO
+        for (int b = warp; b < nc; b += nwarp) {
+            const cplx *col = s.ys + (size_t)b * nr * TL + lane;
+            cplx *out = s.os + (size_t)b * nr * TL + lane;
+            small_gemv(s.HR, nr, [&](int c) { return col[c * TL]; },
+                       [&](int a, cplx v) { out[a * TL] = v; });
+        }
+        __syncthreads();
+        // - (rho Hs_C)[a, :]: one task per row a; (rho Hs)[a][b] = sum_c A_C[b][c] rho[a][c]
+        for (int a = warp; a < nr; a += nwarp) {
+            const cplx *row = s.ys + (size_t)a * TL + lane;
+            cplx *out = s.os + (size_t)a * TL + lane;
+            small_gemv(s.HC, nc, [&](int c) { return row[(size_t)c * nr * TL]; },
+                       [&](int b, cplx v) {
+                           cplx o = out[(size_t)b * nr * TL];
+                           out[(size_t)b * nr * TL] = cmake(o.x - v.x, o.y - v.y);
+                       });
+        }
+        __syncthreads();
+        // diagonal terms, hierarchy links, epilogue: warp = element, lane = ADO
+        const double shift = s.t_shift[lane];
+        const double wscale = s.t_shift[TL + lane];
+        for (int e = warp; e < M; e += nwarp) {
+            const long long gi = ((long long)tile * M + e) * TL + lane;
+            const cplx p = pre(gi);
+            const cplx own = s.ys[e * TL + lane];
+            cplx acc = s.os[e * TL + lane];
+            const double dg = shift + s.dterm[e];
+            acc.x -= dg * own.x;
+            acc.y -= dg * own.y;
+            const int *lrow = s.lbin + e * Lk;
             for (int l = 0; l < Lk; ++l) {
-                int b = lrow[l];
+                const int b = lrow[l];
                 if (b < 0) break;
                 const int k = b % H.K1;
-                const int njk = s.t_n[nl * bins + b];
-                const int iu = s.t_up[nl * bins + b];
-                const int id = s.t_dn[nl * bins + b];
+                const int njk = s.t_n[b * TL + lane];
+                const int iu = s.t_up[b * TL + lane];
+                const int id = s.t_dn[b * TL + lane];
                 if (iu >= 0) {
-                    cplx v = __ldcg(&x[(size_t)iu * M + e]);
-                    cplx g = cscale(s.su[k * H.Lc + njk], s.gu[e * Lk + l]);
-                    cfma(acc, g, v);
+                    cplx v = __ldcg(&x[((size_t)(iu >> 5) * M + e) * TL + (iu & 31)]);
+                    cfma(acc, cscale(s.su[k * H.Lc + njk], s.gu[e * Lk + l]), v);
                 }
                 if (id >= 0) {
-                    cplx v = __ldcg(&x[(size_t)id * M + e]);
-                    cplx g = cscale(s.sd[k * H.Lc + njk], s.gd[e * Lk + l]);
-                    cfma(acc, g, v);
+                    cplx v = __ldcg(&x[((size_t)(id >> 5) * M + e) * TL + (id & 31)]);
+                    cfma(acc, cscale(s.sd[k * H.Lc + njk], s.gd[e * Lk + l]), v);
                 }
             }
-            epi((n0 + nl) * (long long)M + e, acc, own);
+            post(gi, acc, own, p, wscale);
         }
+    }
+};
+
+// Compile-time shaped tile: NR warps per CTA, warp w owns row w of every ADO
+// matrix in the final pass, so the (rho Hs_C) row results stay in registers.
+// All loop bounds and shared-memory offsets are immediates; the hierarchy
+// gathers of element b+1 are issued before element b is finished.
+template <int NR, int NC, int LK, int K1, int PIPE, int MINB>
+struct TileFixed {
+    static constexpr int THREADS = 32 * NR;
+    static constexpr int MIN_BLOCKS = MINB;
+    static constexpr int UNITS = 1;
+    static constexpr int M = NR * NC;
+    static size_t smem_bytes(const HeomDev &H) { size_t o[14]; return tile_smem_layout(H, o); }
+    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
+        tile_smem_setup(H, base, s);
+    }
+
+    struct Gathered { cplx vu[LK], vd[LK]; cplx p; };
+
+    template <class Pre>
+    static __device__ __forceinline__ void gather(const HeomDev &H, const TileSmem &s,
+                                                  const cplx *__restrict__ x, int e, int lane,
+                                                  long long gi, Pre pre, Gathered &g) {
+        g.p = pre(gi);
+#pragma unroll
+        for (int l = 0; l < LK; ++l) {
+            g.vu[l] = g.vd[l] = cmake(0, 0);
+            const int b = s.lbin[e * LK + l];
+            if (b >= 0) {
+                const int iu = s.t_up[b * TL + lane];
+                const int id = s.t_dn[b * TL + lane];
+                if (iu >= 0) g.vu[l] = __ldcg(&x[((size_t)(iu >> 5) * M + e) * TL + (iu & 31)]);
+                if (id >= 0) g.vd[l] = __ldcg(&x[((size_t)(id >> 5) * M + e) * TL + (id & 31)]);
+            }
+        }
+    }
+
+    template <class Pre, class Post>
+    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
+                                               long long tile, int member, Pre pre, Post post) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // w < NR
+        tile_stage(H, s, x, tile, member);
+        // (Hs_R rho)[:, b] for the columns owned by this warp -> shared memory
+        for (int b = w; b < NC; b += NR) {
+            cplx in[NR];
+#pragma unroll
+            for (int c = 0; c < NR; ++c) in[c] = s.ys[(c + NR * b) * TL + lane];
+#pragma unroll
+            for (int a = 0; a < NR; ++a) {
+                cplx acc = cmake(0, 0);
+#pragma unroll
+                for (int c = 0; c < NR; ++c) cfma(acc, s.HR[a * NR + c], in[c]);
+                s.os[(a + NR * b) * TL + lane] = acc;
+            }
+        }
+        // (rho Hs_C)[w, :] -> registers
+        cplx rr[NC];
+        {
+            cplx in[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) in[c] = s.ys[(w + NR * c) * TL + lane];
+#pragma unroll
+            for (int b = 0; b < NC; ++b) {
+                cplx acc = cmake(0, 0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) cfma(acc, s.HC[b * NC + c], in[c]);
+                rr[b] = acc;
+            }
+        }
+        __syncthreads();
+        const double shift = s.t_shift[lane];
+        const double wscale = s.t_shift[TL + lane];
+        const long long gbase = ((long long)tile * M) * TL + lane;
+        Gathered cur, nxt;
+        gather(H, s, x, w, lane, gbase + (long long)w * TL, pre, cur);
+#pragma unroll
+        for (int b = 0; b < NC; ++b) {
+            const int e = w + NR * b;
+            const long long gi = gbase + (long long)e * TL;
+            if (PIPE && b + 1 < NC) gather(H, s, x, e + NR, lane, gi + (long long)NR * TL, pre, nxt);
+            if (!PIPE && b > 0) gather(H, s, x, e, lane, gi, pre, cur);
+            const cplx own = s.ys[e * TL + lane];
+            cplx acc = s.os[e * TL + lane];
+            const double dg = shift + s.dterm[e];
+            acc.x -= rr[b].x + dg * own.x;
+            acc.y -= rr[b].y + dg * own.y;
+#pragma unroll
+            for (int l = 0; l < LK; ++l) {
+                const int bn = s.lbin[e * LK + l];
+                if (bn >= 0) {
+                    const int k = bn % K1;
+                    const int njk = s.t_n[bn * TL + lane];
+                    cfma(acc, cscale(s.su[k * H.Lc + njk], s.gu[e * LK + l]), cur.vu[l]);
+                    cfma(acc, cscale(s.sd[k * H.Lc + njk], s.gd[e * LK + l]), cur.vd[l]);
+                }
+            }
+            post(gi, acc, own, cur.p, wscale);
+            if (PIPE && b + 1 < NC) cur = nxt;
+        }
+    }
+};
+
+
+// Warp-autonomous tile: every warp owns a private staging area and processes
+// whole tiles on its own -- no CTA barriers, so the tile load (cp.async), the two
+// small GEMMs and the hierarchy gathers of different warps overlap freely, and
+// with one CTA per SM each thread can keep dozens of gathers in flight.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int NR, int NC, int LK, int WARPS>
+struct TileWarp {
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int UNITS = WARPS;
+    static constexpr int M = NR * NC;
+    static constexpr int HALF = (NC + 1) / 2;
+
+    static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
+        size_t off = 0;
+        off = al16(off + (size_t)M * sizeof(double));            // dterm
+        off = al16(off + (size_t)M * LK * sizeof(int));          // lbin
+        off = al16(off + (size_t)M * LK * sizeof(cplx));         // gu
+        off = al16(off + (size_t)M * LK * sizeof(cplx));         // gd
+        off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));  // su
+        off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));  // sd
+        return off;
+    }
+    static __host__ __device__ size_t warp_bytes(const HeomDev &H) {
+        size_t off = 0;
+        off = al16(off + (size_t)M * TL * sizeof(cplx));         // ys
+        off = al16(off + (size_t)NR * NR * sizeof(cplx));        // HR
+        off = al16(off + (size_t)NC * NC * sizeof(cplx));        // HC
+        off = al16(off + (size_t)H.bins * TL * sizeof(int));     // t_up
+        off = al16(off + (size_t)H.bins * TL * sizeof(int));     // t_dn
+        off = al16(off + (size_t)H.bins * TL);                   // t_n (uint8)
+        off = al16(off + (size_t)TL * sizeof(double));           // t_shift
+        return off;
+    }
+    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + WARPS * warp_bytes(H); }
+
+    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
+        size_t off = 0;
+        s.dterm = reinterpret_cast<double *>(base + off); off = al16(off + (size_t)M * sizeof(double));
+        s.lbin = reinterpret_cast<int *>(base + off); off = al16(off + (size_t)M * LK * sizeof(int));
+        s.gu = reinterpret_cast<cplx *>(base + off); off = al16(off + (size_t)M * LK * sizeof(cplx));
+        s.gd = reinterpret_cast<cplx *>(base + off); off = al16(off + (size_t)M * LK * sizeof(cplx));
+        s.su = reinterpret_cast<double *>(base + off); off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));
+        s.sd = reinterpret_cast<double *>(base + off); off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));
+        for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
+        for (int i = threadIdx.x; i < M * LK; i += blockDim.x) {
+            s.lbin[i] = H.lbin[i]; s.gu[i] = H.gu[i]; s.gd[i] = H.gd[i];
+        }
+        for (int i = threadIdx.x; i < H.K1 * H.Lc; i += blockDim.x) { s.su[i] = H.su[i]; s.sd[i] = H.sd[i]; }
+        unsigned char *wb = base + shared_bytes(H) + (size_t)(threadIdx.x >> 5) * warp_bytes(H);
+        off = 0;
+        s.ys = reinterpret_cast<cplx *>(wb + off); off = al16(off + (size_t)M * TL * sizeof(cplx));
+        s.HR = reinterpret_cast<cplx *>(wb + off); off = al16(off + (size_t)NR * NR * sizeof(cplx));
+        s.HC = reinterpret_cast<cplx *>(wb + off); off = al16(off + (size_t)NC * NC * sizeof(cplx));
+        s.t_up = reinterpret_cast<int *>(wb + off); off = al16(off + (size_t)H.bins * TL * sizeof(int));
+        s.t_dn = reinterpret_cast<int *>(wb + off); off = al16(off + (size_t)H.bins * TL * sizeof(int));
+        s.t_n = reinterpret_cast<uint8_t *>(wb + off); off = al16(off + (size_t)H.bins * TL);
+        s.t_shift = reinterpret_cast<double *>(wb + off);
+        s.os = nullptr;
+        s.cur_member = -1;
+        __syncthreads();
+    }
+
+    template <class Pre, class Post>
+    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
+                                               long long tile, int member, Pre pre, Post post) {
+        const int lane = threadIdx.x & 31;
+        const int bins = H.bins;
+        uint8_t *t_occ = s.t_n;
+        __syncwarp();
+        if (member != s.cur_member) {
+            const cplx *hr = H.HR + (size_t)member * NR * NR, *hc = H.HC + (size_t)member * NC * NC;
+            for (int i = lane; i < NR * NR; i += 32) s.HR[i] = hr[i];
+            for (int i = lane; i < NC * NC; i += 32) s.HC[i] = hc[i];
+            s.cur_member = member;
+        }
+        // own tile and its index tables: asynchronous copies straight into shared memory
+        const cplx *xs = x + (size_t)tile * M * TL + lane;
+#pragma unroll 7
+        for (int e = 0; e < M; ++e) cp_async16(&s.ys[e * TL + lane], &xs[e * TL]);
+        const size_t tb = (size_t)tile * bins * TL + lane;
+        for (int b = 0; b < bins; ++b) {
+            cp_async4(&s.t_up[b * TL + lane], &H.up[tb + b * TL]);
+            cp_async4(&s.t_dn[b * TL + lane], &H.down[tb + b * TL]);
+        }
+        for (int b = 0; b < bins; ++b) t_occ[b * TL + lane] = __ldg(&H.occ[tb + b * TL]);
+        const double shift = __ldg(&H.shift[tile * TL + lane]);
+        const double wscale = __ldg(&H.scale[tile * TL + lane]);
+        cp_async_wait_all();
+        __syncwarp();
+        const long long gbase = ((long long)tile * M) * TL + lane;
+
+        for (int a = 0; a < NR; ++a) {
+            cplx in_row[NC], acc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) in_row[c] = s.ys[(a + NR * c) * TL + lane];
+            // - (rho Hs_C)[a][b] = - sum_c A_C[b][c] rho[a][c]
+#pragma unroll
+            for (int b = 0; b < NC; ++b) {
+                cplx t = cmake(0, 0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) cfma(t, s.HC[b * NC + c], in_row[c]);
+                const double dg = shift + s.dterm[a + NR * b];
+                acc[b] = cmake(-t.x - dg * in_row[b].x, -t.y - dg * in_row[b].y);
+            }
+            // + (Hs_R rho)[a][b] = sum_c A_R[a][c] rho[c][b]
+#pragma unroll
+            for (int c = 0; c < NR; ++c) {
+                const cplx h = s.HR[a * NR + c];
+#pragma unroll
+                for (int b = 0; b < NC; ++b) cfma(acc[b], h, s.ys[(c + NR * b) * TL + lane]);
+            }
+            // hierarchy links + epilogue, two batches of columns to bound the registers
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int b0 = half * HALF;
+                const int nb = half == 0 ? HALF : NC - HALF;
+                cplx vu[HALF][LK], vd[HALF][LK], pv[HALF];
+#pragma unroll
+                for (int q = 0; q < HALF; ++q) {
+                    if (q < nb) {
+                        const int e = a + NR * (b0 + q);
+                        pv[q] = pre(gbase + (long long)e * TL);
+#pragma unroll
+                        for (int l = 0; l < LK; ++l) {
+                            vu[q][l] = vd[q][l] = cmake(0, 0);
+                            const int bn = s.lbin[e * LK + l];
+                            if (bn >= 0) {
+                                const int iu = s.t_up[bn * TL + lane];
+                                const int id = s.t_dn[bn * TL + lane];
+                                if (iu >= 0) vu[q][l] = __ldcg(&x[((size_t)(iu >> 5) * M + e) * TL + (iu & 31)]);
+                                if (id >= 0) vd[q][l] = __ldcg(&x[((size_t)(id >> 5) * M + e) * TL + (id & 31)]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < HALF; ++q) {
+                    if (q < nb) {
+                        const int b = b0 + q;
+                        const int e = a + NR * b;
+                        cplx r = acc[b];
+#pragma unroll
+                        for (int l = 0; l < LK; ++l) {
+                            const int bn = s.lbin[e * LK + l];
+                            if (bn >= 0) {
+                                const int k = bn % H.K1;
+                                const int njk = t_occ[bn * TL + lane];
+                                cfma(r, cscale(s.su[k * H.Lc + njk], s.gu[e * LK + l]), vu[q][l]);
+                                cfma(r, cscale(s.sd[k * H.Lc + njk], s.gd[e * LK + l]), vd[q][l]);
+                            }
+                        }
+                        post(gbase + (long long)e * TL, r, in_row[b], pv[q], wscale);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------ layout kernels
+// reference [b][n][e]  <->  tile-SoA [b][tile][e][32]
+__global__ void heom_to_internal(const cplx *__restrict__ ref, cplx *__restrict__ internal, int B,
+                                 long long n_ado, long long n_tiles, int M) {
+    const long long per = n_tiles * M * TL;
+    const long long total = per * B;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long b = i / per, r = i % per;
+        long long tile = r / ((long long)M * TL);
+        int e = (int)((r / TL) % M), lane = (int)(r % TL);
+        long long n = tile * TL + lane;
+        internal[i] = (n < n_ado) ? ref[((size_t)b * n_ado + n) * M + e] : cmake(0, 0);
+    }
+}
+
+__global__ void heom_from_internal(const cplx *__restrict__ internal, cplx *__restrict__ ref, int B,
+                                   long long n_ado, long long n_tiles, int M) {
+    const long long per = n_ado * M;
+    const long long total = per * B;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long b = i / per, r = i % per;
+        long long n = r / M;
+        int e = (int)(r % M);
+        ref[i] = internal[((size_t)b * n_tiles * M + (n >> 5) * M + e) * TL + (n & 31)];
     }
 }
 
 // ------------------------------------------------------------------ kernels
 struct HeomApplyArgs {
     HeomDev H;
-    const cplx *x;
-    cplx *y;
+    const cplx *x;          // internal layout
+    cplx *y;                // internal layout
     const int *member_of;   // [B] or null
-    int B, T, tables_in_smem;
-    long long tiles_per_col;
+    int B;
 };
 
-__global__ void __launch_bounds__(256) heom_apply_kernel(HeomApplyArgs a) {
+template <class Tile>
+__global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_apply_kernel(HeomApplyArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem s;
-    tile_smem_setup(a.H, smem_raw, a.T, a.tables_in_smem, s);
-    const long long D = a.H.n_ado * a.H.M;
-    const long long total = a.tiles_per_col * a.B;
-    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        int b = (int)(w / a.tiles_per_col);
-        long long n0 = (w % a.tiles_per_col) * a.T;
-        int T = (int)min((long long)a.T, a.H.n_ado - n0);
+    Tile::setup(a.H, smem_raw, s);
+    const long long Dp = a.H.n_tiles * a.H.M * TL;
+    const long long total = a.H.n_tiles * a.B;
+    const long long w0 = Tile::UNITS == 1 ? blockIdx.x : (long long)blockIdx.x * Tile::UNITS + (threadIdx.x >> 5);
+    const long long wstride = (long long)gridDim.x * Tile::UNITS;
+    for (long long w = w0; w < total; w += wstride) {
+        int b = (int)(w / a.H.n_tiles);
+        long long tile = w % a.H.n_tiles;
         int member = a.member_of ? a.member_of[b] : 0;
-        cplx *yb = a.y + (size_t)b * D;
-        heom_tile(a.H, s, a.x + (size_t)b * D, n0, T, member,
-                  [&](long long i, cplx v, cplx) { yb[i] = v; });
+        cplx *yb = a.y + (size_t)b * Dp;
+        Tile::run(a.H, s, a.x + (size_t)b * Dp, tile, member,
+                  [&](long long) { return cmake(0, 0); },
+                  [&](long long i, cplx v, cplx, cplx, double) { yb[i] = v; });
     }
 }
 
 struct HeomPropArgs {
     HeomDev H;
-    int B, T, tables_in_smem, nt;
-    long long tiles_per_col;
+    int B, nt;
     const int *member_of;
-    const cplx *y0;
-    cplx *Y, *V, *W, *X;        // work vectors [B][D] (X only for RK4)
+    const cplx *y0;             // reference layout [B][n_ado][M]
+    cplx *Y, *V, *W, *X;        // work vectors, internal layout [B][Dp] (X only for RK4)
     const double *t;
     double t0;
-    int method;
     double rtol;
     int rk4_sub, kmax;
     double theta, lnorm;
@@ -242,55 +607,67 @@ struct HeomPropArgs {
 };
 
 __device__ __forceinline__ void heom_save(const HeomPropArgs &a, int it) {
-    const long long D = a.H.n_ado * a.H.M;
+    const long long n_ado = a.H.n_ado, n_tiles = a.H.n_tiles;
     const int M = a.H.M;
+    const long long Dp = n_tiles * M * TL;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsz = (long long)gridDim.x * blockDim.x;
     if (a.save_mode == QSX_SAVE_STATE) {
-        for (long long i = gtid; i < (long long)a.B * D; i += gsz) {
-            long long b = i / D, r = i % D;
-            a.out[((size_t)b * a.nt + it) * a.saved_dim + r] = __ldcg(&a.Y[i]);
+        const long long per = n_ado * M;
+        for (long long i = gtid; i < (long long)a.B * per; i += gsz) {
+            long long b = i / per, r = i % per, n = r / M;
+            int e = (int)(r % M);
+            a.out[((size_t)b * a.nt + it) * a.saved_dim + r] =
+                __ldcg(&a.Y[(size_t)b * Dp + ((n >> 5) * M + e) * TL + (n & 31)]);
         }
     } else if (a.save_mode == QSX_SAVE_ADO0) {
         for (long long i = gtid; i < (long long)a.B * M; i += gsz) {
-            long long b = i / M, r = i % M;
-            a.out[((size_t)b * a.nt + it) * a.saved_dim + r] = __ldcg(&a.Y[(size_t)b * D + r]);
+            long long b = i / M, e = i % M;
+            a.out[((size_t)b * a.nt + it) * a.saved_dim + e] = __ldcg(&a.Y[(size_t)b * Dp + e * TL]);
         }
     } else {
-        const long long per_col = a.H.n_ado * a.save_rows;
+        const long long per_col = n_ado * a.save_rows;
         for (long long i = gtid; i < (long long)a.B * per_col; i += gsz) {
             long long b = i / per_col, r = i % per_col;
             long long n = r / a.save_rows;
             int m = (int)(r % a.save_rows);
-            const cplx *y = a.Y + (size_t)b * D + (size_t)n * M;
+            const cplx *y = a.Y + (size_t)b * Dp + ((n >> 5) * M) * TL + (n & 31);
             cplx acc = cmake(0, 0);
-            for (int e = 0; e < M; ++e) cfma(acc, __ldg(&a.S[(size_t)m * M + e]), __ldcg(&y[e]));
+            for (int e = 0; e < M; ++e) cfma(acc, __ldg(&a.S[(size_t)m * M + e]), __ldcg(&y[(size_t)e * TL]));
             a.out[((size_t)b * a.nt + it) * a.saved_dim + r] = acc;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) heom_propagate_kernel(HeomPropArgs a) {
+template <int METHOD, class Tile>
+__global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagate_kernel(HeomPropArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     TileSmem s;
-    tile_smem_setup(a.H, smem_raw, a.T, a.tables_in_smem, s);
-    const long long D = a.H.n_ado * a.H.M;
-    const long long total = a.tiles_per_col * a.B;
+    Tile::setup(a.H, smem_raw, s);
+    const long long w0 = Tile::UNITS == 1 ? blockIdx.x : (long long)blockIdx.x * Tile::UNITS + (threadIdx.x >> 5);
+    const long long wstride = (long long)gridDim.x * Tile::UNITS;
+    const int M = a.H.M;
+    const long long n_tiles = a.H.n_tiles;
+    const long long Dp = n_tiles * M * TL;
+    const long long total = n_tiles * a.B;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsz = (long long)gridDim.x * blockDim.x;
     const int B = a.B;
 
-    // ---- init: Y = y0, reference norms, control words ---------------------
+    // ---- init: Y = y0 (layout change), reference norms, control words ---------
     for (int i = (int)gtid; i < 3 * B; i += (int)gsz) a.ynorm[i] = 0.0;
     if (gtid < 3) a.flags[gtid] = 0;
     grid.sync();
     for (int b = 0; b < B; ++b) {
         double loc = 0.0;
-        for (long long i = gtid; i < D; i += gsz) {
-            cplx v = a.y0[(size_t)b * D + i];
-            a.Y[(size_t)b * D + i] = v;
-            loc = fmax(loc, cabs1(v));
+        for (long long i = gtid; i < Dp; i += gsz) {
+            long long tile = i / ((long long)M * TL);
+            int e = (int)((i / TL) % M), lane = (int)(i % TL);
+            long long n = tile * TL + lane;
+            cplx v = (n < a.H.n_ado) ? a.y0[((size_t)b * a.H.n_ado + n) * M + e] : cmake(0, 0);
+            a.Y[(size_t)b * Dp + i] = v;
+            loc = fmax(loc, __ldg(&a.H.scale[tile * TL + lane]) * cabs1(v));
         }
         loc = warp_max(loc);
         if ((threadIdx.x & 31) == 0 && loc > 0) atomic_max_nonneg(&a.ynorm[b], loc);
@@ -307,7 +684,10 @@ __global__ void __launch_bounds__(256) heom_propagate_kernel(HeomPropArgs a) {
         const double target = a.t[it];
         if (target != tcur) {
             const double span = target - tcur;
-            if (a.method == QSX_METHOD_TAYLOR) {
+            if (METHOD == QSX_METHOD_TAYLOR) {
+                // Taylor series of exp(hL) y; terms are accumulated into Y in pairs
+                // (even k) so that Y is never read by a neighbour gather while it
+                // is being updated and the Y traffic is halved.
                 int nsub = (int)ceil(fabs(span) * a.lnorm / a.theta);
                 if (nsub < 1) nsub = 1;
                 const double h = span / nsub;
@@ -319,34 +699,33 @@ __global__ void __launch_bounds__(256) heom_propagate_kernel(HeomPropArgs a) {
                         const double fac = h / k;
                         const bool even = (k & 1) == 0;
                         int ok = 1;
-                        // block 0 recycles the control slots that come next
-                        if (even && blockIdx.x == 0) {
+                        if (even && blockIdx.x == 0) {   // recycle the control slots that come next
                             if (threadIdx.x == 0) a.flags[(fslot + 1) % 3] = 0;
                             for (int b = threadIdx.x; b < B; b += blockDim.x) a.ynorm[((nslot + 2) % 3) * B + b] = 0.0;
                         }
-                        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-                            const int b = (int)(w / a.tiles_per_col);
-                            const long long n0 = (w % a.tiles_per_col) * a.T;
-                            const int T = (int)min((long long)a.T, a.H.n_ado - n0);
+                        for (long long w = w0; w < total; w += wstride) {
+                            const int b = (int)(w / n_tiles);
+                            const long long tile = w % n_tiles;
                             const int member = a.member_of ? a.member_of[b] : 0;
-                            cplx *db = dst + (size_t)b * D;
-                            cplx *Yb = a.Y + (size_t)b * D;
+                            cplx *db = dst + (size_t)b * Dp;
+                            cplx *Yb = a.Y + (size_t)b * Dp;
                             if (!even) {
-                                heom_tile(a.H, s, src + (size_t)b * D, n0, T, member,
-                                          [&](long long i, cplx f, cplx) { db[i] = cscale(fac, f); });
+                                Tile::run(a.H, s, src + (size_t)b * Dp, tile, member,
+                                          [&](long long) { return cmake(0, 0); },
+                                          [&](long long i, cplx f, cplx, cplx, double) { __stcs(&db[i], cscale(fac, f)); });
                             } else {
                                 const double yref = a.rtol * __ldcg(&a.ynorm[nslot * B + b]);
                                 double ymax = 0.0;
-                                heom_tile(a.H, s, src + (size_t)b * D, n0, T, member,
-                                          [&](long long i, cplx f, cplx own) {
+                                Tile::run(a.H, s, src + (size_t)b * Dp, tile, member,
+                                          [&](long long i) { return __ldcs(&Yb[i]); },
+                                          [&](long long i, cplx f, cplx own, cplx y, double sc) {
                                               cplx wv = cscale(fac, f);
-                                              db[i] = wv;
-                                              cplx y = Yb[i];
+                                              __stcs(&db[i], wv);
                                               y.x += own.x + wv.x;
                                               y.y += own.y + wv.y;
-                                              Yb[i] = y;
-                                              if (cabs1(own) + cabs1(wv) > yref) ok = 0;
-                                              ymax = fmax(ymax, cabs1(y));
+                                              __stcs(&Yb[i], y);
+                                              if (sc * (cabs1(own) + cabs1(wv)) > yref) ok = 0;
+                                              ymax = fmax(ymax, sc * cabs1(y));
                                           });
                                 ymax = warp_max(ymax);
                                 if ((threadIdx.x & 31) == 0 && ymax > 0)
@@ -380,31 +759,38 @@ __global__ void __launch_bounds__(256) heom_propagate_kernel(HeomPropArgs a) {
                 for (int sub = 0; sub < nsub; ++sub) {
                     for (int stage = 0; stage < 4; ++stage) {
                         const cplx *src = stage == 0 ? a.Y : (stage == 2 ? TB : TA);
-                        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-                            const int b = (int)(w / a.tiles_per_col);
-                            const long long n0 = (w % a.tiles_per_col) * a.T;
-                            const int T = (int)min((long long)a.T, a.H.n_ado - n0);
+                        for (long long w = w0; w < total; w += wstride) {
+                            const int b = (int)(w / n_tiles);
+                            const long long tile = w % n_tiles;
                             const int member = a.member_of ? a.member_of[b] : 0;
-                            const size_t o = (size_t)b * D;
+                            const size_t o = (size_t)b * Dp;
                             cplx *Yb = a.Y + o, *Ab = ACC + o, *TAb = TA + o, *TBb = TB + o;
                             if (stage == 0)
-                                heom_tile(a.H, s, src + o, n0, T, member, [&](long long i, cplx k1, cplx own) {
+                                Tile::run(a.H, s, src + o, tile, member,
+                                          [&](long long) { return cmake(0, 0); },
+                                          [&](long long i, cplx k1, cplx own, cplx, double) {
                                     TAb[i] = cadd(own, cscale(0.5 * h, k1));
                                     Ab[i] = cadd(own, cscale(h / 6.0, k1));
                                 });
                             else if (stage == 1)
-                                heom_tile(a.H, s, src + o, n0, T, member, [&](long long i, cplx k2, cplx) {
-                                    TBb[i] = cadd(Yb[i], cscale(0.5 * h, k2));
+                                Tile::run(a.H, s, src + o, tile, member,
+                                          [&](long long i) { return Yb[i]; },
+                                          [&](long long i, cplx k2, cplx, cplx y, double) {
+                                    TBb[i] = cadd(y, cscale(0.5 * h, k2));
                                     Ab[i] = cadd(Ab[i], cscale(h / 3.0, k2));
                                 });
                             else if (stage == 2)
-                                heom_tile(a.H, s, src + o, n0, T, member, [&](long long i, cplx k3, cplx) {
-                                    TAb[i] = cadd(Yb[i], cscale(h, k3));
+                                Tile::run(a.H, s, src + o, tile, member,
+                                          [&](long long i) { return Yb[i]; },
+                                          [&](long long i, cplx k3, cplx, cplx y, double) {
+                                    TAb[i] = cadd(y, cscale(h, k3));
                                     Ab[i] = cadd(Ab[i], cscale(h / 3.0, k3));
                                 });
                             else
-                                heom_tile(a.H, s, src + o, n0, T, member, [&](long long i, cplx k4, cplx) {
-                                    Yb[i] = cadd(Ab[i], cscale(h / 6.0, k4));
+                                Tile::run(a.H, s, src + o, tile, member,
+                                          [&](long long i) { return Ab[i]; },
+                                          [&](long long i, cplx k4, cplx, cplx acc, double) {
+                                    Yb[i] = cadd(acc, cscale(h / 6.0, k4));
                                 });
                         }
                         grid.sync();
@@ -441,69 +827,75 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     h->n_sites = cfg->n_sites; h->K = cfg->K; h->N = N; h->heisenberg = cfg->heisenberg;
     h->tabs.reset(new AdoTables(bins, Lc));
     AdoTables &tb = *h->tabs;
-    QSX_REQUIRE(tb.n_ado < ((int64_t)1 << 31), "hierarchy too large");
+    QSX_REQUIRE(tb.n_ado < ((int64_t)1 << 31) - 64, "hierarchy too large");
     tb.enumerate();
     const int64_t n_ado = tb.n_ado;
+    const int64_t n_tiles = (n_ado + TL - 1) / TL;
 
-    std::vector<int> ea(M), eb(M);
+    // ---- the Liouville subspace must be one rectangular block rows x cols -----
+    std::vector<int> ea(M), eb(M), rows, cols;
     for (int e = 0; e < M; ++e) {
         int64_t f = cfg->subspace_index[e];
         QSX_REQUIRE(f >= 0 && f < (int64_t)N * N, "subspace index out of range");
         ea[e] = (int)(f % N);
         eb[e] = (int)(f / N);
+        rows.push_back(ea[e]);
+        cols.push_back(eb[e]);
+    }
+    std::sort(rows.begin(), rows.end()); rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    std::sort(cols.begin(), cols.end()); cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+    const int nr = (int)rows.size(), nc = (int)cols.size();
+    bool rect = (nr * nc == M);
+    for (int e = 0; e < M && rect; ++e) rect = (ea[e] == rows[e % nr] && eb[e] == cols[e / nr]);
+    if (!rect) {
+        qsx_set_error("HEOM kernel needs a rectangular Liouville block (rows x cols), e.g. 'ee', 'eg', "
+                      "'fe' or 'gg,ge,eg,ee'; propagate the blocks of a union separately");
+        return QSX_ERR_UNSUPPORTED;
     }
     const zc *Hm = reinterpret_cast<const zc *>(cfg->H);
     const zc *cc = reinterpret_cast<const zc *>(cfg->c);
     const double *v = cfg->coupling_diag;
     const zc mi(0.0, -1.0);
 
-    // ---- commutator rows (ELL), pattern = union over members -----------------
-    auto coef = [&](const zc *H, int e, int e2) -> zc {
-        int a = ea[e], b = eb[e], c = ea[e2], d = eb[e2];
-        zc r = 0;
-        if (!cfg->heisenberg) {
-            if (d == b) r += H[a * N + c];
-            if (a == c) r -= H[d * N + b];
-        } else {
-            if (b == d) r += H[c * N + a];
-            if (c == a) r -= H[b * N + d];
-        }
-        return r;
-    };
-    std::vector<std::vector<int>> pattern(M);
-    for (int e = 0; e < M; ++e) {
-        for (int e2 = 0; e2 < M; ++e2) {
-            bool nz = (e2 == e);
-            if (!nz && (ea[e] == ea[e2] || eb[e] == eb[e2]))
-                for (int m = 0; m < cfg->n_members && !nz; ++m)
-                    nz = coef(Hm + (size_t)m * N * N, e, e2) != zc(0);
-            if (nz) pattern[e].push_back(e2);
-        }
-    }
-    int R = 1;
-    for (auto &p : pattern) R = std::max<int>(R, (int)p.size());
-    std::vector<int> ccol((size_t)M * R, -1);
-    std::vector<cplx> cval((size_t)cfg->n_members * M * R, cmake(0, 0));
-    std::vector<double> dbl(M, 0.0), rowsum(M, 0.0);
-    for (int e = 0; e < M; ++e)
-        for (int j = 0; j < cfg->n_sites; ++j) {
-            double va = v[j * N + ea[e]], vb = v[j * N + eb[e]];
-            dbl[e] += va + vb - 2 * va * vb;
-        }
-    for (int e = 0; e < M; ++e)
-        for (size_t l = 0; l < pattern[e].size(); ++l) ccol[(size_t)e * R + l] = pattern[e][l];
-    for (int m = 0; m < cfg->n_members; ++m)
-        for (int e = 0; e < M; ++e) {
+    // ---- Hs_R and (Hs_C)^T per member, pre-scaled by -i u -----------------------
+    // Schroedinger: d rho = Hs_R rho - rho Hs_C; Heisenberg (generator transposed):
+    // d X = Hs_R^T X - X Hs_C^T.  The kernel wants A_R[a][c] and A_C[b][c] with
+    // (rho Hs_C)[a][b] = sum_c A_C[b][c] rho[a][c]  ->  A_C = Hs_C^T.
+    std::vector<cplx> HR((size_t)cfg->n_members * nr * nr), HC((size_t)cfg->n_members * nc * nc);
+    double hnorm = 0;
+    for (int m = 0; m < cfg->n_members; ++m) {
+        const zc *H = Hm + (size_t)m * N * N;
+        double rs_max = 0, cs_max = 0;
+        for (int a = 0; a < nr; ++a) {
             double rs = 0;
-            for (size_t l = 0; l < pattern[e].size(); ++l) {
-                int e2 = pattern[e][l];
-                zc val = mi * u * coef(Hm + (size_t)m * N * N, e, e2);
-                if (e2 == e) val -= u * cfg->temp_corr * dbl[e];
-                cval[((size_t)m * M + e) * R + l] = cmake(val.real(), val.imag());
+            for (int c = 0; c < nr; ++c) {
+                zc val = mi * u * (cfg->heisenberg ? H[rows[c] * N + rows[a]] : H[rows[a] * N + rows[c]]);
+                HR[((size_t)m * nr + a) * nr + c] = cmake(val.real(), val.imag());
                 rs += std::abs(val);
             }
-            rowsum[e] = std::max(rowsum[e], rs);
+            rs_max = std::max(rs_max, rs);
         }
+        for (int b = 0; b < nc; ++b) {
+            double cs = 0;
+            for (int c = 0; c < nc; ++c) {
+                // A_C[b][c] = Hs_C[c][b] (Schroedinger) or Hs_C^T[c][b] = Hs_C[b][c] (Heisenberg)
+                zc val = mi * u * (cfg->heisenberg ? H[cols[b] * N + cols[c]] : H[cols[c] * N + cols[b]]);
+                HC[((size_t)m * nc + b) * nc + c] = cmake(val.real(), val.imag());
+                cs += std::abs(val);
+            }
+            cs_max = std::max(cs_max, cs);
+        }
+        hnorm = std::max(hnorm, rs_max + cs_max);
+    }
+    std::vector<double> dterm(M, 0.0);
+    for (int e = 0; e < M; ++e) {
+        double dbl = 0;
+        for (int j = 0; j < cfg->n_sites; ++j) {
+            double va = v[j * N + ea[e]], vb = v[j * N + eb[e]];
+            dbl += va + vb - 2 * va * vb;
+        }
+        dterm[e] = u * cfg->temp_corr * dbl;
+    }
 
     // ---- link tables ---------------------------------------------------------
     std::vector<std::vector<int>> lpat(M);
@@ -543,33 +935,70 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
             sd[(size_t)k * Lc + n] = cfg->heisenberg ? (n > 0 ? modU(n - 1) : 0.0) : modD(n);
         }
     }
-    std::vector<double> shift(n_ado);
+    // ---- balancing similarity transform (error norm and sub-step count) ---------
+    // The raw hierarchy couples level n to n+1 with O(1) and n+1 to n with O(n |c_k|)
+    // coefficients, so its inf-norm grossly over-estimates the spectral radius.  With
+    // s_n = prod_b prod_{m<n_b} 1/rho_k(m), rho_k(m) = sqrt(|down(m+1)| / |up(m)|), the
+    // transformed generator S L S^-1 has symmetric couplings; Taylor sub-steps are sized
+    // by its norm and truncation errors are measured in the norm |S y|_inf.  (For
+    // modified_HEOM rho == 1: that option is exactly this rescaling, heom.py:423-437.)
+    std::vector<double> mu(K1, 0.0), md(K1, 0.0);
+    for (int e = 0; e < M; ++e)
+        for (size_t l = 0; l < lpat[e].size(); ++l) {
+            int k = lpat[e][l] % K1;
+            mu[k] = std::max(mu[k], std::abs(lgu[e][l]));
+            md[k] = std::max(md[k], std::abs(lgd[e][l]));
+        }
+    std::vector<double> rho((size_t)K1 * Lc, 1.0);
+    for (int k = 0; k < K1; ++k)
+        for (int n = 0; n + 1 < Lc; ++n) {
+            double upc = su[(size_t)k * Lc + n] * mu[k], dnc = sd[(size_t)k * Lc + n + 1] * md[k];
+            rho[(size_t)k * Lc + n] = (upc > 0 && dnc > 0) ? sqrt(dnc / upc) : 1.0;
+        }
+    // ---- per-ADO tables in tile layout [tile][bin][32] ---------------------------
+    std::vector<double> shift((size_t)n_tiles * TL, 0.0), scale((size_t)n_tiles * TL, 1.0);
+    std::vector<int> up((size_t)n_tiles * bins * TL, -1), down((size_t)n_tiles * bins * TL, -1);
+    std::vector<uint8_t> occ((size_t)n_tiles * bins * TL, 0);
     double lnorm = 0;
     for (int64_t n = 0; n < n_ado; ++n) {
-        double sft = 0;
-        for (int b = 0; b < bins; ++b) sft += tb.index[(size_t)n * bins + b] * cfg->nu[b % K1];
+        double sft = 0, logs = 0;
+        const int64_t tile = n / TL;
+        const int lane = (int)(n % TL);
+        for (int b = 0; b < bins; ++b) {
+            const int njk = tb.index[(size_t)n * bins + b];
+            sft += njk * cfg->nu[b % K1];
+            for (int m = 0; m < njk; ++m) logs -= log(rho[(size_t)(b % K1) * Lc + m]);
+            const size_t o = ((size_t)tile * bins + b) * TL + lane;
+            up[o] = tb.up[(size_t)n * bins + b];
+            down[o] = tb.down[(size_t)n * bins + b];
+            occ[o] = (uint8_t)njk;
+        }
         shift[n] = u * sft;
+        scale[n] = exp(logs);
     }
-    // inf-norm bound: max over (n, e) of the absolute row sum
-    for (int64_t n = 0; n < n_ado; ++n) {
+    // inf-norm of the balanced generator: max over (n, e) of the absolute row sum
+    for (int64_t n = 0; n < n_ado; ++n)
         for (int e = 0; e < M; ++e) {
-            double rs = rowsum[e] + fabs(shift[n]);
+            double rs = hnorm + fabs(shift[n]) + fabs(dterm[e]);
             for (size_t l = 0; l < lpat[e].size(); ++l) {
                 int b = lpat[e][l], k = b % K1, njk = tb.index[(size_t)n * bins + b];
-                if (tb.up[(size_t)n * bins + b] >= 0) rs += su[(size_t)k * Lc + njk] * std::abs(lgu[e][l]);
-                if (tb.down[(size_t)n * bins + b] >= 0) rs += sd[(size_t)k * Lc + njk] * std::abs(lgd[e][l]);
+                if (tb.up[(size_t)n * bins + b] >= 0)
+                    rs += su[(size_t)k * Lc + njk] * std::abs(lgu[e][l]) * rho[(size_t)k * Lc + njk];
+                if (tb.down[(size_t)n * bins + b] >= 0)
+                    rs += sd[(size_t)k * Lc + njk] * std::abs(lgd[e][l]) / rho[(size_t)k * Lc + njk - 1];
             }
             lnorm = std::max(lnorm, rs);
         }
-    }
     h->lnorm = lnorm;
 
-    QSX_CUDA(h->index.upload(tb.index, stream));
-    QSX_CUDA(h->up.upload(tb.up, stream));
-    QSX_CUDA(h->down.upload(tb.down, stream));
+    QSX_CUDA(h->occ.upload(occ, stream));
+    QSX_CUDA(h->up.upload(up, stream));
+    QSX_CUDA(h->down.upload(down, stream));
     QSX_CUDA(h->shift.upload(shift, stream));
-    QSX_CUDA(h->ccol.upload(ccol, stream));
-    QSX_CUDA(h->cval.upload(cval, stream));
+    QSX_CUDA(h->scale.upload(scale, stream));
+    QSX_CUDA(h->HR.upload(HR, stream));
+    QSX_CUDA(h->HC.upload(HC, stream));
+    QSX_CUDA(h->dterm.upload(dterm, stream));
     QSX_CUDA(h->lbin.upload(lbin, stream));
     QSX_CUDA(h->gu.upload(gu, stream));
     QSX_CUDA(h->gd.upload(gd, stream));
@@ -578,11 +1007,19 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     QSX_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
 
     HeomDev &d = h->d;
-    d.M = M; d.bins = bins; d.K1 = K1; d.Lc = Lc; d.R = R; d.Lk = Lk; d.n_members = cfg->n_members;
-    d.n_ado = n_ado;
-    d.index = h->index.p; d.up = h->up.p; d.down = h->down.p; d.shift = h->shift.p;
-    d.ccol = h->ccol.p; d.cval = h->cval.p; d.lbin = h->lbin.p; d.gu = h->gu.p; d.gd = h->gd.p;
-    d.su = h->su.p; d.sd = h->sd.p;
+    d.nr = nr; d.nc = nc; d.M = M; d.bins = bins; d.K1 = K1; d.Lc = Lc; d.Lk = Lk;
+    d.n_members = cfg->n_members; d.n_ado = n_ado; d.n_tiles = n_tiles;
+    d.shift = h->shift.p; d.scale = h->scale.p; d.up = h->up.p; d.down = h->down.p; d.occ = h->occ.p;
+    d.HR = h->HR.p; d.HC = h->HC.p; d.dterm = h->dterm.p; d.lbin = h->lbin.p;
+    d.gu = h->gu.p; d.gd = h->gd.p; d.su = h->su.p; d.sd = h->sd.p;
+    size_t offs[14];
+    int dev = 0, smem_limit = 0;
+    QSX_CUDA(cudaGetDevice(&dev));
+    QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (tile_smem_layout(d, offs) > (size_t)smem_limit) {
+        qsx_set_error("HEOM subspace dimension %d too large for the tile kernel", M);
+        return QSX_ERR_UNSUPPORTED;
+    }
     *out = h.release();
     return QSX_OK;
 }
@@ -600,36 +1037,14 @@ extern "C" int qsx_heom_index_maps(qsx_heom_t h, int64_t *ado_index, int32_t *up
     return QSX_OK;
 }
 
-struct HeomLaunchPlan {
-    int threads, T, tables_in_smem;
-    size_t smem;
-    long long tiles_per_col;
-};
+static bool use_warp_tile(const HeomDev &d) {
+    return d.nr == 7 && d.nc == 7 && d.Lk == 4 && d.bins <= 16;
+}
 
-static int plan_launch(const qsx_heom_s *h, HeomLaunchPlan &p) {
-    const HeomDev &d = h->d;
-    int dev = 0, smem_limit = 0;
-    QSX_CUDA(cudaGetDevice(&dev));
-    QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int threads;
-    if (d.M <= 256) threads = std::max(64, ((256 / d.M) * d.M + 31) / 32 * 32);
-    else threads = 256;
-    threads = std::min(threads, 256);
-    int lanes = d.M <= threads ? threads / d.M : 1;
-    int T = std::max(lanes, std::min(64, std::max(1, 2048 / d.M)));
-    T = (T + lanes - 1) / lanes * lanes;
-    T = (int)std::min<long long>(T, std::max<long long>(1, d.n_ado));
-    int tables = 1;
-    // keep the per-CTA footprint small enough for several CTAs per SM
-    if (tile_smem_bytes(d, T, 1) > (size_t)std::min(smem_limit, 100 * 1024)) tables = 0;
-    while (tile_smem_bytes(d, T, tables) > (size_t)smem_limit && T > 1) T = std::max(1, T / 2);
-    if (tile_smem_bytes(d, T, tables) > (size_t)smem_limit) {
-        qsx_set_error("HEOM subspace dimension %d too large for the tile kernel", d.M);
-        return QSX_ERR_UNSUPPORTED;
-    }
-    p.threads = threads; p.T = T; p.tables_in_smem = tables;
-    p.smem = tile_smem_bytes(d, T, tables);
-    p.tiles_per_col = (d.n_ado + T - 1) / T;
+static int upload_members(DevBuf<int> &buf, const int32_t *host, int n, int n_members, cudaStream_t s) {
+    std::vector<int> m(host, host + n);
+    for (int x : m) QSX_REQUIRE(x >= 0 && x < n_members, "member index out of range");
+    QSX_CUDA(buf.upload(m, s));
     return QSX_OK;
 }
 
@@ -637,28 +1052,35 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
                               const int32_t *member_host, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     QSX_REQUIRE(h && y_dev && dy_dev && n_columns > 0, "qsx_heom_apply: bad arguments");
-    QSX_REQUIRE(y_dev != dy_dev, "qsx_heom_apply: in-place application is not supported");
-    HeomLaunchPlan p;
-    int rc = plan_launch(h, p);
-    if (rc) return rc;
+    const HeomDev &d = h->d;
+    const long long Dp = d.n_tiles * d.M * TL;
     DevBuf<int> member;
-    if (member_host) {
-        std::vector<int> m(member_host, member_host + n_columns);
-        for (int x : m) QSX_REQUIRE(x >= 0 && x < h->d.n_members, "member index out of range");
-        QSX_CUDA(member.upload(m, stream));
-    }
-    HeomApplyArgs a;
-    a.H = h->d; a.x = (const cplx *)y_dev; a.y = (cplx *)dy_dev;
-    a.member_of = member_host ? member.p : nullptr;
-    a.B = n_columns; a.T = p.T; a.tables_in_smem = p.tables_in_smem; a.tiles_per_col = p.tiles_per_col;
-    long long total = p.tiles_per_col * n_columns;
-    int sms = 148, dev = 0;
+    DevBuf<cplx> xi, yi;
+    int rc;
+    if (member_host && (rc = upload_members(member, member_host, n_columns, d.n_members, stream))) return rc;
+    QSX_CUDA(xi.alloc((size_t)n_columns * Dp));
+    QSX_CUDA(yi.alloc((size_t)n_columns * Dp));
+    int dev = 0, sms = 148;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int grid = (int)std::min<long long>(total, (long long)sms * 8);
-    QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    heom_apply_kernel<<<grid, p.threads, p.smem, stream>>>(a);
-    qsx_launch_counter += 1;
+    heom_to_internal<<<sms * 4, 256, 0, stream>>>((const cplx *)y_dev, xi.p, n_columns, d.n_ado, d.n_tiles, d.M);
+    HeomApplyArgs a;
+    a.H = d; a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
+    size_t offs[14];
+    size_t smem = tile_smem_layout(d, offs);
+    long long total = d.n_tiles * n_columns;
+    int grid = (int)std::min<long long>(total, (long long)sms * 6);
+    if (use_warp_tile(d) && d.K1 == 2) {
+        typedef TileFixed<7, 7, 4, 2, 0, 3> T;
+        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
+    } else {
+        typedef TileGeneric T;
+        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
+    }
+    heom_from_internal<<<sms * 4, 256, 0, stream>>>(yi.p, (cplx *)dy_dev, n_columns, d.n_ado, d.n_tiles, d.M);
+    qsx_launch_counter += 3;
     QSX_CUDA(cudaGetLastError());
     QSX_CUDA(cudaStreamSynchronize(stream));
     return QSX_OK;
@@ -670,6 +1092,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     const HeomDev &d = h->d;
     const int B = args->n_columns, nt = args->n_times, M = d.M;
     const long long D = d.n_ado * M;
+    const long long Dp = d.n_tiles * M * TL;
     QSX_REQUIRE(B > 0 && nt > 0 && args->t_host && args->y0_dev && args->out_dev,
                 "qsx_heom_propagate: empty batch or missing buffers");
     QSX_REQUIRE(args->method == QSX_METHOD_TAYLOR || args->method == QSX_METHOD_RK4,
@@ -678,36 +1101,31 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     for (int i = 1; i < nt; ++i)
         QSX_REQUIRE(args->t_host[i] >= args->t_host[i - 1], "output times must be non-decreasing");
     QSX_REQUIRE(args->t_host[0] >= args->t0, "first output time precedes t0");
-    HeomLaunchPlan p;
-    int rc = plan_launch(h, p);
-    if (rc) return rc;
 
     DevBuf<int> member, flags;
     DevBuf<double> d_t, ynorm;
     DevBuf<unsigned long long> stats;
     DevBuf<cplx> Y, V, W, X;
-    if (args->generator_of_column_host) {
-        std::vector<int> m(args->generator_of_column_host, args->generator_of_column_host + B);
-        for (int x : m) QSX_REQUIRE(x >= 0 && x < d.n_members, "member index out of range");
-        QSX_CUDA(member.upload(m, stream));
-    }
+    int rc;
+    if (args->generator_of_column_host &&
+        (rc = upload_members(member, args->generator_of_column_host, B, d.n_members, stream)))
+        return rc;
     QSX_CUDA(d_t.upload(args->t_host, nt, stream));
     QSX_CUDA(flags.alloc(3));
     QSX_CUDA(ynorm.alloc((size_t)3 * B));
     QSX_CUDA(stats.alloc(3));
     QSX_CUDA(cudaMemsetAsync(stats.p, 0, 3 * sizeof(unsigned long long), stream));
-    QSX_CUDA(Y.alloc((size_t)B * D));
-    QSX_CUDA(V.alloc((size_t)B * D));
-    QSX_CUDA(W.alloc((size_t)B * D));
-    if (args->method == QSX_METHOD_RK4) QSX_CUDA(X.alloc((size_t)B * D));
+    QSX_CUDA(Y.alloc((size_t)B * Dp));
+    QSX_CUDA(V.alloc((size_t)B * Dp));
+    QSX_CUDA(W.alloc((size_t)B * Dp));
+    if (args->method == QSX_METHOD_RK4) QSX_CUDA(X.alloc((size_t)B * Dp));
 
     HeomPropArgs a;
-    a.H = d; a.B = B; a.T = p.T; a.tables_in_smem = p.tables_in_smem; a.nt = nt;
-    a.tiles_per_col = p.tiles_per_col;
+    a.H = d; a.B = B; a.nt = nt;
     a.member_of = args->generator_of_column_host ? member.p : nullptr;
     a.y0 = (const cplx *)args->y0_dev;
     a.Y = Y.p; a.V = V.p; a.W = W.p; a.X = X.p;
-    a.t = d_t.p; a.t0 = args->t0; a.method = args->method;
+    a.t = d_t.p; a.t0 = args->t0;
     a.rtol = args->rtol > 0 ? args->rtol : 1e-13;
     a.rk4_sub = args->rk4_substeps > 0 ? args->rk4_substeps : 16;
     a.kmax = 60; a.theta = 2.0; a.lnorm = h->lnorm;
@@ -725,21 +1143,42 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     a.out = (cplx *)args->out_dev;
     a.flags = flags.p; a.ynorm = ynorm.p; a.stats = stats.p;
 
+    const bool taylor = args->method == QSX_METHOD_TAYLOR;
+    const void *kernel;
+    int threads;
+    const char *variant = getenv("QSX_HEOM_VARIANT");
+    size_t smem;
+    int units = 1;
+    if (use_warp_tile(d) && variant && variant[0] == 'w') {
+        typedef TileWarp<7, 7, 4, 7> T;             // warp-autonomous tiles, 1 CTA/SM
+        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;
+        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>
+                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
+    } else if (use_warp_tile(d) && d.K1 == 2 && !(variant && variant[0] == 'g')) {
+        typedef TileFixed<7, 7, 4, 2, 0, 3> T;      // CTA-cooperative shaped tile, 3 CTAs/SM
+        threads = T::THREADS; smem = T::smem_bytes(d);
+        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>
+                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
+    } else {
+        typedef TileGeneric T;
+        threads = T::THREADS; smem = T::smem_bytes(d);
+        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>
+                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
+    }
     int dev = 0, sms = 0, per_sm = 0;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    QSX_CUDA(cudaFuncSetAttribute(heom_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heom_propagate_kernel, p.threads, p.smem));
+    QSX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     QSX_REQUIRE(per_sm > 0, "heom_propagate_kernel does not fit on an SM");
-    long long total = p.tiles_per_col * B;
-    int grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+    long long total = d.n_tiles * B;
+    int grid = (int)std::min<long long>((total + units - 1) / units, (long long)sms * per_sm);
     void *kargs[] = {&a};
     cudaEvent_t e0, e1;
     QSX_CUDA(cudaEventCreate(&e0));
     QSX_CUDA(cudaEventCreate(&e1));
     QSX_CUDA(cudaEventRecord(e0, stream));
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)heom_propagate_kernel, dim3(grid), dim3(p.threads),
-                                                kargs, p.smem, stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), kargs, smem, stream);
     qsx_launch_counter += 1;
     if (e != cudaSuccess) {
         cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -218,8 +218,8 @@ class DenseEOM(DeviceEOM):
 
     def __del__(self):
         h = getattr(self, '_h', None)
-        if h:
-            _capi.lib().qsx_dense_destroy(h)
+        if h and _capi is not None and _capi._lib is not None:
+            _capi._lib.qsx_dense_destroy(h)
             self._h = None
 
     def _apply_dev(self, y, dy, n, gptr):
@@ -274,8 +274,8 @@ class HeomEOM(DeviceEOM):
 
     def __del__(self):
         h = getattr(self, '_h', None)
-        if h:
-            _capi.lib().qsx_heom_destroy(h)
+        if h and _capi is not None and _capi._lib is not None:
+            _capi._lib.qsx_heom_destroy(h)
             self._h = None
 
     def index_maps(self):
