@@ -162,6 +162,37 @@ int qsx_ado_enumerate(int32_t bins, int32_t level_cutoff, int64_t *ado_index,
 
 
 /* ------------------------------------------------------------------------
+ * ZOFE master equation (ZOFEModel).  Replaces rhodot_oopdot_vec and the
+ * closure returned by equation_of_motion (dynamics/zofe.py:121-234).
+ * State layout = reference: [vec_F(rho) ; vec_F(O)], O[p,s,a,b] at
+ * n^2 + p + P (s + S (a + n b))  (zofe.py:84, 110-119).
+ * QSX_SAVE_ADO0 saves the first n^2 entries (rho), QSX_SAVE_MATRIX applies a
+ * [rows][n^2] matrix to them (expectation values, zofe.py:38-41).
+ * ---------------------------------------------------------------------- */
+typedef struct qsx_zofe_s *qsx_zofe_t;
+
+typedef struct {
+    int32_t n_states;             /* n: states of the Hilbert subspace              */
+    int32_t n_sites;              /* S                                              */
+    int32_t n_pm;                 /* P pseudomodes (bath.py:105-144)                */
+    int32_t n_members;            /* distinct Hamiltonians (ensemble), >= 1         */
+    const void *H;                /* [n_members][n][n] complex128 row-major (host)  */
+    const double *coupling_diag;  /* [S][n] diagonals of V_s; L_s = -V_s (zofe.py:216-217) */
+    const void *Gamma;            /* [P][S] complex128: Omega^2 * huang (zofe.py:224) */
+    const void *w;                /* [P][S] complex128: i Omega + gamma (zofe.py:225) */
+    double unit_convert;
+    int32_t ham_hermit, rho_hermit; /* reference shortcut flags (zofe.py:71-87)     */
+} qsx_zofe_config;
+
+int qsx_zofe_create(qsx_zofe_t *out, const qsx_zofe_config *cfg, void *stream);
+int64_t qsx_zofe_state_dim(qsx_zofe_t h);
+int qsx_zofe_apply(qsx_zofe_t h, const void *y_dev, void *dy_dev,
+                   int32_t n_columns, const int32_t *member_of_column_host,
+                   void *stream);
+int qsx_zofe_propagate(qsx_zofe_t h, qsx_propagate_args *args, void *stream);
+void qsx_zofe_destroy(qsx_zofe_t h);
+
+/* ------------------------------------------------------------------------
  * Batched Redfield generator construction for disorder ensembles (K5).
  * Replaces redfield_evolve / redfield_tensor (dynamics/redfield.py:9-104) and
  * DebyeBath.corr_func_complex / Bath.corr_func_real (bath.py:17-31, 84-102),

@@ -20,6 +20,7 @@ from .dynamics.liouville_space import (matrix_to_ket_vec, ket_vec_to_matrix,
 from .dynamics.redfield import RedfieldModel
 from .dynamics.unitary import UnitaryModel
 from .dynamics.heom import HEOMModel
+from .dynamics.zofe import ZOFEModel
 from .simulate.eom import (simulate_dynamics, simulate_with_fields,
                            simulate_pump)
 from .simulate.response import (linear_response, absorption_spectra,

@@ -58,6 +58,15 @@ class QsxHeomConfig(C.Structure):
                 ('modified', C.c_int32), ('heisenberg', C.c_int32)]
 
 
+class QsxZofeConfig(C.Structure):
+    _fields_ = [('n_states', C.c_int32), ('n_sites', C.c_int32),
+                ('n_pm', C.c_int32), ('n_members', C.c_int32),
+                ('H', C.c_void_p), ('coupling_diag', C.POINTER(C.c_double)),
+                ('Gamma', C.c_void_p), ('w', C.c_void_p),
+                ('unit_convert', C.c_double), ('ham_hermit', C.c_int32),
+                ('rho_hermit', C.c_int32)]
+
+
 class QsxBath(C.Structure):
     _fields_ = [('kind', C.c_int32), ('matsubara_cutoff', C.c_int32),
                 ('temperature', C.c_double), ('reorg_energy', C.c_double),
@@ -73,7 +82,8 @@ EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches',
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
            'qsx_ado_enumerate', 'qsx_redfield_build', 'qsx_reduce_members',
-           'qsx_sample_streams']
+           'qsx_sample_streams', 'qsx_zofe_create', 'qsx_zofe_state_dim',
+           'qsx_zofe_apply', 'qsx_zofe_propagate', 'qsx_zofe_destroy']
 
 _lib = None
 
@@ -124,6 +134,16 @@ def lib():
         C.c_double, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
     L.qsx_reduce_members.argtypes = [C.c_void_p, C.c_int32, C.c_int64,
                                      C.c_double, C.c_void_p, C.c_void_p]
+    L.qsx_zofe_create.argtypes = [C.POINTER(C.c_void_p),
+                                  C.POINTER(QsxZofeConfig), C.c_void_p]
+    L.qsx_zofe_state_dim.restype = C.c_int64
+    L.qsx_zofe_state_dim.argtypes = [C.c_void_p]
+    L.qsx_zofe_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.POINTER(C.c_int32), C.c_void_p]
+    L.qsx_zofe_propagate.argtypes = [C.c_void_p, C.POINTER(QsxPropagateArgs),
+                                     C.c_void_p]
+    L.qsx_zofe_destroy.argtypes = [C.c_void_p]
+    L.qsx_zofe_destroy.restype = None
     L.qsx_sample_streams.argtypes = [C.POINTER(C.c_uint32), C.c_int32, C.c_int64,
                                      C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p]

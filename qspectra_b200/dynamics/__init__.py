@@ -3,3 +3,4 @@ from .liouville_space import LiouvilleSpaceModel, LiouvilleSpaceOperator
 from .redfield import RedfieldModel
 from .unitary import UnitaryModel
 from .heom import HEOMModel
+from .zofe import ZOFEModel

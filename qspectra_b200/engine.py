@@ -321,6 +321,75 @@ class HeomEOM(DeviceEOM):
         return self.n_ado * S.shape[0]
 
 
+class ZofeEOM(DeviceEOM):
+    """ZOFE master equation (kernel K3/K4, csrc/zofe.cu); nonlinear, so the
+    integrators are DOPRI5 (default) and RK4."""
+    lti = False
+
+    def __init__(self, H, coupling_diag, Gamma, w, unit_convert,
+                 ham_hermit=False, rho_hermit=False):
+        lib = _capi.lib()
+        _capi.torch_cuda()
+        H = np.ascontiguousarray(H, dtype=np.complex128)
+        if H.ndim == 2:
+            H = H[None]
+        v = np.ascontiguousarray(coupling_diag, dtype=np.float64)
+        Gamma = np.ascontiguousarray(Gamma, dtype=np.complex128)
+        w = np.ascontiguousarray(w, dtype=np.complex128)
+        if Gamma.shape != w.shape or Gamma.shape[1] != v.shape[0] \
+                or v.shape[1] != H.shape[-1]:
+            raise ValueError('inconsistent ZOFE array shapes')
+        cfg = _capi.QsxZofeConfig()
+        cfg.n_states, cfg.n_sites, cfg.n_pm = H.shape[-1], v.shape[0], Gamma.shape[0]
+        cfg.n_members = H.shape[0]
+        cfg.H = H.ctypes.data
+        cfg.coupling_diag = v.ctypes.data_as(C.POINTER(C.c_double))
+        cfg.Gamma, cfg.w = Gamma.ctypes.data, w.ctypes.data
+        cfg.unit_convert = float(unit_convert)
+        cfg.ham_hermit, cfg.rho_hermit = int(bool(ham_hermit)), int(bool(rho_hermit))
+        self._h = C.c_void_p()
+        _capi.check(lib.qsx_zofe_create(C.byref(self._h), C.byref(cfg),
+                                        _capi.current_stream_ptr()))
+        self.n_generators = H.shape[0]
+        self.n_states = H.shape[-1]
+        self.head = self.n_states ** 2
+        self.dim = int(lib.qsx_zofe_state_dim(self._h))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h and _capi is not None and _capi._lib is not None:
+            _capi._lib.qsx_zofe_destroy(h)
+            self._h = None
+
+    def _apply_dev(self, y, dy, n, gptr):
+        _capi.check(_capi.lib().qsx_zofe_apply(
+            self._h, y.data_ptr(), dy.data_ptr(), n, gptr,
+            _capi.current_stream_ptr()))
+
+    def _propagate(self, args):
+        _capi.check(_capi.lib().qsx_zofe_propagate(
+            self._h, C.byref(args), _capi.current_stream_ptr()))
+
+    def _configure_ado0(self, args):      # "head" = the density-matrix part
+        args.save_mode = _capi.SAVE_ADO0
+        return self.head
+
+    def _configure_matrix(self, args, matrix, save, keep):
+        S = np.asarray(matrix)
+        if S.ndim == 1:
+            S = S[None]
+        if S.shape[-1] != self.head:
+            raise ValueError('ZOFE save matrix must act on vec(rho) (%d columns)'
+                             % self.head)
+        Sd = _capi.to_device(S)
+        keep.append(Sd)
+        args.save_mode = _capi.SAVE_MATRIX
+        args.save_rows = S.shape[0]
+        args.save_dev = Sd.data_ptr()
+        args.n_save = 1
+        return S.shape[0]
+
+
 def reduce_members(batch_dev, scale=1.0):
     """out[...] = scale * sum_m batch[m, ...] on the device (kernel K6)."""
     torch = _capi.torch_cuda()

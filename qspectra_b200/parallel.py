@@ -1,0 +1,96 @@
+"""
+Multi-GPU sharding of the embarrassingly parallel outer loops:
+disorder members (reference simulate/decorators.py:55-60) are block-partitioned
+over the ranks of a ``torch.distributed`` job -- one process per GPU -- each
+rank replays its own members' seeded disorder streams (no communication), and
+the partial ensemble sums are combined with ONE reduce (NCCL over NVLink on
+GPUs, gloo in the CPU tests).  A single HEOM trajectory does not shard
+("replicas only").
+"""
+import numpy as np
+
+
+def shard_members(ensemble_size, rank, world_size):
+    """(first member, count) of this rank's contiguous block; the blocks tile
+    range(ensemble_size) exactly and differ in size by at most one."""
+    if not 0 <= rank < world_size:
+        raise ValueError('rank out of range')
+    base, extra = divmod(int(ensemble_size), int(world_size))
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def world():
+    """(rank, world_size) of the current torch.distributed job, (0, 1) if none."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def reduce_sum(tensor, dst=None):
+    """Sum a (complex or real) tensor over all ranks: all-reduce when ``dst`` is
+    None, otherwise reduce to rank ``dst``.  Complex tensors are reduced through
+    their real view (NCCL has no complex type)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tensor
+    buf = torch.view_as_real(tensor) if tensor.is_complex() else tensor
+    buf = buf.contiguous()
+    if dst is None:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    else:
+        dist.reduce(buf, dst=dst, op=dist.ReduceOp.SUM)
+    return torch.view_as_complex(buf) if tensor.is_complex() else buf
+
+
+def sharded_ensemble_mean(partial_sum_fn, ensemble_size, dst=None):
+    """Generic driver: ``partial_sum_fn(first, count)`` returns this rank's SUM
+    over members first .. first+count-1 as a tensor (or None when count == 0 is
+    not supported by the caller); returns the global mean."""
+    import torch
+    rank, size = world()
+    first, count = shard_members(ensemble_size, rank, size)
+    part = partial_sum_fn(first, count)
+    if not isinstance(part, torch.Tensor):
+        part = torch.from_numpy(np.ascontiguousarray(part))
+    total = reduce_sum(part, dst)
+    return total / ensemble_size
+
+
+def simulate_dynamics_sharded(dynamical_model, initial_state, duration=None,
+                              times=None, liouville_subspace='ee',
+                              ensemble_size=None, dst=None, **integrate_kwargs):
+    """``simulate_dynamics`` with the disorder ensemble sharded over the ranks
+    of the current torch.distributed job; every rank (or only ``dst``) receives
+    the ensemble-averaged density matrices."""
+    import torch
+    from . import _capi, engine
+    from .simulate.eom import ensemble_mean
+    rank, size = world()
+    first, count = shard_members(ensemble_size, rank, size)
+    initial_state = np.asarray(initial_state)
+    if initial_state.ndim == 1:
+        initial_state = np.outer(initial_state.conj(), initial_state)
+    t = (np.arange(0, duration, dynamical_model.time_step)
+         if times is None else np.asarray(times, dtype=float))
+    y0 = dynamical_model.density_matrix_to_state_vector(initial_state,
+                                                        liouville_subspace)
+    save = dynamical_model.dynamics_save
+    if count > 0:
+        eom = dynamical_model.ensemble_eom(count, False, liouville_subspace,
+                                           member0=first)
+        part = ensemble_mean(eom, y0, t, count, save, return_device=True,
+                             scale=1.0 / ensemble_size, **integrate_kwargs)
+    else:
+        torch_ = _capi.torch_cuda()
+        dim = y0.size if save is None else None
+        part = torch_.zeros((len(t), dim), dtype=torch_.complex128, device='cuda')
+    total = reduce_sum(part, dst)
+    states = total.cpu().numpy()
+    return t, dynamical_model.saved_states_to_density_matrix(states)

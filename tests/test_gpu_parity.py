@@ -302,3 +302,43 @@ def test_edge_cases(fmo_model):
         qb.HEOMModel(systems.dimer(), aki_temp_corr=True)
     with pytest.raises(qb.operator_tools.SubspaceError):
         fmo_model.equation_of_motion('eg')
+
+
+# ------------------------------------------------------------------- K3 ZOFE
+def test_zofe_rhs_all_flag_branches(golden):
+    g = golden('zofe')
+    h3 = systems.fmo(bath='pseudomode', n_sites=3)
+    for hh in (0, 1):
+        for rh in (0, 1):
+            m = qb.ZOFEModel(h3, hilbert_subspace='ge', unit_convert=CM_FS,
+                             ham_hermit=bool(hh), rho_hermit=bool(rh))
+            dy = m.equation_of_motion('ee')(0, g['fmo3_y_%d%d' % (hh, rh)])
+            assert rel_l2(dy, g['fmo3_dy_%d%d' % (hh, rh)]) < 1e-13, (hh, rh)
+    with pytest.raises(NotImplementedError):
+        m.equation_of_motion('ee', heisenberg_picture=True)
+
+
+def test_zofe_trajectory_and_absorption(golden):
+    g = golden('zofe')
+    m7 = qb.ZOFEModel(systems.fmo(bath='pseudomode'), hilbert_subspace='e',
+                      unit_convert=CM_FS)
+    t, rho = qb.simulate_dynamics(m7, np.eye(7)[0], 150, rtol=1e-11, atol=1e-13)
+    assert np.array_equal(t, g['fmo7_t'])
+    assert rel_l2(rho, g['fmo7_rho']) < TOL
+    t, rho4 = qb.simulate_dynamics(m7, np.eye(7)[0], 150, method_name='rk4',
+                                   rk4_substeps=40)
+    assert rel_l2(rho4, g['fmo7_rho']) < TOL
+    md = qb.ZOFEModel(systems.dimer(bath='pseudomode'), hilbert_subspace='ge',
+                      unit_convert=CM_FS)
+    f, X = qb.absorption_spectra(md, 1500, rtol=1e-11, atol=1e-13)
+    assert np.array_equal(f, g['dimer_abs_f'])
+    assert rel_l2(X, g['dimer_abs_X']) < TOL
+
+
+def test_zofe_ensemble_batch_equals_single_runs():
+    ham = systems.fmo(bath='pseudomode', n_sites=3)
+    m = qb.ZOFEModel(ham, hilbert_subspace='e', unit_convert=CM_FS)
+    t, avg = qb.simulate_dynamics(m, np.eye(3)[0], 60, ensemble_size=3)
+    singles = [qb.simulate_dynamics(mm, np.eye(3)[0], 60)[1]
+               for mm in m.sample_ensemble(3)]
+    assert rel_l2(avg, np.mean(singles, axis=0)) < 1e-9
