@@ -44,6 +44,7 @@ namespace cg = cooperative_groups;
 typedef std::complex<double> zc;
 
 #define TL 32            // ADOs per tile = warp lanes
+#define COMMA ,
 #define REG_DIM 8        // small-GEMM register path for block dimensions <= REG_DIM
 
 struct HeomDev {
@@ -53,6 +54,10 @@ struct HeomDev {
     const double *scale;      // [n_tiles*32] similarity scale s_n of the balanced hierarchy (error norm)
     const int *up, *down;     // [n_tiles][bins][32]
     const uint8_t *occ;       // [n_tiles][bins][32]
+    const int *off_up, *off_dn;   // [n_tiles][bins][32] element offsets of the neighbour (tile*M*32 + lane), -1 = absent
+    int ee;                   // 1: rows/cols are site-projector states (electronic block), TileEE applicable
+    int real_h;               // 1: Hs_R, Hs_C purely imaginary (real Hamiltonian)
+    cplx GuR[4], GdR[4], GuC[4], GdC[4];   // link coefficients per Matsubara index (row-site / col-site)
     const cplx *HR, *HC;      // [n_members][nr][nr], [n_members][nc][nc]  (pre-scaled by -i u)
     const double *dterm;      // [M]  u * tc * dbl[e]
     const int *lbin;          // [M][Lk]  (-1 padded)
@@ -66,7 +71,7 @@ struct qsx_heom_s {
     double lnorm = 0;         // inf-norm bound of the generator
     std::unique_ptr<AdoTables> tabs;
     DevBuf<uint8_t> occ;
-    DevBuf<int> up, down, lbin;
+    DevBuf<int> up, down, lbin, off_up, off_dn;
     DevBuf<double> shift, scale, su, sd, dterm;
     DevBuf<cplx> HR, HC, gu, gd;
 };
@@ -84,6 +89,11 @@ struct TileSmem {
     cplx *gu, *gd;       // [M][Lk]
     double *su, *sd;     // [K1][Lc]
     int cur_member;
+    // cross-tile prefetch hints (set by the kernel loops, used by TileEE)
+    int cur_col, next_col;
+    long long next_tile;
+    const cplx *loaded;      // tile data currently staged (or in flight) in buffer `buf`
+    int buf;
 };
 
 __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -528,6 +538,248 @@ struct TileWarp {
     }
 };
 
+
+// Electronic-block tile ("ee"-type Liouville blocks whose row/column states are
+// site projectors, e.g. FMO 'ee'): warp w owns row w of every ADO matrix of the
+// tile.  Structure used:
+//   * links of element (a,b): bins of site a ("row-site") and of site b
+//     ("col-site") with coefficients that depend only on the Matsubara index;
+//     neighbour offsets are precomputed, so a gather is base + immediate;
+//   * Hs = -i u H with real H: each complex MAC is 2 DFMA;
+//   * no commutator staging buffer: row w of Hs rho and of rho Hs is formed in
+//     registers straight from the source tile;
+//   * source tiles are double buffered with cp.async: the next tile of this CTA
+//     is in flight while the current one is processed (one barrier per tile).
+template <int NS, int K1, int MINB, bool REAL_H, bool BATCH = false>
+struct TileEE {
+    static constexpr int THREADS = 32 * NS;
+    static constexpr int MIN_BLOCKS = MINB;
+    static constexpr int UNITS = 1;
+    static constexpr int M = NS * NS;
+    static constexpr int BINS = NS * K1;
+
+    static __host__ __device__ size_t buf_bytes() {
+        return al16((size_t)M * TL * sizeof(cplx)) + 2 * al16((size_t)BINS * TL * sizeof(int)) +
+               al16((size_t)BINS * TL) + al16((size_t)2 * TL * sizeof(double));
+    }
+    static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
+        return al16((size_t)NS * NS * sizeof(cplx)) * 2 + al16((size_t)M * sizeof(double)) +
+               2 * al16((size_t)K1 * H.Lc * sizeof(double));
+    }
+    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + 2 * buf_bytes(); }
+
+    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
+        size_t off = 0;
+        s.HR = reinterpret_cast<cplx *>(base + off); off += al16((size_t)NS * NS * sizeof(cplx));
+        s.HC = reinterpret_cast<cplx *>(base + off); off += al16((size_t)NS * NS * sizeof(cplx));
+        s.dterm = reinterpret_cast<double *>(base + off); off += al16((size_t)M * sizeof(double));
+        s.su = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
+        s.sd = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
+        s.os = reinterpret_cast<cplx *>(base + off);       // start of the two tile buffers
+        for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
+        for (int i = threadIdx.x; i < K1 * H.Lc; i += blockDim.x) { s.su[i] = H.su[i]; s.sd[i] = H.sd[i]; }
+        s.cur_member = -1;
+        s.loaded = nullptr;
+        s.buf = 0;
+        __syncthreads();
+    }
+
+    struct Buf {
+        cplx *ys; int *o_up, *o_dn; uint8_t *occ; double *sh;
+    };
+    static __device__ __forceinline__ Buf buffer(const TileSmem &s, int which) {
+        unsigned char *p = reinterpret_cast<unsigned char *>(s.os) + (size_t)which * buf_bytes();
+        Buf b;
+        b.ys = reinterpret_cast<cplx *>(p); p += al16((size_t)M * TL * sizeof(cplx));
+        b.o_up = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
+        b.o_dn = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
+        b.occ = p; p += al16((size_t)BINS * TL);
+        b.sh = reinterpret_cast<double *>(p);
+        return b;
+    }
+    // asynchronous copy of one source tile and its tables into a buffer
+    static __device__ __forceinline__ void issue(const HeomDev &H, const Buf &b, const cplx *tile_data,
+                                                 long long tile) {
+        for (int i = threadIdx.x; i < M * TL; i += THREADS) cp_async16(&b.ys[i], &tile_data[i]);
+        const size_t tb = (size_t)tile * BINS * TL;
+        for (int i = threadIdx.x; i < BINS * TL / 4; i += THREADS) {
+            cp_async16(&b.o_up[4 * i], &H.off_up[tb + 4 * i]);
+            cp_async16(&b.o_dn[4 * i], &H.off_dn[tb + 4 * i]);
+        }
+        for (int i = threadIdx.x; i < BINS * TL / 16; i += THREADS) cp_async16(&b.occ[16 * i], &H.occ[tb + 16 * i]);
+        if (threadIdx.x < TL / 2) {
+            cp_async16(&b.sh[2 * threadIdx.x], &H.shift[tile * TL + 2 * threadIdx.x]);
+            cp_async16(&b.sh[TL + 2 * threadIdx.x], &H.scale[tile * TL + 2 * threadIdx.x]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+
+    template <class Pre, class Post>
+    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
+                                               long long tile, int member, Pre pre, Post post) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // w = row a
+        const size_t Dp = (size_t)H.n_tiles * M * TL;
+        const cplx *tile_data = x + (size_t)tile * M * TL;
+        if (s.loaded != tile_data) {        // first tile of a phase: nothing in flight yet
+            s.buf = 0;
+            issue(H, buffer(s, 0), tile_data, tile);
+        }
+        if (member != s.cur_member) {
+            const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
+            for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.HR[i] = hr[i]; s.HC[i] = hc[i]; }
+            s.cur_member = member;
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                    // tile visible; every warp is done with the other buffer
+        const Buf cur = buffer(s, s.buf);
+        if (s.next_tile >= 0) {             // prefetch this CTA's next tile into the other buffer
+            const cplx *nd = (x - (size_t)s.cur_col * Dp) + (size_t)s.next_col * Dp + (size_t)s.next_tile * M * TL;
+            issue(H, buffer(s, s.buf ^ 1), nd, s.next_tile);
+            s.loaded = nd;
+            s.buf ^= 1;
+        } else {
+            s.loaded = nullptr;
+        }
+        const long long gbase = ((long long)tile * M) * TL + lane + (long long)w * TL;   // element (w, 0)
+        // integrator prefetch (e.g. the accumulator Y) for the 7 owned elements
+        cplx pv[NS];
+#pragma unroll
+        for (int b = 0; b < NS; ++b) pv[b] = pre(gbase + (long long)b * NS * TL);
+        // own row and diagonal terms
+        cplx own[NS], acc[NS];
+        const double shift = cur.sh[lane];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) own[c] = cur.ys[(w + NS * c) * TL + lane];
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+            const double dg = shift + s.dterm[w + NS * b];
+            acc[b] = cmake(-dg * own[b].x, -dg * own[b].y);
+        }
+        // hierarchy links: row-site bins (site w), then col-site bins (site b)
+        const cplx *xw = x + (size_t)w * TL;
+        if (BATCH) {
+            // issue every gather of this row first (56 independent loads per lane), then accumulate
+            cplx vru[K1][NS], vrd[K1][NS], vcu[NS][K1], vcd[NS][K1];
+#pragma unroll
+            for (int k = 0; k < K1; ++k) {
+                const int bin = w * K1 + k;
+                const int ou = cur.o_up[bin * TL + lane], od = cur.o_dn[bin * TL + lane];
+#pragma unroll
+                for (int b = 0; b < NS; ++b) {
+                    vru[k][b] = ou >= 0 ? __ldcg(xw + ou + b * NS * TL) : cmake(0, 0);
+                    vrd[k][b] = od >= 0 ? __ldcg(xw + od + b * NS * TL) : cmake(0, 0);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+#pragma unroll
+                for (int k = 0; k < K1; ++k) {
+                    const int bin = b * K1 + k;
+                    const int ou = cur.o_up[bin * TL + lane], od = cur.o_dn[bin * TL + lane];
+                    vcu[b][k] = ou >= 0 ? __ldcg(xw + ou + b * NS * TL) : cmake(0, 0);
+                    vcd[b][k] = od >= 0 ? __ldcg(xw + od + b * NS * TL) : cmake(0, 0);
+                }
+#pragma unroll
+            for (int k = 0; k < K1; ++k) {
+                const int njk = cur.occ[(w * K1 + k) * TL + lane];
+                const cplx gu = cscale(s.su[k * H.Lc + njk], H.GuR[k]);
+                const cplx gd = cscale(s.sd[k * H.Lc + njk], H.GdR[k]);
+#pragma unroll
+                for (int b = 0; b < NS; ++b) { cfma(acc[b], gu, vru[k][b]); cfma(acc[b], gd, vrd[k][b]); }
+            }
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+#pragma unroll
+                for (int k = 0; k < K1; ++k) {
+                    const int njk = cur.occ[(b * K1 + k) * TL + lane];
+                    cfma(acc[b], cscale(s.su[k * H.Lc + njk], H.GuC[k]), vcu[b][k]);
+                    cfma(acc[b], cscale(s.sd[k * H.Lc + njk], H.GdC[k]), vcd[b][k]);
+                }
+        } else {
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+            const int bin = w * K1 + k;
+            const int njk = cur.occ[bin * TL + lane];
+            const int ou = cur.o_up[bin * TL + lane], od = cur.o_dn[bin * TL + lane];
+            if (__any_sync(0xffffffffu, ou >= 0)) {
+                const cplx g = cscale(s.su[k * H.Lc + njk], H.GuR[k]);
+                const cplx *base = xw + (ou >= 0 ? ou : 0);
+#pragma unroll
+                for (int b = 0; b < NS; ++b) {
+                    cplx v = ou >= 0 ? __ldcg(base + b * NS * TL) : cmake(0, 0);
+                    cfma(acc[b], g, v);
+                }
+            }
+            if (__any_sync(0xffffffffu, od >= 0)) {
+                const cplx g = cscale(s.sd[k * H.Lc + njk], H.GdR[k]);
+                const cplx *base = xw + (od >= 0 ? od : 0);
+#pragma unroll
+                for (int b = 0; b < NS; ++b) {
+                    cplx v = od >= 0 ? __ldcg(base + b * NS * TL) : cmake(0, 0);
+                    cfma(acc[b], g, v);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+#pragma unroll
+            for (int k = 0; k < K1; ++k) {
+                const int bin = b * K1 + k;
+                const int njk = cur.occ[bin * TL + lane];
+                const int ou = cur.o_up[bin * TL + lane], od = cur.o_dn[bin * TL + lane];
+                if (__any_sync(0xffffffffu, ou >= 0)) {
+                    cplx v = ou >= 0 ? __ldcg(xw + ou + b * NS * TL) : cmake(0, 0);
+                    cfma(acc[b], cscale(s.su[k * H.Lc + njk], H.GuC[k]), v);
+                }
+                if (__any_sync(0xffffffffu, od >= 0)) {
+                    cplx v = od >= 0 ? __ldcg(xw + od + b * NS * TL) : cmake(0, 0);
+                    cfma(acc[b], cscale(s.sd[k * H.Lc + njk], H.GdC[k]), v);
+                }
+            }
+        }
+        }
+        // commutator: row w of Hs_R rho - rho Hs_C (A_C stored transposed: A_C[b][c] = Hs_C[c][b])
+        if (REAL_H) {
+            // Hs = i h with real h: (i h) z = h (-z.y, z.x)
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                const double h = s.HR[w * NS + c].y;
+#pragma unroll
+                for (int b = 0; b < NS; ++b) {
+                    const cplx z = cur.ys[(c + NS * b) * TL + lane];
+                    acc[b].x = fma(-h, z.y, acc[b].x);
+                    acc[b].y = fma(h, z.x, acc[b].y);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+#pragma unroll
+                for (int c = 0; c < NS; ++c) {
+                    const double h = s.HC[b * NS + c].y;
+                    acc[b].x = fma(h, own[c].y, acc[b].x);
+                    acc[b].y = fma(-h, own[c].x, acc[b].y);
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                const cplx h = s.HR[w * NS + c];
+#pragma unroll
+                for (int b = 0; b < NS; ++b) cfma(acc[b], h, cur.ys[(c + NS * b) * TL + lane]);
+            }
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+#pragma unroll
+                for (int c = 0; c < NS; ++c) {
+                    const cplx h = s.HC[b * NS + c];
+                    cfma(acc[b], cmake(-h.x, -h.y), own[c]);
+                }
+        }
+        const double wscale = cur.sh[TL + lane];
+#pragma unroll
+        for (int b = 0; b < NS; ++b) post(gbase + (long long)b * NS * TL, acc[b], own[b], pv[b], wscale);
+    }
+};
+
 // ------------------------------------------------------------ layout kernels
 // reference [b][n][e]  <->  tile-SoA [b][tile][e][32]
 __global__ void heom_to_internal(const cplx *__restrict__ ref, cplx *__restrict__ internal, int B,
@@ -578,6 +830,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_apply_ke
     for (long long w = w0; w < total; w += wstride) {
         int b = (int)(w / a.H.n_tiles);
         long long tile = w % a.H.n_tiles;
+        { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % a.H.n_tiles : -1; s.next_col = wn < total ? (int)(wn / a.H.n_tiles) : 0; }
         int member = a.member_of ? a.member_of[b] : 0;
         cplx *yb = a.y + (size_t)b * Dp;
         Tile::run(a.H, s, a.x + (size_t)b * Dp, tile, member,
@@ -706,6 +959,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                         for (long long w = w0; w < total; w += wstride) {
                             const int b = (int)(w / n_tiles);
                             const long long tile = w % n_tiles;
+                            { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
                             const int member = a.member_of ? a.member_of[b] : 0;
                             cplx *db = dst + (size_t)b * Dp;
                             cplx *Yb = a.Y + (size_t)b * Dp;
@@ -762,6 +1016,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                         for (long long w = w0; w < total; w += wstride) {
                             const int b = (int)(w / n_tiles);
                             const long long tile = w % n_tiles;
+                            { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
                             const int member = a.member_of ? a.member_of[b] : 0;
                             const size_t o = (size_t)b * Dp;
                             cplx *Yb = a.Y + o, *Ab = ACC + o, *TAb = TA + o, *TBb = TB + o;
@@ -959,6 +1214,7 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     std::vector<double> shift((size_t)n_tiles * TL, 0.0), scale((size_t)n_tiles * TL, 1.0);
     std::vector<int> up((size_t)n_tiles * bins * TL, -1), down((size_t)n_tiles * bins * TL, -1);
     std::vector<uint8_t> occ((size_t)n_tiles * bins * TL, 0);
+    std::vector<int> off_up((size_t)n_tiles * bins * TL, -1), off_dn((size_t)n_tiles * bins * TL, -1);
     double lnorm = 0;
     for (int64_t n = 0; n < n_ado; ++n) {
         double sft = 0, logs = 0;
@@ -972,6 +1228,8 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
             up[o] = tb.up[(size_t)n * bins + b];
             down[o] = tb.down[(size_t)n * bins + b];
             occ[o] = (uint8_t)njk;
+            if (up[o] >= 0) off_up[o] = (int)(((int64_t)(up[o] / TL) * M) * TL + up[o] % TL);
+            if (down[o] >= 0) off_dn[o] = (int)(((int64_t)(down[o] / TL) * M) * TL + down[o] % TL);
         }
         shift[n] = u * sft;
         scale[n] = exp(logs);
@@ -994,6 +1252,8 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     QSX_CUDA(h->occ.upload(occ, stream));
     QSX_CUDA(h->up.upload(up, stream));
     QSX_CUDA(h->down.upload(down, stream));
+    QSX_CUDA(h->off_up.upload(off_up, stream));
+    QSX_CUDA(h->off_dn.upload(off_dn, stream));
     QSX_CUDA(h->shift.upload(shift, stream));
     QSX_CUDA(h->scale.upload(scale, stream));
     QSX_CUDA(h->HR.upload(HR, stream));
@@ -1010,6 +1270,24 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     d.nr = nr; d.nc = nc; d.M = M; d.bins = bins; d.K1 = K1; d.Lc = Lc; d.Lk = Lk;
     d.n_members = cfg->n_members; d.n_ado = n_ado; d.n_tiles = n_tiles;
     d.shift = h->shift.p; d.scale = h->scale.p; d.up = h->up.p; d.down = h->down.p; d.occ = h->occ.p;
+    d.off_up = h->off_up.p; d.off_dn = h->off_dn.p;
+    // electronic-block structure: row state a <-> site a, column state b <-> site b
+    d.ee = (nr == cfg->n_sites && nc == cfg->n_sites && K1 <= 4 &&
+            (int64_t)n_tiles * M * TL < ((int64_t)1 << 31));
+    for (int j = 0; j < cfg->n_sites && d.ee; ++j)
+        for (int a = 0; a < nr && d.ee; ++a)
+            d.ee = (v[j * N + rows[a]] == (j == a ? 1.0 : 0.0)) && (v[j * N + cols[a]] == (j == a ? 1.0 : 0.0));
+    for (int k = 0; k < K1 && k < 4; ++k) {
+        zc guR = mi * u * (cfg->heisenberg ? cc[k] : zc(1.0));
+        zc gdR = mi * u * (cfg->heisenberg ? zc(1.0) : cc[k]);
+        zc guC = mi * u * (cfg->heisenberg ? -std::conj(cc[k]) : zc(-1.0));
+        zc gdC = mi * u * (cfg->heisenberg ? zc(-1.0) : -std::conj(cc[k]));
+        d.GuR[k] = cmake(guR.real(), guR.imag()); d.GdR[k] = cmake(gdR.real(), gdR.imag());
+        d.GuC[k] = cmake(guC.real(), guC.imag()); d.GdC[k] = cmake(gdC.real(), gdC.imag());
+    }
+    d.real_h = 1;
+    for (auto &z : HR) if (z.x != 0.0) d.real_h = 0;
+    for (auto &z : HC) if (z.x != 0.0) d.real_h = 0;
     d.HR = h->HR.p; d.HC = h->HC.p; d.dterm = h->dterm.p; d.lbin = h->lbin.p;
     d.gu = h->gu.p; d.gd = h->gd.p; d.su = h->su.p; d.sd = h->sd.p;
     size_t offs[14];
@@ -1070,8 +1348,16 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     size_t smem = tile_smem_layout(d, offs);
     long long total = d.n_tiles * n_columns;
     int grid = (int)std::min<long long>(total, (long long)sms * 6);
-    if (use_warp_tile(d) && d.K1 == 2) {
-        typedef TileFixed<7, 7, 4, 2, 0, 3> T;
+    const char *variant = getenv("QSX_HEOM_VARIANT");
+    const bool generic_only = variant && variant[0] == 'g';
+    if (d.ee && d.nr == 7 && d.K1 == 2 && d.real_h && !generic_only) {
+        typedef TileEE<7, 2, 2, true> T;
+        smem = T::smem_bytes(d);
+        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
+    } else if (d.ee && d.nr == 7 && d.K1 == 2 && !generic_only) {
+        typedef TileEE<7, 2, 2, false> T;
+        smem = T::smem_bytes(d);
         QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
     } else {
@@ -1147,24 +1433,26 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     const void *kernel;
     int threads;
     const char *variant = getenv("QSX_HEOM_VARIANT");
+    const char vsel = variant ? variant[0] : ' ';
     size_t smem;
     int units = 1;
-    if (use_warp_tile(d) && variant && variant[0] == 'w') {
-        typedef TileWarp<7, 7, 4, 7> T;             // warp-autonomous tiles, 1 CTA/SM
-        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;
-        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>
-                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
-    } else if (use_warp_tile(d) && d.K1 == 2 && !(variant && variant[0] == 'g')) {
-        typedef TileFixed<7, 7, 4, 2, 0, 3> T;      // CTA-cooperative shaped tile, 3 CTAs/SM
-        threads = T::THREADS; smem = T::smem_bytes(d);
-        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>
-                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
-    } else {
-        typedef TileGeneric T;
-        threads = T::THREADS; smem = T::smem_bytes(d);
-        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>
-                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
+#define QSX_PICK(TILE)                                                                        \
+    {                                                                                         \
+        typedef TILE T;                                                                       \
+        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;                      \
+        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>           \
+                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;             \
     }
+    const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
+    if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+    else if (ee7 && d.real_h && vsel == '2') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
+    else if (ee7 && d.real_h && vsel == '3') QSX_PICK(TileEE<7 COMMA 2 COMMA 3 COMMA true>)
+    else if (ee7 && d.real_h && vsel == 'c') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
+    else if (ee7 && !d.real_h && vsel != 'g' && vsel != 'f' && vsel != 'w') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
+    else if (use_warp_tile(d) && vsel == 'w') QSX_PICK(TileWarp<7 COMMA 7 COMMA 4 COMMA 7>)
+    else if (use_warp_tile(d) && d.K1 == 2 && vsel != 'g') QSX_PICK(TileFixed<7 COMMA 7 COMMA 4 COMMA 2 COMMA 0 COMMA 3>)
+    else QSX_PICK(TileGeneric)
+#undef QSX_PICK
     int dev = 0, sms = 0, per_sm = 0;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

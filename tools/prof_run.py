@@ -25,7 +25,8 @@ else:
     model = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=qb.CM_FS, level_cutoff=depth, K=1)
     eom = model.equation_of_motion('ee')
     y0 = model.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
-    t = model.time_step * np.arange(2 if depth == 8 else 11)
+    import os
+    t = model.time_step * np.arange(int(os.environ.get('NPTS', 2 if depth == 8 else 11)))
     y0_dev = torch.from_numpy(y0).cuda().reshape(1, -1)
     for _ in range(repeat):
         eom.propagate(y0_dev, t, save=('ado0',), return_device=True)
