@@ -221,6 +221,20 @@ int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_dev,
                        int32_t M, const int64_t *subspace_index_host,
                        void *L_out_dev, void *stream);
 
+/* Same, with the members' eigensystems computed on the device too (cyclic Jacobi):
+ * member m has the real symmetric lab-frame Hamiltonian
+ *   H_m = H0 + diag(sum_j site_shifts[m][j] * coupling_diag[j][.])
+ * (static diagonal disorder, hamiltonian.py:458-461); its eigen-energies are moved to the
+ * rotating frame as E[a] - quanta[a] * rw_freq (hamiltonian.py:310-328).
+ * H0_host [N][N], quanta_host [N] (0/1/2 per basis state), site_shifts_dev [n_members][n_baths]. */
+int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const double *H0_host,
+                               const void *site_shifts_dev, const double *quanta_host,
+                               double rw_freq, int32_t n_baths,
+                               const double *coupling_diag_host, const qsx_bath *bath,
+                               int32_t secular, int32_t eigen_basis, double unit_convert,
+                               int32_t M, const int64_t *subspace_index_host,
+                               void *L_out_dev, void *stream);
+
 /* ------------------------------------------------------------------------
  * K6 (single-GPU part): weighted sum over ensemble members / columns,
  *   out[i] = scale * sum_m in[m][i]   (complex128, i < n)

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <thread>
 
 static thread_local char g_error[1024] = "";
 std::atomic<uint64_t> qsx_launch_counter{0};
@@ -226,34 +227,49 @@ extern "C" int qsx_sample_streams(const uint32_t *seed_prefix, int32_t n_prefix,
     QSX_REQUIRE(n_prefix >= 0 && n_prefix < 15 && n_members >= 0 && n_gauss >= 0 && n_uniform >= 0,
                 "qsx_sample_streams: bad arguments");
     QSX_REQUIRE(member0 >= 0 && member0 + n_members <= (int64_t)0xffffffffLL, "member index out of range");
-    uint32_t key[16];
-    for (int i = 0; i < n_prefix; ++i) key[i] = seed_prefix[i];
-    MT19937 g;
-    for (int m = 0; m < n_members; ++m) {
-        key[n_prefix] = (uint32_t)(member0 + m);
-        g.init_by_array(key, n_prefix + 1);
-        bool has = false;
-        double cached = 0.0;
-        for (int i = 0; i < n_gauss; ++i) {
-            double val;
-            if (has) {
-                val = cached;
-                has = false;
-            } else {
-                double x1, x2, r2;
-                do {
-                    x1 = 2.0 * g.next_double() - 1.0;
-                    x2 = 2.0 * g.next_double() - 1.0;
-                    r2 = x1 * x1 + x2 * x2;
-                } while (r2 >= 1.0 || r2 == 0.0);
-                double f = sqrt(-2.0 * log(r2) / r2);
-                cached = f * x1;
-                has = true;
-                val = f * x2;
+    // members are independent streams: spread them over the host cores
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, (unsigned)((n_members + 255) / 256)));
+    auto work = [&](int lo, int hi) {
+        uint32_t key[16];
+        for (int i = 0; i < n_prefix; ++i) key[i] = seed_prefix[i];
+        MT19937 g;
+        for (int m = lo; m < hi; ++m) {
+            key[n_prefix] = (uint32_t)(member0 + m);
+            g.init_by_array(key, n_prefix + 1);
+            bool has = false;
+            double cached = 0.0;
+            for (int i = 0; i < n_gauss; ++i) {
+                double val;
+                if (has) {
+                    val = cached;
+                    has = false;
+                } else {
+                    double x1, x2, r2;
+                    do {
+                        x1 = 2.0 * g.next_double() - 1.0;
+                        x2 = 2.0 * g.next_double() - 1.0;
+                        r2 = x1 * x1 + x2 * x2;
+                    } while (r2 >= 1.0 || r2 == 0.0);
+                    double f = sqrt(-2.0 * log(r2) / r2);
+                    cached = f * x1;
+                    has = true;
+                    val = f * x2;
+                }
+                gauss_out[(size_t)m * n_gauss + i] = val;
             }
-            gauss_out[(size_t)m * n_gauss + i] = val;
+            for (int i = 0; i < n_uniform; ++i) uniform_out[(size_t)m * n_uniform + i] = g.next_double();
         }
-        for (int i = 0; i < n_uniform; ++i) uniform_out[(size_t)m * n_uniform + i] = g.next_double();
+    };
+    if (n_threads <= 1) {
+        work(0, n_members);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; ++t) {
+            int lo = (int)((int64_t)n_members * t / n_threads), hi = (int)((int64_t)n_members * (t + 1) / n_threads);
+            pool.emplace_back(work, lo, hi);
+        }
+        for (auto &th : pool) th.join();
     }
     return QSX_OK;
 }

@@ -29,7 +29,81 @@ struct RedfieldBuildArgs {
     cplx *L;                // [m][M][M]
     cplx *scratch;          // [gridDim][2][N^4] when the tensors do not fit in shared memory
     int tensors_in_smem;
+    // on-device eigensystems (jacobi != 0): H_m = H0 + diag(sum_j shift[m][j] v[j][.]), lab frame
+    int jacobi;
+    const double *H0;       // [N][N] real symmetric
+    const double *shifts;   // [m][nb]
+    const double *quanta;   // [N] excitation number of each basis state (rotating-frame shift)
+    double rw_freq;
 };
+
+// Cyclic Jacobi eigensolver for one real symmetric N x N matrix held in shared
+// memory (A is overwritten, eigenvalues end on its diagonal in the original
+// basis-state order -- no sorting, so block-diagonal manifolds stay in place;
+// V receives the eigenvectors as columns).  Round-robin pairing gives N/2
+// independent rotations per round.  Called by the whole thread block.
+__device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int Nn = (N + 1) & ~1, half = Nn / 2;
+    double *cs = work, *sn = work + half;
+    int *pp = reinterpret_cast<int *>(work + 2 * half), *qq = pp + half;
+    for (int i = tid; i < N * N; i += nthr) V[i] = (i / N == i % N) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        // convergence: all off-diagonal entries negligible against the diagonal scale
+        int big = 0;
+        for (int i = tid; i < N * N; i += nthr) {
+            int p = i / N, q = i % N;
+            if (p < q && fabs(A[i]) > 1e-17 * (fabs(A[p * N + p]) + fabs(A[q * N + q])) && A[i] != 0.0) big = 1;
+        }
+        if (!__syncthreads_or(big)) break;
+        for (int r = 0; r < Nn - 1; ++r) {
+            if (tid < half) {
+                int a = (tid == 0) ? Nn - 1 : (r + tid) % (Nn - 1);
+                int b = (r + Nn - 1 - tid) % (Nn - 1);
+                int p = min(a, b), q = max(a, b);
+                double c = 1.0, s = 0.0;
+                if (q < N) {
+                    double apq = A[p * N + q];
+                    if (apq != 0.0) {
+                        double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+                        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                    }
+                } else {
+                    p = q = -1;       // pairing with the padding slot
+                }
+                cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+            }
+            __syncthreads();
+            for (int i = tid; i < half * N; i += nthr) {      // A <- A P, V <- V P
+                int pr = i / N, k = i % N;
+                int p = pp[pr], q = qq[pr];
+                if (p < 0) continue;
+                double c = cs[pr], s = sn[pr];
+                double ap = A[k * N + p], aq = A[k * N + q];
+                A[k * N + p] = c * ap - s * aq;
+                A[k * N + q] = s * ap + c * aq;
+                double vp = V[k * N + p], vq = V[k * N + q];
+                V[k * N + p] = c * vp - s * vq;
+                V[k * N + q] = s * vp + c * vq;
+            }
+            __syncthreads();
+            for (int i = tid; i < half * N; i += nthr) {      // A <- P^T A
+                int pr = i / N, k = i % N;
+                int p = pp[pr], q = qq[pr];
+                if (p < 0) continue;
+                double c = cs[pr], s = sn[pr];
+                double ap = A[p * N + k], aq = A[q * N + k];
+                A[p * N + k] = c * ap - s * aq;
+                A[q * N + k] = s * ap + c * aq;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 
 __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     double d = b.x * b.x + b.y * b.y;
@@ -86,8 +160,25 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
 
     for (int mem = blockIdx.x; mem < a.m; mem += gridDim.x) {
         __syncthreads();
-        for (int i = tid; i < N2; i += nthr) Us[i] = a.U[(size_t)mem * N2 + i];
-        for (int i = tid; i < N; i += nthr) Es[i] = a.E[(size_t)mem * N + i];
+        if (a.jacobi) {
+            // workspaces: Cs (complex N^2) holds A and V as doubles, Gs the rotation scratch
+            double *A = reinterpret_cast<double *>(Cs), *V = A + N2;
+            double *work = reinterpret_cast<double *>(Gs);
+            for (int i = tid; i < N2; i += nthr) {
+                int r = i / N, c = i % N;
+                double h = a.H0[i];
+                if (r == c)
+                    for (int j = 0; j < nb; ++j) h += a.shifts[(size_t)mem * nb + j] * a.v[j * N + r];
+                A[i] = h;
+            }
+            __syncthreads();
+            jacobi_eigh(A, V, N, work);
+            for (int i = tid; i < N2; i += nthr) Us[i] = cmake(V[i], 0.0);
+            for (int i = tid; i < N; i += nthr) Es[i] = A[i * N + i] - a.quanta[i] * a.rw_freq;
+        } else {
+            for (int i = tid; i < N2; i += nthr) Us[i] = a.U[(size_t)mem * N2 + i];
+            for (int i = tid; i < N; i += nthr) Es[i] = a.E[(size_t)mem * N + i];
+        }
         __syncthreads();
         // correlation matrix, one warp per entry
         for (int p = warp; p < N2; p += nwarp) {
@@ -170,14 +261,17 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
     }
 }
 
-extern "C" int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_dev, const void *U_dev,
-                                  int32_t n_baths, const double *coupling_diag_host,
-                                  const qsx_bath *bath, int32_t secular, int32_t eigen_basis,
-                                  double unit_convert, int32_t M, const int64_t *subspace_index_host,
-                                  void *L_out_dev, void *stream_) {
+static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, const void *U_dev,
+                               const double *H0_host, const double *shifts_dev, const double *quanta_host,
+                               double rw_freq, int32_t n_baths, const double *coupling_diag_host,
+                               const qsx_bath *bath, int32_t secular, int32_t eigen_basis,
+                               double unit_convert, int32_t M, const int64_t *subspace_index_host,
+                               void *L_out_dev, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    QSX_REQUIRE(n_members > 0 && N > 0 && n_baths > 0 && M > 0 && E_dev && U_dev && bath &&
-                coupling_diag_host && subspace_index_host && L_out_dev,
+    const bool jacobi = H0_host != nullptr;
+    QSX_REQUIRE(n_members > 0 && N > 0 && n_baths > 0 && M > 0 && bath &&
+                coupling_diag_host && subspace_index_host && L_out_dev &&
+                (jacobi ? (shifts_dev && quanta_host) : (E_dev && U_dev)),
                 "qsx_redfield_build: bad arguments");
     QSX_REQUIRE(bath->kind == QSX_BATH_DEBYE_COMPLEX || bath->kind == QSX_BATH_DEBYE_REAL,
                 "qsx_redfield_build: unknown bath kind %d", bath->kind);
@@ -189,8 +283,12 @@ extern "C" int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_de
         idx[i] = (int)subspace_index_host[i];
     }
     DevBuf<int> d_idx;
-    DevBuf<double> d_v;
+    DevBuf<double> d_v, d_H0, d_quanta;
     DevBuf<cplx> scratch;
+    if (jacobi) {
+        QSX_CUDA(d_H0.upload(H0_host, (size_t)N * N, stream));
+        QSX_CUDA(d_quanta.upload(quanta_host, (size_t)N, stream));
+    }
     QSX_CUDA(d_idx.upload(idx, stream));
     QSX_CUDA(d_v.upload(coupling_diag_host, (size_t)n_baths * N, stream));
 
@@ -218,10 +316,34 @@ extern "C" int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_de
     if (a.bath.matsubara_cutoff <= 0) a.bath.matsubara_cutoff = 1000;
     a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;
     a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem;
+    a.jacobi = jacobi; a.H0 = d_H0.p; a.shifts = shifts_dev; a.quanta = d_quanta.p; a.rw_freq = rw_freq;
     QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     redfield_build_kernel<<<grid, 256, smem, stream>>>(a);
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
     QSX_CUDA(cudaStreamSynchronize(stream));
     return QSX_OK;
+}
+
+extern "C" int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_dev, const void *U_dev,
+                                  int32_t n_baths, const double *coupling_diag_host,
+                                  const qsx_bath *bath, int32_t secular, int32_t eigen_basis,
+                                  double unit_convert, int32_t M, const int64_t *subspace_index_host,
+                                  void *L_out_dev, void *stream) {
+    return redfield_build_impl(n_members, N, E_dev, U_dev, nullptr, nullptr, nullptr, 0.0, n_baths,
+                               coupling_diag_host, bath, secular, eigen_basis, unit_convert, M,
+                               subspace_index_host, L_out_dev, stream);
+}
+
+extern "C" int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const double *H0_host,
+                                          const void *site_shifts_dev, const double *quanta_host,
+                                          double rw_freq, int32_t n_baths,
+                                          const double *coupling_diag_host, const qsx_bath *bath,
+                                          int32_t secular, int32_t eigen_basis, double unit_convert,
+                                          int32_t M, const int64_t *subspace_index_host,
+                                          void *L_out_dev, void *stream) {
+    QSX_REQUIRE(H0_host, "qsx_redfield_build_sampled: H0 missing");
+    return redfield_build_impl(n_members, N, nullptr, nullptr, H0_host, (const double *)site_shifts_dev,
+                               quanta_host, rw_freq, n_baths, coupling_diag_host, bath, secular,
+                               eigen_basis, unit_convert, M, subspace_index_host, L_out_dev, stream);
 }

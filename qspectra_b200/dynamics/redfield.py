@@ -175,18 +175,40 @@ class RedfieldModel(LiouvilleSpaceModel):
 
     def ensemble_eom(self, ensemble_size, random_orientations,
                      liouville_subspace, heisenberg_picture=False, member0=0):
-        eig = self.ensemble_eigensystems(ensemble_size, member0) \
+        """Device-side construction of all members' generators (K5): the host
+        only replays the members' seeded disorder draws; eigensystems (cyclic
+        Jacobi), bath correlation matrices, Redfield tensors and the site-basis
+        transform are computed on the GPU."""
+        ham, ss = self.hamiltonian, self.hilbert_subspace
+        shifts = ham.sampled_site_shifts(ensemble_size, member0) \
             if self._device_buildable() else None
-        if eig is None:
+        if shifts is None:
             return super(RedfieldModel, self).ensemble_eom(
                 ensemble_size, random_orientations, liouville_subspace,
                 heisenberg_picture, member0)
-        ham, ss, bath = self.hamiltonian, self.hilbert_subspace, self.hamiltonian.bath
+        bath = ham.bath
+        if self.evolve_basis == 'eigen':
+            # the eigenbasis ordering/sign gauge is LAPACK's: keep the host eigh
+            E, U = self.ensemble_eigensystems(ensemble_size, member0)
+            number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
+            kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
+                    else _capi.BATH_DEBYE_COMPLEX)
+            L = engine.redfield_build(
+                E, U, number, kind, bath.temperature, bath.reorg_energy,
+                bath.cutoff_freq, self.secular, True, self.unit_convert,
+                self.liouville_subspace_index(liouville_subspace))
+            return engine.DenseEOM(L, heisenberg_picture)
         number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
         kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
                 else _capi.BATH_DEBYE_COMPLEX)
-        L = engine.redfield_build(
-            eig[0], eig[1], number, kind, bath.temperature, bath.reorg_energy,
-            bath.cutoff_freq, self.secular, self.evolve_basis == 'eigen',
-            self.unit_convert, self.liouville_subspace_index(liouville_subspace))
+        lab = ham._not_sampled._not_rotating
+        quanta = np.zeros(ham.n_states(ss))
+        for letter, n_exc in (('e', 1), ('f', 2)):
+            if letter in ss:
+                quanta[ham.hilbert_subspace_index(letter, ss)] = n_exc
+        L = engine.redfield_build_sampled(
+            np.asarray(lab.H(ss), dtype=float), shifts, quanta, ham.rw_freq,
+            number, kind, bath.temperature, bath.reorg_energy, bath.cutoff_freq,
+            self.secular, self.evolve_basis == 'eigen', self.unit_convert,
+            self.liouville_subspace_index(liouville_subspace))
         return engine.DenseEOM(L, heisenberg_picture)

@@ -428,3 +428,33 @@ def redfield_build(E, U, coupling_diag, bath_kind, temperature, reorg_energy,
         idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), out.data_ptr(),
         _capi.current_stream_ptr()))
     return out
+
+
+def redfield_build_sampled(H0, site_shifts, quanta, rw_freq, coupling_diag,
+                           bath_kind, temperature, reorg_energy, cutoff_freq,
+                           secular, eigen_basis, unit_convert, subspace_index,
+                           matsubara_cutoff=1000):
+    """Kernel K5 with on-device Jacobi eigensystems: only the (m, n_sites)
+    disorder shifts cross the PCIe bus.  H0: real symmetric lab-frame
+    Hamiltonian of the un-sampled system in the Hilbert subspace."""
+    torch = _capi.torch_cuda()
+    H0 = np.ascontiguousarray(H0, dtype=np.float64)
+    shifts = _capi.to_device(np.ascontiguousarray(site_shifts, dtype=np.float64),
+                             dtype=torch.float64)
+    q = np.ascontiguousarray(quanta, dtype=np.float64)
+    v = np.ascontiguousarray(coupling_diag, dtype=np.float64)
+    idx = np.ascontiguousarray(subspace_index, dtype=np.int64)
+    m, N = shifts.shape[0], H0.shape[0]
+    bath = _capi.QsxBath(int(bath_kind), int(matsubara_cutoff),
+                         float(temperature), float(reorg_energy),
+                         float(cutoff_freq))
+    out = torch.empty((m, idx.size, idx.size), dtype=torch.complex128,
+                      device=shifts.device)
+    dptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _capi.check(_capi.lib().qsx_redfield_build_sampled(
+        m, N, dptr(H0), shifts.data_ptr(), dptr(q), float(rw_freq), v.shape[0],
+        dptr(v), C.byref(bath), int(bool(secular)), int(bool(eigen_basis)),
+        float(unit_convert), idx.size,
+        idx.ctypes.data_as(C.POINTER(C.c_int64)), out.data_ptr(),
+        _capi.current_stream_ptr()))
+    return out
