@@ -14,10 +14,12 @@ whole grid.  With N GPUs every rank propagates its own 1e4 members (weak
 scaling) and the ensemble mean is combined with one NCCL reduce.
 
 Units: a *state-step* is one ensemble member advanced by one accepted
-integrator step (adaptive-order Taylor step of exp(hL): one per output interval
-here, `rhs_per_state_step` right-hand-side applications each).  The CPU arms
-report grid-steps (one member advanced by one output interval at rtol=1e-10),
-which is the same unit for this integrator.
+integrator step = one output interval here (the default integrator for a
+constant generator on a uniform grid builds exp(L dt) once per member on the
+FP64 tensor cores and applies it once per interval; `rhs_per_state_step` counts
+the matrix-vector applications of the stepping phase, the propagator build is
+reported under `roofline`).  The CPU arms report grid-steps (one member advanced
+by one output interval at rtol=1e-10), i.e. the same unit.
 """
 import argparse
 import json
@@ -57,8 +59,10 @@ def workload_config(members, n_gpus):
                         "'ee' subspace (M=49), %d static-disorder members per GPU, "
                         '1 ps / 197 output points' % members,
             'members_per_gpu': members, 'state_dim': 49, 'grid_points': 197,
-            'integrator': 'adaptive-order Taylor (one step per output interval, '
-                          'rtol 1e-13), on-device control',
+            'integrator': 'propagator stepping: exp(L dt) per member on the FP64 tensor '
+                          'cores (scaled Taylor series + squarings, on-device truncation '
+                          'control at 1e-17), then y <- P y per output interval; the '
+                          'propagators are rebuilt in every timed step',
             'parallelism': 'ensemble members sharded over %d GPU(s), one NCCL '
                            'reduce' % n_gpus,
             'l2_policy': 'inputs larger than L2 (1e4 generators = 384 MB vs 126 MB L2)'}
@@ -214,6 +218,16 @@ def measure_fp64_peak(torch):
     return best
 
 
+def ncu_traffic(key):
+    """dram bytes per launch of a kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -255,7 +269,7 @@ def heom_leg(torch, qb, systems, engine):
             'kernel_ms': best['kernel_ms'], 'setup_s': build_s,
             'roofline': {'bound': 'hbm', 'achieved': achieved,
                          'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                         'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                         'frac': achieved / peaks['hbm_gbs'], 'traffic': ncu_traffic('heom_depth%d' % depth),
                          'peak_source': src,
                          'algorithmic_bytes_per_rhs': 32 * D}}
         del eom, model
@@ -293,6 +307,7 @@ def run_ours(args):
     gens = np.arange(E)
 
     def resident_step():
+        eom.__dict__.pop('_propagators', None)    # rebuild exp(L dt) every step
         out = eom.propagate(y0_dev, t, generators=gens, return_device=True)
         mean = engine.reduce_members(out, 1.0 / (E * world))
         return reduce_across(mean)
@@ -319,6 +334,7 @@ def run_ours(args):
     elapsed_ms = e0.elapsed_time(e1)
     launches = _capi.kernel_launches() - launches0
     stats = engine.PropagationStats
+    stats_expm_ms, stats_expm_gemms, stats_expm_builds = stats.expm_ms, stats.expm_gemms, stats.expm_builds
     kernel_ms = stats.kernel_ms / max(1, stats.propagations)
     rhs_per_launch = stats.rhs_evaluations / max(1, stats.propagations)
     steps_per_launch = stats.accepted_steps / max(1, stats.propagations)
@@ -373,8 +389,12 @@ def run_ours(args):
 
     peaks, peak_src = measured_peaks()
     fp64_peak = measure_fp64_peak(torch)
-    flops_per_launch = 8.0 * 49 * 49 * rhs_per_launch
-    achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    # dominant kernel of the step: the tensor-core propagator build (dense_expm_kernel);
+    # algorithmic flops = complex M x M GEMMs x 8 M^3 (M = 49, padding not counted)
+    expm_ms = stats_expm_ms / max(1, stats_expm_builds)
+    flops_per_launch = 8.0 * 49 ** 3 * stats_expm_gemms / max(1, stats_expm_builds)
+    achieved_tf = flops_per_launch / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else 0.0
+    map_flops = 8.0 * 49 * 49 * rhs_per_launch
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
@@ -394,11 +414,18 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved_tf / fp64_peak,
-                     'traffic': None, 'kernel': 'dense_propagate_kernel<1>',
-                     'kernel_ms': kernel_ms,
+                     'traffic': ncu_traffic('dense_expm'),
+                     'kernel': 'dense_expm_kernel<7> (FP64 DMMA m8n8k4: exp(L dt) per member)',
+                     'kernel_ms': expm_ms,
                      'algorithmic_flops_per_launch': flops_per_launch,
                      'peak_source': 'cuBLAS FP64 GEMM 6144^3 measured in this run '
-                                    '(FP64 is not in MEASURED_PEAKS.json)'},
+                                    '(cutlass d884 DMMA kernel; FP64 is not in '
+                                    'MEASURED_PEAKS.json)'},
+        'other_kernels': {
+            'dense_propagate_kernel<1> (y <- P y stepping, FP64 pipe)': {
+                'kernel_ms': kernel_ms, 'achieved_tflops': map_flops / (kernel_ms * 1e-3) / 1e12},
+            'share_note': 'per step: expm build + stepping + member reduction; see '
+                          'profiles/ for the ncu launch list'},
     }
     if world == 1 and not args.no_heom:
         line['heom'] = heom_leg(torch, qb, systems, engine)

@@ -38,7 +38,9 @@ typedef enum {
 typedef enum {
     QSX_METHOD_TAYLOR = 0,     /* adaptive-order Taylor of exp(hL), LTI generators only */
     QSX_METHOD_RK4 = 1,        /* classic RK4, fixed sub-steps per output interval      */
-    QSX_METHOD_DOPRI5 = 2      /* Dormand-Prince 5(4), on-device step-size control      */
+    QSX_METHOD_DOPRI5 = 2,     /* Dormand-Prince 5(4), on-device step-size control      */
+    QSX_METHOD_MAP = 3         /* y <- P y per output interval; the handle holds the
+                                  propagators P = exp(L dt) made by qsx_dense_expm      */
 } qsx_method;
 
 typedef enum {
@@ -114,6 +116,22 @@ int qsx_dense_apply(qsx_dense_t h, const void *y_dev, void *dy_dev,
                     int32_t n_columns, const int32_t *generator_of_column_host,
                     void *stream);
 int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void *stream);
+/* New handle holding P_g = exp(L_g * dt) for every generator of `h`, computed on the FP64
+ * tensor cores (scaled Taylor series + squarings, on-device truncation control).  Use it
+ * with QSX_METHOD_MAP on a uniform output grid of spacing dt: the exact counterpart of the
+ * reference's ZVODE loop for a constant generator (simulate/utils.py:45-49). */
+int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnorm_dev,
+                   qsx_dense_t *out, void *stream);
+/* Handle over caller-owned device storage: Lt_dev [n_generators][M][M] in the engine's
+ * transposed storage (Lt[g][c][r] = L_g[r][c]; what qsx_redfield_build* write with
+ * transposed_out = 1 and qsx_dense_expm writes to Pt_dev) and lnorm_dev [n_generators]
+ * float64 scratch that receives the inf-norms.  No copy is made; the caller keeps the
+ * buffers alive for the lifetime of the handle. */
+int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_dev,
+                   void *lnorm_dev, void *stream);
+/* Device time (CUDA events) and number of M x M complex GEMMs of the qsx_dense_expm call
+ * that produced `h` (bench.py: FP64 tensor roofline). */
+int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_gemms);
 void qsx_dense_destroy(qsx_dense_t h);
 
 /* ------------------------------------------------------------------------
@@ -213,13 +231,14 @@ typedef struct {
  * U[x][a] = <site x | eigenstate a>) are the members' eigen-systems in the
  * rotating frame (hamiltonian.py:310-328); coupling_diag_host [n_baths][N] the
  * diagonals of the system-bath operators; subspace_index_host [M] the Liouville
- * subspace.  Writes unit_convert * L[idx, idx] to L_out_dev [n_members][M][M]. */
+ * subspace.  Writes unit_convert * L[idx, idx] to L_out_dev [n_members][M][M]
+ * (row-major, or the transposed storage of qsx_dense_wrap when transposed_out != 0). */
 int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_dev,
                        const void *U_dev, int32_t n_baths,
                        const double *coupling_diag_host, const qsx_bath *bath,
                        int32_t secular, int32_t eigen_basis, double unit_convert,
                        int32_t M, const int64_t *subspace_index_host,
-                       void *L_out_dev, void *stream);
+                       int32_t transposed_out, void *L_out_dev, void *stream);
 
 /* Same, with the members' eigensystems computed on the device too (cyclic Jacobi):
  * member m has the real symmetric lab-frame Hamiltonian
@@ -233,7 +252,7 @@ int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const double *H0_ho
                                const double *coupling_diag_host, const qsx_bath *bath,
                                int32_t secular, int32_t eigen_basis, double unit_convert,
                                int32_t M, const int64_t *subspace_index_host,
-                               void *L_out_dev, void *stream);
+                               int32_t transposed_out, void *L_out_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * K6 (single-GPU part): weighted sum over ensemble members / columns,

@@ -15,10 +15,11 @@ LIB_PATH = os.path.join(_HERE, 'libqsx.so')
 
 QSX_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_INTEGRATOR, ERR_UNSUPPORTED = -1, -2, -3, -4
-METHOD_TAYLOR, METHOD_RK4, METHOD_DOPRI5 = 0, 1, 2
+METHOD_TAYLOR, METHOD_RK4, METHOD_DOPRI5, METHOD_MAP = 0, 1, 2, 3
 SAVE_STATE, SAVE_MATRIX, SAVE_ADO0 = 0, 1, 2
 MAX_PULSES = 4
-METHODS = {'taylor': METHOD_TAYLOR, 'rk4': METHOD_RK4, 'dopri5': METHOD_DOPRI5}
+METHODS = {'taylor': METHOD_TAYLOR, 'rk4': METHOD_RK4, 'dopri5': METHOD_DOPRI5,
+           'map': METHOD_MAP}
 
 
 class IntegratorError(Exception):
@@ -78,7 +79,8 @@ BATH_DEBYE_COMPLEX, BATH_DEBYE_REAL = 0, 1
 #: every symbol include/qspectra_b200.h declares (checked by the CPU tests)
 EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches',
            'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
-           'qsx_dense_propagate', 'qsx_dense_destroy', 'qsx_heom_create',
+           'qsx_dense_propagate', 'qsx_dense_expm', 'qsx_dense_wrap', 'qsx_dense_build_stats',
+           'qsx_dense_destroy', 'qsx_heom_create',
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
            'qsx_ado_enumerate', 'qsx_redfield_build', 'qsx_redfield_build_sampled',
@@ -117,6 +119,12 @@ def lib():
                                   C.POINTER(C.c_int32), C.c_void_p]
     L.qsx_dense_propagate.argtypes = [C.c_void_p, C.POINTER(QsxPropagateArgs),
                                       C.c_void_p]
+    L.qsx_dense_expm.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_void_p), C.c_void_p]
+    L.qsx_dense_build_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_uint64)]
+    L.qsx_dense_wrap.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
     L.qsx_dense_destroy.argtypes = [C.c_void_p]
     L.qsx_dense_destroy.restype = None
     L.qsx_heom_create.argtypes = [C.POINTER(C.c_void_p),
@@ -132,12 +140,13 @@ def lib():
     L.qsx_redfield_build.argtypes = [
         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
         C.POINTER(C.c_double), C.POINTER(QsxBath), C.c_int32, C.c_int32,
-        C.c_double, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+        C.c_double, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_void_p,
+        C.c_void_p]
     L.qsx_redfield_build_sampled.argtypes = [
         C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_void_p,
         C.POINTER(C.c_double), C.c_double, C.c_int32, C.POINTER(C.c_double),
         C.POINTER(QsxBath), C.c_int32, C.c_int32, C.c_double, C.c_int32,
-        C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+        C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]
     L.qsx_reduce_members.argtypes = [C.c_void_p, C.c_int32, C.c_int64,
                                      C.c_double, C.c_void_p, C.c_void_p]
     L.qsx_zofe_create.argtypes = [C.POINTER(C.c_void_p),

@@ -118,6 +118,15 @@ __device__ void cta_propagate(Rhs &rhs, Saver &save, const CtaProp &P, cplx *vec
                     st.steps += 1;
                     tcur += h;
                 }
+            } else if (P.method == QSX_METHOD_MAP) {
+                // the "generator" is the one-step propagator exp(L dt): y <- P y
+                cplx *TA = vec + n;
+                rhs.apply(Y, tcur, [&](int i, cplx f) { TA[i] = f; });
+                __syncthreads();
+                for (int i = tid; i < n; i += nthr) Y[i] = TA[i];
+                __syncthreads();
+                st.rhs += 1;
+                st.steps += 1;
             } else if (P.method == QSX_METHOD_RK4) {
                 // ---- classic RK4, fixed sub-steps -----------------------------
                 cplx *ACC = vec + n, *TA = vec + 2 * n, *TB = vec + 3 * n;

@@ -15,8 +15,15 @@
 struct qsx_dense_s {
     int M = 0;
     int n_gen = 0;
-    DevBuf<cplx> Lt;        // [n_gen][c][r] = L[r][c]   (transposed storage)
-    DevBuf<double> lnorm;   // [n_gen] inf-norm of L
+    // [n_gen][c][r] = L[r][c] (transposed storage) and [n_gen] inf-norms; either owned
+    // by the handle or borrowed from the caller (qsx_dense_wrap / qsx_dense_expm)
+    struct Ref { cplx *p = nullptr; } Lt;
+    struct RefD { double *p = nullptr; } lnorm;
+    DevBuf<cplx> own_Lt;
+    DevBuf<double> own_lnorm;
+    // statistics of the kernel that produced this handle (qsx_dense_expm)
+    double build_ms = 0.0;
+    unsigned long long build_gemms = 0;
 };
 
 // ------------------------------------------------------------------ kernels
@@ -220,7 +227,7 @@ dense_propagate_kernel(DenseKernelArgs a) {
 
 // --------------------------------------------------------------------- host
 static int n_vectors_for(int method) {
-    return method == QSX_METHOD_TAYLOR ? 3 : method == QSX_METHOD_RK4 ? 4 : 10;
+    return method == QSX_METHOD_TAYLOR ? 3 : method == QSX_METHOD_RK4 ? 4 : method == QSX_METHOD_MAP ? 2 : 10;
 }
 
 extern "C" int qsx_dense_create(qsx_dense_t *out, int32_t M, int32_t n_generators, const void *L,
@@ -233,8 +240,10 @@ extern "C" int qsx_dense_create(qsx_dense_t *out, int32_t M, int32_t n_generator
     size_t count = (size_t)n_generators * M * M;
     DevBuf<cplx> staging;
     const cplx *src = (const cplx *)L;
-    cudaError_t e = h->Lt.alloc(count);
-    if (e == cudaSuccess) e = h->lnorm.alloc(n_generators);
+    cudaError_t e = h->own_Lt.alloc(count);
+    if (e == cudaSuccess) e = h->own_lnorm.alloc(n_generators);
+    h->Lt.p = h->own_Lt.p;
+    h->lnorm.p = h->own_lnorm.p;
     if (e == cudaSuccess && !on_device) {
         e = staging.upload((const cplx *)L, count, stream);
         src = staging.p;
@@ -305,8 +314,19 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
     const int M = h->M, B = args->n_columns, nt = args->n_times;
     QSX_REQUIRE(B > 0 && nt > 0 && args->t_host && args->y0_dev && args->out_dev,
                 "qsx_dense_propagate: empty batch or missing buffers");
-    QSX_REQUIRE(args->method >= QSX_METHOD_TAYLOR && args->method <= QSX_METHOD_DOPRI5,
+    QSX_REQUIRE(args->method >= QSX_METHOD_TAYLOR && args->method <= QSX_METHOD_MAP,
                 "qsx_dense_propagate: unknown method %d", args->method);
+    if (args->method == QSX_METHOD_MAP) {
+        // the handle holds propagators exp(L dt): the grid must be uniform and start at t0
+        QSX_REQUIRE(args->n_pulses == 0, "propagator stepping needs a time-independent generator");
+        QSX_REQUIRE(args->t_host[0] == args->t0, "propagator stepping starts at the first output time");
+        if (nt > 2) {
+            const double d0 = args->t_host[1] - args->t_host[0];
+            for (int i = 2; i < nt; ++i)
+                QSX_REQUIRE(fabs((args->t_host[i] - args->t_host[i - 1]) - d0) <= 1e-9 * fabs(d0),
+                            "propagator stepping needs a uniform output grid");
+        }
+    }
     QSX_REQUIRE(args->n_pulses >= 0 && args->n_pulses <= QSX_MAX_PULSES, "too many pulses");
     QSX_REQUIRE(!(args->n_pulses > 0 && args->method == QSX_METHOD_TAYLOR),
                 "Taylor propagation needs a time-independent generator");
@@ -434,4 +454,221 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
         return QSX_ERR_INTEGRATOR;
     }
     return QSX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Propagator construction on the FP64 tensor cores (DMMA).
+//
+// For a constant generator sampled on a uniform output grid the trajectory is
+// y_{i+1} = P y_i with P = exp(L dt).  P is formed per generator by a scaled
+// Taylor series  T_{k+1} = A T_k / (k+1),  A = L dt / 2^s  (|A|_inf <= 1/2,
+// terms added until two consecutive ones are below 1e-17 |P|_max: on-device
+// error control) followed by s squarings -- all dense complex 8x8x4 FP64 MMAs
+// (mma.sync.m8n8k4.f64 -> DMMA).  Matrices live in shared memory as planar
+// re/im arrays with a leading dimension = 12 (mod 16) so that both the B-fragment
+// loads and the C-fragment stores are bank-conflict free per half warp; the A
+// fragments (one 8-row block per warp) stay in registers for the whole series.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <int MT>      // matrix padded to 8*MT rows/cols; MT warps per CTA
+__global__ void __launch_bounds__(32 * MT)
+dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm, int M, double dt,
+                  cplx *__restrict__ Pt_out, unsigned long long *__restrict__ status) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    constexpr int KS = 2 * MT;              // k-steps of 4
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *planes = reinterpret_cast<double *>(smem_raw);
+    double *Tr = planes, *Ti = Tr + MP * LD, *Ur = Ti + MP * LD, *Ui = Ur + MP * LD,
+           *Pr = Ui + MP * LD, *Pi = Pr + MP * LD;
+    __shared__ double red[2 * MT];
+    const int gen = blockIdx.x;
+    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const cplx *Lg = Lt + (size_t)gen * M * M;      // transposed storage: Lt[c*M + r]
+
+    // scaling: |A|_inf <= 1/2
+    int sq = 0;
+    {
+        double nrm = fabs(dt) * lnorm[gen];
+        while (nrm > 0.5 && sq < 40) { nrm *= 0.5; ++sq; }
+    }
+    const double scale = dt / (double)(1ULL << sq);
+    // A fragments (registers): rows rb*8+g, cols ks*4+t
+    double a_re[KS], a_im[KS], a_nim[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        int r = rb * 8 + g, c = ks * 4 + t;
+        cplx v = (r < M && c < M) ? Lg[c * M + r] : cmake(0, 0);
+        a_re[ks] = scale * v.x;
+        a_im[ks] = scale * v.y;
+        a_nim[ks] = -a_im[ks];
+    }
+    for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
+        int r = i / LD, c = i % LD;
+        double one = (r == c && r < MP) ? 1.0 : 0.0;
+        Tr[i] = one; Ti[i] = 0.0; Pr[i] = one; Pi[i] = 0.0;
+    }
+    __syncthreads();
+
+    // C = A_frag x B (B planar in shared memory) for this warp's row block; epilogue functor
+    auto row_block_gemm = [&](const double *Br, const double *Bi, auto &&epi) {
+#pragma unroll
+        for (int nb = 0; nb < MT; ++nb) {
+            double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double br = Br[(ks * 4 + t) * LD + nb * 8 + g];
+                const double bi = Bi[(ks * 4 + t) * LD + nb * 8 + g];
+                dmma884(cr0, cr1, a_re[ks], br);
+                dmma884(cr0, cr1, a_nim[ks], bi);
+                dmma884(ci0, ci1, a_re[ks], bi);
+                dmma884(ci0, ci1, a_im[ks], br);
+            }
+            epi((rb * 8 + g) * LD + nb * 8 + 2 * t, cr0, cr1, ci0, ci1);
+        }
+    };
+
+    int small_terms = 0, failed = 1, n_gemm = 0;
+    for (int k = 1; k <= 40; ++k) {
+        ++n_gemm;
+        const double inv = 1.0 / k;
+        double tmax = 0.0, pmax = 0.0;
+        row_block_gemm(Tr, Ti, [&](int o, double r0, double r1, double i0, double i1) {
+            r0 *= inv; r1 *= inv; i0 *= inv; i1 *= inv;
+            Ur[o] = r0; Ur[o + 1] = r1; Ui[o] = i0; Ui[o + 1] = i1;
+            double p0 = Pr[o] + r0, p1 = Pr[o + 1] + r1, q0 = Pi[o] + i0, q1 = Pi[o + 1] + i1;
+            Pr[o] = p0; Pr[o + 1] = p1; Pi[o] = q0; Pi[o + 1] = q1;
+            tmax = fmax(tmax, fmax(fmax(fabs(r0), fabs(r1)), fmax(fabs(i0), fabs(i1))));
+            pmax = fmax(pmax, fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(q0), fabs(q1))));
+        });
+        tmax = warp_max(tmax);
+        pmax = warp_max(pmax);
+        if (lane == 0) { red[rb] = tmax; red[MT + rb] = pmax; }
+        __syncthreads();
+        double tm = 0.0, pm = 0.0;
+#pragma unroll
+        for (int w = 0; w < MT; ++w) { tm = fmax(tm, red[w]); pm = fmax(pm, red[MT + w]); }
+        { double *x = Tr; Tr = Ur; Ur = x; x = Ti; Ti = Ui; Ui = x; }
+        small_terms = (tm <= 1e-17 * pm) ? small_terms + 1 : 0;
+        __syncthreads();          // red[] may be rewritten next iteration
+        if (small_terms >= 2) { failed = 0; break; }
+    }
+    // squarings P <- P P
+    for (int q = 0; q < sq; ++q) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            a_re[ks] = Pr[(rb * 8 + g) * LD + ks * 4 + t];
+            a_im[ks] = Pi[(rb * 8 + g) * LD + ks * 4 + t];
+            a_nim[ks] = -a_im[ks];
+        }
+        row_block_gemm(Pr, Pi, [&](int o, double r0, double r1, double i0, double i1) {
+            Ur[o] = r0; Ur[o + 1] = r1; Ui[o] = i0; Ui[o + 1] = i1;
+        });
+        __syncthreads();
+        { double *x = Pr; Pr = Ur; Ur = x; x = Pi; Pi = Ui; Ui = x; }
+    }
+    cplx *Pg = Pt_out + (size_t)gen * M * M;
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+        int c = i / M, r = i % M;
+        Pg[i] = cmake(Pr[r * LD + c], Pi[r * LD + c]);        // transposed storage
+    }
+    if (threadIdx.x == 0) {
+        if (failed) atomicAdd(&status[0], 1ULL);
+        atomicAdd(&status[1], (unsigned long long)(n_gemm + sq));
+    }
+}
+
+template <int MT>
+static cudaError_t launch_expm(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
+                               int n_gen, cudaStream_t stream) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    size_t smem = (size_t)6 * MP * LD * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(dense_expm_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dense_expm_kernel<MT><<<n_gen, 32 * MT, smem, stream>>>(Lt, lnorm, M, dt, Pt, status);
+    return cudaGetLastError();
+}
+
+extern "C" int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_gemms) {
+    QSX_REQUIRE(h, "null handle");
+    if (kernel_ms) *kernel_ms = h->build_ms;
+    if (complex_gemms) *complex_gemms = h->build_gemms;
+    return QSX_OK;
+}
+
+extern "C" int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_dev,
+                              void *lnorm_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(out && Lt_dev && lnorm_dev && M > 0 && n_generators > 0, "qsx_dense_wrap: bad arguments");
+    qsx_dense_s *h = new qsx_dense_s();
+    h->M = M; h->n_gen = n_generators;
+    h->Lt.p = (cplx *)Lt_dev;
+    h->lnorm.p = (double *)lnorm_dev;
+    dense_norm_kernel<<<n_generators, 64, 0, stream>>>(h->Lt.p, h->lnorm.p, M);
+    qsx_launch_counter += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        delete h;
+        qsx_set_error("qsx_dense_wrap: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    *out = h;
+    return QSX_OK;
+}
+
+extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnorm_dev, qsx_dense_t *out,
+                              void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(h && out && Pt_dev && lnorm_dev, "qsx_dense_expm: null argument");
+    const int M = h->M;
+    if (M > 56) {
+        qsx_set_error("qsx_dense_expm: state dimension %d > 56 is not supported by the tensor-core "
+                      "propagator kernel", M);
+        return QSX_ERR_UNSUPPORTED;
+    }
+    DevBuf<unsigned long long> status;
+    QSX_CUDA(status.alloc(2));
+    QSX_CUDA(cudaMemsetAsync(status.p, 0, 2 * sizeof(unsigned long long), stream));
+    cplx *Pt = (cplx *)Pt_dev;
+    cudaError_t e;
+    cudaEvent_t e0, e1;
+    QSX_CUDA(cudaEventCreate(&e0));
+    QSX_CUDA(cudaEventCreate(&e1));
+    QSX_CUDA(cudaEventRecord(e0, stream));
+    const int MT = (M + 7) / 8;
+    switch (MT) {
+        case 1: e = launch_expm<1>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+        case 2: e = launch_expm<2>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+        case 3: e = launch_expm<3>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+        case 4: e = launch_expm<4>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+        case 5: e = launch_expm<5>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+        case 6: e = launch_expm<6>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+        default: e = launch_expm<7>(h->Lt.p, h->lnorm.p, M, dt, Pt, status.p, h->n_gen, stream); break;
+    }
+    qsx_launch_counter += 1;
+    if (e != cudaSuccess) {
+        qsx_set_error("qsx_dense_expm: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    QSX_CUDA(cudaEventRecord(e1, stream));
+    unsigned long long st[2] = {0, 0};
+    QSX_CUDA(cudaMemcpyAsync(st, status.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
+    QSX_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (st[0]) {
+        qsx_set_error("qsx_dense_expm: Taylor series of the propagator did not converge for %llu generator(s)", st[0]);
+        return QSX_ERR_INTEGRATOR;
+    }
+    int rc = qsx_dense_wrap(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_);
+    if (rc == QSX_OK) { (*out)->build_ms = ms; (*out)->build_gemms = st[1]; }
+    return rc;
 }

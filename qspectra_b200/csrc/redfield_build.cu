@@ -30,6 +30,7 @@ struct RedfieldBuildArgs {
     cplx *scratch;          // [gridDim][2][N^4] when the tensors do not fit in shared memory
     int tensors_in_smem;
     // on-device eigensystems (jacobi != 0): H_m = H0 + diag(sum_j shift[m][j] v[j][.]), lab frame
+    int transposed_out;     // write Lt[m][c][r] (storage of qsx_dense_wrap) instead of L[m][r][c]
     int jacobi;
     const double *H0;       // [N][N] real symmetric
     const double *shifts;   // [m][nb]
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
             int fr = a.idx[r], fc = a.idx[c];
             int i = fr % N, j = fr / N, k = fc % N, l = fc / N;
             cplx val = src[(((size_t)i * N + j) * N + k) * N + l];
-            Lout[p] = cscale(a.unit_convert, val);
+            Lout[a.transposed_out ? c * a.M + r : p] = cscale(a.unit_convert, val);
         }
     }
 }
@@ -266,7 +267,7 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
                                double rw_freq, int32_t n_baths, const double *coupling_diag_host,
                                const qsx_bath *bath, int32_t secular, int32_t eigen_basis,
                                double unit_convert, int32_t M, const int64_t *subspace_index_host,
-                               void *L_out_dev, void *stream_) {
+                               int32_t transposed_out, void *L_out_dev, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool jacobi = H0_host != nullptr;
     QSX_REQUIRE(n_members > 0 && N > 0 && n_baths > 0 && M > 0 && bath &&
@@ -316,6 +317,7 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     if (a.bath.matsubara_cutoff <= 0) a.bath.matsubara_cutoff = 1000;
     a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;
     a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem;
+    a.transposed_out = transposed_out;
     a.jacobi = jacobi; a.H0 = d_H0.p; a.shifts = shifts_dev; a.quanta = d_quanta.p; a.rw_freq = rw_freq;
     QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     redfield_build_kernel<<<grid, 256, smem, stream>>>(a);
@@ -329,10 +331,10 @@ extern "C" int qsx_redfield_build(int32_t n_members, int32_t N, const void *E_de
                                   int32_t n_baths, const double *coupling_diag_host,
                                   const qsx_bath *bath, int32_t secular, int32_t eigen_basis,
                                   double unit_convert, int32_t M, const int64_t *subspace_index_host,
-                                  void *L_out_dev, void *stream) {
+                                  int32_t transposed_out, void *L_out_dev, void *stream) {
     return redfield_build_impl(n_members, N, E_dev, U_dev, nullptr, nullptr, nullptr, 0.0, n_baths,
                                coupling_diag_host, bath, secular, eigen_basis, unit_convert, M,
-                               subspace_index_host, L_out_dev, stream);
+                               subspace_index_host, transposed_out, L_out_dev, stream);
 }
 
 extern "C" int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const double *H0_host,
@@ -341,9 +343,10 @@ extern "C" int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const do
                                           const double *coupling_diag_host, const qsx_bath *bath,
                                           int32_t secular, int32_t eigen_basis, double unit_convert,
                                           int32_t M, const int64_t *subspace_index_host,
-                                          void *L_out_dev, void *stream) {
+                                          int32_t transposed_out, void *L_out_dev, void *stream) {
     QSX_REQUIRE(H0_host, "qsx_redfield_build_sampled: H0 missing");
     return redfield_build_impl(n_members, N, nullptr, nullptr, H0_host, (const double *)site_shifts_dev,
                                quanta_host, rw_freq, n_baths, coupling_diag_host, bath, secular,
-                               eigen_basis, unit_convert, M, subspace_index_host, L_out_dev, stream);
+                               eigen_basis, unit_convert, M, subspace_index_host, transposed_out,
+                               L_out_dev, stream);
 }

@@ -196,8 +196,9 @@ class RedfieldModel(LiouvilleSpaceModel):
             L = engine.redfield_build(
                 E, U, number, kind, bath.temperature, bath.reorg_energy,
                 bath.cutoff_freq, self.secular, True, self.unit_convert,
-                self.liouville_subspace_index(liouville_subspace))
-            return engine.DenseEOM(L, heisenberg_picture)
+                self.liouville_subspace_index(liouville_subspace),
+                transposed=not heisenberg_picture)
+            return engine.DenseEOM.from_transposed(L)
         number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
         kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
                 else _capi.BATH_DEBYE_COMPLEX)
@@ -210,5 +211,8 @@ class RedfieldModel(LiouvilleSpaceModel):
             np.asarray(lab.H(ss), dtype=float), shifts, quanta, ham.rw_freq,
             number, kind, bath.temperature, bath.reorg_energy, bath.cutoff_freq,
             self.secular, self.evolve_basis == 'eigen', self.unit_convert,
-            self.liouville_subspace_index(liouville_subspace))
-        return engine.DenseEOM(L, heisenberg_picture)
+            self.liouville_subspace_index(liouville_subspace),
+            transposed=not heisenberg_picture)
+        # the builder wrote the engine's storage layout directly (the Heisenberg
+        # picture L^T in that layout is plain row-major L): no copy, no cudaMalloc
+        return engine.DenseEOM.from_transposed(L)

@@ -21,6 +21,9 @@ class PropagationStats(object):
     accepted_steps = 0
     kernel_ms = 0.0
     propagations = 0
+    expm_ms = 0.0
+    expm_gemms = 0
+    expm_builds = 0
 
     @classmethod
     def reset(cls):
@@ -28,6 +31,9 @@ class PropagationStats(object):
         cls.accepted_steps = 0
         cls.kernel_ms = 0.0
         cls.propagations = 0
+        cls.expm_ms = 0.0
+        cls.expm_gemms = 0
+        cls.expm_builds = 0
 
 
 class LinearMap(object):
@@ -68,8 +74,8 @@ def resolve_method(method_name, lti):
         return 'dopri5'
     if name not in _capi.METHODS:
         raise ValueError('unknown integration method %r (device methods: '
-                         'taylor, rk4, dopri5)' % method_name)
-    if name == 'taylor' and not lti:
+                         'taylor, rk4, dopri5, expm)' % method_name)
+    if name in ('taylor', 'map') and not lti:
         raise ValueError('taylor needs a time-independent linear generator')
     return name
 
@@ -221,6 +227,88 @@ class DenseEOM(DeviceEOM):
         if h and _capi is not None and _capi._lib is not None:
             _capi._lib.qsx_dense_destroy(h)
             self._h = None
+
+    #: largest state dimension of the tensor-core propagator kernel
+    EXPM_MAX_DIM = 56
+
+    def propagator(self, dt):
+        """DenseEOM holding P_g = exp(L_g dt) for every generator (FP64 tensor
+        cores, csrc/dense.cu: dense_expm_kernel); cached per dt."""
+        cache = self.__dict__.setdefault('_propagators', {})
+        key = float(dt)
+        if key not in cache:
+            torch = _capi.torch_cuda()
+            prop = DenseEOM.__new__(DenseEOM)
+            prop.n_generators, prop.dim = self.n_generators, self.dim
+            prop.heisenberg_picture = self.heisenberg_picture
+            # storage from torch's caching allocator, borrowed by the handle
+            prop._storage = (torch.empty((self.n_generators, self.dim, self.dim),
+                                         dtype=torch.complex128, device='cuda'),
+                             torch.empty(self.n_generators, dtype=torch.float64,
+                                         device='cuda'))
+            prop._h = C.c_void_p()
+            _capi.check(_capi.lib().qsx_dense_expm(
+                self._h, key, prop._storage[0].data_ptr(),
+                prop._storage[1].data_ptr(), C.byref(prop._h),
+                _capi.current_stream_ptr()))
+            ms, gemms = C.c_double(), C.c_uint64()
+            _capi.check(_capi.lib().qsx_dense_build_stats(prop._h, C.byref(ms),
+                                                          C.byref(gemms)))
+            prop.build_ms, prop.build_gemms = ms.value, int(gemms.value)
+            PropagationStats.expm_ms += ms.value
+            PropagationStats.expm_gemms += int(gemms.value)
+            PropagationStats.expm_builds += 1
+            cache[key] = prop
+        return cache[key]
+
+    @classmethod
+    def from_transposed(cls, Lt_dev):
+        """Wrap a CUDA tensor that already has the engine's transposed storage
+        Lt[g][c][r] = L_g[r][c] (no copy; e.g. the output of the K5 builders)."""
+        torch = _capi.torch_cuda()
+        obj = cls.__new__(cls)
+        obj.n_generators, obj.dim = int(Lt_dev.shape[0]), int(Lt_dev.shape[1])
+        obj.heisenberg_picture = False
+        obj._storage = (Lt_dev, torch.empty(obj.n_generators, dtype=torch.float64,
+                                            device=Lt_dev.device))
+        obj._h = C.c_void_p()
+        _capi.check(_capi.lib().qsx_dense_wrap(
+            C.byref(obj._h), obj.dim, obj.n_generators, Lt_dev.data_ptr(),
+            obj._storage[1].data_ptr(), _capi.current_stream_ptr()))
+        return obj
+
+    def _uniform_step(self, t, t0):
+        """dt if `t` is a uniform grid starting at t0, else None."""
+        t = np.asarray(t, dtype=float)
+        if t.size < 3 or (t0 is not None and t0 != t[0]):
+            return None
+        d = np.diff(t)
+        if d[0] <= 0 or np.abs(d - d[0]).max() > 1e-9 * abs(d[0]):
+            return None
+        return float(d[0])
+
+    def propagate(self, y0, t, t0=None, method='zvode', **kw):
+        """Adds method 'expm' (propagator stepping: y_{i+1} = exp(L dt) y_i,
+        built once per generator on the tensor cores).  It is also what the
+        default ('zvode') selects for a uniform grid when it pays off, i.e.
+        when the series for exp(L dt) (~16 M matrix-vector equivalents) is
+        cheaper than integrating every column step by step."""
+        name = (method or 'zvode').lower()
+        if name in ('expm', 'zvode', 'auto') and not kw.get('pulses'):
+            dt = self._uniform_step(t, t0)
+            n_cols = int(np.prod(np.shape(y0)[:-1])) if np.ndim(y0) > 1 else 1
+            worth = len(t) * max(1, n_cols // self.n_generators) >= 64
+            if dt is not None and self.dim <= self.EXPM_MAX_DIM and \
+                    (name == 'expm' or worth):
+                prop = self.propagator(dt)
+                out = DeviceEOM.propagate(prop, y0, t, t0=t0, method='map', **kw)
+                self.last = dict(prop.last, method='expm')
+                return out
+            if name == 'expm':
+                raise ValueError('expm needs a uniform output grid starting at '
+                                 't0 and a state dimension <= %d'
+                                 % self.EXPM_MAX_DIM)
+        return DeviceEOM.propagate(self, y0, t, t0=t0, method=method, **kw)
 
     def _apply_dev(self, y, dy, n, gptr):
         _capi.check(_capi.lib().qsx_dense_apply(
@@ -404,7 +492,7 @@ def reduce_members(batch_dev, scale=1.0):
 
 def redfield_build(E, U, coupling_diag, bath_kind, temperature, reorg_energy,
                    cutoff_freq, secular, eigen_basis, unit_convert,
-                   subspace_index, matsubara_cutoff=1000):
+                   subspace_index, matsubara_cutoff=1000, transposed=False):
     """Batched Redfield generators on the device (kernel K5).
 
     E (m, N) float, U (m, N, N): eigen-systems of the members in the rotating
@@ -425,15 +513,15 @@ def redfield_build(E, U, coupling_diag, bath_kind, temperature, reorg_energy,
         m, N, E_dev.data_ptr(), U_dev.data_ptr(), v.shape[0],
         v.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bath),
         int(bool(secular)), int(bool(eigen_basis)), float(unit_convert),
-        idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), out.data_ptr(),
-        _capi.current_stream_ptr()))
+        idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), int(bool(transposed)),
+        out.data_ptr(), _capi.current_stream_ptr()))
     return out
 
 
 def redfield_build_sampled(H0, site_shifts, quanta, rw_freq, coupling_diag,
                            bath_kind, temperature, reorg_energy, cutoff_freq,
                            secular, eigen_basis, unit_convert, subspace_index,
-                           matsubara_cutoff=1000):
+                           matsubara_cutoff=1000, transposed=False):
     """Kernel K5 with on-device Jacobi eigensystems: only the (m, n_sites)
     disorder shifts cross the PCIe bus.  H0: real symmetric lab-frame
     Hamiltonian of the un-sampled system in the Hilbert subspace."""
@@ -455,6 +543,6 @@ def redfield_build_sampled(H0, site_shifts, quanta, rw_freq, coupling_diag,
         m, N, dptr(H0), shifts.data_ptr(), dptr(q), float(rw_freq), v.shape[0],
         dptr(v), C.byref(bath), int(bool(secular)), int(bool(eigen_basis)),
         float(unit_convert), idx.size,
-        idx.ctypes.data_as(C.POINTER(C.c_int64)), out.data_ptr(),
-        _capi.current_stream_ptr()))
+        idx.ctypes.data_as(C.POINTER(C.c_int64)), int(bool(transposed)),
+        out.data_ptr(), _capi.current_stream_ptr()))
     return out

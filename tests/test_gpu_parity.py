@@ -388,3 +388,33 @@ def test_device_redfield_build_variants(secular, dic, basis):
                 # eigenvector signs are a gauge in the eigenbasis (numpy vs scipy
                 # LAPACK drivers): compare magnitudes
                 assert rel_l2(np.abs(Ln), np.abs(ref[n])) < 1e-10, (ss, n)
+
+
+# ------------------------------------------------ tensor-core propagator (expm)
+def test_expm_propagator_matches_reference(fmo_model, golden):
+    g = golden('redfield')
+    t, rho = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 1000, method_name='expm')
+    assert rel_l2(rho, g['fmo_rho_1ps']) < TOL
+    eom = fmo_model.equation_of_motion('ee')
+    assert eom.last['method'] == 'expm'
+    # the propagator itself against scipy's expm of the reference generator
+    import scipy.linalg
+    dt = fmo_model.time_step
+    P = eom.propagator(dt).apply(np.eye(49, dtype=complex)).T
+    assert rel_l2(P, scipy.linalg.expm(g['fmo_L_ee'] * dt)) < 1e-13
+    # default method picks it for long uniform grids and agrees with Taylor
+    t, a = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 3000)
+    assert eom.last['method'] == 'expm'
+    t, b = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 3000, method_name='taylor')
+    assert rel_l2(a, b) < 1e-10
+    # small systems (dimer, M = 2..4) and the ensemble path
+    t, rho = qb.simulate_dynamics(fmo_model, np.eye(7)[0], 300, ensemble_size=4,
+                                  method_name='expm')
+    assert rel_l2(rho, g['fmo_ens4_rho_300fs']) < TOL
+    m = qb.RedfieldModel(systems.dimer(), hilbert_subspace='gef', unit_convert=CM_FS,
+                         discard_imag_corr=True)
+    f, X = qb.absorption_spectra(m, 10000, method_name='expm')
+    assert rel_l2(X, g['dimer_abs_X']) < TOL
+    with pytest.raises(ValueError):
+        qb.integrate(eom, np.eye(49, dtype=complex)[0], np.array([0., 1., 5.]),
+                     method_name='expm')
