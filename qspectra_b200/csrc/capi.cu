@@ -8,6 +8,9 @@
 #include <math.h>
 #include <algorithm>
 #include <thread>
+#include <map>
+#include <mutex>
+#include <vector>
 
 static thread_local char g_error[1024] = "";
 std::atomic<uint64_t> qsx_launch_counter{0};
@@ -17,6 +20,59 @@ void qsx_set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+}
+
+// ------------------------------------------------------------ device scratch pool
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::map<void *, size_t> live;                       // ptr -> size class (0: not pooled)
+    std::map<std::pair<int, size_t>, std::vector<void *>> idle;   // (device, class) -> blocks
+};
+Pool &pool() { static Pool p; return p; }
+const size_t kPoolMax = (size_t)64 << 20;
+}  // namespace
+
+cudaError_t qsx_pool_alloc(void **ptr, size_t bytes) {
+    size_t cls = 256;
+    while (cls < bytes) cls <<= 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Pool &P = pool();
+    if (bytes <= kPoolMax) {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto &v = P.idle[std::make_pair(dev, cls)];
+        if (!v.empty()) {
+            *ptr = v.back();
+            v.pop_back();
+            P.live[*ptr] = cls;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(ptr, bytes <= kPoolMax ? cls : bytes);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(P.mu);
+        P.live[*ptr] = bytes <= kPoolMax ? cls : 0;
+    }
+    return e;
+}
+
+void qsx_pool_free(void *ptr) {
+    if (!ptr) return;
+    Pool &P = pool();
+    size_t cls = 0;
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.live.find(ptr);
+        if (it != P.live.end()) { cls = it->second; P.live.erase(it); }
+        if (cls) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            P.idle[std::make_pair(dev, cls)].push_back(ptr);
+            return;
+        }
+    }
+    cudaFree(ptr);
 }
 
 extern "C" const char *qsx_last_error(void) { return g_error; }

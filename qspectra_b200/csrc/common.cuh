@@ -107,7 +107,14 @@ extern std::atomic<uint64_t> qsx_launch_counter;
         }                                                                     \
     } while (0)
 
-// small RAII device buffer for handle-owned tables
+// Device scratch comes from a small caching pool (power-of-two size classes, blocks up
+// to 64 MB are kept for reuse; larger ones go straight to cudaMalloc/cudaFree): the
+// per-call metadata buffers of the propagate entry points must not cost a
+// cudaMalloc + synchronising cudaFree each time.
+cudaError_t qsx_pool_alloc(void **ptr, size_t bytes);
+void qsx_pool_free(void *ptr);
+
+// small RAII device buffer for handle-owned tables and per-call scratch
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -116,7 +123,7 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        return qsx_pool_alloc(reinterpret_cast<void **>(&p), count * sizeof(T));
     }
     cudaError_t upload(const T *src, size_t count, cudaStream_t s) {
         cudaError_t e = alloc(count);
@@ -125,7 +132,7 @@ struct DevBuf {
     }
     cudaError_t upload(const std::vector<T> &v, cudaStream_t s) { return upload(v.data(), v.size(), s); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) qsx_pool_free(p);
         p = nullptr;
         n = 0;
     }
