@@ -269,7 +269,8 @@ def heom_leg(torch, qb, systems, engine):
             'kernel_ms': best['kernel_ms'], 'setup_s': build_s,
             'roofline': {'bound': 'hbm', 'achieved': achieved,
                          'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                         'frac': achieved / peaks['hbm_gbs'], 'traffic': ncu_traffic('heom_depth%d' % depth),
+                         'frac': achieved / peaks['hbm_gbs'], 'traffic': ((ncu_traffic('heom_depth%d_per_rhs' % depth) or 0) * best['rhs']) or None,
+                         'achieved_is': 'rhs_per_s x 32 D (algorithmic bytes per RHS application)',
                          'peak_source': src,
                          'algorithmic_bytes_per_rhs': 32 * D}}
         del eom, model
@@ -417,7 +418,7 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved_tf / fp64_peak,
-                     'traffic': ncu_traffic('dense_expm'),
+                     'traffic': (ncu_traffic('dense_expm_per_member') or 0) * E or None,
                      'kernel': 'dense_expm_kernel<7> (FP64 DMMA m8n8k4: exp(L dt) per member)',
                      'kernel_ms': expm_ms,
                      'algorithmic_flops_per_launch': flops_per_launch,
