@@ -281,7 +281,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import qspectra_b200 as qb
-    from qspectra_b200 import systems, engine, _capi
+    from qspectra_b200 import systems, engine, _capi, parallel
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -354,12 +354,12 @@ def run_ours(args):
     # ---- end-to-end leg through the public API, host buffers ------------------
     def e2e_once():
         # the call a user makes: host arrays in, host arrays out
-        _, rho = qb.simulate_dynamics(model, psi0, DURATION_FS, ensemble_size=E,
-                                      member_offset=rank * E)
-        if world > 1:
-            buf = torch.view_as_real(torch.from_numpy(rho).cuda() / world)
-            dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-            rho = torch.view_as_complex(buf).cpu().numpy()
+        if world == 1:
+            _, rho = qb.simulate_dynamics(model, psi0, DURATION_FS, ensemble_size=E)
+        else:
+            # one process per GPU: contiguous member blocks, one NCCL reduce to rank 0
+            _, rho = parallel.simulate_dynamics_sharded(
+                model, psi0, DURATION_FS, ensemble_size=E * world, dst=0)
         return rho
 
     del eom
