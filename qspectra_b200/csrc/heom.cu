@@ -1349,22 +1349,27 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     long long total = d.n_tiles * n_columns;
     int grid = (int)std::min<long long>(total, (long long)sms * 6);
     const char *variant = getenv("QSX_HEOM_VARIANT");
-    const bool generic_only = variant && variant[0] == 'g';
-    if (d.ee && d.nr == 7 && d.K1 == 2 && d.real_h && !generic_only) {
-        typedef TileEE<7, 2, 2, true> T;
-        smem = T::smem_bytes(d);
-        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
-    } else if (d.ee && d.nr == 7 && d.K1 == 2 && !generic_only) {
-        typedef TileEE<7, 2, 2, false> T;
-        smem = T::smem_bytes(d);
-        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
-    } else {
-        typedef TileGeneric T;
-        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);
+    const char vsel = variant ? variant[0] : ' ';
+    int apply_occ = 0;
+#define QSX_APPLY(TILE)                                                                                  \
+    {                                                                                                    \
+        typedef TILE T;                                                                                  \
+        smem = T::smem_bytes(d);                                                                         \
+        QSX_CUDA(cudaFuncSetAttribute(heom_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                       \
+        QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&apply_occ, heom_apply_kernel<T>,         \
+                                                               T::THREADS, smem));                       \
+        grid = (int)std::min<long long>((total + T::UNITS - 1) / T::UNITS,                               \
+                                        (long long)sms * std::max(1, apply_occ));                        \
+        heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);                                     \
     }
+    const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
+    if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+    else if (ee7 && d.real_h && vsel == 'c') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
+    else if (ee7 && d.real_h && vsel == '2') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
+    else if (ee7 && !d.real_h && vsel != 'g') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
+    else QSX_APPLY(TileGeneric)
+#undef QSX_APPLY
     heom_from_internal<<<sms * 4, 256, 0, stream>>>(yi.p, (cplx *)dy_dev, n_columns, d.n_ado, d.n_tiles, d.M);
     qsx_launch_counter += 3;
     QSX_CUDA(cudaGetLastError());
