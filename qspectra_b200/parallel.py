@@ -94,3 +94,48 @@ def simulate_dynamics_sharded(dynamical_model, initial_state, duration=None,
     total = reduce_sum(part, dst)
     states = total.cpu().numpy()
     return t, dynamical_model.saved_states_to_density_matrix(states)
+
+
+def ensemble_signal_sharded(func, dynamical_model, ensemble_size,
+                            random_orientations=False, dst=None):
+    """Ensemble average of any simulate-layer signal with the members sharded
+    over the ranks: ``func(member_model) -> (ticks, signal)`` is evaluated for
+    this rank's block of members (same member numbering as the reference's
+    serial loop, decorators.py:55-60) and the partial sums are combined with one
+    reduce.  Used for disorder-averaged third-order / 2D responses."""
+    import torch
+    rank, size = world()
+    first, count = shard_members(ensemble_size, rank, size)
+    ticks, total = None, None
+    for n in range(first, first + count):
+        ticks, signal = func(dynamical_model.sample(n, random_orientations))
+        total = signal if total is None else total + signal
+    if total is None:           # more ranks than members: contribute zeros
+        ticks, probe = func(dynamical_model.sample(0, random_orientations))
+        total = np.zeros_like(probe)
+    part = torch.from_numpy(np.ascontiguousarray(total))
+    if torch.cuda.is_available() and size > 1:
+        part = part.cuda()
+    total = reduce_sum(part, dst)
+    return ticks, (total / ensemble_size).cpu().numpy()
+
+
+def third_order_response_sharded(dynamical_model, coherence_time_max,
+                                 ensemble_size, population_time_max=None,
+                                 population_times=None, geometry='-++',
+                                 polarization='xxxx', include_signal=None,
+                                 ensemble_random_orientations=False,
+                                 exact_isotropic_average=False, dst=None,
+                                 **integrate_kwargs):
+    """``third_order_response`` (reference response.py:340-427) for a disorder
+    ensemble sharded over the GPUs of the current torch.distributed job."""
+    from .simulate.response import third_order_response
+
+    def one(member):
+        return third_order_response(
+            member, coherence_time_max, population_time_max, population_times,
+            geometry, polarization, include_signal,
+            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+
+    return ensemble_signal_sharded(one, dynamical_model, ensemble_size,
+                                   ensemble_random_orientations, dst)
