@@ -659,9 +659,10 @@ struct TileEE {
         }
         // hierarchy links: row-site bins (site w), then col-site bins (site b)
         const cplx *xw = x + (size_t)w * TL;
+        cplx vru[BATCH ? K1 : 1][NS], vrd[BATCH ? K1 : 1][NS], vcu[NS][BATCH ? K1 : 1], vcd[NS][BATCH ? K1 : 1];
         if (BATCH) {
-            // issue every gather of this row first (56 independent loads per lane), then accumulate
-            cplx vru[K1][NS], vrd[K1][NS], vcu[NS][K1], vcd[NS][K1];
+            // issue every gather of this row first (56 independent loads per lane); they
+            // are consumed after the commutator, whose arithmetic hides their latency
 #pragma unroll
             for (int k = 0; k < K1; ++k) {
                 const int bin = w * K1 + k;
@@ -680,22 +681,6 @@ struct TileEE {
                     const int ou = cur.o_up[bin * TL + lane], od = cur.o_dn[bin * TL + lane];
                     vcu[b][k] = ou >= 0 ? __ldcg(xw + ou + b * NS * TL) : cmake(0, 0);
                     vcd[b][k] = od >= 0 ? __ldcg(xw + od + b * NS * TL) : cmake(0, 0);
-                }
-#pragma unroll
-            for (int k = 0; k < K1; ++k) {
-                const int njk = cur.occ[(w * K1 + k) * TL + lane];
-                const cplx gu = cscale(s.su[k * H.Lc + njk], H.GuR[k]);
-                const cplx gd = cscale(s.sd[k * H.Lc + njk], H.GdR[k]);
-#pragma unroll
-                for (int b = 0; b < NS; ++b) { cfma(acc[b], gu, vru[k][b]); cfma(acc[b], gd, vrd[k][b]); }
-            }
-#pragma unroll
-            for (int b = 0; b < NS; ++b)
-#pragma unroll
-                for (int k = 0; k < K1; ++k) {
-                    const int njk = cur.occ[(b * K1 + k) * TL + lane];
-                    cfma(acc[b], cscale(s.su[k * H.Lc + njk], H.GuC[k]), vcu[b][k]);
-                    cfma(acc[b], cscale(s.sd[k * H.Lc + njk], H.GdC[k]), vcd[b][k]);
                 }
         } else {
 #pragma unroll
@@ -774,6 +759,24 @@ struct TileEE {
                 for (int c = 0; c < NS; ++c) {
                     const cplx h = s.HC[b * NS + c];
                     cfma(acc[b], cmake(-h.x, -h.y), own[c]);
+                }
+        }
+        if (BATCH) {
+#pragma unroll
+            for (int k = 0; k < K1; ++k) {
+                const int njk = cur.occ[(w * K1 + k) * TL + lane];
+                const cplx gu = cscale(s.su[k * H.Lc + njk], H.GuR[k]);
+                const cplx gd = cscale(s.sd[k * H.Lc + njk], H.GdR[k]);
+#pragma unroll
+                for (int b = 0; b < NS; ++b) { cfma(acc[b], gu, vru[k][b]); cfma(acc[b], gd, vrd[k][b]); }
+            }
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+#pragma unroll
+                for (int k = 0; k < K1; ++k) {
+                    const int njk = cur.occ[(b * K1 + k) * TL + lane];
+                    cfma(acc[b], cscale(s.su[k * H.Lc + njk], H.GuC[k]), vcu[b][k]);
+                    cfma(acc[b], cscale(s.sd[k * H.Lc + njk], H.GdC[k]), vcd[b][k]);
                 }
         }
         const double wscale = cur.sh[TL + lane];
