@@ -57,6 +57,10 @@ struct HeomDev {
     const int *off_up, *off_dn;   // [n_tiles][bins][32] element offsets of the neighbour (tile*M*32 + lane), -1 = absent
     const int *e_off, *e_stride;  // [M] position of element e inside a tile: e_off[e] + lane * e_stride[e]
     int layout;               // 0: tile-SoA [e][32]; 1: pair-packed [rho_ab, rho_ba] (TileEEP)
+    int n_pulse, Rp;          // time-dependent terms: per-ADO operator rows in ELL form
+    const int *pcol;          // [n_pulse][M][Rp] (-1 padded)
+    const cplx *pval;         // [n_pulse][M][Rp]
+    qsx_pulse pulses[QSX_MAX_PULSES];
     int ee;                   // 1: rows/cols are site-projector states (electronic block), TileEE applicable
     int real_h;               // 1: Hs_R, Hs_C purely imaginary (real Hamiltonian)
     cplx GuR[4], GdR[4], GuC[4], GdC[4];   // link coefficients per Matsubara index (row-site / col-site)
@@ -96,6 +100,7 @@ struct TileSmem {
     long long next_tile;
     const cplx *loaded;      // tile data currently staged (or in flight) in buffer `buf`
     int buf;
+    double t_eval;           // time at which the pulse envelopes are evaluated
 };
 
 __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -242,10 +247,24 @@ struct TileGeneric {
             const long long gi = ((long long)tile * M + e) * TL + lane;
             const cplx p = pre(gi);
             const cplx own = s.ys[e * TL + lane];
+            const cplx *yn_base = s.ys + lane;
             cplx acc = s.os[e * TL + lane];
             const double dg = shift + s.dterm[e];
             acc.x -= dg * own.x;
             acc.y -= dg * own.y;
+            for (int p = 0; p < H.n_pulse; ++p) {
+                // (-i E_p(t)) [V_p, rho_n][e]: the dipole commutator acts on every ADO alike
+                const cplx gp = pulse_coefficient(H.pulses[p], s.t_eval);
+                const int *pc = H.pcol + ((size_t)p * M + e) * H.Rp;
+                const cplx *pw = H.pval + ((size_t)p * M + e) * H.Rp;
+                cplx tmp = cmake(0, 0);
+                for (int l = 0; l < H.Rp; ++l) {
+                    const int c = __ldg(&pc[l]);
+                    if (c < 0) break;
+                    cfma(tmp, __ldg(&pw[l]), yn_base[c * TL]);
+                }
+                cfma(acc, gp, tmp);
+            }
             const int *lrow = s.lbin + e * Lk;
             for (int l = 0; l < Lk; ++l) {
                 const int b = lrow[l];
@@ -1094,6 +1113,9 @@ struct HeomPropArgs {
     const int *member_of;
     const cplx *y0;             // reference layout [B][n_ado][M]
     cplx *Y, *V, *W, *X;        // work vectors, internal layout [B][Dp] (X only for RK4)
+    cplx *K[7];                 // DOPRI5 stage derivatives (TA = V, TB = W)
+    double atol;
+    double *red;                // [4] rotating error accumulators (DOPRI5)
     const double *t;
     double t0;
     double rtol;
@@ -1162,6 +1184,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
     // ---- init: Y = y0 (layout change), reference norms, control words ---------
     for (int i = (int)gtid; i < 3 * B; i += (int)gsz) a.ynorm[i] = 0.0;
     if (gtid < 3) a.flags[gtid] = 0;
+    if (gtid < 4 && a.red) a.red[gtid] = 0.0;
     grid.sync();
     for (int b = 0; b < B; ++b) {
         double loc = 0.0;
@@ -1180,9 +1203,13 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
 
     unsigned long long n_rhs = 0, n_steps = 0;
     int status = 0;
+    s.t_eval = a.t0;
     int fslot = 0;      // flag slot of the current convergence check
     int nslot = 0;      // norm slot that holds the latest reference norms
     double tcur = a.t0;
+    double dp_h = 0.0;          // DOPRI5 step carried across output points
+    bool dp_have_k1 = false;    // DOPRI5 FSAL
+    int dp_slot = 0;            // rotating error accumulator
 
     for (int it = 0; it < a.nt; ++it) {
         const double target = a.t[it];
@@ -1255,6 +1282,111 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                     if (!done) status = QSX_ERR_INTEGRATOR;
                     n_steps += 1;
                     tcur += h;
+                }
+            } else if (METHOD == QSX_METHOD_DOPRI5) {
+                // Dormand-Prince 5(4) on the whole hierarchy: 7 tile sweeps per step attempt,
+                // error norm through atomics + grid barrier, step size kept in registers
+                // (identical on every thread).  TA = V, TB = W.
+                cplx *TA = a.V, *TB = a.W;
+                cplx *K1 = a.K[0], *K2 = a.K[1], *K3 = a.K[2], *K4 = a.K[3], *K5 = a.K[4], *K6 = a.K[5], *K7 = a.K[6];
+                const long long ntot = Dp * B;
+                const double dir = span >= 0 ? 1.0 : -1.0;
+                auto sweep = [&](const cplx *src, double tt, auto &&post) {
+                    s.t_eval = tt;
+                    for (long long w = w0; w < total; w += wstride) {
+                        const int b = (int)(w / n_tiles);
+                        const long long tile = w % n_tiles;
+                        { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                        const int member = a.member_of ? a.member_of[b] : 0;
+                        const size_t o = (size_t)b * Dp;
+                        Tile::run(a.H, s, src + o, tile, member, [&](long long) { return cmake(0, 0); },
+                                  [&](long long i, cplx f, cplx, cplx, double) { post(o + i, f); });
+                    }
+                    n_rhs += 1;
+                    grid.sync();
+                };
+                if (!dp_have_k1) {
+                    sweep(a.Y, tcur, [&](size_t i, cplx f) { K1[i] = f; });
+                    dp_have_k1 = true;
+                }
+                if (dp_h == 0.0) dp_h = fmin(fabs(span), 0.05 / fmax(a.lnorm, 1e-300));
+                int guard = 0;
+                while ((target - tcur) * dir > 0) {
+                    double h = dir * fabs(dp_h);
+                    bool clipped = false;
+                    if ((tcur + h - target) * dir >= 0 || fabs(target - (tcur + h)) < 1e-12 * fabs(h)) {
+                        h = target - tcur;
+                        clipped = true;
+                    }
+                    for (long long i = gtid; i < ntot; i += gsz) TA[i] = cadd(a.Y[i], cscale(h * DP_A21, K1[i]));
+                    if (blockIdx.x == 0 && threadIdx.x == 0) a.red[(dp_slot + 1) & 3] = 0.0;
+                    grid.sync();
+                    sweep(TA, tcur + DP_C2 * h, [&](size_t i, cplx f) {
+                        K2[i] = f;
+                        cplx v = a.Y[i]; rfma(v, h * DP_A31, K1[i]); rfma(v, h * DP_A32, f); TB[i] = v;
+                    });
+                    sweep(TB, tcur + DP_C3 * h, [&](size_t i, cplx f) {
+                        K3[i] = f;
+                        cplx v = a.Y[i]; rfma(v, h * DP_A41, K1[i]); rfma(v, h * DP_A42, K2[i]); rfma(v, h * DP_A43, f); TA[i] = v;
+                    });
+                    sweep(TA, tcur + DP_C4 * h, [&](size_t i, cplx f) {
+                        K4[i] = f;
+                        cplx v = a.Y[i]; rfma(v, h * DP_A51, K1[i]); rfma(v, h * DP_A52, K2[i]);
+                        rfma(v, h * DP_A53, K3[i]); rfma(v, h * DP_A54, f); TB[i] = v;
+                    });
+                    sweep(TB, tcur + DP_C5 * h, [&](size_t i, cplx f) {
+                        K5[i] = f;
+                        cplx v = a.Y[i]; rfma(v, h * DP_A61, K1[i]); rfma(v, h * DP_A62, K2[i]);
+                        rfma(v, h * DP_A63, K3[i]); rfma(v, h * DP_A64, K4[i]); rfma(v, h * DP_A65, f); TA[i] = v;
+                    });
+                    sweep(TA, tcur + h, [&](size_t i, cplx f) {
+                        K6[i] = f;
+                        cplx v = a.Y[i]; rfma(v, h * DP_A71, K1[i]); rfma(v, h * DP_A73, K3[i]);
+                        rfma(v, h * DP_A74, K4[i]); rfma(v, h * DP_A75, K5[i]); rfma(v, h * DP_A76, f); TB[i] = v;
+                    });
+                    double errsq = 0.0;
+                    s.t_eval = tcur + h;
+                    for (long long w = w0; w < total; w += wstride) {
+                        const int b = (int)(w / n_tiles);
+                        const long long tile = w % n_tiles;
+                        { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                        const int member = a.member_of ? a.member_of[b] : 0;
+                        const size_t o = (size_t)b * Dp;
+                        Tile::run(a.H, s, TB + o, tile, member, [&](long long) { return cmake(0, 0); },
+                                  [&](long long il, cplx f, cplx ynew, cplx, double) {
+                                      const size_t i = o + il;
+                                      K7[i] = f;
+                                      cplx e = cmake(0, 0);
+                                      rfma(e, DP_E1, K1[i]); rfma(e, DP_E3, K3[i]); rfma(e, DP_E4, K4[i]);
+                                      rfma(e, DP_E5, K5[i]); rfma(e, DP_E6, K6[i]); rfma(e, DP_E7, f);
+                                      const double sc = a.atol + a.rtol * sqrt(fmax(cabs2(a.Y[i]), cabs2(ynew)));
+                                      errsq += (h * h) * cabs2(e) / (sc * sc);
+                                  });
+                    }
+                    n_rhs += 1;
+                    errsq = warp_sum(errsq);
+                    if ((threadIdx.x & 31) == 0 && errsq != 0.0) atomicAdd(&a.red[dp_slot & 3], errsq);
+                    grid.sync();
+                    const double err = sqrt(__ldcg(&a.red[dp_slot & 3]) / (double)((long long)B * a.H.n_ado * M));
+                    dp_slot += 1;
+                    const bool finite = (err == err) && err < 1e300;
+                    double fac;
+                    if (finite && err <= 1.0) {
+                        for (long long i = gtid; i < ntot; i += gsz) { a.Y[i] = TB[i]; K1[i] = K7[i]; }
+                        grid.sync();
+                        tcur = clipped ? target : tcur + h;
+                        n_steps += 1;
+                        fac = (err < 1e-10) ? 5.0 : fmin(5.0, fmax(0.2, 0.9 * pow(err, -0.2)));
+                        if (!clipped || fac < 1.0) dp_h = fabs(h) * fac;
+                        else dp_h = fmax(fabs(dp_h), fabs(h) * fmin(fac, 1.0));
+                    } else {
+                        fac = finite ? fmax(0.2, 0.9 * pow(err, -0.2)) : 0.2;
+                        dp_h = fabs(h) * fmin(fac, 1.0);
+                    }
+                    if (dp_h < 1e-14 * fmax(1.0, fabs(tcur)) || ++guard > 1000000) {
+                        status = QSX_ERR_INTEGRATOR;
+                        break;
+                    }
                 }
             } else {
                 // classic RK4 with fixed sub-steps; ACC = V, TA = W, TB = X
@@ -1523,6 +1655,7 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     d.shift = h->shift.p; d.scale = h->scale.p; d.up = h->up.p; d.down = h->down.p; d.occ = h->occ.p;
     d.off_up = h->off_up.p; d.off_dn = h->off_dn.p;
     d.layout = 0;
+    d.n_pulse = 0; d.Rp = 0; d.pcol = nullptr; d.pval = nullptr;
     // electronic-block structure: row state a <-> site a, column state b <-> site b
     d.ee = (nr == cfg->n_sites && nc == cfg->n_sites && K1 <= 4 &&
             (int64_t)n_tiles * M * TL < ((int64_t)1 << 31));
@@ -1666,9 +1799,12 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     const long long Dp = d.n_tiles * M * TL;
     QSX_REQUIRE(B > 0 && nt > 0 && args->t_host && args->y0_dev && args->out_dev,
                 "qsx_heom_propagate: empty batch or missing buffers");
-    QSX_REQUIRE(args->method == QSX_METHOD_TAYLOR || args->method == QSX_METHOD_RK4,
-                "HEOM propagation supports the Taylor and RK4 integrators");
-    QSX_REQUIRE(args->n_pulses == 0, "pulse-driven HEOM propagation is not available in this build");
+    QSX_REQUIRE(args->method == QSX_METHOD_TAYLOR || args->method == QSX_METHOD_RK4 ||
+                args->method == QSX_METHOD_DOPRI5, "HEOM propagation supports taylor, rk4 and dopri5");
+    QSX_REQUIRE(args->n_pulses >= 0 && args->n_pulses <= QSX_MAX_PULSES, "too many pulses");
+    QSX_REQUIRE(!(args->n_pulses > 0 && args->method == QSX_METHOD_TAYLOR),
+                "Taylor propagation needs a time-independent generator");
+    const bool dopri = args->method == QSX_METHOD_DOPRI5;
     for (int i = 1; i < nt; ++i)
         QSX_REQUIRE(args->t_host[i] >= args->t_host[i - 1], "output times must be non-decreasing");
     QSX_REQUIRE(args->t_host[0] >= args->t0, "first output time precedes t0");
@@ -1690,14 +1826,61 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_CUDA(V.alloc((size_t)B * Dp));
     QSX_CUDA(W.alloc((size_t)B * Dp));
     if (args->method == QSX_METHOD_RK4) QSX_CUDA(X.alloc((size_t)B * Dp));
+    DevBuf<cplx> Kbuf, pval;
+    DevBuf<int> pcol;
+    DevBuf<double> red;
+    QSX_CUDA(red.alloc(4));
+    if (dopri) QSX_CUDA(Kbuf.alloc((size_t)7 * B * Dp));
 
     HeomPropArgs a;
     a.H = d; a.B = B; a.nt = nt;
+    for (int k = 0; k < 7; ++k) a.K[k] = dopri ? Kbuf.p + (size_t)k * B * Dp : nullptr;
+    a.atol = args->atol > 0 ? args->atol : 1e-12;
+    a.red = red.p;
+    if (args->n_pulses > 0) {
+        // per-ADO pulse operators: dense [n_pulses][M][M] on the device -> ELL rows
+        QSX_REQUIRE(args->pulse_ops_dev && args->n_pulse_sets == 1,
+                    "HEOM pulse operators must be one shared set of [n_pulses][M][M] matrices");
+        const int np = args->n_pulses;
+        std::vector<cplx> dense((size_t)np * M * M);
+        QSX_CUDA(cudaMemcpyAsync(dense.data(), args->pulse_ops_dev, dense.size() * sizeof(cplx),
+                                 cudaMemcpyDeviceToHost, stream));
+        QSX_CUDA(cudaStreamSynchronize(stream));
+        int Rp = 1;
+        for (int p = 0; p < np; ++p)
+            for (int e = 0; e < M; ++e) {
+                int nz = 0;
+                for (int c = 0; c < M; ++c) {
+                    const cplx v = dense[((size_t)p * M + e) * M + c];
+                    nz += (v.x != 0.0 || v.y != 0.0);
+                }
+                Rp = std::max(Rp, nz);
+            }
+        std::vector<int> hcol((size_t)np * M * Rp, -1);
+        std::vector<cplx> hval((size_t)np * M * Rp, cmake(0, 0));
+        for (int p = 0; p < np; ++p)
+            for (int e = 0; e < M; ++e) {
+                int l = 0;
+                for (int c = 0; c < M; ++c) {
+                    const cplx v = dense[((size_t)p * M + e) * M + c];
+                    if (v.x != 0.0 || v.y != 0.0) {
+                        hcol[((size_t)p * M + e) * Rp + l] = c;
+                        hval[((size_t)p * M + e) * Rp + l] = v;
+                        ++l;
+                    }
+                }
+            }
+        QSX_CUDA(pcol.upload(hcol, stream));
+        QSX_CUDA(pval.upload(hval, stream));
+        QSX_CUDA(cudaStreamSynchronize(stream));
+        a.H.n_pulse = np; a.H.Rp = Rp; a.H.pcol = pcol.p; a.H.pval = pval.p;
+        for (int p = 0; p < np; ++p) a.H.pulses[p] = args->pulses[p];
+    }
     a.member_of = args->generator_of_column_host ? member.p : nullptr;
     a.y0 = (const cplx *)args->y0_dev;
     a.Y = Y.p; a.V = V.p; a.W = W.p; a.X = X.p;
     a.t = d_t.p; a.t0 = args->t0;
-    a.rtol = args->rtol > 0 ? args->rtol : 1e-13;
+    a.rtol = args->rtol > 0 ? args->rtol : (dopri ? 1e-10 : 1e-13);
     a.rk4_sub = args->rk4_substeps > 0 ? args->rk4_substeps : 16;
     a.kmax = 60; a.theta = 2.0; a.lnorm = h->lnorm;
     a.save_mode = args->save_mode; a.save_rows = args->save_rows;
@@ -1729,7 +1912,14 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
                         : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;             \
     }
     const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
-    if (d.layout == 1) QSX_PICK(TileEEP<7 COMMA 2 COMMA true>)
+    if (dopri || args->n_pulses > 0) {
+        // time-dependent right-hand sides run on the generic tile (any rectangular block)
+        QSX_REQUIRE(d.layout == 0, "pulse-driven propagation needs the element-major layout");
+        typedef TileGeneric T;
+        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;
+        kernel = dopri ? (const void *)heom_propagate_kernel<QSX_METHOD_DOPRI5, T>
+                       : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
+    } else if (d.layout == 1) QSX_PICK(TileEEP<7 COMMA 2 COMMA true>)
     else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
     else if (ee7 && d.real_h && vsel == '2') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
     else if (ee7 && d.real_h && vsel == '3') QSX_PICK(TileEE<7 COMMA 2 COMMA 3 COMMA true>)
@@ -1770,7 +1960,8 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     args->accepted_steps = st[1];
     args->kernel_ms = ms;
     if (st[2] != 0) {
-        qsx_set_error("HEOM Taylor series did not converge within %d terms", a.kmax);
+        qsx_set_error("HEOM integration failed (Taylor series not converged within %d terms, or DOPRI5 "
+                      "step-size underflow)", a.kmax);
         return QSX_ERR_INTEGRATOR;
     }
     return QSX_OK;

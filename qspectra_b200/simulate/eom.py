@@ -88,10 +88,12 @@ def _field_terms(dynamical_model, pulses, geometry, polarization,
                 'GPU integrator (got %r)' % (pulse,))
         descr.append(pulse.device_params(dynamical_model.rw_freq)
                      + (trans == '+',))
-    n_ado = getattr(V[0].commutator, 'n_ado', 1)
-    if n_ado != 1:
-        raise NotImplementedError('pulse-driven HEOM propagation is not '
-                                  'available yet')
+    comm = V[0].commutator
+    if not hasattr(comm, 'matrix'):
+        raise NotImplementedError('pulse-driven propagation is available for '
+                                  'Liouville-space and HEOM models')
+    # dense models: (M, M) commutator blocks; HEOM: the same block acts on every
+    # ADO (heom.py:22-58), the device applies it per ADO
     ops = np.array([Vi.commutator.matrix for Vi in V], dtype=complex)
     return descr, ops
 

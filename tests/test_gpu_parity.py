@@ -418,3 +418,25 @@ def test_expm_propagator_matches_reference(fmo_model, golden):
     with pytest.raises(ValueError):
         qb.integrate(eom, np.eye(49, dtype=complex)[0], np.array([0., 1., 5.]),
                      method_name='expm')
+
+
+# ------------------------------------------------ pulse-driven HEOM (grid-resident DOPRI5)
+def test_heom_pump_matches_oracle():
+    ham = systems.dimer()
+    kw = dict(hilbert_subspace='gef', unit_convert=CM_FS, level_cutoff=3, K=1)
+    hm = qb.HEOMModel(ham, **kw)
+    ho = oracle.OracleHEOM(ham, **kw)
+    pump = qb.GaussianPulse(12800, 40, scale=1e-3, freq_convert=CM_FS)
+    t, st = qb.simulate_pump(hm, pump, 'x', time_extra=100, rtol=1e-11, atol=1e-14)
+    to, so = oracle.simulate_with_fields(ho, [pump, pump], '-+', 'xx', time_extra=100,
+                                         **TIGHT)
+    assert np.array_equal(t, to)
+    assert st.shape == so.shape == (len(t), 15 * 9)
+    assert rel_l2(st, so) < TOL
+    # free HEOM evolution with the adaptive integrator agrees with the Taylor default
+    y0 = hm.density_matrix_to_state_vector(np.diag([1., 0]).astype(complex), 'ee')
+    tt = np.arange(0, 200, hm.time_step)
+    a = qb.integrate(hm.equation_of_motion('ee'), y0, tt, method_name='dopri5',
+                     rtol=1e-11, atol=1e-14)
+    b = qb.integrate(hm.equation_of_motion('ee'), y0, tt)
+    assert rel_l2(a, b) < 1e-9
