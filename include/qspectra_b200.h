@@ -78,8 +78,9 @@ typedef struct {
     int32_t n_save;               /* 1 (shared) or n_generators (per member)         */
     int32_t n_pulses;             /* time-dependent terms, <= QSX_MAX_PULSES         */
     qsx_pulse pulses[QSX_MAX_PULSES];
-    const void *pulse_ops_dev;    /* C_p: [n_pulse_sets][n_pulses][D][D] (dense) or
-                                     [n_pulse_sets][n_pulses][M][M] per-ADO (HEOM)   */
+    const void *pulse_ops_dev;    /* C_p: [n_pulse_sets][n_pulses][D][D] commutator blocks (dense),
+                                     [1][n_pulses][M][M] per-ADO commutator blocks (HEOM),
+                                     [1][n_pulses][n][n] Hilbert-space dipole operators (ZOFE) */
     int32_t n_pulse_sets;         /* 1 (shared) or n_generators                      */
     void *out_dev;                /* [n_columns][n_times][saved_dim] complex128      */
     /* results */

@@ -40,10 +40,15 @@ struct ZofeRhs {
     cplx *Sg;               // [S][n][n] shared (row-major per site)
     cplx *bop, *aop, *rho;  // [n][n] shared (row-major)
     cplx *cop;              // [n][n]
+    int n_pulse;
+    const qsx_pulse *pulses;
+    const cplx *Vp;         // [n_pulse][n][n] row-major Hilbert-space dipole operators (global)
 
     template <class Epi>
-    __device__ __forceinline__ void apply(const cplx *x, double, Epi epi) {
+    __device__ __forceinline__ void apply(const cplx *x, double t, Epi epi) {
         const int n = Z.n, S = Z.S, P = Z.P, nn = n * n;
+        cplx gp[QSX_MAX_PULSES];
+        for (int p = 0; p < n_pulse; ++p) gp[p] = pulse_coefficient(pulses[p], t);
         const int tid = threadIdx.x, nthr = blockDim.x;
         const cplx *O = x + nn;
         __syncthreads();        // previous users of the shared operators are done
@@ -121,7 +126,20 @@ struct ZofeRhs {
                     }
                 }
             }
-            epi(xr + n * yc, cscale(Z.u, cadd(d, f)));
+            cplx tot = cscale(Z.u, cadd(d, f));
+            // field terms (-i E_p(t)) [V_p, rho]  (eom.py:87-94; not scaled by unit_convert)
+            for (int p = 0; p < n_pulse; ++p) {
+                const cplx *V = Vp + (size_t)p * nn;
+                cplx c2 = cmake(0, 0);
+                for (int z = 0; z < n; ++z) {
+                    cfma(c2, __ldg(&V[xr * n + z]), rho[z * n + yc]);
+                    cplx vz = __ldg(&V[z * n + yc]), rz = rho[xr * n + z];
+                    c2.x -= rz.x * vz.x - rz.y * vz.y;
+                    c2.y -= rz.x * vz.y + rz.y * vz.x;
+                }
+                cfma(tot, gp[p], c2);
+            }
+            epi(xr + n * yc, tot);
         }
         // O' elements; consecutive threads = consecutive pseudomodes (coalesced)
         const long long no = (long long)P * S * nn;
@@ -147,7 +165,20 @@ struct ZofeRhs {
                 acc.x -= oz.x * bz.x - oz.y * bz.y;
                 acc.y -= oz.x * bz.y + oz.y * bz.x;
             }
-            epi((int)(nn + i), cscale(Z.u, acc));
+            cplx tot = cscale(Z.u, acc);
+            for (int p = 0; p < n_pulse; ++p) {
+                // the dipole operator multiplies every auxiliary operator too (zofe.py:24-35)
+                const cplx *V = Vp + (size_t)p * nn;
+                cplx c2 = cmake(0, 0);
+                for (int z = 0; z < n; ++z) {
+                    cfma(c2, __ldg(&V[xr * n + z]), Ops[st * (z + n * yc)]);
+                    cplx vz = __ldg(&V[z * n + yc]), oz = Ops[st * (xr + n * z)];
+                    c2.x -= oz.x * vz.x - oz.y * vz.y;
+                    c2.y -= oz.x * vz.y + oz.y * vz.x;
+                }
+                cfma(tot, gp[p], c2);
+            }
+            epi((int)(nn + i), tot);
         }
     }
 };
@@ -188,6 +219,9 @@ struct ZofeKernelArgs {
     cplx *out;
     long long saved_dim;
     unsigned long long *stats;
+    int n_pulse;
+    qsx_pulse pulses[QSX_MAX_PULSES];
+    const cplx *Vp;
 };
 
 __device__ __forceinline__ void zofe_rhs_setup(const ZofeDev &Z, unsigned char *smem, int member, ZofeRhs &r,
@@ -202,6 +236,7 @@ __device__ __forceinline__ void zofe_rhs_setup(const ZofeDev &Z, unsigned char *
     r.aop = p; p += nn;
     r.rho = p; p += nn;
     r.cop = p;
+    r.n_pulse = 0; r.pulses = nullptr; r.Vp = nullptr;
 }
 
 __global__ void __launch_bounds__(256) zofe_propagate_kernel(ZofeKernelArgs a) {
@@ -210,6 +245,7 @@ __global__ void __launch_bounds__(256) zofe_propagate_kernel(ZofeKernelArgs a) {
     ZofeRhs rhs;
     double *scratch;
     zofe_rhs_setup(a.Z, smem_raw, a.member_of ? a.member_of[col] : 0, rhs, scratch);
+    rhs.n_pulse = a.n_pulse; rhs.pulses = a.pulses; rhs.Vp = a.Vp;
     cplx *vec = a.work + (size_t)col * a.n_vec * a.Z.dim;
     for (long long i = threadIdx.x; i < a.Z.dim; i += blockDim.x) vec[i] = a.y0[(size_t)col * a.Z.dim + i];
     __syncthreads();
@@ -317,7 +353,9 @@ extern "C" int qsx_zofe_propagate(qsx_zofe_t h, qsx_propagate_args *args, void *
                 "qsx_zofe_propagate: empty batch or missing buffers");
     QSX_REQUIRE(args->method == QSX_METHOD_RK4 || args->method == QSX_METHOD_DOPRI5,
                 "the ZOFE equation is nonlinear: use the RK4 or DOPRI5 integrator");
-    QSX_REQUIRE(args->n_pulses == 0, "pulse-driven ZOFE propagation is not available in this build");
+    QSX_REQUIRE(args->n_pulses >= 0 && args->n_pulses <= QSX_MAX_PULSES, "too many pulses");
+    QSX_REQUIRE(args->n_pulses == 0 || (args->pulse_ops_dev && args->n_pulse_sets == 1),
+                "ZOFE pulse operators must be one shared set of [n_pulses][n][n] Hilbert-space matrices");
     for (int i = 1; i < nt; ++i)
         QSX_REQUIRE(args->t_host[i] >= args->t_host[i - 1], "output times must be non-decreasing");
     QSX_REQUIRE(args->t_host[0] >= args->t0, "first output time precedes t0");
@@ -352,6 +390,9 @@ extern "C" int qsx_zofe_propagate(qsx_zofe_t h, qsx_propagate_args *args, void *
     }
     a.out = (cplx *)args->out_dev;
     a.stats = stats.p;
+    a.n_pulse = args->n_pulses;
+    for (int p = 0; p < QSX_MAX_PULSES; ++p) a.pulses[p] = args->pulses[p];
+    a.Vp = (const cplx *)args->pulse_ops_dev;
     size_t smem = zofe_smem(d);
     QSX_CUDA(cudaFuncSetAttribute(zofe_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;

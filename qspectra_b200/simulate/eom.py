@@ -90,8 +90,9 @@ def _field_terms(dynamical_model, pulses, geometry, polarization,
                      + (trans == '+',))
     comm = V[0].commutator
     if not hasattr(comm, 'matrix'):
-        raise NotImplementedError('pulse-driven propagation is available for '
-                                  'Liouville-space and HEOM models')
+        # ZOFE: the Hilbert-space dipole operator multiplies rho and every
+        # auxiliary operator from the left / right (zofe.py:24-35)
+        return descr, np.array([Vi.operator for Vi in V], dtype=complex)
     # dense models: (M, M) commutator blocks; HEOM: the same block acts on every
     # ADO (heom.py:22-58), the device applies it per ADO
     ops = np.array([Vi.commutator.matrix for Vi in V], dtype=complex)

@@ -440,3 +440,32 @@ def test_heom_pump_matches_oracle():
                      rtol=1e-11, atol=1e-14)
     b = qb.integrate(hm.equation_of_motion('ee'), y0, tt)
     assert rel_l2(a, b) < 1e-9
+
+
+def test_zofe_pump_matches_oracle():
+    """pulse-driven ZOFE: the dipole operator acts on rho and on every auxiliary
+    operator; checked against a host restatement of the reference closure
+    (eom.py:87-94 with ZOFESpaceOperator, zofe.py:8-41)."""
+    ham = systems.dimer(bath='pseudomode')
+    zm = qb.ZOFEModel(ham, hilbert_subspace='ge', unit_convert=CM_FS)
+    zo = oracle.OracleZOFE(ham, hilbert_subspace='ge', unit_convert=CM_FS)
+    pump = qb.GaussianPulse(12800, 40, scale=1e-3, freq_convert=CM_FS)
+    t, st = qb.simulate_pump(zm, pump, 'x', time_extra=60, rtol=1e-11, atol=1e-14)
+    eom = zo.equation_of_motion('gg,ge,eg,ee')
+    Vm = zm.hamiltonian.dipole_operator('ge', 'x', '-')
+    Vp = zm.hamiltonian.dipole_operator('ge', 'x', '+')
+    n, shape = 3, zm.oop_shape
+
+    def comm(V, y):
+        rho = y[:n * n].reshape((n, n), order='F')
+        O = y[n * n:].reshape(shape, order='F')
+        drho = V @ rho - rho @ V
+        dO = np.einsum('cd,psde->psce', V, O) - O @ V
+        return np.append(drho.reshape(-1, order='F'), dO.reshape(-1, order='F'))
+
+    def rhs(tt, y):
+        E = pump(tt, zm.rw_freq)
+        return eom(tt, y) + (-1j * E) * comm(Vm, y) + (-1j * np.conj(E)) * comm(Vp, y)
+
+    ref = oracle.integrate(rhs, zm.thermal_state('gg,ge,eg,ee'), t, t0=pump.t_init, **TIGHT)
+    assert rel_l2(st, ref) < TOL
