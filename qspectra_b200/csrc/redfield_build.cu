@@ -14,15 +14,26 @@
 //   L        = -i (E_a - E_b) d_ac d_bd - R (.) secular mask    (redfield.py:71-98)
 //   L_site   = W^+ L W, W = kron(U^+, U^+)                      (redfield.py:99-100)
 // and writes unit_convert * L[idx, idx] for the requested Liouville subspace.
+//
+// Only the part of the tensor the subspace needs is built: with A the ket
+// states and B the bra states the subspace index touches, T[a][b][c][d] is
+// formed for a, c in A and b, d in B only, over the Hilbert space A u B --
+// provided H couples neither set to its complement, so that the eigenvectors
+// (and with them K_n, Gs and the site-basis transform) stay inside the sets.
+// For 'fe' of FMO (28 x 7 states) that is 38 416 tensor entries instead of
+// 36^4 = 1.7 M.  The host checks the block structure and falls back to the
+// full range when it does not hold.
 #include "common.cuh"
 #include <algorithm>
 
 struct RedfieldBuildArgs {
     int m, N, nb, M;
+    int na, nbb;            // ket / bra state counts of the tensor block
+    const int *ra, *rb;     // [na], [nbb] their positions in the N-state space
+    const int *oa, *ob;     // [M] ket / bra slot (into ra / rb) of each subspace element
     const double *E;        // [m][N]
     const cplx *U;          // [m][N][N] row-major, U[x][a] = <x|a>
     const double *v;        // [nb][N] coupling diagonals
-    const int *idx;         // [M] flat column-major positions
     qsx_bath bath;
     int secular, eigen_basis;
     double unit_convert;
@@ -142,7 +153,8 @@ __device__ cplx warp_corr(const qsx_bath &b, double x) {
 __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, nb = a.nb, N2 = N * N;
-    const size_t N4 = (size_t)N2 * N2;
+    const int na = a.na, nbb = a.nbb;
+    const size_t N4 = (size_t)na * nbb * na * nbb;       // entries of the tensor block
     cplx *Us = reinterpret_cast<cplx *>(smem_raw);       // [N][N]
     cplx *Cs = Us + N2;                                  // [N][N]
     cplx *Gs = Cs + N2;                                  // [N][N]
@@ -211,9 +223,11 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
             Gs[p] = acc;
         }
         __syncthreads();
-        // eigenbasis generator as a 4-index tensor T[a][b][c][d] = L[a + N b, c + N d]
+        // eigenbasis generator as a 4-index tensor T[a][b][c][d] = L[a + N b, c + N d],
+        // a, c over the ket states ra[], b, d over the bra states rb[]
         for (size_t p = tid; p < N4; p += nthr) {
-            int dd = (int)(p % N), cc = (int)((p / N) % N), bb = (int)((p / N2) % N), aa = (int)(p / ((size_t)N2 * N));
+            int dd = a.rb[p % nbb], cc = a.ra[(p / nbb) % na];
+            int bb = a.rb[(p / ((size_t)nbb * na)) % nbb], aa = a.ra[p / ((size_t)nbb * na * nbb)];
             cplx g1 = cmake(0, 0), g2 = cmake(0, 0);       // G[c,a,b,d], G[d,b,a,c]
             for (int n = 0; n < nb; ++n) {
                 cfma(g1, Ks[n * N2 + cc * N + aa], Ks[n * N2 + bb * N + dd]);
@@ -234,13 +248,17 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
         if (!a.eigen_basis) {
             // L_site[i,j,k,l] = sum U[i,p] U[j,q] T[p,q,r,s] conj(U[k,r]) conj(U[l,s])
             for (int pos = 0; pos < 4; ++pos) {
-                size_t stride = pos == 0 ? (size_t)N2 * N : pos == 1 ? (size_t)N2 : pos == 2 ? (size_t)N : 1;
+                size_t stride = pos == 0 ? (size_t)nbb * na * nbb : pos == 1 ? (size_t)na * nbb
+                              : pos == 2 ? (size_t)nbb : 1;
+                const int n = (pos & 1) ? nbb : na;
+                const int *states = (pos & 1) ? a.rb : a.ra;
                 for (size_t p = tid; p < N4; p += nthr) {
-                    int i = (int)((p / stride) % N);
+                    int i = (int)((p / stride) % n);
                     size_t base = p - (size_t)i * stride;
+                    const cplx *urow = Us + states[i] * N;
                     cplx acc = cmake(0, 0);
-                    for (int q = 0; q < N; ++q) {
-                        cplx u = Us[i * N + q];
+                    for (int q = 0; q < n; ++q) {
+                        cplx u = urow[states[q]];
                         if (pos >= 2) u.y = -u.y;
                         cfma(acc, u, src[base + (size_t)q * stride]);
                     }
@@ -254,9 +272,7 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
         cplx *Lout = a.L + (size_t)mem * a.M * a.M;
         for (int p = tid; p < a.M * a.M; p += nthr) {
             int r = p / a.M, c = p % a.M;
-            int fr = a.idx[r], fc = a.idx[c];
-            int i = fr % N, j = fr / N, k = fc % N, l = fc / N;
-            cplx val = src[(((size_t)i * N + j) * N + k) * N + l];
+            cplx val = src[(((size_t)a.oa[r] * nbb + a.ob[r]) * na + a.oa[c]) * nbb + a.ob[c]];
             Lout[a.transposed_out ? c * a.M + r : p] = cscale(a.unit_convert, val);
         }
     }
@@ -277,27 +293,72 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     QSX_REQUIRE(bath->kind == QSX_BATH_DEBYE_COMPLEX || bath->kind == QSX_BATH_DEBYE_REAL,
                 "qsx_redfield_build: unknown bath kind %d", bath->kind);
     QSX_REQUIRE(N <= 64, "qsx_redfield_build: Hilbert dimension %d too large", N);
-    std::vector<int> idx(M);
+    const int Nfull = N;
+    std::vector<char> in_a(Nfull, 0), in_b(Nfull, 0);
     for (int i = 0; i < M; ++i) {
         QSX_REQUIRE(subspace_index_host[i] >= 0 && subspace_index_host[i] < (int64_t)N * N,
                     "subspace index out of range");
-        idx[i] = (int)subspace_index_host[i];
+        in_a[subspace_index_host[i] % Nfull] = 1;      // ket state (column-major vec)
+        in_b[subspace_index_host[i] / Nfull] = 1;      // bra state
     }
-    DevBuf<int> d_idx;
+    // the tensor block may be restricted to the ket set A and bra set B only when H
+    // does not couple a set to its complement; otherwise widen to A u B, then to all
+    auto closed = [&](const std::vector<char> &set) {
+        if (!jacobi) return false;                     // eigenvectors supplied: structure unknown
+        for (int x = 0; x < Nfull; ++x)
+            for (int y = 0; y < Nfull; ++y)
+                if (set[x] && !set[y] &&
+                    (H0_host[(size_t)x * Nfull + y] != 0.0 || H0_host[(size_t)y * Nfull + x] != 0.0))
+                    return false;
+        return true;
+    };
+    if (!closed(in_a) || !closed(in_b)) {
+        for (int x = 0; x < Nfull; ++x) in_a[x] = in_b[x] = (char)(in_a[x] | in_b[x]);
+        if (!closed(in_a)) std::fill(in_a.begin(), in_a.end(), (char)1), in_b = in_a;
+    }
+    // Hilbert space of the build: S = A u B, compressed
+    std::vector<int> slot(Nfull, -1), states, ra, rb;
+    for (int x = 0; x < Nfull; ++x)
+        if (in_a[x] || in_b[x]) { slot[x] = (int)states.size(); states.push_back(x); }
+    std::vector<int> slot_a(Nfull, -1), slot_b(Nfull, -1);
+    for (int x = 0; x < Nfull; ++x) {
+        if (in_a[x]) { slot_a[x] = (int)ra.size(); ra.push_back(slot[x]); }
+        if (in_b[x]) { slot_b[x] = (int)rb.size(); rb.push_back(slot[x]); }
+    }
+    std::vector<int> oa(M), ob(M);
+    for (int i = 0; i < M; ++i) {
+        oa[i] = slot_a[subspace_index_host[i] % Nfull];
+        ob[i] = slot_b[subspace_index_host[i] / Nfull];
+    }
+    N = (int)states.size();
+    const int na = (int)ra.size(), nbb = (int)rb.size();
+    std::vector<double> v_s((size_t)n_baths * N), H0_s, quanta_s;
+    for (int j = 0; j < n_baths; ++j)
+        for (int x = 0; x < N; ++x) v_s[(size_t)j * N + x] = coupling_diag_host[(size_t)j * Nfull + states[x]];
+    DevBuf<int> d_ra, d_rb, d_oa, d_ob;
     DevBuf<double> d_v, d_H0, d_quanta;
     DevBuf<cplx> scratch;
     if (jacobi) {
-        QSX_CUDA(d_H0.upload(H0_host, (size_t)N * N, stream));
-        QSX_CUDA(d_quanta.upload(quanta_host, (size_t)N, stream));
+        H0_s.resize((size_t)N * N);
+        quanta_s.resize(N);
+        for (int x = 0; x < N; ++x) {
+            quanta_s[x] = quanta_host[states[x]];
+            for (int y = 0; y < N; ++y) H0_s[(size_t)x * N + y] = H0_host[(size_t)states[x] * Nfull + states[y]];
+        }
+        QSX_CUDA(d_H0.upload(H0_s, stream));
+        QSX_CUDA(d_quanta.upload(quanta_s, stream));
     }
-    QSX_CUDA(d_idx.upload(idx, stream));
-    QSX_CUDA(d_v.upload(coupling_diag_host, (size_t)n_baths * N, stream));
+    QSX_CUDA(d_ra.upload(ra, stream));
+    QSX_CUDA(d_rb.upload(rb, stream));
+    QSX_CUDA(d_oa.upload(oa, stream));
+    QSX_CUDA(d_ob.upload(ob, stream));
+    QSX_CUDA(d_v.upload(v_s, stream));
 
     int dev = 0, smem_limit = 0, sms = 0;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t N2 = (size_t)N * N, N4 = N2 * N2;
+    const size_t N2 = (size_t)N * N, N4 = (size_t)na * nbb * na * nbb;
     size_t base = (3 * N2 + (size_t)n_baths * N2) * sizeof(cplx) + (size_t)((N + 1) & ~1) * sizeof(double);
     size_t with_t = base + 2 * N4 * sizeof(cplx);
     QSX_REQUIRE(base <= (size_t)smem_limit, "qsx_redfield_build: too many baths/states for shared memory");
@@ -312,7 +373,8 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     }
     RedfieldBuildArgs a;
     a.m = n_members; a.N = N; a.nb = n_baths; a.M = M;
-    a.E = (const double *)E_dev; a.U = (const cplx *)U_dev; a.v = d_v.p; a.idx = d_idx.p;
+    a.E = (const double *)E_dev; a.U = (const cplx *)U_dev; a.v = d_v.p;
+    a.na = na; a.nbb = nbb; a.ra = d_ra.p; a.rb = d_rb.p; a.oa = d_oa.p; a.ob = d_ob.p;
     a.bath = *bath;
     if (a.bath.matsubara_cutoff <= 0) a.bath.matsubara_cutoff = 1000;
     a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;

@@ -129,7 +129,22 @@ def third_order_response_sharded(dynamical_model, coherence_time_max,
                                  **integrate_kwargs):
     """``third_order_response`` (reference response.py:340-427) for a disorder
     ensemble sharded over the GPUs of the current torch.distributed job."""
-    from .simulate.response import third_order_response
+    from .simulate.response import (third_order_response, _batchable,
+                                    _third_order_response_batched)
+    if _batchable(dynamical_model):
+        # each rank propagates its block of members as one device batch
+        import torch
+        rank, size = world()
+        first, count = shard_members(ensemble_size, rank, size)
+        ticks, part = _third_order_response_batched(
+            dynamical_model, coherence_time_max, population_time_max,
+            population_times, geometry, polarization, include_signal,
+            max(count, 1), ensemble_random_orientations, first, False,
+            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+        if count == 0:
+            part = torch.zeros_like(part)
+        total = reduce_sum(part, dst)
+        return ticks, (total / ensemble_size).cpu().numpy()
 
     def one(member):
         return third_order_response(

@@ -173,6 +173,86 @@ def _third_order_response(dynamical_model, coherence_time_max,
     return (t1, t2, t3), total_signal
 
 
+@optional_4th_order_isotropic_average
+def _third_order_response_batched(dynamical_model, coherence_time_max,
+                                  population_time_max, population_times,
+                                  geometry, polarization, include_signal,
+                                  ensemble_size, random_orientations,
+                                  member_offset, normalize, **integrate_kwargs):
+    """Disorder-ensemble third-order response with ALL members on the device at
+    once (dense-generator models): per pathway three batched propagations --
+    t1: one column per member, t2: n_t1 columns per member under that member's
+    generator, t3: one Heisenberg column per member -- and one contraction
+    sum_m einsum('ci,abi') on the device.  The reference runs
+    ensemble_size x (1 + n_t1 + 1) serial ZVODE solves per pathway
+    (decorators.py:55-60, utils.py:103-109)."""
+    from .. import _capi
+    torch = _capi.torch_cuda()
+    model = dynamical_model
+    t1 = np.arange(0, coherence_time_max, model.time_step)
+    t2 = (np.arange(0, population_time_max, model.time_step)
+          if population_times is None
+          else np.asarray(population_times, dtype=float))
+    t3 = t1.copy()
+    opts = {k: integrate_kwargs[k] for k in ('rtol', 'atol', 'rk4_substeps')
+            if k in integrate_kwargs}
+    method = integrate_kwargs.get('method_name', 'zvode')
+    paths = _parse_pathways(THIRD_ORDER_PATHWAYS[geometry], include_signal)
+    total = torch.zeros((len(t1), len(t2), len(t3)), dtype=torch.complex128,
+                        device='cuda')
+    # bound the (members x t1 x t2 x M3) intermediate to ~2 GB per chunk
+    n_big = max(len(model.liouville_subspace_index(p.split('->')[3])) for p in paths)
+    chunk = max(1, int(2e9 // (len(t1) * len(t2) * n_big * 16)))
+    rho0 = model.thermal_state('gg')
+    for lo in range(0, ensemble_size, chunk):
+        E = min(chunk, ensemble_size - lo)
+        first = member_offset + lo
+        gens = np.arange(E)
+        dip = ([model.sample(first + n, True) for n in range(E)]
+               if random_orientations else [model])
+        eoms = {}
+
+        def eom_for(subspace, heisenberg=False):
+            # pathways share stage subspaces: build each batch of generators once
+            key = (subspace, heisenberg)
+            if key not in eoms:
+                eoms[key] = model.ensemble_eom(E, random_orientations, subspace,
+                                               heisenberg_picture=heisenberg,
+                                               member0=first)
+            return eoms[key]
+
+        for path in paths:
+            ss = path.split('->')
+            V = [[m.dipole_operator('{}->{}'.format(a, b), polar, trans)
+                  for a, b, polar, trans in zip(ss[:-1], ss[1:], polarization,
+                                                geometry + '-')] for m in dip]
+            stack = lambda i, attr: (getattr(V[0][i], attr).matrix if len(V) == 1 else
+                                     np.array([getattr(v[i], attr).matrix for v in V]))
+            eom_a, eom_b, eom_c = eom_for(ss[1]), eom_for(ss[2]), eom_for(ss[3], True)
+            y0 = np.array([v[0].commutator(rho0) for v in V])
+            y0 = np.broadcast_to(y0, (E,) + y0.shape[1:]) if len(V) == 1 else y0
+            out1 = eom_a.propagate(y0, t1, method=method, save=stack(1, 'commutator'),
+                                   generators=gens, return_device=True, **opts)
+            out2 = eom_b.propagate(out1.reshape(E * len(t1), -1), t2, t0=0,
+                                   method=method, save=stack(2, 'commutator'),
+                                   generators=np.repeat(gens, len(t1)),
+                                   return_device=True, **opts)
+            bra = np.array([v[3].bra_vector for v in V])
+            bra = np.broadcast_to(bra, (E,) + bra.shape[1:]) if len(V) == 1 else bra
+            out3 = eom_c.propagate(bra, t3, method=method, generators=gens,
+                                   return_device=True, **opts)
+            total += torch.einsum('eabi,eci->abc',
+                                  out2.reshape(E, len(t1), len(t2), -1), out3)
+    if normalize:
+        total = total / ensemble_size
+    return (t1, t2, t3), total
+
+
+def _batchable(dynamical_model):
+    from ..dynamics.liouville_space import LiouvilleSpaceModel
+    return isinstance(dynamical_model, LiouvilleSpaceModel)
+
+
 def third_order_response(dynamical_model, coherence_time_max,
                          population_time_max=None, population_times=None,
                          geometry='-++', polarization='xxxx',
@@ -180,7 +260,16 @@ def third_order_response(dynamical_model, coherence_time_max,
                          ensemble_random_orientations=False,
                          exact_isotropic_average=False, **integrate_kwargs):
     """Third-order response ((t1, t2, t3), signal[t1, t2, t3]) in the rotating
-    wave approximation, summed over the selected Liouville pathways."""
+    wave approximation, summed over the selected Liouville pathways.  Disorder
+    ensembles of dense-generator models are propagated as one device batch."""
+    if ensemble_size is not None and _batchable(dynamical_model):
+        ticks, total = _third_order_response_batched(
+            dynamical_model, coherence_time_max, population_time_max,
+            population_times, geometry, polarization, include_signal,
+            ensemble_size, ensemble_random_orientations,
+            integrate_kwargs.pop('member_offset', 0), True,
+            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+        return ticks, total.cpu().numpy()
     return _third_order_response(
         dynamical_model, coherence_time_max, population_time_max,
         population_times, geometry, polarization, include_signal,
