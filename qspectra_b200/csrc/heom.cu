@@ -56,6 +56,8 @@ struct HeomDev {
     const uint8_t *occ;       // [n_tiles][bins][32]
     const int *off_up, *off_dn;   // [n_tiles][bins][32] element offsets of the neighbour (tile*M*32 + lane), -1 = absent
     const int *e_off, *e_stride;  // [M] position of element e inside a tile: e_off[e] + lane * e_stride[e]
+    int heis;                 // 1: Heisenberg picture (generator transposed)
+    long long top_tile;       // first tile made of top-level ADOs only (no up-neighbours)
     int layout;               // 0: tile-SoA [e][32]; 1: pair-packed [rho_ab, rho_ba] (TileEEP)
     int n_pulse, Rp;          // time-dependent terms: per-ADO operator rows in ELL form
     const int *pcol;          // [n_pulse][M][Rp] (-1 padded)
@@ -90,6 +92,8 @@ struct TileSmem {
     uint8_t *t_n;        // [bins][32]
     double *t_shift;     // [32]
     cplx *HR, *HC;       // [nr][nr], [nc][nc] of the current member
+    double *hR, *hC;     // imaginary parts of the above (real Hamiltonian, TileLean)
+    cplx *tD;            // [K1][Lc] ready-multiplied down-link coefficients (TileLean)
     double *dterm;       // [M]
     int *lbin;           // [M][Lk]
     cplx *gu, *gd;       // [M][Lk]
@@ -801,6 +805,217 @@ struct TileEE {
         const double wscale = cur.sh[TL + lane];
 #pragma unroll
         for (int b = 0; b < NS; ++b) post(gbase + (long long)b * NS * TL, acc[b], own[b], pv[b], wscale);
+    }
+};
+
+
+// Lean electronic-block tile: the same ownership as TileEE (warp w = row w of the 32
+// ADO matrices of a tile) rebuilt for occupancy instead of per-thread memory
+// parallelism -- <= 96 registers, three CTAs (21 warps) per SM, no batch of 56
+// gathers held in registers.  What makes the instruction stream short:
+//   * Schroedinger picture, real H: up-links carry the purely imaginary coefficient
+//     -+i u s_up(n) (2 DFMA), down-links -i u c_k s_dn(n) and its conjugate (4 DFMA);
+//     both come ready-multiplied from two small shared tables indexed by the occupation
+//     number, so a link costs no coefficient arithmetic;
+//   * a diagonal element (a == b) sees the row-site and the column-site link of the
+//     same neighbour: the up terms cancel and the down terms add to 2 Re(.), so it
+//     gathers 2 instead of 8 neighbours;
+//   * tiles of the top hierarchy level (two thirds of all tiles at depth 8) have no
+//     up-neighbours: a CTA-uniform branch takes a body without those 28 gathers;
+//   * the integrator's own-value and accumulator operands are re-read (shared memory /
+//     streaming load) in the epilogue instead of living in registers across the tile.
+template <int NS, int K1, int MINB>
+struct TileLean {
+    static constexpr int THREADS = 32 * NS;
+    static constexpr int MIN_BLOCKS = MINB;
+    static constexpr int UNITS = 1;
+    static constexpr int M = NS * NS;
+    static constexpr int BINS = NS * K1;
+
+    static __host__ __device__ size_t buf_bytes() {
+        return al16((size_t)M * TL * sizeof(cplx)) + 2 * al16((size_t)BINS * TL * sizeof(int)) +
+               al16((size_t)BINS * TL) + al16((size_t)2 * TL * sizeof(double));
+    }
+    static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
+        return 2 * al16((size_t)NS * NS * sizeof(double)) + al16((size_t)M * sizeof(double)) +
+               al16((size_t)K1 * H.Lc * sizeof(double)) + al16((size_t)K1 * H.Lc * sizeof(cplx));
+    }
+    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + 2 * buf_bytes(); }
+
+    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
+        size_t off = 0;
+        s.hR = reinterpret_cast<double *>(base + off); off += al16((size_t)NS * NS * sizeof(double));
+        s.hC = reinterpret_cast<double *>(base + off); off += al16((size_t)NS * NS * sizeof(double));
+        s.dterm = reinterpret_cast<double *>(base + off); off += al16((size_t)M * sizeof(double));
+        s.su = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
+        s.tD = reinterpret_cast<cplx *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(cplx));
+        s.os = reinterpret_cast<cplx *>(base + off);       // start of the two tile buffers
+        for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
+        for (int i = threadIdx.x; i < K1 * H.Lc; i += blockDim.x) {
+            const int k = i / H.Lc;
+            s.su[i] = -H.GuR[k].y * H.su[i];               // u s_up(n):  row coefficient -i t, column +i t
+            s.tD[i] = cscale(H.sd[i], H.GdR[k]);           // -i u c_k s_dn(n); the column-site one is its conjugate
+        }
+        s.cur_member = -1;
+        s.loaded = nullptr;
+        s.buf = 0;
+        __syncthreads();
+    }
+
+    typedef typename TileEE<NS, K1, 1, true, true>::Buf Buf;
+    static __device__ __forceinline__ Buf buffer(const TileSmem &s, int which) {
+        return TileEE<NS, K1, 1, true, true>::buffer(s, which);
+    }
+    static __device__ __forceinline__ void issue(const HeomDev &H, const Buf &b, const cplx *tile_data, long long tile) {
+        TileEE<NS, K1, 1, true, true>::issue(H, b, tile_data, tile);
+    }
+
+    // Hs_R rho for source rows c in [c0, c1): (i h) z = h (-z.y, z.x)
+    template <int C0, int C1>
+    static __device__ __forceinline__ void left_product(const TileSmem &s, const cplx *ys, int w, cplx (&acc)[NS]) {
+#pragma unroll
+        for (int c = C0; c < C1; ++c) {
+            const double h = s.hR[w * NS + c];
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                const cplx z = ys[(c + NS * b) * TL];
+                acc[b].x = fma(-h, z.y, acc[b].x);
+                acc[b].y = fma(h, z.x, acc[b].y);
+            }
+        }
+    }
+
+    // The 2 K1 gather batches of a row (row-site k = 0.., column-site k = 0..) are each
+    // issued as one group of up to 2 NS independent loads and consumed after a slice of
+    // the commutator arithmetic: four round trips per tile instead of one per link.
+    template <bool UP, class Pre, class Post>
+    static __device__ __forceinline__ void body(const HeomDev &H, const TileSmem &s, const Buf &cur,
+                                                const cplx *__restrict__ x, long long tile, Pre pre, Post post) {
+        static_assert(K1 == 2, "phase split below is written for K = 1 (two exponentials per site)");
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // w = row a
+        const cplx *ys = cur.ys + lane;
+        const cplx *xw = x + (size_t)w * TL;
+        cplx acc[NS];
+        {
+            // diagonal terms and - rho Hs_C from the own row (A_C stored transposed)
+            cplx own[NS];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) own[c] = ys[(w + NS * c) * TL];
+            const double shift = cur.sh[lane];
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                const double dg = shift + s.dterm[w + NS * b];
+                acc[b] = cmake(-dg * own[b].x, -dg * own[b].y);
+#pragma unroll
+                for (int c = 0; c < NS; ++c) {
+                    const double h = s.hC[b * NS + c];
+                    acc[b].x = fma(h, own[c].y, acc[b].x);
+                    acc[b].y = fma(-h, own[c].x, acc[b].y);
+                }
+            }
+        }
+        cplx gu[UP ? NS : 1], gd[NS];
+        // ---- row-site links (site w): the whole row shares neighbour and coefficient
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+            const int bin = w * K1 + k;
+            const int njk = cur.occ[bin * TL + lane];
+            const int od = cur.o_dn[bin * TL + lane];
+            const int ou = UP ? cur.o_up[bin * TL + lane] : -1;
+            const cplx *pd = xw + (od >= 0 ? od : 0), *pu = xw + (ou >= 0 ? ou : 0);
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                if (UP) { gu[b] = cmake(0, 0); if (ou >= 0 && b != w) gu[b] = __ldcg(pu + b * NS * TL); }
+                gd[b] = cmake(0, 0);
+                if (od >= 0) gd[b] = __ldcg(pd + b * NS * TL);
+            }
+            if (k == 0) left_product<0, 2>(s, ys, w, acc); else left_product<2, 4>(s, ys, w, acc);
+            const cplx cd = s.tD[k * H.Lc + njk];
+            if (UP) {
+                const double tu = s.su[k * H.Lc + njk];
+#pragma unroll
+                for (int b = 0; b < NS; ++b) {                 // (-i tu) v
+                    acc[b].x = fma(tu, gu[b].y, acc[b].x);
+                    acc[b].y = fma(-tu, gu[b].x, acc[b].y);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                // off the diagonal cd v; on it cd v + conj(cd) v = 2 Re(cd) v
+                const double gr = b == w ? 2.0 * cd.x : cd.x, gi = b == w ? 0.0 : cd.y;
+                acc[b].x = fma(gr, gd[b].x, acc[b].x);
+                acc[b].x = fma(-gi, gd[b].y, acc[b].x);
+                acc[b].y = fma(gr, gd[b].y, acc[b].y);
+                acc[b].y = fma(gi, gd[b].x, acc[b].y);
+            }
+        }
+        // ---- column-site links (site b) of the off-diagonal elements
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                const int bin = b * K1 + k;
+                const int od = cur.o_dn[bin * TL + lane];
+                if (UP) {
+                    const int ou = cur.o_up[bin * TL + lane];
+                    gu[b] = cmake(0, 0);
+                    if (ou >= 0 && b != w) gu[b] = __ldcg(xw + ou + b * NS * TL);
+                }
+                gd[b] = cmake(0, 0);
+                if (od >= 0 && b != w) gd[b] = __ldcg(xw + od + b * NS * TL);
+            }
+            if (k == 0) left_product<4, 6>(s, ys, w, acc); else left_product<6, NS>(s, ys, w, acc);
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                const int njk = cur.occ[(b * K1 + k) * TL + lane];
+                const cplx cd = s.tD[k * H.Lc + njk];
+                if (UP) {
+                    const double tu = s.su[k * H.Lc + njk];
+                    acc[b].x = fma(-tu, gu[b].y, acc[b].x);     // (+i tu) v
+                    acc[b].y = fma(tu, gu[b].x, acc[b].y);
+                }
+                acc[b].x = fma(cd.x, gd[b].x, acc[b].x);        // conj(cd) v
+                acc[b].x = fma(cd.y, gd[b].y, acc[b].x);
+                acc[b].y = fma(cd.x, gd[b].y, acc[b].y);
+                acc[b].y = fma(-cd.y, gd[b].x, acc[b].y);
+            }
+        }
+        const double wscale = cur.sh[TL + lane];
+        const long long gbase = ((long long)tile * M) * TL + lane + (long long)w * TL;   // element (w, 0)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+            const long long i = gbase + (long long)b * NS * TL;
+            post(i, acc[b], ys[(w + NS * b) * TL], pre(i), wscale);
+        }
+    }
+
+    template <class Pre, class Post>
+    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
+                                               long long tile, int member, Pre pre, Post post) {
+        const size_t Dp = (size_t)H.n_tiles * M * TL;
+        const cplx *tile_data = x + (size_t)tile * M * TL;
+        if (s.loaded != tile_data) {        // first tile of a phase: nothing in flight yet
+            s.buf = 0;
+            issue(H, buffer(s, 0), tile_data, tile);
+        }
+        if (member != s.cur_member) {
+            const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
+            for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.hR[i] = hr[i].y; s.hC[i] = hc[i].y; }
+            s.cur_member = member;
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                    // tile visible; every warp is done with the other buffer
+        const Buf cur = buffer(s, s.buf);
+        if (s.next_tile >= 0) {             // prefetch this CTA's next tile into the other buffer
+            const cplx *nd = (x - (size_t)s.cur_col * Dp) + (size_t)s.next_col * Dp + (size_t)s.next_tile * M * TL;
+            issue(H, buffer(s, s.buf ^ 1), nd, s.next_tile);
+            s.loaded = nd;
+            s.buf ^= 1;
+        } else {
+            s.loaded = nullptr;
+        }
+        if (tile >= H.top_tile) body<false>(H, s, cur, x, tile, pre, post);
+        else body<true>(H, s, cur, x, tile, pre, post);
     }
 };
 
@@ -1655,6 +1870,8 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     d.shift = h->shift.p; d.scale = h->scale.p; d.up = h->up.p; d.down = h->down.p; d.occ = h->occ.p;
     d.off_up = h->off_up.p; d.off_dn = h->off_dn.p;
     d.layout = 0;
+    d.heis = cfg->heisenberg ? 1 : 0;
+    d.top_tile = (tb.level_offset[Lc - 1] + TL - 1) / TL;
     d.n_pulse = 0; d.Rp = 0; d.pcol = nullptr; d.pval = nullptr;
     // electronic-block structure: row state a <-> site a, column state b <-> site b
     d.ee = (nr == cfg->n_sites && nc == cfg->n_sites && K1 <= 4 &&
@@ -1775,7 +1992,12 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
         heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);                                     \
     }
     const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
+    // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
+    // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
+    const bool lean_pays = d.n_tiles * (long long)n_columns >= 2048;
     if (d.layout == 1) QSX_APPLY(TileEEP<7 COMMA 2 COMMA true>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'l') QSX_APPLY(TileLean<7 COMMA 2 COMMA 3>)
+    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'm')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2>)
     else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
     else if (ee7 && d.real_h && vsel == 'c') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
     else if (ee7 && d.real_h && vsel == '2') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
@@ -1912,6 +2134,9 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
                         : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;             \
     }
     const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
+    // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
+    // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
+    const bool lean_pays = d.n_tiles * (long long)B >= 2048;
     if (dopri || args->n_pulses > 0) {
         // time-dependent right-hand sides run on the generic tile (any rectangular block)
         QSX_REQUIRE(d.layout == 0, "pulse-driven propagation needs the element-major layout");
@@ -1920,6 +2145,8 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         kernel = dopri ? (const void *)heom_propagate_kernel<QSX_METHOD_DOPRI5, T>
                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
     } else if (d.layout == 1) QSX_PICK(TileEEP<7 COMMA 2 COMMA true>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'l') QSX_PICK(TileLean<7 COMMA 2 COMMA 3>)
+    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'm')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2>)
     else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
     else if (ee7 && d.real_h && vsel == '2') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
     else if (ee7 && d.real_h && vsel == '3') QSX_PICK(TileEE<7 COMMA 2 COMMA 3 COMMA true>)
@@ -1937,6 +2164,9 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_REQUIRE(per_sm > 0, "heom_propagate_kernel does not fit on an SM");
     long long total = d.n_tiles * B;
     int grid = (int)std::min<long long>((total + units - 1) / units, (long long)sms * per_sm);
+    if (const char *gs = getenv("QSX_HEOM_GRID")) grid = std::min(grid, std::max(1, atoi(gs)));   // experiments only
+    if (getenv("QSX_HEOM_VERBOSE"))
+        fprintf(stderr, "heom_propagate: variant '%c' threads %d smem %zu B, %d CTA/SM, grid %d\n", vsel, threads, smem, per_sm, grid);
     void *kargs[] = {&a};
     cudaEvent_t e0, e1;
     QSX_CUDA(cudaEventCreate(&e0));
