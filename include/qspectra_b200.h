@@ -265,6 +265,20 @@ int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const double *H0_ho
 int qsx_reduce_members(const void *in_dev, int32_t n_members, int64_t n,
                        double scale, void *out_dev, void *stream);
 
+/* ------------------------------------------------------------------------
+ * K7: Fourier transform of a response function sampled on t = 0, dt, ..., (n-1) dt,
+ * along the middle axis of x[outer][n][inner] (complex128):
+ *   out[o][k][i] = dt * sum_j x[o][j][i] * exp(sign * 2 pi i * j * (k - n + 1) / (2n - 1)),
+ *   k = 0 .. 2n - 2.
+ * This is exactly what `fourier_transform` (simulate/utils.py:154-219) computes
+ * through zero-padding to a grid symmetric around t = 0 (`_symmetrize`,
+ * utils.py:128-151), ifftshift -> fft -> fftshift and the flip for sign = +1; the
+ * frequency axis (fftfreq, rw_freq shift) stays on the host.  Called twice by
+ * `two_dimensional_spectra` (response.py:430-455).  n <= 4096.
+ * ---------------------------------------------------------------------- */
+int qsx_fourier_transform(const void *x_dev, int64_t outer, int32_t n, int64_t inner,
+                          double dt, int32_t sign, void *out_dev, void *stream);
+
 
 /* ------------------------------------------------------------------------
  * Seeded disorder streams (host only).  Bit-exact replay of

@@ -490,6 +490,25 @@ def reduce_members(batch_dev, scale=1.0):
     return out
 
 
+def fourier_transform(x_dev, axis, dt, sign):
+    """Kernel K7: X[k] = dt sum_j x[j] exp(sign 2 pi i j (k - n + 1) / (2n - 1)) along
+    `axis` of a CUDA tensor (the zero-padded, shifted FFT of simulate/utils.py:154-219
+    for samples at t = 0, dt, ...).  Returns a CUDA tensor with 2n - 1 points on that axis."""
+    torch = _capi.torch_cuda()
+    x_dev = x_dev.contiguous()
+    axis = axis % x_dev.dim()
+    n = x_dev.shape[axis]
+    outer = int(np.prod(x_dev.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(x_dev.shape[axis + 1:], dtype=np.int64))
+    shape = list(x_dev.shape)
+    shape[axis] = 2 * n - 1
+    out = torch.empty(shape, dtype=torch.complex128, device=x_dev.device)
+    _capi.check(_capi.lib().qsx_fourier_transform(
+        x_dev.data_ptr(), outer, n, inner, float(dt), int(sign), out.data_ptr(),
+        _capi.current_stream_ptr()))
+    return out
+
+
 def redfield_build(E, U, coupling_diag, bath_kind, temperature, reorg_energy,
                    cutoff_freq, secular, eigen_basis, unit_convert,
                    subspace_index, matsubara_cutoff=1000, transposed=False):

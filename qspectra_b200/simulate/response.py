@@ -287,15 +287,28 @@ def two_dimensional_spectra(dynamical_model, coherence_time_max,
                             **integrate_kwargs):
     """2D spectrum: Fourier transform of the third-order response over t1
     (sign -1) and t3."""
-    (t1, t2, t3), X = third_order_response(
-        dynamical_model, coherence_time_max, population_time_max,
-        population_times, geometry, polarization, include_signal,
-        ensemble_size, ensemble_random_orientations, exact_isotropic_average,
-        **integrate_kwargs)
+    from .. import _capi
+    if ensemble_size is not None and _batchable(dynamical_model):
+        # the ensemble-summed signal never leaves the device before the transforms
+        (t1, t2, t3), X = _third_order_response_batched(
+            dynamical_model, coherence_time_max, population_time_max,
+            population_times, geometry, polarization, include_signal,
+            ensemble_size, ensemble_random_orientations,
+            integrate_kwargs.pop('member_offset', 0), True,
+            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+    else:
+        (t1, t2, t3), X = third_order_response(
+            dynamical_model, coherence_time_max, population_time_max,
+            population_times, geometry, polarization, include_signal,
+            ensemble_size, ensemble_random_orientations, exact_isotropic_average,
+            **integrate_kwargs)
+        X = _capi.to_device(np.ascontiguousarray(X, dtype=complex))
     rw_freq = dynamical_model.rw_freq
     unit_convert = dynamical_model.unit_convert
     f1, X_ftt = fourier_transform(t1, X, 0, rw_freq=rw_freq, sign=-1,
                                   unit_convert=unit_convert)
     f3, X_ftf = fourier_transform(t3, X_ftt, 2, rw_freq=rw_freq,
                                   unit_convert=unit_convert)
+    if not isinstance(X_ftf, np.ndarray):
+        X_ftf = X_ftf.cpu().numpy()
     return (f1, t2, f3), X_ftf

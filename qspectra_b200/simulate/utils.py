@@ -135,7 +135,11 @@ def fourier_transform(t, x, axis=-1, rw_freq=0, unit_convert=1, sign=1,
     """X(w) = int exp(+-i (w - w0) t) x(t) dt by FFT of the zero-padded,
     symmetrised signal; returns (frequencies, X)."""
     t = np.asarray(t)
-    x = np.asarray(x)
+    on_device = not isinstance(x, np.ndarray) and hasattr(x, 'is_cuda') and x.is_cuda
+    if on_device and _dft_grid(t):
+        return _fourier_transform_device(t, x, axis, rw_freq, unit_convert, sign,
+                                         convention)
+    x = x.cpu().numpy() if on_device else np.asarray(x)
     if t.ndim != 1:
         raise ValueError('t must be one dimensional')
     if t.size != x.shape[axis]:
@@ -157,6 +161,38 @@ def fourier_transform(t, x, axis=-1, rw_freq=0, unit_convert=1, sign=1,
         f = -f[::-1]
         X = np.flip(X, axis=axis)
     return f + rw_freq, X
+
+
+def _dft_grid(t):
+    """True when `_symmetrize` would pad t = 0, dt, ... to exactly 2n - 1 points
+    (n - 1 before, none after) -- the case kernel K7 evaluates directly."""
+    if t.ndim != 1 or t.size < 2 or t.size > 4096 or t[0] != 0:
+        return False
+    if not is_constant(np.diff(t), positive=True):
+        return False
+    dt = t[1] - t[0]
+    T = max(t[-1], -t[0])
+    return (int((T - t[-1]) / dt) + 1 == 1) and (int((T + t[0]) / dt) + 1 == t.size)
+
+
+def _fourier_transform_device(t, x_dev, axis, rw_freq, unit_convert, sign, convention):
+    """`fourier_transform` for a CUDA tensor: same frequencies, transform by the
+    device kernel (engine.fourier_transform); the result stays on the device."""
+    from .. import engine
+    if t.size != x_dev.shape[axis]:
+        raise ValueError('t must have the same length as the shape of x along '
+                         'the given axis')
+    if sign not in (-1, +1):
+        raise ValueError('sign must be +1 or -1')
+    if convention == 'angular':
+        unit_convert = unit_convert / (2 * np.pi)
+    elif convention != 'linear':
+        raise ValueError("convention must be 'angular' or 'linear'")
+    dt = t[1] - t[0]
+    f = np.fft.fftshift(np.fft.fftfreq(2 * t.size - 1, dt * unit_convert))
+    if sign == 1:
+        f = -f[::-1]
+    return f + rw_freq, engine.fourier_transform(x_dev, axis, dt, sign)
 
 
 def bound_signal(ticks, signal, bounds, axis=0):

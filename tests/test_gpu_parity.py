@@ -518,3 +518,46 @@ def test_batched_third_order_ensemble(golden):
     singles = [qb.third_order_response(m, 200, population_times=tn)[1]
                for m in dred.sample_ensemble(2)]
     assert rel_l2(B, np.mean(singles, axis=0)) < 1e-9
+
+
+# ------------------------------------------------- device Fourier transform (K7)
+@pytest.mark.parametrize('shape,axis,sign', [((103,), 0, 1), ((37, 5, 41), 0, -1),
+                                             ((37, 5, 41), 2, 1), ((6, 130, 3), 1, -1),
+                                             ((1028,), -1, 1)])
+def test_device_fourier_transform_matches_host(shape, axis, sign):
+    """the device transform against the host restatement of the reference's
+    symmetrise-pad + shifted FFT (simulate/utils.py:128-219)"""
+    import torch
+    rng = np.random.RandomState(5)
+    x = rng.randn(*shape) + 1j * rng.randn(*shape)
+    t = 4.0 * np.arange(shape[axis])
+    f_host, X_host = qb.fourier_transform(t, x, axis, rw_freq=12345.0, unit_convert=CM_FS,
+                                          sign=sign)
+    f_dev, X_dev = qb.fourier_transform(t, torch.from_numpy(x).cuda(), axis, rw_freq=12345.0,
+                                        unit_convert=CM_FS, sign=sign)
+    assert X_dev.is_cuda and tuple(X_dev.shape) == X_host.shape
+    np.testing.assert_array_equal(f_dev, f_host)
+    assert rel_l2(X_dev.cpu().numpy(), X_host) < 1e-13
+    # grids that do not start at zero fall back to the host restatement
+    f2, X2 = qb.fourier_transform(t + 8.0, torch.from_numpy(x).cuda(), axis, sign=sign)
+    f3, X3 = qb.fourier_transform(t + 8.0, x, axis, sign=sign)
+    assert isinstance(X2, np.ndarray) and rel_l2(X2, X3) < 1e-15
+
+
+def test_two_dimensional_spectra_ensemble_on_device(golden):
+    """disorder-ensemble 2D spectrum: batched propagation + device transforms against
+    the reference's Fourier transform of the (golden) ensemble response"""
+    g = golden('response')
+    t2 = np.linspace(0, 200, 3)
+    dred = qb.RedfieldModel(systems.dimer(disorder=80), hilbert_subspace='gef',
+                            unit_convert=CM_FS, discard_imag_corr=True)
+    (f1, _, f3), X = qb.two_dimensional_spectra(dred, 300, population_times=t2,
+                                                ensemble_size=3, include_signal='GSB,ESE')
+    t1 = np.arange(0, 300, dred.time_step)
+    r1, R = qb.fourier_transform(t1, g['red_ens3_gsb_ese'], 0, rw_freq=dred.rw_freq,
+                                 sign=-1, unit_convert=dred.unit_convert)
+    r3, R = qb.fourier_transform(t1, R, 2, rw_freq=dred.rw_freq,
+                                 unit_convert=dred.unit_convert)
+    np.testing.assert_allclose(f1, r1)
+    np.testing.assert_allclose(f3, r3)
+    assert rel_l2(X, R) < TOL
