@@ -154,3 +154,36 @@ def third_order_response_sharded(dynamical_model, coherence_time_max,
 
     return ensemble_signal_sharded(one, dynamical_model, ensemble_size,
                                    ensemble_random_orientations, dst)
+
+
+def two_dimensional_spectra_sharded(dynamical_model, coherence_time_max,
+                                    ensemble_size, population_time_max=None,
+                                    population_times=None, geometry='-++',
+                                    polarization='xxxx', include_signal=None,
+                                    ensemble_random_orientations=False,
+                                    exact_isotropic_average=False, dst=None,
+                                    **integrate_kwargs):
+    """``two_dimensional_spectra`` (reference response.py:430-455) for a disorder
+    ensemble of a dense-generator model: every rank propagates its block of
+    members as one device batch, the partial third-order signals meet in ONE
+    NCCL reduce, and the two Fourier transforms (kernel K7) run on the reduced
+    signal."""
+    import torch
+    from .simulate.response import _batchable, _third_order_response_batched
+    from .simulate.utils import fourier_transform
+    if not _batchable(dynamical_model):
+        raise NotImplementedError('sharded 2D spectra need a dense-generator model')
+    rank, size = world()
+    first, count = shard_members(ensemble_size, rank, size)
+    (t1, t2, t3), part = _third_order_response_batched(
+        dynamical_model, coherence_time_max, population_time_max,
+        population_times, geometry, polarization, include_signal,
+        max(count, 1), ensemble_random_orientations, first, False,
+        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+    if count == 0:
+        part = torch.zeros_like(part)
+    X = reduce_sum(part, dst) / ensemble_size
+    rw_freq, unit_convert = dynamical_model.rw_freq, dynamical_model.unit_convert
+    f1, X = fourier_transform(t1, X, 0, rw_freq=rw_freq, sign=-1, unit_convert=unit_convert)
+    f3, X = fourier_transform(t3, X, 2, rw_freq=rw_freq, unit_convert=unit_convert)
+    return (f1, t2, f3), (X.cpu().numpy() if not isinstance(X, np.ndarray) else X)
