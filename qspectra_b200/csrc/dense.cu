@@ -225,6 +225,109 @@ dense_propagate_kernel(DenseKernelArgs a) {
     }
 }
 
+// Propagator stepping y <- P y (QSX_METHOD_MAP) with P held in REGISTERS: four threads
+// share a row (thread (r, q) keeps P[r][q], P[r][q+4], ...: at most 14 complex numbers),
+// the state ping-pongs between two small shared buffers and the four partial sums meet
+// in two shuffles.  One barrier per output step, no shared-memory traffic for P (the
+// CTA-resident integrator streams all M^2 entries from shared memory every step with
+// M threads on one dependent chain each), NB columns of one generator per CTA.
+template <int CQ, int NB, int RPT>
+__global__ void __launch_bounds__((4 * ((4 * CQ + 7) / 8 * 8) / RPT + 31) / 32 * 32)
+dense_map_kernel(DenseKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int XS = 4 * CQ * NB;
+    constexpr int H = 4 * CQ / RPT;                      // rows per pass over the thread block
+    cplx *xb = reinterpret_cast<cplx *>(smem_raw);      // [2][4 CQ][NB], zero padded
+    const int M = a.M, g = blockIdx.x;
+    const int col0 = a.grp_col0[g], ncol = a.grp_ncol[g], gen = a.grp_gen[g];
+    const int tid = threadIdx.x, rr = tid >> 2, q = tid & 3;
+    const cplx *Lg = a.Lt + (size_t)gen * M * M;        // transposed storage: Lt[c*M + r]
+    cplx p[RPT][CQ];
+#pragma unroll
+    for (int h = 0; h < RPT; ++h)
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+            const int r = rr + h * H, c = q + 4 * i;
+            p[h][i] = (rr < H && r < M && c < M) ? Lg[c * M + r] : cmake(0, 0);
+        }
+    for (int i = tid; i < 2 * XS; i += blockDim.x) xb[i] = cmake(0, 0);
+    __syncthreads();
+    for (int i = tid; i < M * ncol; i += blockDim.x) {
+        const int j = i / M, c = i % M;
+        xb[c * NB + j] = a.y0[(size_t)(col0 + j) * M + c];
+    }
+    __syncthreads();
+    DenseSaver<NB> saver;
+    saver.M = M; saver.ncol = ncol; saver.nt = a.nt; saver.mode = a.save_mode;
+    saver.save_rows = a.save_rows; saver.saved_dim = a.saved_dim;
+    saver.S = a.S ? a.S + (size_t)gen * a.S_stride : nullptr;
+    saver.out = a.out + (size_t)col0 * a.nt * a.saved_dim;
+    saver(0, xb);
+    for (int it = 1; it < a.nt; ++it) {
+        const cplx *xc = xb + ((it - 1) & 1) * XS;
+        cplx *xn = xb + (it & 1) * XS;
+        // independent FMA chains (xx, yy, xy, yx products of even / odd terms) keep the
+        // dependent chain CQ/2 long; every loaded state element feeds RPT rows
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            double sxx[RPT][2], syy[RPT][2], sxy[RPT][2], syx[RPT][2];
+#pragma unroll
+            for (int h = 0; h < RPT; ++h)
+                sxx[h][0] = sxx[h][1] = syy[h][0] = syy[h][1] = sxy[h][0] = sxy[h][1] = syx[h][0] = syx[h][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < CQ; ++i) {
+                const cplx v = xc[(q + 4 * i) * NB + j];
+#pragma unroll
+                for (int h = 0; h < RPT; ++h) {
+                    sxx[h][i & 1] = fma(p[h][i].x, v.x, sxx[h][i & 1]);
+                    syy[h][i & 1] = fma(p[h][i].y, v.y, syy[h][i & 1]);
+                    sxy[h][i & 1] = fma(p[h][i].x, v.y, sxy[h][i & 1]);
+                    syx[h][i & 1] = fma(p[h][i].y, v.x, syx[h][i & 1]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < RPT; ++h) {
+                cplx acc = cmake((sxx[h][0] + sxx[h][1]) - (syy[h][0] + syy[h][1]),
+                                 (sxy[h][0] + sxy[h][1]) + (syx[h][0] + syx[h][1]));
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+                const int r = rr + h * H;
+                if (q == 0 && rr < H && r < M) xn[r * NB + j] = acc;
+            }
+        }
+        __syncthreads();
+        saver(it, xn);
+    }
+    if (tid == 0) {
+        atomicAdd(&a.stats[0], (unsigned long long)(a.nt - 1) * ncol);
+        atomicAdd(&a.stats[1], (unsigned long long)(a.nt - 1) * ncol);
+    }
+}
+
+template <int CQ, int NB, int RPT>
+static cudaError_t launch_map(const DenseKernelArgs &a, int groups, cudaStream_t stream) {
+    const int rows = RPT == 1 ? (a.M + 7) / 8 * 8 : 4 * CQ / RPT;
+    const int threads = (4 * rows + 31) / 32 * 32;
+    const size_t smem = (size_t)2 * 4 * CQ * NB * sizeof(cplx);
+    dense_map_kernel<CQ, NB, RPT><<<groups, threads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_map_cq(const DenseKernelArgs &a, int groups, cudaStream_t stream) {
+    const int cq = (a.M + 3) / 4;
+    if (cq <= 1) return launch_map<1, NB, 1>(a, groups, stream);
+    if (cq <= 2) return launch_map<2, NB, 1>(a, groups, stream);
+    if (cq <= 4) return launch_map<4, NB, 1>(a, groups, stream);
+    if (cq <= 7) return launch_map<7, NB, 1>(a, groups, stream);
+    // wide states: two rows per thread, so that every shared-memory read of the state
+    // feeds twice the arithmetic (the one-row mapping is bound by those reads)
+    if (NB == 1 && !getenv("QSX_MAP_RPT1")) return launch_map<14, NB, 2>(a, groups, stream);
+    return launch_map<14, NB, 1>(a, groups, stream);
+}
+
 // --------------------------------------------------------------------- host
 static int n_vectors_for(int method) {
     return method == QSX_METHOD_TAYLOR ? 3 : method == QSX_METHOD_RK4 ? 4 : method == QSX_METHOD_MAP ? 2 : 10;
@@ -346,6 +449,8 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
         max_run = std::max(max_run, run);
     }
     int NB = max_run >= 8 ? 8 : max_run >= 4 ? 4 : max_run >= 2 ? 2 : 1;
+    const bool reg_map = args->method == QSX_METHOD_MAP && M <= 56;     // register-resident stepping kernel
+    if (reg_map && NB > 4) NB = 4;
     const int n_vec = n_vectors_for(args->method);
 
     int dev = 0, smem_limit = 0;
@@ -427,6 +532,10 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
     QSX_CUDA(cudaEventCreate(&e1));
     QSX_CUDA(cudaEventRecord(e0, stream));
     cudaError_t e;
+    if (reg_map) {
+        e = NB == 4 ? launch_map_cq<4>(a, groups, stream) : NB == 2 ? launch_map_cq<2>(a, groups, stream)
+                                                                  : launch_map_cq<1>(a, groups, stream);
+    } else
     switch (NB) {
         case 8: e = launch_dense<8>(a, groups, threads, smem, stream); break;
         case 4: e = launch_dense<4>(a, groups, threads, smem, stream); break;
@@ -475,6 +584,10 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "d"(a), "d"(b));
 }
 
+__constant__ double inv_fact[15] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040,
+                                    1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
+                                    1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0};
+
 template <int MT>      // matrix padded to 8*MT rows/cols; MT warps per CTA
 __global__ void __launch_bounds__(32 * MT)
 dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm, int M, double dt,
@@ -484,9 +597,8 @@ dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm,
     constexpr int KS = 2 * MT;              // k-steps of 4
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *planes = reinterpret_cast<double *>(smem_raw);
-    double *Tr = planes, *Ti = Tr + MP * LD, *Ur = Ti + MP * LD, *Ui = Ur + MP * LD,
-           *Pr = Ui + MP * LD, *Pi = Pr + MP * LD;
-    __shared__ double red[2 * MT];
+    double *A1r = planes, *A1i = A1r + MP * LD, *A2r = A1i + MP * LD, *A2i = A2r + MP * LD,
+           *Pr = A2i + MP * LD, *Pi = Pr + MP * LD, *Ur = Pi + MP * LD, *Ui = Ur + MP * LD;
     const int gen = blockIdx.x;
     const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -511,8 +623,8 @@ dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm,
     }
     for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
         int r = i / LD, c = i % LD;
-        double one = (r == c && r < MP) ? 1.0 : 0.0;
-        Tr[i] = one; Ti[i] = 0.0; Pr[i] = one; Pi[i] = 0.0;
+        cplx v = (r < M && c < M) ? Lg[c * M + r] : cmake(0, 0);
+        A1r[i] = scale * v.x; A1i[i] = scale * v.y;
     }
     __syncthreads();
 
@@ -533,40 +645,53 @@ dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm,
             epi((rb * 8 + g) * LD + nb * 8 + 2 * t, cr0, cr1, ci0, ci1);
         }
     };
-
-    int small_terms = 0, failed = 1, n_gemm = 0;
-    for (int k = 1; k <= 40; ++k) {
-        ++n_gemm;
-        const double inv = 1.0 / k;
-        double tmax = 0.0, pmax = 0.0;
-        row_block_gemm(Tr, Ti, [&](int o, double r0, double r1, double i0, double i1) {
-            r0 *= inv; r1 *= inv; i0 *= inv; i1 *= inv;
-            Ur[o] = r0; Ur[o + 1] = r1; Ui[o] = i0; Ui[o + 1] = i1;
-            double p0 = Pr[o] + r0, p1 = Pr[o + 1] + r1, q0 = Pi[o] + i0, q1 = Pi[o + 1] + i1;
-            Pr[o] = p0; Pr[o + 1] = p1; Pi[o] = q0; Pi[o + 1] = q1;
-            tmax = fmax(tmax, fmax(fmax(fabs(r0), fabs(r1)), fmax(fabs(i0), fabs(i1))));
-            pmax = fmax(pmax, fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(q0), fabs(q1))));
-        });
-        tmax = warp_max(tmax);
-        pmax = warp_max(pmax);
-        if (lane == 0) { red[rb] = tmax; red[MT + rb] = pmax; }
-        __syncthreads();
-        double tm = 0.0, pm = 0.0;
+    auto load_fragments = [&](const double *Xr, const double *Xi) {
 #pragma unroll
-        for (int w = 0; w < MT; ++w) { tm = fmax(tm, red[w]); pm = fmax(pm, red[MT + w]); }
-        { double *x = Tr; Tr = Ur; Ur = x; x = Ti; Ti = Ui; Ui = x; }
-        small_terms = (tm <= 1e-17 * pm) ? small_terms + 1 : 0;
-        __syncthreads();          // red[] may be rewritten next iteration
-        if (small_terms >= 2) { failed = 0; break; }
+        for (int ks = 0; ks < KS; ++ks) {
+            a_re[ks] = Xr[(rb * 8 + g) * LD + ks * 4 + t];
+            a_im[ks] = Xi[(rb * 8 + g) * LD + ks * 4 + t];
+            a_nim[ks] = -a_im[ks];
+        }
+    };
+
+    // exp(A) ~ sum_{k<=14} A^k / k!  (|A|_inf <= 1/2: remainder < 2.4e-17) evaluated by
+    // Paterson-Stockmeyer in blocks of three:
+    //   p(A) = B0 + A^3 (B1 + A^3 (B2 + A^3 (B3 + A^3 B4))),  B_i = c_3i I + c_3i+1 A + c_3i+2 A^2
+    // -> A^2, A^3 and four Horner products: 6 complex GEMMs instead of one per Taylor term.
+    int n_gemm = 6;
+    const int failed = 0;
+    row_block_gemm(A1r, A1i, [&](int o, double r0, double r1, double i0, double i1) {       // A^2
+        A2r[o] = r0; A2r[o + 1] = r1; A2i[o] = i0; A2i[o + 1] = i1;
+    });
+    __syncthreads();
+    row_block_gemm(A2r, A2i, [&](int o, double r0, double r1, double i0, double i1) {       // A^3
+        Ur[o] = r0; Ur[o + 1] = r1; Ui[o] = i0; Ui[o + 1] = i1;
+    });
+    // Horner start: P = B4 (element-wise, own row block only)
+    for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
+        const int r = i / LD, c = i % LD;
+        Pr[i] = (r == c ? inv_fact[12] : 0.0) + inv_fact[13] * A1r[i] + inv_fact[14] * A2r[i];
+        Pi[i] = inv_fact[13] * A1i[i] + inv_fact[14] * A2i[i];
+    }
+    __syncthreads();
+    load_fragments(Ur, Ui);                     // left operand from here on: A^3
+    __syncthreads();                            // U is free again
+#pragma unroll 1
+    for (int blk = 3; blk >= 0; --blk) {
+        const double c0 = inv_fact[3 * blk], c1 = inv_fact[3 * blk + 1], c2 = inv_fact[3 * blk + 2];
+        row_block_gemm(Pr, Pi, [&](int o, double r0, double r1, double i0, double i1) {
+            const int r = o / LD, c = o % LD;
+            Ur[o] = r0 + c1 * A1r[o] + c2 * A2r[o] + (r == c ? c0 : 0.0);
+            Ur[o + 1] = r1 + c1 * A1r[o + 1] + c2 * A2r[o + 1] + (r == c + 1 ? c0 : 0.0);
+            Ui[o] = i0 + c1 * A1i[o] + c2 * A2i[o];
+            Ui[o + 1] = i1 + c1 * A1i[o + 1] + c2 * A2i[o + 1];
+        });
+        __syncthreads();
+        { double *x = Pr; Pr = Ur; Ur = x; x = Pi; Pi = Ui; Ui = x; }
     }
     // squarings P <- P P
     for (int q = 0; q < sq; ++q) {
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            a_re[ks] = Pr[(rb * 8 + g) * LD + ks * 4 + t];
-            a_im[ks] = Pi[(rb * 8 + g) * LD + ks * 4 + t];
-            a_nim[ks] = -a_im[ks];
-        }
+        load_fragments(Pr, Pi);
         row_block_gemm(Pr, Pi, [&](int o, double r0, double r1, double i0, double i1) {
             Ur[o] = r0; Ur[o + 1] = r1; Ui[o] = i0; Ui[o + 1] = i1;
         });
@@ -589,7 +714,7 @@ static cudaError_t launch_expm(const cplx *Lt, const double *lnorm, int M, doubl
                                int n_gen, cudaStream_t stream) {
     constexpr int MP = 8 * MT;
     constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
-    size_t smem = (size_t)6 * MP * LD * sizeof(double);
+    size_t smem = (size_t)8 * MP * LD * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(dense_expm_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dense_expm_kernel<MT><<<n_gen, 32 * MT, smem, stream>>>(Lt, lnorm, M, dt, Pt, status);
