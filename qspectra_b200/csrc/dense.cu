@@ -231,23 +231,23 @@ dense_propagate_kernel(DenseKernelArgs a) {
 // in two shuffles.  One barrier per output step, no shared-memory traffic for P (the
 // CTA-resident integrator streams all M^2 entries from shared memory every step with
 // M threads on one dependent chain each), NB columns of one generator per CTA.
-template <int CQ, int NB, int RPT>
-__global__ void __launch_bounds__((4 * ((4 * CQ + 7) / 8 * 8) / RPT + 31) / 32 * 32)
+template <int Q, int CQ, int NB, int RPT>
+__global__ void __launch_bounds__((Q * ((Q * CQ + 7) / 8 * 8) / RPT + 31) / 32 * 32, RPT == 2 ? 3 : 1)
 dense_map_kernel(DenseKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int XS = 4 * CQ * NB;
-    constexpr int H = 4 * CQ / RPT;                      // rows per pass over the thread block
-    cplx *xb = reinterpret_cast<cplx *>(smem_raw);      // [2][4 CQ][NB], zero padded
+    constexpr int XS = Q * CQ * NB;
+    constexpr int H = Q * CQ / RPT;                      // rows per pass over the thread block
+    cplx *xb = reinterpret_cast<cplx *>(smem_raw);      // [2][Q CQ][NB], zero padded
     const int M = a.M, g = blockIdx.x;
     const int col0 = a.grp_col0[g], ncol = a.grp_ncol[g], gen = a.grp_gen[g];
-    const int tid = threadIdx.x, rr = tid >> 2, q = tid & 3;
+    const int tid = threadIdx.x, rr = tid / Q, q = tid % Q;
     const cplx *Lg = a.Lt + (size_t)gen * M * M;        // transposed storage: Lt[c*M + r]
     cplx p[RPT][CQ];
 #pragma unroll
     for (int h = 0; h < RPT; ++h)
 #pragma unroll
         for (int i = 0; i < CQ; ++i) {
-            const int r = rr + h * H, c = q + 4 * i;
+            const int r = rr + h * H, c = q + Q * i;
             p[h][i] = (rr < H && r < M && c < M) ? Lg[c * M + r] : cmake(0, 0);
         }
     for (int i = tid; i < 2 * XS; i += blockDim.x) xb[i] = cmake(0, 0);
@@ -276,7 +276,7 @@ dense_map_kernel(DenseKernelArgs a) {
                 sxx[h][0] = sxx[h][1] = syy[h][0] = syy[h][1] = sxy[h][0] = sxy[h][1] = syx[h][0] = syx[h][1] = 0.0;
 #pragma unroll
             for (int i = 0; i < CQ; ++i) {
-                const cplx v = xc[(q + 4 * i) * NB + j];
+                const cplx v = xc[(q + Q * i) * NB + j];
 #pragma unroll
                 for (int h = 0; h < RPT; ++h) {
                     sxx[h][i & 1] = fma(p[h][i].x, v.x, sxx[h][i & 1]);
@@ -289,10 +289,11 @@ dense_map_kernel(DenseKernelArgs a) {
             for (int h = 0; h < RPT; ++h) {
                 cplx acc = cmake((sxx[h][0] + sxx[h][1]) - (syy[h][0] + syy[h][1]),
                                  (sxy[h][0] + sxy[h][1]) + (syx[h][0] + syx[h][1]));
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+#pragma unroll
+                for (int o = 1; o < Q; o <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                }
                 const int r = rr + h * H;
                 if (q == 0 && rr < H && r < M) xn[r * NB + j] = acc;
             }
@@ -306,26 +307,27 @@ dense_map_kernel(DenseKernelArgs a) {
     }
 }
 
-template <int CQ, int NB, int RPT>
+template <int Q, int CQ, int NB, int RPT>
 static cudaError_t launch_map(const DenseKernelArgs &a, int groups, cudaStream_t stream) {
-    const int rows = RPT == 1 ? (a.M + 7) / 8 * 8 : 4 * CQ / RPT;
-    const int threads = (4 * rows + 31) / 32 * 32;
-    const size_t smem = (size_t)2 * 4 * CQ * NB * sizeof(cplx);
-    dense_map_kernel<CQ, NB, RPT><<<groups, threads, smem, stream>>>(a);
+    const int rows = RPT == 1 ? (a.M + 7) / 8 * 8 : Q * CQ / RPT;
+    const int threads = (Q * rows + 31) / 32 * 32;
+    const size_t smem = (size_t)2 * Q * CQ * NB * sizeof(cplx);
+    dense_map_kernel<Q, CQ, NB, RPT><<<groups, threads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
 template <int NB>
 static cudaError_t launch_map_cq(const DenseKernelArgs &a, int groups, cudaStream_t stream) {
     const int cq = (a.M + 3) / 4;
-    if (cq <= 1) return launch_map<1, NB, 1>(a, groups, stream);
-    if (cq <= 2) return launch_map<2, NB, 1>(a, groups, stream);
-    if (cq <= 4) return launch_map<4, NB, 1>(a, groups, stream);
-    if (cq <= 7) return launch_map<7, NB, 1>(a, groups, stream);
+    if (cq <= 1) return launch_map<4, 1, NB, 1>(a, groups, stream);
+    if (cq <= 2) return launch_map<4, 2, NB, 1>(a, groups, stream);
+    if (cq <= 4) return launch_map<4, 4, NB, 1>(a, groups, stream);
+    if (cq <= 7) return launch_map<4, 7, NB, 1>(a, groups, stream);
     // wide states: two rows per thread, so that every shared-memory read of the state
     // feeds twice the arithmetic (the one-row mapping is bound by those reads)
-    if (NB == 1 && !getenv("QSX_MAP_RPT1")) return launch_map<14, NB, 2>(a, groups, stream);
-    return launch_map<14, NB, 1>(a, groups, stream);
+    // (eight threads per row with full-width shared-memory wavefronts measured slower: 4.4 vs 3.9 ms)
+    if (NB == 1) return launch_map<4, 14, NB, 2>(a, groups, stream);
+    return launch_map<4, 14, NB, 1>(a, groups, stream);
 }
 
 // --------------------------------------------------------------------- host
