@@ -382,7 +382,11 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     e2e_value = world * E * (len(t) - 1) / e2e_s
-    h2d = E * 7 * 8 + 49 * 16 + E * 4 * 3 + len(t) * 8 + 7 * 7 * 8 + 2 * 7 * 8
+    # bytes that actually cross PCIe per call: the user's inputs are the model (7x7 H, bath
+    # parameters, seed), psi0 and the time grid -- the members' disorder is replayed from the
+    # seed ON THE DEVICE (as the reference replays it inside the call on the host); plus the
+    # per-launch column tables (3 ints per member) of the propagate entry point
+    h2d = 49 * 16 + E * 4 * 3 + len(t) * 8 + 7 * 7 * 8 + 4 * 7 * 8 + 49 * 8 + 8
     d2h = len(t) * 49 * 16
 
     if rank != 0:
@@ -412,9 +416,10 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'seconds_per_step': e2e_s,
                 'seconds_each_step': [round(x, 5) for x in e2e_times],
-                'path': 'host replay of the seeded disorder draws -> H2D of the site shifts '
-                        '-> K5 (Jacobi eigensystems + Redfield generators) -> K1/K4 '
-                        'propagation -> K6 mean -> D2H'},
+                'path': 'simulate_dynamics(model, psi0, duration, ensemble_size) from host objects: '
+                        'seed -> device replay of the seeded disorder streams -> K5 (Jacobi '
+                        'eigensystems + Redfield generators) -> K1\' propagators -> K1/K4 '
+                        'stepping -> K6 mean -> D2H of the averaged density matrices'},
         'gpu_launches': int(launches),
         'roofline': None,
     }

@@ -292,6 +292,16 @@ int qsx_sample_streams(const uint32_t *seed_prefix, int32_t n_prefix,
                        int64_t member0, int32_t n_members, int32_t n_gauss,
                        int32_t n_uniform, double *gauss_out, double *uniform_out);
 
+/* The Gaussian part of the same streams generated on the GPU, one thread per member:
+ *   out_dev[m][i] = scale * RandomState(list(seed) + [member0 + m]).randn(n_gauss)[i]
+ * (integer stream and uniform doubles bit-identical with numpy; the Box-Muller
+ * log/sqrt are the device functions, <= 1 ulp from the host libm).  Used for the
+ * static-disorder shifts of an ensemble (hamiltonian.py:458-461, 566-573) so that
+ * neither the host replay nor an H2D copy sits on the end-to-end path. */
+int qsx_sample_gauss_device(const uint32_t *seed_prefix, int32_t n_prefix, int64_t member0,
+                            int32_t n_members, int32_t n_gauss, double scale, void *out_dev,
+                            void *stream);
+
 #ifdef __cplusplus
 }
 #endif

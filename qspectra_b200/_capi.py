@@ -85,7 +85,7 @@ EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
            'qsx_ado_enumerate', 'qsx_redfield_build', 'qsx_redfield_build_sampled',
            'qsx_reduce_members', 'qsx_fourier_transform',
-           'qsx_sample_streams', 'qsx_zofe_create', 'qsx_zofe_state_dim',
+           'qsx_sample_streams', 'qsx_sample_gauss_device', 'qsx_zofe_create', 'qsx_zofe_state_dim',
            'qsx_zofe_apply', 'qsx_zofe_propagate', 'qsx_zofe_destroy']
 
 _lib = None
@@ -164,6 +164,9 @@ def lib():
     L.qsx_sample_streams.argtypes = [C.POINTER(C.c_uint32), C.c_int32, C.c_int64,
                                      C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p]
+    L.qsx_sample_gauss_device.argtypes = [C.POINTER(C.c_uint32), C.c_int32, C.c_int64,
+                                          C.c_int32, C.c_int32, C.c_double,
+                                          C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -239,6 +242,21 @@ def int32_ptr(values):
         return None, None
     arr = np.ascontiguousarray(values, dtype=np.int32)
     return arr, arr.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def sample_gauss_device(seed, member0, n_members, n_gauss, scale=1.0):
+    """CUDA tensor [n_members, n_gauss] = scale * RandomState(list(seed) + [n]).randn(n_gauss)
+    for n = member0 .. member0 + n_members - 1, generated on the device."""
+    torch = torch_cuda()
+    prefix = np.ascontiguousarray(np.atleast_1d(seed), dtype=np.int64)
+    if ((prefix < 0) | (prefix > 2 ** 32 - 1)).any():
+        raise ValueError('seed entries must fit in uint32')
+    prefix = prefix.astype(np.uint32)
+    out = torch.empty((n_members, n_gauss), dtype=torch.float64, device='cuda')
+    check(lib().qsx_sample_gauss_device(
+        prefix.ctypes.data_as(C.POINTER(C.c_uint32)), prefix.size, int(member0),
+        int(n_members), int(n_gauss), float(scale), out.data_ptr(), current_stream_ptr()))
+    return out
 
 
 def sample_streams(seed, member0, n_members, n_gauss, n_uniform=0):

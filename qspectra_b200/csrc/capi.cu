@@ -234,12 +234,12 @@ namespace {
 struct MT19937 {
     uint32_t mt[624];
     int pos;
-    void init_genrand(uint32_t s) {
+    __host__ __device__ void init_genrand(uint32_t s) {
         mt[0] = s;
         for (int i = 1; i < 624; ++i) mt[i] = 1812433253U * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
         pos = 624;
     }
-    void init_by_array(const uint32_t *key, int len) {
+    __host__ __device__ void init_by_array(const uint32_t *key, int len) {
         init_genrand(19650218U);
         int i = 1, j = 0;
         for (int k = (624 > len ? 624 : len); k; --k) {
@@ -254,14 +254,14 @@ struct MT19937 {
         mt[0] = 0x80000000U;
         pos = 624;
     }
-    void twist() {
+    __host__ __device__ void twist() {
         for (int k = 0; k < 624; ++k) {
             uint32_t y = (mt[k] & 0x80000000U) | (mt[(k + 1) % 624] & 0x7fffffffU);
             mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
         }
         pos = 0;
     }
-    uint32_t next32() {
+    __host__ __device__ uint32_t next32() {
         if (pos >= 624) twist();
         uint32_t y = mt[pos++];
         y ^= (y >> 11);
@@ -270,7 +270,7 @@ struct MT19937 {
         y ^= (y >> 18);
         return y;
     }
-    double next_double() {
+    __host__ __device__ double next_double() {
         uint32_t a = next32() >> 5, b = next32() >> 6;
         return (a * 67108864.0 + b) / 9007199254740992.0;
     }
@@ -327,5 +327,61 @@ extern "C" int qsx_sample_streams(const uint32_t *seed_prefix, int32_t n_prefix,
         }
         for (auto &th : pool) th.join();
     }
+    return QSX_OK;
+}
+
+// ------------------------------------------- seeded disorder streams (device)
+// The same streams generated on the GPU, one thread per ensemble member (the
+// Mersenne-Twister state lives in the thread's local memory): integer arithmetic and
+// the uniform doubles are bit-identical with the host replay; the polar Box-Muller
+// transform uses the device log/sqrt (<= 1 ulp from the host libm).  Writes
+// out[m][i] = scale * randn_i of member member0 + m.  Removes the host replay and the
+// H2D copy from the end-to-end path of a disorder ensemble.
+__global__ void __launch_bounds__(64) sample_streams_kernel(const uint32_t *prefix, int n_prefix, long long member0,
+                                                            int n_members, int n_gauss, double scale, double *out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_members) return;
+    uint32_t key[16];
+    for (int i = 0; i < n_prefix; ++i) key[i] = prefix[i];
+    key[n_prefix] = (uint32_t)(member0 + m);
+    MT19937 g;
+    g.init_by_array(key, n_prefix + 1);
+    bool has = false;
+    double cached = 0.0;
+    for (int i = 0; i < n_gauss; ++i) {
+        double val;
+        if (has) {
+            val = cached;
+            has = false;
+        } else {
+            double x1, x2, r2;
+            do {
+                x1 = 2.0 * g.next_double() - 1.0;
+                x2 = 2.0 * g.next_double() - 1.0;
+                r2 = x1 * x1 + x2 * x2;
+            } while (r2 >= 1.0 || r2 == 0.0);
+            double f = sqrt(-2.0 * log(r2) / r2);
+            cached = f * x1;
+            has = true;
+            val = f * x2;
+        }
+        out[(size_t)m * n_gauss + i] = scale * val;
+    }
+}
+
+extern "C" int qsx_sample_gauss_device(const uint32_t *seed_prefix, int32_t n_prefix, int64_t member0,
+                                       int32_t n_members, int32_t n_gauss, double scale, void *out_dev,
+                                       void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(n_prefix >= 0 && n_prefix < 15 && n_members > 0 && n_gauss > 0 && out_dev,
+                "qsx_sample_gauss_device: bad arguments");
+    QSX_REQUIRE(member0 >= 0 && member0 + n_members <= (int64_t)0xffffffffLL, "member index out of range");
+    DevBuf<uint32_t> prefix;
+    if (n_prefix > 0) QSX_CUDA(prefix.upload(seed_prefix, (size_t)n_prefix, stream));
+    sample_streams_kernel<<<(n_members + 63) / 64, 64, 0, stream>>>(prefix.p, n_prefix, member0, n_members, n_gauss,
+                                                                    scale, (double *)out_dev);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    QSX_CUDA(cudaStreamSynchronize(stream));        // `prefix` goes out of scope
     return QSX_OK;
 }

@@ -35,6 +35,7 @@ struct RedfieldBuildArgs {
     const cplx *U;          // [m][N][N] row-major, U[x][a] = <x|a>
     const double *v;        // [nb][N] coupling diagonals
     qsx_bath bath;
+    int n_mats;             // Matsubara terms tabulated in shared memory (0 for the real spectrum)
     int secular, eigen_basis;
     double unit_convert;
     cplx *L;                // [m][M][M]
@@ -54,13 +55,16 @@ struct RedfieldBuildArgs {
 // basis-state order -- no sorting, so block-diagonal manifolds stay in place;
 // V receives the eigenvectors as columns).  Round-robin pairing gives N/2
 // independent rotations per round.  Called by the whole thread block.
+template <bool WARP>
 __device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    // WARP: executed by the first warp alone (small matrices): barriers become __syncwarp
+    const int tid = threadIdx.x, nthr = WARP ? 32 : blockDim.x;
+    auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const int Nn = (N + 1) & ~1, half = Nn / 2;
     double *cs = work, *sn = work + half;
     int *pp = reinterpret_cast<int *>(work + 2 * half), *qq = pp + half;
     for (int i = tid; i < N * N; i += nthr) V[i] = (i / N == i % N) ? 1.0 : 0.0;
-    __syncthreads();
+    sync();
     for (int sweep = 0; sweep < 16; ++sweep) {
         // convergence: all off-diagonal entries negligible against the diagonal scale
         int big = 0;
@@ -68,7 +72,7 @@ __device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
             int p = i / N, q = i % N;
             if (p < q && fabs(A[i]) > 1e-17 * (fabs(A[p * N + p]) + fabs(A[q * N + q])) && A[i] != 0.0) big = 1;
         }
-        if (!__syncthreads_or(big)) break;
+        if (!(WARP ? __any_sync(0xffffffffu, big) : __syncthreads_or(big))) break;
         for (int r = 0; r < Nn - 1; ++r) {
             if (tid < half) {
                 int a = (tid == 0) ? Nn - 1 : (r + tid) % (Nn - 1);
@@ -88,7 +92,7 @@ __device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
                 }
                 cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
             }
-            __syncthreads();
+            sync();
             for (int i = tid; i < half * N; i += nthr) {      // A <- A P, V <- V P
                 int pr = i / N, k = i % N;
                 int p = pp[pr], q = qq[pr];
@@ -101,7 +105,7 @@ __device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
                 V[k * N + p] = c * vp - s * vq;
                 V[k * N + q] = s * vp + c * vq;
             }
-            __syncthreads();
+            sync();
             for (int i = tid; i < half * N; i += nthr) {      // A <- P^T A
                 int pr = i / N, k = i % N;
                 int p = pp[pr], q = qq[pr];
@@ -111,7 +115,7 @@ __device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
                 A[p * N + k] = c * ap - s * aq;
                 A[q * N + k] = s * ap + c * aq;
             }
-            __syncthreads();
+            sync();
         }
     }
 }
@@ -122,32 +126,39 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return cmake((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
 }
 
-// one-sided correlation spectrum evaluated by a full warp (all lanes get the value)
-__device__ cplx warp_corr(const qsx_bath &b, double x) {
+// One-sided correlation spectrum C(x) of the Debye bath (bath.py:17-31, 79-102).  The
+// complex form needs the 1000-term Matsubara sum
+//   S(x) = sum_m nu_m / ((nu_m^2 - g^2) (nu_m - i x)),  nu_m = 2 pi m T,
+// whose x-independent factors live in shared tables (one division per term is left) and
+// which satisfies S(-x) = conj(S(x)): a warp sums once per pair of eigenstates.
+__device__ __forceinline__ cplx corr_real(const qsx_bath &b, double x) {
     const double T = b.temperature, lam = b.reorg_energy, g = b.cutoff_freq;
-    if (b.kind == QSX_BATH_DEBYE_REAL) {
-        // (n(x)+1) J_anti(x);  T J'(0) at x == 0        (bath.py:17-31, 79-82)
-        if (x == 0.0) return cmake(T * 2.0 * lam / g, 0.0);
-        double ax = fabs(x);
-        double J = 2.0 * lam * g * ax / (g * g + ax * ax);
-        if (x < 0) J = -J;
-        return cmake((1.0 / expm1(x / T) + 1.0) * J, 0.0);
-    }
+    // (n(x)+1) J_anti(x);  T J'(0) at x == 0
+    if (x == 0.0) return cmake(T * 2.0 * lam / g, 0.0);
+    double ax = fabs(x);
+    double J = 2.0 * lam * g * ax / (g * g + ax * ax);
+    if (x < 0) J = -J;
+    return cmake((1.0 / expm1(x / T) + 1.0) * J, 0.0);
+}
+__device__ __forceinline__ cplx corr_complex_finish(const qsx_bath &b, double x, double sr, double si) {
+    const double T = b.temperature, lam = b.reorg_energy, g = b.cutoff_freq;
     if (x == 0.0) return cmake(lam * 2.0 * T / g, -lam);
-    const int lane = threadIdx.x & 31;
-    double sr = 0.0, si = 0.0;
-    for (int mth = lane; mth < b.matsubara_cutoff; mth += 32) {
-        double nu = 2.0 * M_PI * mth * T;
-        // nu / ((nu^2 - g^2) (nu - i x))
-        double pre = nu / (nu * nu - g * g);
-        double den = nu * nu + x * x;
-        sr += pre * nu / den;
-        si += pre * x / den;
-    }
-    sr = warp_sum(sr);
-    si = warp_sum(si);
     cplx drude = cdiv(cmake(1.0 / tan(g / (2.0 * T)), -1.0), cmake(g, -x));
     return cmake(lam * g * (drude.x + 4.0 * T * sr), lam * g * (drude.y + 4.0 * T * si));
+}
+__device__ __forceinline__ void matsubara_sum(const double *m_nu, const double *m_pre, int cutoff, double x,
+                                              double &sr, double &si) {
+    const int lane = threadIdx.x & 31;
+    double ar = 0.0, ai = 0.0;
+    const double x2 = x * x;
+    for (int mth = lane; mth < cutoff; mth += 32) {
+        const double nu = m_nu[mth], pre = m_pre[mth];
+        const double q = pre / (nu * nu + x2);
+        ar = fma(q, nu, ar);
+        ai = fma(q, x, ai);
+    }
+    sr = warp_sum(ar);
+    si = warp_sum(ai);
 }
 
 __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a) {
@@ -160,9 +171,11 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
     cplx *Gs = Cs + N2;                                  // [N][N]
     cplx *Ks = Gs + N2;                                  // [nb][N][N]
     double *Es = reinterpret_cast<double *>(Ks + (size_t)nb * N2);   // [N]
+    const int NE = (N + 1) & ~1;
+    double *m_nu = Es + NE, *m_pre = m_nu + a.n_mats;                // [n_mats] Matsubara tables
     cplx *TA, *TB;
     if (a.tensors_in_smem) {
-        TA = reinterpret_cast<cplx *>(Es + ((N + 1) & ~1));
+        TA = reinterpret_cast<cplx *>(m_pre + a.n_mats);
         TB = TA + N4;
     } else {
         TA = a.scratch + (size_t)blockIdx.x * 2 * N4;
@@ -171,6 +184,11 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, nwarp = nthr >> 5;
 
+    for (int mth = tid; mth < a.n_mats; mth += nthr) {
+        const double nu = 2.0 * M_PI * mth * a.bath.temperature, g = a.bath.cutoff_freq;
+        m_nu[mth] = nu;
+        m_pre[mth] = mth < a.bath.matsubara_cutoff ? nu / (nu * nu - g * g) : 0.0;
+    }
     for (int mem = blockIdx.x; mem < a.m; mem += gridDim.x) {
         __syncthreads();
         if (a.jacobi) {
@@ -185,7 +203,12 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
                 A[i] = h;
             }
             __syncthreads();
-            jacobi_eigh(A, V, N, work);
+            if (N <= 16) {
+                if (warp == 0) jacobi_eigh<true>(A, V, N, work);
+                __syncthreads();
+            } else {
+                jacobi_eigh<false>(A, V, N, work);
+            }
             for (int i = tid; i < N2; i += nthr) Us[i] = cmake(V[i], 0.0);
             for (int i = tid; i < N; i += nthr) Es[i] = A[i * N + i] - a.quanta[i] * a.rw_freq;
         } else {
@@ -193,11 +216,23 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
             for (int i = tid; i < N; i += nthr) Es[i] = a.E[(size_t)mem * N + i];
         }
         __syncthreads();
-        // correlation matrix, one warp per entry
-        for (int p = warp; p < N2; p += nwarp) {
-            int i = p / N, j = p % N;
-            cplx c = warp_corr(a.bath, Es[i] - Es[j]);
-            if ((tid & 31) == 0) Cs[p] = c;
+        // correlation matrix: one warp per pair of eigenstates (both orderings), diagonal apart
+        if (a.bath.kind == QSX_BATH_DEBYE_REAL) {
+            for (int p = tid; p < N2; p += nthr) Cs[p] = corr_real(a.bath, Es[p / N] - Es[p % N]);
+        } else {
+            for (int i = tid; i < N; i += nthr) Cs[i * N + i] = corr_complex_finish(a.bath, 0.0, 0.0, 0.0);
+            for (int p = warp; p < N * (N - 1) / 2; p += nwarp) {
+                int i = 0, rem = p;
+                while (rem >= N - 1 - i) { rem -= N - 1 - i; ++i; }
+                const int j = i + 1 + rem;
+                const double x = Es[i] - Es[j];
+                double sr, si;
+                matsubara_sum(m_nu, m_pre, a.n_mats, x, sr, si);
+                if ((tid & 31) == 0) {
+                    Cs[i * N + j] = corr_complex_finish(a.bath, x, sr, si);
+                    Cs[j * N + i] = corr_complex_finish(a.bath, -x, sr, -si);
+                }
+            }
         }
         // couplings in the eigenbasis: K_n[a][b] = sum_x conj(U[x][a]) v_n[x] U[x][b]
         for (int p = tid; p < nb * N2; p += nthr) {
@@ -225,9 +260,10 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
         __syncthreads();
         // eigenbasis generator as a 4-index tensor T[a][b][c][d] = L[a + N b, c + N d],
         // a, c over the ket states ra[], b, d over the bra states rb[]
-        for (size_t p = tid; p < N4; p += nthr) {
+        const int n4 = (int)N4;                  // N <= 64: fits 32 bits (cheap index arithmetic)
+        for (int p = tid; p < n4; p += nthr) {
             int dd = a.rb[p % nbb], cc = a.ra[(p / nbb) % na];
-            int bb = a.rb[(p / ((size_t)nbb * na)) % nbb], aa = a.ra[p / ((size_t)nbb * na * nbb)];
+            int bb = a.rb[(p / (nbb * na)) % nbb], aa = a.ra[p / (nbb * na * nbb)];
             cplx g1 = cmake(0, 0), g2 = cmake(0, 0);       // G[c,a,b,d], G[d,b,a,c]
             for (int n = 0; n < nb; ++n) {
                 cfma(g1, Ks[n * N2 + cc * N + aa], Ks[n * N2 + bb * N + dd]);
@@ -248,19 +284,18 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
         if (!a.eigen_basis) {
             // L_site[i,j,k,l] = sum U[i,p] U[j,q] T[p,q,r,s] conj(U[k,r]) conj(U[l,s])
             for (int pos = 0; pos < 4; ++pos) {
-                size_t stride = pos == 0 ? (size_t)nbb * na * nbb : pos == 1 ? (size_t)na * nbb
-                              : pos == 2 ? (size_t)nbb : 1;
+                const int stride = pos == 0 ? nbb * na * nbb : pos == 1 ? na * nbb : pos == 2 ? nbb : 1;
                 const int n = (pos & 1) ? nbb : na;
                 const int *states = (pos & 1) ? a.rb : a.ra;
-                for (size_t p = tid; p < N4; p += nthr) {
-                    int i = (int)((p / stride) % n);
-                    size_t base = p - (size_t)i * stride;
+                for (int p = tid; p < n4; p += nthr) {
+                    const int i = (p / stride) % n;
+                    const int base = p - i * stride;
                     const cplx *urow = Us + states[i] * N;
                     cplx acc = cmake(0, 0);
                     for (int q = 0; q < n; ++q) {
                         cplx u = urow[states[q]];
                         if (pos >= 2) u.y = -u.y;
-                        cfma(acc, u, src[base + (size_t)q * stride]);
+                        cfma(acc, u, src[base + q * stride]);
                     }
                     dst[p] = acc;
                 }
@@ -359,7 +394,9 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t N2 = (size_t)N * N, N4 = (size_t)na * nbb * na * nbb;
-    size_t base = (3 * N2 + (size_t)n_baths * N2) * sizeof(cplx) + (size_t)((N + 1) & ~1) * sizeof(double);
+    const int n_mats = bath->kind == QSX_BATH_DEBYE_COMPLEX ? (bath->matsubara_cutoff > 0 ? bath->matsubara_cutoff : 1000) : 0;
+    size_t base = (3 * N2 + (size_t)n_baths * N2) * sizeof(cplx) +
+                  ((size_t)((N + 1) & ~1) + 2 * (size_t)((n_mats + 1) & ~1)) * sizeof(double);
     size_t with_t = base + 2 * N4 * sizeof(cplx);
     QSX_REQUIRE(base <= (size_t)smem_limit, "qsx_redfield_build: too many baths/states for shared memory");
     int tensors_in_smem = with_t <= (size_t)smem_limit;
@@ -377,6 +414,7 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     a.na = na; a.nbb = nbb; a.ra = d_ra.p; a.rb = d_rb.p; a.oa = d_oa.p; a.ob = d_ob.p;
     a.bath = *bath;
     if (a.bath.matsubara_cutoff <= 0) a.bath.matsubara_cutoff = 1000;
+    a.n_mats = (n_mats + 1) & ~1;       // padded entries are zero terms
     a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;
     a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem;
     a.transposed_out = transposed_out;

@@ -180,8 +180,13 @@ class RedfieldModel(LiouvilleSpaceModel):
         Jacobi), bath correlation matrices, Redfield tensors and the site-basis
         transform are computed on the GPU."""
         ham, ss = self.hamiltonian, self.hilbert_subspace
-        shifts = ham.sampled_site_shifts(ensemble_size, member0) \
-            if self._device_buildable() else None
+        # site-basis evolution: the members' disorder shifts are generated on the device
+        # as well (nothing but the seed crosses PCIe); the eigenbasis path below needs
+        # them on the host for LAPACK's eigenvector gauge
+        on_device = self._device_buildable() and self.evolve_basis != 'eigen'
+        shifts = (ham.sampled_site_shifts_device(ensemble_size, member0) if on_device
+                  else ham.sampled_site_shifts(ensemble_size, member0)
+                  if self._device_buildable() else None)
         if shifts is None:
             return super(RedfieldModel, self).ensemble_eom(
                 ensemble_size, random_orientations, liouville_subspace,

@@ -546,8 +546,9 @@ def redfield_build_sampled(H0, site_shifts, quanta, rw_freq, coupling_diag,
     Hamiltonian of the un-sampled system in the Hilbert subspace."""
     torch = _capi.torch_cuda()
     H0 = np.ascontiguousarray(H0, dtype=np.float64)
-    shifts = _capi.to_device(np.ascontiguousarray(site_shifts, dtype=np.float64),
-                             dtype=torch.float64)
+    shifts = (site_shifts.contiguous() if isinstance(site_shifts, torch.Tensor) else
+              _capi.to_device(np.ascontiguousarray(site_shifts, dtype=np.float64),
+                              dtype=torch.float64))
     q = np.ascontiguousarray(quanta, dtype=np.float64)
     v = np.ascontiguousarray(coupling_diag, dtype=np.float64)
     idx = np.ascontiguousarray(subspace_index, dtype=np.int64)

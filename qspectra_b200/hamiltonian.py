@@ -282,6 +282,20 @@ class ElectronicHamiltonian(Hamiltonian):
                                   base.n_sites)
         return (base.disorder * GAUSSIAN_SD_FWHM) * gauss
 
+    def sampled_site_shifts_device(self, ensemble_size, member0=0):
+        """The same shifts as a CUDA tensor generated on the device (kernel
+        `sample_streams_kernel`: integer stream identical, Box-Muller through the
+        device log/sqrt), or None when `disorder` is a user callable."""
+        base = self._not_sampled
+        if base.disorder is not None and not isinstance(base.disorder, Number):
+            return None
+        from . import _capi
+        if base.disorder is None:
+            torch = _capi.torch_cuda()
+            return torch.zeros((ensemble_size, base.n_sites), dtype=torch.float64, device='cuda')
+        return _capi.sample_gauss_device(base.random_seed, member0, ensemble_size,
+                                         base.n_sites, base.disorder * GAUSSIAN_SD_FWHM)
+
     def _sample(self, n, random_orientations):
         rng = self.disorder_stream(n)
         if self.disorder is None:

@@ -561,3 +561,18 @@ def test_two_dimensional_spectra_ensemble_on_device(golden):
     np.testing.assert_allclose(f1, r1)
     np.testing.assert_allclose(f3, r3)
     assert rel_l2(X, R) < TOL
+
+
+def test_device_disorder_streams_match_numpy():
+    """static-disorder shifts generated on the device against numpy's seeded legacy
+    streams (hamiltonian.py:458-461, 566-573): same integer stream, Box-Muller within
+    a few ulp of the host libm"""
+    ham = systems.fmo()
+    dev = ham.sampled_site_shifts_device(300, member0=5).cpu().numpy()
+    host = ham.sampled_site_shifts(300, member0=5)
+    ref = np.array([ham.sample(n).H_1exc.diagonal() - ham.H_1exc.diagonal()
+                    for n in range(5, 12)])
+    assert np.abs(host[:7] - ref).max() < 1e-9          # (H + shift) - H rounding only
+    assert dev.shape == host.shape
+    assert np.abs(dev - host).max() <= 8 * np.finfo(float).eps * np.abs(host).max()
+    assert (dev == host).mean() > 0.5
