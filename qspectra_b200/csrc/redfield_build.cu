@@ -41,6 +41,7 @@ struct RedfieldBuildArgs {
     cplx *L;                // [m][M][M]
     cplx *scratch;          // [gridDim][2][N^4] when the tensors do not fit in shared memory
     int tensors_in_smem;
+    int in_place;           // ket/bra blocks of at most 8 states: site-basis transform in one buffer
     // on-device eigensystems (jacobi != 0): H_m = H0 + diag(sum_j shift[m][j] v[j][.]), lab frame
     int transposed_out;     // write Lt[m][c][r] (storage of qsx_dense_wrap) instead of L[m][r][c]
     int jacobi;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void matsubara_sum(const double *m_nu, const double *
     si = warp_sum(ai);
 }
 
-__global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a) {
+__global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, nb = a.nb, N2 = N * N;
     const int na = a.na, nbb = a.nbb;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
     cplx *TA, *TB;
     if (a.tensors_in_smem) {
         TA = reinterpret_cast<cplx *>(m_pre + a.n_mats);
-        TB = TA + N4;
+        TB = a.in_place ? TA : TA + N4;
     } else {
         TA = a.scratch + (size_t)blockIdx.x * 2 * N4;
         TB = TA + N4;
@@ -287,6 +288,32 @@ __global__ void __launch_bounds__(256) redfield_build_kernel(RedfieldBuildArgs a
                 const int stride = pos == 0 ? nbb * na * nbb : pos == 1 ? na * nbb : pos == 2 ? nbb : 1;
                 const int n = (pos & 1) ? nbb : na;
                 const int *states = (pos & 1) ? a.rb : a.ra;
+                if (a.in_place) {
+                    // small blocks (n <= 8): a thread owns a whole line of the tensor along the
+                    // transformed index, so the pass runs in place and the second tensor
+                    // buffer is not needed (twice as many members resident per SM)
+                    for (int l = tid; l < n4 / n; l += nthr) {
+                        const int base = (l / stride) * (n * stride) + (l % stride);
+                        cplx v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = q < n ? src[base + q * stride] : cmake(0, 0);
+                        for (int i = 0; i < n; ++i) {
+                            const cplx *urow = Us + states[i] * N;
+                            cplx acc = cmake(0, 0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (q < n) {
+                                    cplx u = urow[states[q]];
+                                    if (pos >= 2) u.y = -u.y;
+                                    cfma(acc, u, v[q]);
+                                }
+                            }
+                            src[base + i * stride] = acc;
+                        }
+                    }
+                    __syncthreads();
+                    continue;
+                }
                 for (int p = tid; p < n4; p += nthr) {
                     const int i = (p / stride) % n;
                     const int base = p - i * stride;
@@ -397,7 +424,8 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     const int n_mats = bath->kind == QSX_BATH_DEBYE_COMPLEX ? (bath->matsubara_cutoff > 0 ? bath->matsubara_cutoff : 1000) : 0;
     size_t base = (3 * N2 + (size_t)n_baths * N2) * sizeof(cplx) +
                   ((size_t)((N + 1) & ~1) + 2 * (size_t)((n_mats + 1) & ~1)) * sizeof(double);
-    size_t with_t = base + 2 * N4 * sizeof(cplx);
+    const int in_place = (na <= 8 && nbb <= 8) ? 1 : 0;
+    size_t with_t = base + (in_place ? 1 : 2) * N4 * sizeof(cplx);
     QSX_REQUIRE(base <= (size_t)smem_limit, "qsx_redfield_build: too many baths/states for shared memory");
     int tensors_in_smem = with_t <= (size_t)smem_limit;
     size_t smem = tensors_in_smem ? with_t : base;
@@ -416,7 +444,7 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     if (a.bath.matsubara_cutoff <= 0) a.bath.matsubara_cutoff = 1000;
     a.n_mats = (n_mats + 1) & ~1;       // padded entries are zero terms
     a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;
-    a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem;
+    a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem; a.in_place = in_place;
     a.transposed_out = transposed_out;
     a.jacobi = jacobi; a.H0 = d_H0.p; a.shifts = shifts_dev; a.quanta = d_quanta.p; a.rw_freq = rw_freq;
     QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
