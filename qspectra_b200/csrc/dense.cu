@@ -590,13 +590,12 @@ __constant__ double inv_fact[15] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120,
                                     1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
                                     1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0};
 
-template <int MT>      // matrix padded to 8*MT rows/cols; MT warps per CTA
+template <int MT, int KS>      // matrix padded to 8*MT rows/cols (4*KS along the contraction); MT warps per CTA
 __global__ void __launch_bounds__(32 * MT)
 dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm, int M, double dt,
                   cplx *__restrict__ Pt_out, unsigned long long *__restrict__ status) {
     constexpr int MP = 8 * MT;
     constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
-    constexpr int KS = 2 * MT;              // k-steps of 4
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *planes = reinterpret_cast<double *>(smem_raw);
     double *A1r = planes, *A1i = A1r + MP * LD, *A2r = A1i + MP * LD, *A2i = A2r + MP * LD,
@@ -711,16 +710,24 @@ dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm,
     }
 }
 
-template <int MT>
-static cudaError_t launch_expm(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
-                               int n_gen, cudaStream_t stream) {
+template <int MT, int KS>
+static cudaError_t launch_expm_ks(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
+                                  int n_gen, cudaStream_t stream) {
     constexpr int MP = 8 * MT;
     constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
     size_t smem = (size_t)8 * MP * LD * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(dense_expm_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dense_expm_kernel<MT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dense_expm_kernel<MT><<<n_gen, 32 * MT, smem, stream>>>(Lt, lnorm, M, dt, Pt, status);
+    dense_expm_kernel<MT, KS><<<n_gen, 32 * MT, smem, stream>>>(Lt, lnorm, M, dt, Pt, status);
     return cudaGetLastError();
+}
+
+// the contraction dimension is padded to a multiple of 4 only (M = 49: 13 k-steps, not 14)
+template <int MT>
+static cudaError_t launch_expm(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
+                               int n_gen, cudaStream_t stream) {
+    if ((M + 3) / 4 == 2 * MT - 1) return launch_expm_ks<MT, 2 * MT - 1>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
+    return launch_expm_ks<MT, 2 * MT>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
 }
 
 extern "C" int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_gemms) {
