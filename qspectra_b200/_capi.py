@@ -40,7 +40,8 @@ class QsxPropagateArgs(C.Structure):
                 ('method', C.c_int32), ('rtol', C.c_double), ('atol', C.c_double),
                 ('rk4_substeps', C.c_int32), ('save_mode', C.c_int32),
                 ('save_rows', C.c_int32), ('save_dev', C.c_void_p),
-                ('n_save', C.c_int32), ('n_pulses', C.c_int32),
+                ('n_save', C.c_int32),
+                ('save_of_column_host', C.POINTER(C.c_int32)), ('n_pulses', C.c_int32),
                 ('pulses', QsxPulse * MAX_PULSES),
                 ('pulse_ops_dev', C.c_void_p), ('n_pulse_sets', C.c_int32),
                 ('out_dev', C.c_void_p),

@@ -75,6 +75,7 @@ struct DenseKernelArgs {
     const double *t;
     double t0;
     const int *grp_col0, *grp_ncol, *grp_gen;
+    const int *grp_save;        // save-matrix index of each group, or null (= generator index)
     int method;
     double rtol, atol;
     int rk4_sub, kmax;
@@ -209,7 +210,7 @@ dense_propagate_kernel(DenseKernelArgs a) {
     DenseSaver<NB> saver;
     saver.M = M; saver.ncol = ncol; saver.nt = a.nt; saver.mode = a.save_mode;
     saver.save_rows = a.save_rows; saver.saved_dim = a.saved_dim;
-    saver.S = a.S ? a.S + (size_t)gen * a.S_stride : nullptr;
+    saver.S = a.S ? a.S + (size_t)(a.grp_save ? a.grp_save[g] : gen) * a.S_stride : nullptr;
     saver.out = a.out + (size_t)col0 * a.nt * a.saved_dim;
 
     CtaProp P;
@@ -260,7 +261,7 @@ dense_map_kernel(DenseKernelArgs a) {
     DenseSaver<NB> saver;
     saver.M = M; saver.ncol = ncol; saver.nt = a.nt; saver.mode = a.save_mode;
     saver.save_rows = a.save_rows; saver.saved_dim = a.saved_dim;
-    saver.S = a.S ? a.S + (size_t)gen * a.S_stride : nullptr;
+    saver.S = a.S ? a.S + (size_t)(a.grp_save ? a.grp_save[g] : gen) * a.S_stride : nullptr;
     saver.out = a.out + (size_t)col0 * a.nt * a.saved_dim;
     saver(0, xb);
     for (int it = 1; it < a.nt; ++it) {
@@ -474,19 +475,28 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
             return QSX_ERR_UNSUPPORTED;
         }
     }
-    std::vector<int> col0, ncol, gens;
+    std::vector<int> col0, ncol, gens, saves;
+    const int32_t *save_of = args->save_mode == QSX_SAVE_MATRIX ? args->save_of_column_host : nullptr;
     prev = -1;
+    int prev_save = -1;
     for (int c = 0; c < B; ++c) {
         int g = args->generator_of_column_host ? args->generator_of_column_host[c] : 0;
-        if (g == prev && ncol.back() < NB) {
+        int sv = save_of ? save_of[c] : 0;
+        QSX_REQUIRE(!save_of || (sv >= 0 && sv < args->n_save), "save index %d out of range", sv);
+        if (g == prev && sv == prev_save && ncol.back() < NB) {
             ncol.back() += 1;
         } else {
-            col0.push_back(c); ncol.push_back(1); gens.push_back(g);
+            col0.push_back(c); ncol.push_back(1); gens.push_back(g); saves.push_back(sv);
         }
         prev = g;
+        prev_save = sv;
     }
     const int groups = (int)col0.size();
-    DevBuf<int> d_col0, d_ncol, d_gen;
+    DevBuf<int> d_col0, d_ncol, d_gen, d_save;
+    if (save_of) {
+        int rc_s = upload_ints(d_save, saves, stream);
+        if (rc_s) return rc_s;
+    }
     DevBuf<double> d_t;
     DevBuf<unsigned long long> d_stats;
     int rc;
@@ -501,6 +511,7 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
     a.M = M; a.nt = nt; a.Lt = h->Lt.p; a.lnorm = h->lnorm.p;
     a.y0 = (const cplx *)args->y0_dev; a.t = d_t.p; a.t0 = args->t0;
     a.grp_col0 = d_col0.p; a.grp_ncol = d_ncol.p; a.grp_gen = d_gen.p;
+    a.grp_save = save_of ? d_save.p : nullptr;
     a.method = args->method;
     a.rtol = args->rtol > 0 ? args->rtol : (args->method == QSX_METHOD_TAYLOR ? 1e-13 : 1e-10);
     a.atol = args->atol > 0 ? args->atol : 1e-12;
@@ -511,7 +522,8 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
     a.S_stride = (args->n_save > 1) ? (long long)args->save_rows * M : 0;
     if (a.save_mode == QSX_SAVE_MATRIX) {
         QSX_REQUIRE(a.S && a.save_rows > 0, "save matrix missing");
-        QSX_REQUIRE(args->n_save == 1 || args->n_save == h->n_gen, "n_save must be 1 or n_generators");
+        QSX_REQUIRE(save_of || args->n_save == 1 || args->n_save == h->n_gen,
+                    "n_save must be 1 or n_generators unless save_of_column is given");
     }
     a.saved_dim = a.save_mode == QSX_SAVE_MATRIX ? a.save_rows : M;
     a.n_pulse = args->n_pulses;

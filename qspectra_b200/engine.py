@@ -102,12 +102,15 @@ class DeviceEOM(object):
 
     def propagate(self, y0, t, t0=None, method='zvode', save=None,
                   generators=None, pulses=None, pulse_ops=None, rtol=None,
-                  atol=None, rk4_substeps=None, return_device=False, **ignored):
+                  atol=None, rk4_substeps=None, return_device=False,
+                  save_index=None, **ignored):
         """Integrate a batch: y0 (B, dim) -> (B, len(t), saved_dim).
 
         save      : None | LinearMap | ('ado0',) | ndarray (rows, dim[/n_ado])
                     or stack (n_generators, rows, dim)
         generators: int array (B,) choosing the generator of each column
+        save_index: int array (B,) choosing the matrix of a save stack for each
+                    column (dense generators; default: the column's generator)
         pulses    : list of (scale, detuning, t_peak, inv_two_sigma_sq, conj)
         pulse_ops : (n_sets, n_pulses, d, d) complex
         """
@@ -137,6 +140,13 @@ class DeviceEOM(object):
 
         keep = []
         saved_dim = self._configure_save(args, save, keep)
+        sarr, sptr = _capi.int32_ptr(save_index)
+        if sarr is not None:
+            if sarr.shape != (B,):
+                raise ValueError('save_index must have one entry per column')
+            if not isinstance(self, DenseEOM):
+                raise ValueError('per-column save matrices need a dense generator')
+            args.save_of_column_host = sptr
         n_p = len(pulses) if pulses else 0
         if n_p > _capi.MAX_PULSES:
             raise ValueError('at most %d pulses' % _capi.MAX_PULSES)

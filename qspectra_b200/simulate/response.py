@@ -173,19 +173,40 @@ def _third_order_response(dynamical_model, coherence_time_max,
     return (t1, t2, t3), total_signal
 
 
-@optional_4th_order_isotropic_average
+def _polarization_variants(polarization, exact_isotropic_average):
+    """[(weight, polarization)] whose weighted sum is the requested signal: the
+    polarization itself, or the Cartesian configurations of the fourth-order
+    isotropic average with their invariant weights summed per configuration
+    (decorators.py:64-101, same 1e-8 weight cut-off)."""
+    if not exact_isotropic_average:
+        return [(1.0, polarization)]
+    from collections import OrderedDict
+    from ..polarization import (FOURTH_ORDER_INVARIANTS, invariant_polarizations,
+                                invariant_weights_4th_order)
+    acc = OrderedDict()
+    for invariant, weight in zip(FOURTH_ORDER_INVARIANTS,
+                                 invariant_weights_4th_order(polarization)):
+        if weight > 1e-8:
+            for p in invariant_polarizations(invariant):
+                acc[p] = acc.get(p, 0.0) + weight
+    return [(w, p) for p, w in acc.items()]
+
+
 def _third_order_response_batched(dynamical_model, coherence_time_max,
                                   population_time_max, population_times,
                                   geometry, polarization, include_signal,
                                   ensemble_size, random_orientations,
-                                  member_offset, normalize, **integrate_kwargs):
-    """Disorder-ensemble third-order response with ALL members on the device at
-    once (dense-generator models): per pathway three batched propagations --
-    t1: one column per member, t2: n_t1 columns per member under that member's
-    generator, t3: one Heisenberg column per member -- and one contraction
-    sum_m einsum('ci,abi') on the device.  The reference runs
-    ensemble_size x (1 + n_t1 + 1) serial ZVODE solves per pathway
-    (decorators.py:55-60, utils.py:103-109)."""
+                                  member_offset, normalize,
+                                  exact_isotropic_average=False,
+                                  **integrate_kwargs):
+    """Third-order response of a dense-generator model with ALL independent units
+    on the device at once: ensemble members (`ensemble_size`, or the model itself
+    when None) x polarisation configurations of the isotropic average (up to 21).
+    Per pathway three batched propagations -- t1: one column per unit, t2: n_t1
+    columns per unit under that member's generator, t3: one Heisenberg column per
+    unit -- and one weighted contraction on the device.  The reference runs
+    ensemble_size x 21 x (1 + n_t1 + 1) serial ZVODE solves per pathway
+    (decorators.py:55-60, 86-92; utils.py:103-109).  Returns a CUDA tensor."""
     from .. import _capi
     torch = _capi.torch_cuda()
     model = dynamical_model
@@ -198,52 +219,69 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
             if k in integrate_kwargs}
     method = integrate_kwargs.get('method_name', 'zvode')
     paths = _parse_pathways(THIRD_ORDER_PATHWAYS[geometry], include_signal)
+    variants = _polarization_variants(polarization, exact_isotropic_average)
+    nv = len(variants)
+    wv = torch.tensor([w for w, _ in variants], dtype=torch.complex128, device='cuda')
+    single = ensemble_size is None
+    n_members = 1 if single else ensemble_size
     total = torch.zeros((len(t1), len(t2), len(t3)), dtype=torch.complex128,
                         device='cuda')
-    # bound the (members x t1 x t2 x M3) intermediate to ~2 GB per chunk
+    # bound the (units x t1 x t2 x M3) intermediate to ~2 GB per chunk
     n_big = max(len(model.liouville_subspace_index(p.split('->')[3])) for p in paths)
-    chunk = max(1, int(2e9 // (len(t1) * len(t2) * n_big * 16)))
+    chunk = max(1, int(2e9 // (len(t1) * len(t2) * n_big * 16 * nv)))
     rho0 = model.thermal_state('gg')
-    for lo in range(0, ensemble_size, chunk):
-        E = min(chunk, ensemble_size - lo)
+    for lo in range(0, n_members, chunk):
+        E = min(chunk, n_members - lo)
         first = member_offset + lo
-        gens = np.arange(E)
         dip = ([model.sample(first + n, True) for n in range(E)]
-               if random_orientations else [model])
+               if random_orientations and not single else [model])
+        nm = len(dip)
+        gens = np.repeat(np.arange(E), nv)                  # generator of unit (e, v)
+        sidx = (np.arange(E * nv) if nm == E else np.tile(np.arange(nv), E))
         eoms = {}
 
         def eom_for(subspace, heisenberg=False):
             # pathways share stage subspaces: build each batch of generators once
             key = (subspace, heisenberg)
             if key not in eoms:
-                eoms[key] = model.ensemble_eom(E, random_orientations, subspace,
-                                               heisenberg_picture=heisenberg,
-                                               member0=first)
+                eoms[key] = (model.equation_of_motion(subspace, heisenberg_picture=heisenberg)
+                             if single else
+                             model.ensemble_eom(E, random_orientations, subspace,
+                                                heisenberg_picture=heisenberg,
+                                                member0=first))
             return eoms[key]
 
         for path in paths:
             ss = path.split('->')
-            V = [[m.dipole_operator('{}->{}'.format(a, b), polar, trans)
-                  for a, b, polar, trans in zip(ss[:-1], ss[1:], polarization,
-                                                geometry + '-')] for m in dip]
-            stack = lambda i, attr: (getattr(V[0][i], attr).matrix if len(V) == 1 else
-                                     np.array([getattr(v[i], attr).matrix for v in V]))
+            # V[m][v][i]: dipole operator of interaction i for member m, configuration v
+            V = [[[m.dipole_operator('{}->{}'.format(a, b), polar, trans)
+                   for a, b, polar, trans in zip(ss[:-1], ss[1:], pol, geometry + '-')]
+                  for _, pol in variants] for m in dip]
+
+            def per_unit(f):
+                """(E * nv, ...) array of f(V[m][v]) with members broadcast if shared"""
+                a = np.array([[f(V[m][v]) for v in range(nv)] for m in range(nm)])
+                if nm != E:
+                    a = np.broadcast_to(a, (E,) + a.shape[1:])
+                return np.ascontiguousarray(a).reshape((E * nv,) + a.shape[2:])
+
+            stack = lambda i: np.array([[V[m][v][i].commutator.matrix for v in range(nv)]
+                                        for m in range(nm)]).reshape((nm * nv,) + V[0][0][i].commutator.matrix.shape)
             eom_a, eom_b, eom_c = eom_for(ss[1]), eom_for(ss[2]), eom_for(ss[3], True)
-            y0 = np.array([v[0].commutator(rho0) for v in V])
-            y0 = np.broadcast_to(y0, (E,) + y0.shape[1:]) if len(V) == 1 else y0
-            out1 = eom_a.propagate(y0, t1, method=method, save=stack(1, 'commutator'),
-                                   generators=gens, return_device=True, **opts)
-            out2 = eom_b.propagate(out1.reshape(E * len(t1), -1), t2, t0=0,
-                                   method=method, save=stack(2, 'commutator'),
+            out1 = eom_a.propagate(per_unit(lambda v: v[0].commutator(rho0)), t1,
+                                   method=method, save=stack(1), generators=gens,
+                                   save_index=sidx, return_device=True, **opts)
+            out2 = eom_b.propagate(out1.reshape(E * nv * len(t1), -1), t2, t0=0,
+                                   method=method, save=stack(2),
                                    generators=np.repeat(gens, len(t1)),
+                                   save_index=np.repeat(sidx, len(t1)),
                                    return_device=True, **opts)
-            bra = np.array([v[3].bra_vector for v in V])
-            bra = np.broadcast_to(bra, (E,) + bra.shape[1:]) if len(V) == 1 else bra
-            out3 = eom_c.propagate(bra, t3, method=method, generators=gens,
-                                   return_device=True, **opts)
-            total += torch.einsum('eabi,eci->abc',
-                                  out2.reshape(E, len(t1), len(t2), -1), out3)
-    if normalize:
+            out3 = eom_c.propagate(per_unit(lambda v: v[3].bra_vector), t3, method=method,
+                                   generators=gens, return_device=True, **opts)
+            total += torch.einsum('v,evabi,evci->abc', wv,
+                                  out2.reshape(E, nv, len(t1), len(t2), -1),
+                                  out3.reshape(E, nv, len(t3), -1))
+    if normalize and not single:
         total = total / ensemble_size
     return (t1, t2, t3), total
 
@@ -262,7 +300,7 @@ def third_order_response(dynamical_model, coherence_time_max,
     """Third-order response ((t1, t2, t3), signal[t1, t2, t3]) in the rotating
     wave approximation, summed over the selected Liouville pathways.  Disorder
     ensembles of dense-generator models are propagated as one device batch."""
-    if ensemble_size is not None and _batchable(dynamical_model):
+    if _batchable(dynamical_model):
         ticks, total = _third_order_response_batched(
             dynamical_model, coherence_time_max, population_time_max,
             population_times, geometry, polarization, include_signal,
@@ -288,8 +326,8 @@ def two_dimensional_spectra(dynamical_model, coherence_time_max,
     """2D spectrum: Fourier transform of the third-order response over t1
     (sign -1) and t3."""
     from .. import _capi
-    if ensemble_size is not None and _batchable(dynamical_model):
-        # the ensemble-summed signal never leaves the device before the transforms
+    if _batchable(dynamical_model):
+        # the (ensemble- and orientation-summed) signal never leaves the device before the transforms
         (t1, t2, t3), X = _third_order_response_batched(
             dynamical_model, coherence_time_max, population_time_max,
             population_times, geometry, polarization, include_signal,
