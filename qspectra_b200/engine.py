@@ -226,6 +226,9 @@ class DenseEOM(DeviceEOM):
             raise ValueError('generators must have shape (n, M, M)')
         self.n_generators, self.dim = int(shape[0]), int(shape[1])
         self.heisenberg_picture = bool(heisenberg_picture)
+        if self.dim > self.EXPM_MAX_DIM:
+            # kept for the library propagator of wide states (see propagator())
+            self._L_source = Ld if on_device else Lh
         self._h = C.c_void_p()
         _capi.check(lib.qsx_dense_create(C.byref(self._h), self.dim,
                                          self.n_generators, ptr, int(on_device),
@@ -240,12 +243,34 @@ class DenseEOM(DeviceEOM):
 
     #: largest state dimension of the tensor-core propagator kernel
     EXPM_MAX_DIM = 56
+    #: wider states (e.g. FMO 'fe', 147) get exp(L dt) from the library
+    #: (torch.linalg.matrix_exp -> cuBLAS batched ZGEMM) and are stepped by the
+    #: CTA-resident kernel with P streamed from L2
+    EXPM_LIBRARY_MAX_DIM = 512
+
+    def _stored_matrices(self):
+        """(n, M, M) CUDA tensor in the engine's storage layout (transposed
+        generator; for the Heisenberg picture that is L itself)."""
+        torch = _capi.torch_cuda()
+        if hasattr(self, '_storage'):
+            return self._storage[0]
+        L = self._L_source
+        Ld = L if isinstance(L, torch.Tensor) else torch.from_numpy(L).cuda()
+        return Ld if self.heisenberg_picture else Ld.transpose(1, 2)
 
     def propagator(self, dt):
         """DenseEOM holding P_g = exp(L_g dt) for every generator (FP64 tensor
         cores, csrc/dense.cu: dense_expm_kernel); cached per dt."""
         cache = self.__dict__.setdefault('_propagators', {})
         key = float(dt)
+        if key not in cache and self.dim > self.EXPM_MAX_DIM:
+            torch = _capi.torch_cuda()
+            # exp(G dt) in transposed storage is exp(G^T dt): exponentiate the stored matrices
+            P = torch.linalg.matrix_exp(self._stored_matrices() * key).contiguous()
+            prop = DenseEOM.from_transposed(P)
+            prop.heisenberg_picture = self.heisenberg_picture
+            prop.build_ms, prop.build_gemms = 0.0, 0
+            cache[key] = prop
         if key not in cache:
             torch = _capi.torch_cuda()
             prop = DenseEOM.__new__(DenseEOM)
@@ -308,7 +333,7 @@ class DenseEOM(DeviceEOM):
             dt = self._uniform_step(t, t0)
             n_cols = int(np.prod(np.shape(y0)[:-1])) if np.ndim(y0) > 1 else 1
             worth = len(t) * max(1, n_cols // self.n_generators) >= 64
-            if dt is not None and self.dim <= self.EXPM_MAX_DIM and \
+            if dt is not None and self.dim <= self.EXPM_LIBRARY_MAX_DIM and \
                     (name == 'expm' or worth):
                 prop = self.propagator(dt)
                 out = DeviceEOM.propagate(prop, y0, t, t0=t0, method='map', **kw)
@@ -317,7 +342,7 @@ class DenseEOM(DeviceEOM):
             if name == 'expm':
                 raise ValueError('expm needs a uniform output grid starting at '
                                  't0 and a state dimension <= %d'
-                                 % self.EXPM_MAX_DIM)
+                                 % self.EXPM_LIBRARY_MAX_DIM)
         return DeviceEOM.propagate(self, y0, t, t0=t0, method=method, **kw)
 
     def _apply_dev(self, y, dy, n, gptr):

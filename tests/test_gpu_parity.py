@@ -576,3 +576,24 @@ def test_device_disorder_streams_match_numpy():
     assert dev.shape == host.shape
     assert np.abs(dev - host).max() <= 8 * np.finfo(float).eps * np.abs(host).max()
     assert (dev == host).mean() > 0.5
+
+
+def test_wide_state_propagator_stepping():
+    """state dimensions above the tensor-core kernel's 56 (FMO 'fe', M = 147):
+    library matrix exponential + streamed propagator stepping against Taylor"""
+    mf = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef', unit_convert=CM_FS)
+    rng = np.random.RandomState(2)
+    for heis in (False, True):
+        eom = mf.equation_of_motion('fe', heisenberg_picture=heis)
+        assert eom.dim == 147
+        y0 = rng.randn(2, 147) + 1j * rng.randn(2, 147)
+        t = mf.time_step * np.arange(80)
+        a = eom.propagate(y0, t)
+        assert eom.last['method'] == 'expm'
+        b = eom.propagate(y0, t, method='taylor')
+        assert rel_l2(a, b) < 1e-10
+    ens = mf.ensemble_eom(3, False, 'fe', heisenberg_picture=True)
+    y0 = rng.randn(3, 147) + 1j * rng.randn(3, 147)
+    a = ens.propagate(y0, t, generators=np.arange(3))
+    b = ens.propagate(y0, t, generators=np.arange(3), method='taylor')
+    assert ens.last['method'] == 'taylor' and rel_l2(a, b) < 1e-10
