@@ -102,6 +102,11 @@ struct TileSmem {
     // cross-tile prefetch hints (set by the kernel loops, used by TileEE)
     int cur_col, next_col;
     long long next_tile;
+    long long w, wstride, total;   // work index of the current tile, CTA stride, number of (column, tile) units
+    uint64_t *bars;          // mbarriers of the bulk-copy tile pipeline (TileLean OPT 8)
+    int q;                   // number of tiles this CTA has processed so far (pipeline sequence number)
+    const int *member_of;    // generator of each column (nullptr: member 0), for tiles staged ahead
+    const cplx *pf;          // integrator operand (accumulator column) worth prefetching to L2, or nullptr
     const cplx *loaded;      // tile data currently staged (or in flight) in buffer `buf`
     int buf;
     double t_eval;           // time at which the pulse envelopes are evaluated
@@ -650,6 +655,7 @@ struct TileEE {
             issue(H, buffer(s, 0), tile_data, tile);
         }
         if (member != s.cur_member) {
+            __syncthreads();                // slower warps may still read the previous member's coefficients
             const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
             for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.HR[i] = hr[i]; s.HC[i] = hc[i]; }
             s.cur_member = member;
@@ -824,8 +830,45 @@ struct TileEE {
 //     up-neighbours: a CTA-uniform branch takes a body without those 28 gathers;
 //   * the integrator's own-value and accumulator operands are re-read (shared memory /
 //     streaming load) in the epilogue instead of living in registers across the tile.
-template <int NS, int K1, int MINB>
+// OPT bits:
+//   1  the integrator operands of the 7 owned elements are loaded as one batch before the
+//      epilogue (otherwise every accumulator load waits behind the previous element's
+//      stores: 7 serial DRAM round trips per tile in the even Taylor stages);
+//   2  the accumulator lines of the tile are prefetched to L2 when the tile body starts;
+//   4  three source-tile buffers (prefetch distance 2 instead of 1);
+//   8  barrier-free tile pipeline: one elected thread stages tile + tables + member H with
+//      bulk asynchronous copies (cp.async.bulk, completion on an mbarrier), every warp waits
+//      on the "full" mbarrier of its buffer and releases it through an "empty" mbarrier, so
+//      the row-warps of a CTA are no longer in lock step (always three buffers).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, int bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NS, int K1, int MINB, int OPT = 0>
 struct TileLean {
+    static constexpr bool PIPE = (OPT & 8) != 0;
+    static constexpr int NBUF = (OPT & 12) ? 3 : 2;
+    static constexpr int HS = PIPE ? 2 : 1;       // stride of the H coefficients (PIPE reads Im of the complex tables)
     static constexpr int THREADS = 32 * NS;
     static constexpr int MIN_BLOCKS = MINB;
     static constexpr int UNITS = 1;
@@ -834,13 +877,14 @@ struct TileLean {
 
     static __host__ __device__ size_t buf_bytes() {
         return al16((size_t)M * TL * sizeof(cplx)) + 2 * al16((size_t)BINS * TL * sizeof(int)) +
-               al16((size_t)BINS * TL) + al16((size_t)2 * TL * sizeof(double));
+               al16((size_t)BINS * TL) + al16((size_t)2 * TL * sizeof(double)) +
+               (PIPE ? 2 * al16((size_t)NS * NS * sizeof(cplx)) : 0);
     }
     static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
         return 2 * al16((size_t)NS * NS * sizeof(double)) + al16((size_t)M * sizeof(double)) +
-               al16((size_t)K1 * H.Lc * sizeof(double)) + al16((size_t)K1 * H.Lc * sizeof(cplx));
+               al16((size_t)K1 * H.Lc * sizeof(double)) + al16((size_t)K1 * H.Lc * sizeof(cplx)) + 64;
     }
-    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + 2 * buf_bytes(); }
+    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + NBUF * buf_bytes(); }
 
     static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
         size_t off = 0;
@@ -849,33 +893,91 @@ struct TileLean {
         s.dterm = reinterpret_cast<double *>(base + off); off += al16((size_t)M * sizeof(double));
         s.su = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
         s.tD = reinterpret_cast<cplx *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(cplx));
-        s.os = reinterpret_cast<cplx *>(base + off);       // start of the two tile buffers
+        s.bars = reinterpret_cast<uint64_t *>(base + off); off += 64;   // full[0..2], empty[0..2]
+        s.os = reinterpret_cast<cplx *>(base + off);       // start of the tile buffers
         for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
         for (int i = threadIdx.x; i < K1 * H.Lc; i += blockDim.x) {
             const int k = i / H.Lc;
             s.su[i] = -H.GuR[k].y * H.su[i];               // u s_up(n):  row coefficient -i t, column +i t
             s.tD[i] = cscale(H.sd[i], H.GdR[k]);           // -i u c_k s_dn(n); the column-site one is its conjugate
         }
+        if (PIPE && threadIdx.x == 0) {
+            for (int i = 0; i < 3; ++i) { mbar_init(&s.bars[i], 1); mbar_init(&s.bars[3 + i], NS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         s.cur_member = -1;
         s.loaded = nullptr;
         s.buf = 0;
+        s.q = 0;
+        s.member_of = nullptr;
         __syncthreads();
     }
 
-    typedef typename TileEE<NS, K1, 1, true, true>::Buf Buf;
+    struct Buf {
+        cplx *ys; int *o_up, *o_dn; uint8_t *occ; double *sh; const double *hR, *hC;
+    };
     static __device__ __forceinline__ Buf buffer(const TileSmem &s, int which) {
-        return TileEE<NS, K1, 1, true, true>::buffer(s, which);
+        unsigned char *p = reinterpret_cast<unsigned char *>(s.os) + (size_t)which * buf_bytes();
+        Buf b;
+        b.ys = reinterpret_cast<cplx *>(p); p += al16((size_t)M * TL * sizeof(cplx));
+        b.o_up = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
+        b.o_dn = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
+        b.occ = p; p += al16((size_t)BINS * TL);
+        b.sh = reinterpret_cast<double *>(p); p += al16((size_t)2 * TL * sizeof(double));
+        if (PIPE) {     // complex member tables staged with the tile; the coefficients are their imaginary parts
+            b.hR = reinterpret_cast<const double *>(p) + 1; p += al16((size_t)NS * NS * sizeof(cplx));
+            b.hC = reinterpret_cast<const double *>(p) + 1;
+        } else {
+            b.hR = s.hR; b.hC = s.hC;
+        }
+        return b;
     }
+    // asynchronous copy of one source tile and its tables into a buffer (cp.async, all threads)
     static __device__ __forceinline__ void issue(const HeomDev &H, const Buf &b, const cplx *tile_data, long long tile) {
-        TileEE<NS, K1, 1, true, true>::issue(H, b, tile_data, tile);
+        for (int i = threadIdx.x; i < M * TL; i += THREADS) cp_async16(&b.ys[i], &tile_data[i]);
+        const size_t tb = (size_t)tile * BINS * TL;
+        for (int i = threadIdx.x; i < BINS * TL / 4; i += THREADS) {
+            cp_async16(&b.o_up[4 * i], &H.off_up[tb + 4 * i]);
+            cp_async16(&b.o_dn[4 * i], &H.off_dn[tb + 4 * i]);
+        }
+        for (int i = threadIdx.x; i < BINS * TL / 16; i += THREADS) cp_async16(&b.occ[16 * i], &H.occ[tb + 16 * i]);
+        if (threadIdx.x < TL / 2) {
+            cp_async16(&b.sh[2 * threadIdx.x], &H.shift[tile * TL + 2 * threadIdx.x]);
+            cp_async16(&b.sh[TL + 2 * threadIdx.x], &H.scale[tile * TL + 2 * threadIdx.x]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    // bulk-copy staging of the q-th tile of this CTA (one thread): waits until every warp has
+    // released the buffer's previous occupant, then arms the "full" barrier with the byte count
+    static __device__ __forceinline__ void fill(const HeomDev &H, const TileSmem &s, int q, const cplx *tile_data,
+                                                long long tile, int member) {
+        const int bi = q % 3;
+        if (q >= 3) mbar_wait(&s.bars[3 + bi], ((q / 3) - 1) & 1);
+        const Buf b = buffer(s, bi);
+        uint64_t *full = &s.bars[bi];
+        const bool top = tile >= H.top_tile;
+        const int tab = BINS * TL * (int)sizeof(int);
+        const int bytes = M * TL * (int)sizeof(cplx) + (top ? 1 : 2) * tab + BINS * TL + 2 * TL * (int)sizeof(double) +
+                          2 * NS * NS * (int)sizeof(cplx);
+        mbar_expect_tx(full, bytes);
+        const size_t tb = (size_t)tile * BINS * TL;
+        bulk_g2s(b.ys, tile_data, M * TL * (int)sizeof(cplx), full);
+        if (!top) bulk_g2s(b.o_up, H.off_up + tb, tab, full);
+        bulk_g2s(b.o_dn, H.off_dn + tb, tab, full);
+        bulk_g2s(b.occ, H.occ + tb, BINS * TL, full);
+        bulk_g2s(b.sh, H.shift + tile * TL, TL * (int)sizeof(double), full);
+        bulk_g2s(b.sh + TL, H.scale + tile * TL, TL * (int)sizeof(double), full);
+        bulk_g2s(const_cast<double *>(b.hR) - 1, H.HR + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
+        bulk_g2s(const_cast<double *>(b.hC) - 1, H.HC + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
     }
 
     // Hs_R rho for source rows c in [c0, c1): (i h) z = h (-z.y, z.x)
     template <int C0, int C1>
-    static __device__ __forceinline__ void left_product(const TileSmem &s, const cplx *ys, int w, cplx (&acc)[NS]) {
+    static __device__ __forceinline__ void left_product(const Buf &cur, const cplx *ys, int w, cplx (&acc)[NS]) {
 #pragma unroll
         for (int c = C0; c < C1; ++c) {
-            const double h = s.hR[w * NS + c];
+            const double h = cur.hR[(w * NS + c) * HS];
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
                 const cplx z = ys[(c + NS * b) * TL];
@@ -895,6 +997,12 @@ struct TileLean {
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // w = row a
         const cplx *ys = cur.ys + lane;
         const cplx *xw = x + (size_t)w * TL;
+        const long long gbase = ((long long)tile * M) * TL + lane + (long long)w * TL;   // element (w, 0)
+        if ((OPT & 2) && s.pf != nullptr && (lane & 7) == 0) {
+#pragma unroll
+            for (int b = 0; b < NS; ++b)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.pf + gbase + (long long)b * NS * TL));
+        }
         cplx acc[NS];
         {
             // diagonal terms and - rho Hs_C from the own row (A_C stored transposed)
@@ -908,7 +1016,7 @@ struct TileLean {
                 acc[b] = cmake(-dg * own[b].x, -dg * own[b].y);
 #pragma unroll
                 for (int c = 0; c < NS; ++c) {
-                    const double h = s.hC[b * NS + c];
+                    const double h = cur.hC[(b * NS + c) * HS];
                     acc[b].x = fma(h, own[c].y, acc[b].x);
                     acc[b].y = fma(-h, own[c].x, acc[b].y);
                 }
@@ -929,7 +1037,7 @@ struct TileLean {
                 gd[b] = cmake(0, 0);
                 if (od >= 0) gd[b] = __ldcg(pd + b * NS * TL);
             }
-            if (k == 0) left_product<0, 2>(s, ys, w, acc); else left_product<2, 4>(s, ys, w, acc);
+            if (k == 0) left_product<0, 2>(cur, ys, w, acc); else left_product<2, 4>(cur, ys, w, acc);
             const cplx cd = s.tD[k * H.Lc + njk];
             if (UP) {
                 const double tu = s.su[k * H.Lc + njk];
@@ -964,7 +1072,7 @@ struct TileLean {
                 gd[b] = cmake(0, 0);
                 if (od >= 0 && b != w) gd[b] = __ldcg(xw + od + b * NS * TL);
             }
-            if (k == 0) left_product<4, 6>(s, ys, w, acc); else left_product<6, NS>(s, ys, w, acc);
+            if (k == 0) left_product<4, 6>(cur, ys, w, acc); else left_product<6, NS>(cur, ys, w, acc);
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
                 const int njk = cur.occ[(b * K1 + k) * TL + lane];
@@ -981,11 +1089,21 @@ struct TileLean {
             }
         }
         const double wscale = cur.sh[TL + lane];
-        const long long gbase = ((long long)tile * M) * TL + lane + (long long)w * TL;   // element (w, 0)
+        if (OPT & 1) {
+            cplx pv[NS];
 #pragma unroll
-        for (int b = 0; b < NS; ++b) {
-            const long long i = gbase + (long long)b * NS * TL;
-            post(i, acc[b], ys[(w + NS * b) * TL], pre(i), wscale);
+            for (int b = 0; b < NS; ++b) pv[b] = pre(gbase + (long long)b * NS * TL);
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                const long long i = gbase + (long long)b * NS * TL;
+                post(i, acc[b], ys[(w + NS * b) * TL], pv[b], wscale);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                const long long i = gbase + (long long)b * NS * TL;
+                post(i, acc[b], ys[(w + NS * b) * TL], pre(i), wscale);
+            }
         }
     }
 
@@ -994,25 +1112,65 @@ struct TileLean {
                                                long long tile, int member, Pre pre, Post post) {
         const size_t Dp = (size_t)H.n_tiles * M * TL;
         const cplx *tile_data = x + (size_t)tile * M * TL;
+        const cplx *x0 = x - (size_t)s.cur_col * Dp;          // column 0 of the source
+        // source tile of the unit `ahead` places further down this CTA's work list (nullptr: none)
+        auto unit_ptr = [&](int ahead, long long &t, int &col) -> const cplx * {
+            const long long wn = s.w + ahead * s.wstride;
+            if (wn >= s.total) return nullptr;
+            t = wn % H.n_tiles;
+            col = (int)(wn / H.n_tiles);
+            return x0 + (size_t)col * Dp + (size_t)t * M * TL;
+        };
+        long long tn = 0;
+        int cn = 0;
+        if (PIPE) {
+            const int q = s.q;
+            if (threadIdx.x == 0) {
+                if (s.loaded != tile_data) {    // first tile of a phase: nothing in flight yet
+                    fill(H, s, q, tile_data, tile, member);
+                    const cplx *n1 = unit_ptr(1, tn, cn);
+                    if (n1) fill(H, s, q + 1, n1, tn, s.member_of ? s.member_of[cn] : 0);
+                }
+                const cplx *n2 = unit_ptr(2, tn, cn);
+                if (n2) fill(H, s, q + 2, n2, tn, s.member_of ? s.member_of[cn] : 0);
+            }
+            __syncwarp();
+            mbar_wait(&s.bars[q % 3], (q / 3) & 1);
+            const Buf cur = buffer(s, q % 3);
+            if (tile >= H.top_tile) body<false>(H, s, cur, x, tile, pre, post);
+            else body<true>(H, s, cur, x, tile, pre, post);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&s.bars[3 + q % 3]);
+            s.loaded = unit_ptr(1, tn, cn);
+            s.q = q + 1;
+            return;
+        }
         if (s.loaded != tile_data) {        // first tile of a phase: nothing in flight yet
             s.buf = 0;
             issue(H, buffer(s, 0), tile_data, tile);
+            if (NBUF == 3) {
+                const cplx *n1 = unit_ptr(1, tn, cn);
+                if (n1) issue(H, buffer(s, 1), n1, tn);
+                else asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
         }
         if (member != s.cur_member) {
+            __syncthreads();                // slower warps may still read the previous member's coefficients
             const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
             for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.hR[i] = hr[i].y; s.hC[i] = hc[i].y; }
             s.cur_member = member;
         }
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncthreads();                    // tile visible; every warp is done with the other buffer
+        if (NBUF == 3) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                    // tile visible; every warp is done with the buffer refilled next
         const Buf cur = buffer(s, s.buf);
-        if (s.next_tile >= 0) {             // prefetch this CTA's next tile into the other buffer
-            const cplx *nd = (x - (size_t)s.cur_col * Dp) + (size_t)s.next_col * Dp + (size_t)s.next_tile * M * TL;
-            issue(H, buffer(s, s.buf ^ 1), nd, s.next_tile);
-            s.loaded = nd;
-            s.buf ^= 1;
-        } else {
-            s.loaded = nullptr;
+        {
+            const cplx *nd = unit_ptr(NBUF - 1, tn, cn);      // refill the buffer the previous tile used
+            const int into = (s.buf + NBUF - 1) % NBUF;
+            if (nd) issue(H, buffer(s, into), nd, tn);
+            else if (NBUF == 3) asm volatile("cp.async.commit_group;\n" ::: "memory");
+            s.loaded = unit_ptr(1, tn, cn);
+            s.buf = (s.buf + 1) % NBUF;
         }
         if (tile >= H.top_tile) body<false>(H, s, cur, x, tile, pre, post);
         else body<true>(H, s, cur, x, tile, pre, post);
@@ -1151,6 +1309,7 @@ struct TileEEP {
             issue(H, s, buffer(s, 0), tile_data, tile);
         }
         if (member != s.cur_member) {
+            __syncthreads();                // slower warps may still read the previous member's coefficients
             const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
             for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.HR[i] = hr[i]; s.HC[i] = hc[i]; }
             s.cur_member = member;
@@ -1306,6 +1465,8 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_apply_ke
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem s;
     Tile::setup(a.H, smem_raw, s);
+    s.pf = nullptr;
+    s.member_of = a.member_of;
     const long long Dp = a.H.n_tiles * a.H.M * TL;
     const long long total = a.H.n_tiles * a.B;
     const long long w0 = Tile::UNITS == 1 ? blockIdx.x : (long long)blockIdx.x * Tile::UNITS + (threadIdx.x >> 5);
@@ -1313,7 +1474,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_apply_ke
     for (long long w = w0; w < total; w += wstride) {
         int b = (int)(w / a.H.n_tiles);
         long long tile = w % a.H.n_tiles;
-        { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % a.H.n_tiles : -1; s.next_col = wn < total ? (int)(wn / a.H.n_tiles) : 0; }
+        { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % a.H.n_tiles : -1; s.next_col = wn < total ? (int)(wn / a.H.n_tiles) : 0; }
         int member = a.member_of ? a.member_of[b] : 0;
         cplx *yb = a.y + (size_t)b * Dp;
         Tile::run(a.H, s, a.x + (size_t)b * Dp, tile, member,
@@ -1386,6 +1547,8 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
     cg::grid_group grid = cg::this_grid();
     TileSmem s;
     Tile::setup(a.H, smem_raw, s);
+    s.pf = nullptr;
+    s.member_of = a.member_of;
     const long long w0 = Tile::UNITS == 1 ? blockIdx.x : (long long)blockIdx.x * Tile::UNITS + (threadIdx.x >> 5);
     const long long wstride = (long long)gridDim.x * Tile::UNITS;
     const int M = a.H.M;
@@ -1452,10 +1615,11 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                         for (long long w = w0; w < total; w += wstride) {
                             const int b = (int)(w / n_tiles);
                             const long long tile = w % n_tiles;
-                            { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                            { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
                             const int member = a.member_of ? a.member_of[b] : 0;
                             cplx *db = dst + (size_t)b * Dp;
                             cplx *Yb = a.Y + (size_t)b * Dp;
+                            s.pf = even ? Yb : nullptr;
                             if (!even) {
                                 Tile::run(a.H, s, src + (size_t)b * Dp, tile, member,
                                           [&](long long) { return cmake(0, 0); },
@@ -1511,7 +1675,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                     for (long long w = w0; w < total; w += wstride) {
                         const int b = (int)(w / n_tiles);
                         const long long tile = w % n_tiles;
-                        { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                        { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
                         const int member = a.member_of ? a.member_of[b] : 0;
                         const size_t o = (size_t)b * Dp;
                         Tile::run(a.H, s, src + o, tile, member, [&](long long) { return cmake(0, 0); },
@@ -1564,7 +1728,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                     for (long long w = w0; w < total; w += wstride) {
                         const int b = (int)(w / n_tiles);
                         const long long tile = w % n_tiles;
-                        { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                        { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
                         const int member = a.member_of ? a.member_of[b] : 0;
                         const size_t o = (size_t)b * Dp;
                         Tile::run(a.H, s, TB + o, tile, member, [&](long long) { return cmake(0, 0); },
@@ -1614,7 +1778,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagat
                         for (long long w = w0; w < total; w += wstride) {
                             const int b = (int)(w / n_tiles);
                             const long long tile = w % n_tiles;
-                            { const long long wn = w + wstride; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                            { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
                             const int member = a.member_of ? a.member_of[b] : 0;
                             const size_t o = (size_t)b * Dp;
                             cplx *Yb = a.Y + o, *Ab = ACC + o, *TAb = TA + o, *TBb = TB + o;
@@ -1896,7 +2060,11 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
         // element-major TileEE (150 vs 111 us per apply) because of the heavier per-element
         // commutator and partial-sector stores; kept for the round-2 work on this kernel.
         const char *variant = getenv("QSX_HEOM_VARIANT");
+#ifdef QSX_HEOM_EXPERIMENTS
         const bool want_pairs = variant && variant[0] == 'p';
+#else
+        const bool want_pairs = false; (void)variant;
+#endif
         if (d.ee && d.real_h && nr == 7 && K1 == 2 && want_pairs) d.layout = 1;
         std::vector<int> e_off(M), e_stride(M);
         for (int e = 0; e < M; ++e) {
@@ -1995,12 +2163,17 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
     // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
     const bool lean_pays = d.n_tiles * (long long)n_columns >= 2048;
-    if (d.layout == 1) QSX_APPLY(TileEEP<7 COMMA 2 COMMA true>)
+    if (false) {}
+#ifdef QSX_HEOM_EXPERIMENTS
+    else if (d.layout == 1) QSX_APPLY(TileEEP<7 COMMA 2 COMMA true>)
     else if (ee7 && d.real_h && !d.heis && vsel == 'l') QSX_APPLY(TileLean<7 COMMA 2 COMMA 3>)
-    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'm')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2>)
-    else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+    else if (ee7 && d.real_h && !d.heis && (vsel == 'C' || vsel == 'D')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 4>)
     else if (ee7 && d.real_h && vsel == 'c') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
     else if (ee7 && d.real_h && vsel == '2') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
+#endif
+    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P' || vsel == 'Q')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 8>)
+    else if (ee7 && d.real_h && !d.heis && (vsel == 'm' || vsel == 'A')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2>)
+    else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
     else if (ee7 && !d.real_h && vsel != 'g') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
     else QSX_APPLY(TileGeneric)
 #undef QSX_APPLY
@@ -2144,16 +2317,25 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;
         kernel = dopri ? (const void *)heom_propagate_kernel<QSX_METHOD_DOPRI5, T>
                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
-    } else if (d.layout == 1) QSX_PICK(TileEEP<7 COMMA 2 COMMA true>)
+    }
+#ifdef QSX_HEOM_EXPERIMENTS
+    else if (d.layout == 1) QSX_PICK(TileEEP<7 COMMA 2 COMMA true>)
     else if (ee7 && d.real_h && !d.heis && vsel == 'l') QSX_PICK(TileLean<7 COMMA 2 COMMA 3>)
-    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'm')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2>)
-    else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'm') QSX_PICK(TileLean<7 COMMA 2 COMMA 2>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'B') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 3>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'C') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 7>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'D') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 5>)
     else if (ee7 && d.real_h && vsel == '2') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
     else if (ee7 && d.real_h && vsel == '3') QSX_PICK(TileEE<7 COMMA 2 COMMA 3 COMMA true>)
     else if (ee7 && d.real_h && vsel == 'c') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
-    else if (ee7 && !d.real_h && vsel != 'g' && vsel != 'f' && vsel != 'w') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
     else if (use_warp_tile(d) && vsel == 'w') QSX_PICK(TileWarp<7 COMMA 7 COMMA 4 COMMA 7>)
-    else if (use_warp_tile(d) && d.K1 == 2 && vsel != 'g') QSX_PICK(TileFixed<7 COMMA 7 COMMA 4 COMMA 2 COMMA 0 COMMA 3>)
+    else if (use_warp_tile(d) && d.K1 == 2 && vsel == 'f') QSX_PICK(TileFixed<7 COMMA 7 COMMA 4 COMMA 2 COMMA 0 COMMA 3>)
+#endif
+    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 9>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'Q') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 11>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'A') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 1>)
+    else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+    else if (ee7 && !d.real_h && vsel != 'g' && vsel != 'f' && vsel != 'w') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
     else QSX_PICK(TileGeneric)
 #undef QSX_PICK
     int dev = 0, sms = 0, per_sm = 0;
