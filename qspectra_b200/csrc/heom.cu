@@ -71,6 +71,11 @@ struct HeomDev {
     const int *lbin;          // [M][Lk]  (-1 padded)
     const cplx *gu, *gd;      // [M][Lk]
     const double *su, *sd;    // [K1][Lc]
+    int dbg;                  // experiment switches (only read when built with -DQSX_HEOM_DBG_FLAGS)
+    int linear;               // 1: su[k][n] == 1 and sd[k][n] == n (plain hierarchy, Schroedinger picture)
+    int const_h;              // 1: hRc / hCc below hold the single member's coefficients
+    double hRc[49], hCc[49];  // Im(HR), Im(HC) of a single-member 7 x 7 real-H handle: read through the
+                              // constant bank (kernel parameters) instead of shared memory
 };
 
 struct qsx_heom_s {
@@ -839,7 +844,13 @@ struct TileEE {
 //   8  barrier-free tile pipeline: one elected thread stages tile + tables + member H with
 //      bulk asynchronous copies (cp.async.bulk, completion on an mbarrier), every warp waits
 //      on the "full" mbarrier of its buffer and releases it through an "empty" mbarrier, so
-//      the row-warps of a CTA are no longer in lock step (always three buffers).
+//      the row-warps of a CTA are no longer in lock step (always three buffers);
+//  16  single-member handle: the 7 x 7 H coefficients are DFMA constant-bank operands
+//      (kernel parameters) instead of warp-uniform shared-memory loads (98 LDS per thread and tile);
+//  32  plain hierarchy (no modified_HEOM rescaling): up coefficient = const, down coefficient =
+//      n_jk x const, formed arithmetically from the occupation number instead of two
+//      per-lane shared-memory table look-ups per link;
+//  64  PIPE with two tile buffers (64 KB per CTA: three CTAs per SM under a 96-register cap).
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -864,10 +875,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, int bytes, 
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// exact double of a small non-negative integer without the conversion pipe: 2^52 + n - 2^52
+__device__ __forceinline__ double small_to_double(int n) {
+    return __hiloint2double(0x43300000, n) - 4503599627370496.0;
+}
+
 template <int NS, int K1, int MINB, int OPT = 0>
 struct TileLean {
     static constexpr bool PIPE = (OPT & 8) != 0;
-    static constexpr int NBUF = (OPT & 12) ? 3 : 2;
+    static constexpr bool CONSTH = (OPT & 16) != 0;
+    static constexpr bool LINEAR = (OPT & 32) != 0;
+    static constexpr int NBUF = (OPT & 64) ? 2 : ((OPT & 12) ? 3 : 2);   // 64: two buffers also in PIPE mode
     static constexpr int HS = PIPE ? 2 : 1;       // stride of the H coefficients (PIPE reads Im of the complex tables)
     static constexpr int THREADS = 32 * NS;
     static constexpr int MIN_BLOCKS = MINB;
@@ -952,14 +970,14 @@ struct TileLean {
     // released the buffer's previous occupant, then arms the "full" barrier with the byte count
     static __device__ __forceinline__ void fill(const HeomDev &H, const TileSmem &s, int q, const cplx *tile_data,
                                                 long long tile, int member) {
-        const int bi = q % 3;
-        if (q >= 3) mbar_wait(&s.bars[3 + bi], ((q / 3) - 1) & 1);
+        const int bi = q % NBUF;
+        if (q >= NBUF) mbar_wait(&s.bars[3 + bi], ((q / NBUF) - 1) & 1);
         const Buf b = buffer(s, bi);
         uint64_t *full = &s.bars[bi];
         const bool top = tile >= H.top_tile;
         const int tab = BINS * TL * (int)sizeof(int);
         const int bytes = M * TL * (int)sizeof(cplx) + (top ? 1 : 2) * tab + BINS * TL + 2 * TL * (int)sizeof(double) +
-                          2 * NS * NS * (int)sizeof(cplx);
+                          (CONSTH ? 0 : 2 * NS * NS * (int)sizeof(cplx));
         mbar_expect_tx(full, bytes);
         const size_t tb = (size_t)tile * BINS * TL;
         bulk_g2s(b.ys, tile_data, M * TL * (int)sizeof(cplx), full);
@@ -968,16 +986,22 @@ struct TileLean {
         bulk_g2s(b.occ, H.occ + tb, BINS * TL, full);
         bulk_g2s(b.sh, H.shift + tile * TL, TL * (int)sizeof(double), full);
         bulk_g2s(b.sh + TL, H.scale + tile * TL, TL * (int)sizeof(double), full);
-        bulk_g2s(const_cast<double *>(b.hR) - 1, H.HR + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
-        bulk_g2s(const_cast<double *>(b.hC) - 1, H.HC + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
+        if (!CONSTH) {
+            bulk_g2s(const_cast<double *>(b.hR) - 1, H.HR + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
+            bulk_g2s(const_cast<double *>(b.hC) - 1, H.HC + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
+        }
     }
 
     // Hs_R rho for source rows c in [c0, c1): (i h) z = h (-z.y, z.x)
     template <int C0, int C1>
-    static __device__ __forceinline__ void left_product(const Buf &cur, const cplx *ys, int w, cplx (&acc)[NS]) {
+    static __device__ __forceinline__ void left_product(const HeomDev &H, const Buf &cur, const cplx *ys, int w,
+                                                        cplx (&acc)[NS]) {
+#ifdef QSX_HEOM_DBG_FLAGS
+        if (H.dbg & 4) return;
+#endif
 #pragma unroll
         for (int c = C0; c < C1; ++c) {
-            const double h = cur.hR[(w * NS + c) * HS];
+            const double h = CONSTH ? H.hRc[w * NS + c] : cur.hR[(w * NS + c) * HS];
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
                 const cplx z = ys[(c + NS * b) * TL];
@@ -1016,7 +1040,7 @@ struct TileLean {
                 acc[b] = cmake(-dg * own[b].x, -dg * own[b].y);
 #pragma unroll
                 for (int c = 0; c < NS; ++c) {
-                    const double h = cur.hC[(b * NS + c) * HS];
+                    const double h = CONSTH ? H.hCc[b * NS + c] : cur.hC[(b * NS + c) * HS];
                     acc[b].x = fma(h, own[c].y, acc[b].x);
                     acc[b].y = fma(-h, own[c].x, acc[b].y);
                 }
@@ -1028,8 +1052,12 @@ struct TileLean {
         for (int k = 0; k < K1; ++k) {
             const int bin = w * K1 + k;
             const int njk = cur.occ[bin * TL + lane];
-            const int od = cur.o_dn[bin * TL + lane];
-            const int ou = UP ? cur.o_up[bin * TL + lane] : -1;
+            int od = cur.o_dn[bin * TL + lane];
+            int ou = UP ? cur.o_up[bin * TL + lane] : -1;
+#ifdef QSX_HEOM_DBG_FLAGS
+            if (H.dbg & 1) { if (od >= 0) od = (int)(tile * M * TL) + lane; if (ou >= 0) ou = (int)(tile * M * TL) + lane; }
+            if (H.dbg & 2) { od = -1; ou = -1; }
+#endif
             const cplx *pd = xw + (od >= 0 ? od : 0), *pu = xw + (ou >= 0 ? ou : 0);
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
@@ -1037,10 +1065,10 @@ struct TileLean {
                 gd[b] = cmake(0, 0);
                 if (od >= 0) gd[b] = __ldcg(pd + b * NS * TL);
             }
-            if (k == 0) left_product<0, 2>(cur, ys, w, acc); else left_product<2, 4>(cur, ys, w, acc);
-            const cplx cd = s.tD[k * H.Lc + njk];
+            if (k == 0) left_product<0, 2>(H, cur, ys, w, acc); else left_product<2, 4>(H, cur, ys, w, acc);
+            const cplx cd = LINEAR ? cscale(small_to_double(njk), H.GdR[k]) : s.tD[k * H.Lc + njk];
             if (UP) {
-                const double tu = s.su[k * H.Lc + njk];
+                const double tu = LINEAR ? -H.GuR[k].y : s.su[k * H.Lc + njk];
 #pragma unroll
                 for (int b = 0; b < NS; ++b) {                 // (-i tu) v
                     acc[b].x = fma(tu, gu[b].y, acc[b].x);
@@ -1063,22 +1091,30 @@ struct TileLean {
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
                 const int bin = b * K1 + k;
-                const int od = cur.o_dn[bin * TL + lane];
+                int od = cur.o_dn[bin * TL + lane];
+#ifdef QSX_HEOM_DBG_FLAGS
+                if ((H.dbg & 1) && od >= 0) od = (int)(tile * M * TL) + lane;
+                if (H.dbg & 2) od = -1;
+#endif
                 if (UP) {
-                    const int ou = cur.o_up[bin * TL + lane];
+                    int ou = cur.o_up[bin * TL + lane];
+#ifdef QSX_HEOM_DBG_FLAGS
+                    if ((H.dbg & 1) && ou >= 0) ou = (int)(tile * M * TL) + lane;
+                    if (H.dbg & 2) ou = -1;
+#endif
                     gu[b] = cmake(0, 0);
                     if (ou >= 0 && b != w) gu[b] = __ldcg(xw + ou + b * NS * TL);
                 }
                 gd[b] = cmake(0, 0);
                 if (od >= 0 && b != w) gd[b] = __ldcg(xw + od + b * NS * TL);
             }
-            if (k == 0) left_product<4, 6>(cur, ys, w, acc); else left_product<6, NS>(cur, ys, w, acc);
+            if (k == 0) left_product<4, 6>(H, cur, ys, w, acc); else left_product<6, NS>(H, cur, ys, w, acc);
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
                 const int njk = cur.occ[(b * K1 + k) * TL + lane];
-                const cplx cd = s.tD[k * H.Lc + njk];
+                const cplx cd = LINEAR ? cscale(small_to_double(njk), H.GdR[k]) : s.tD[k * H.Lc + njk];
                 if (UP) {
-                    const double tu = s.su[k * H.Lc + njk];
+                    const double tu = LINEAR ? -H.GuR[k].y : s.su[k * H.Lc + njk];
                     acc[b].x = fma(-tu, gu[b].y, acc[b].x);     // (+i tu) v
                     acc[b].y = fma(tu, gu[b].x, acc[b].y);
                 }
@@ -1128,19 +1164,21 @@ struct TileLean {
             if (threadIdx.x == 0) {
                 if (s.loaded != tile_data) {    // first tile of a phase: nothing in flight yet
                     fill(H, s, q, tile_data, tile, member);
-                    const cplx *n1 = unit_ptr(1, tn, cn);
-                    if (n1) fill(H, s, q + 1, n1, tn, s.member_of ? s.member_of[cn] : 0);
+                    if (NBUF == 3) {
+                        const cplx *n1 = unit_ptr(1, tn, cn);
+                        if (n1) fill(H, s, q + 1, n1, tn, s.member_of ? s.member_of[cn] : 0);
+                    }
                 }
-                const cplx *n2 = unit_ptr(2, tn, cn);
-                if (n2) fill(H, s, q + 2, n2, tn, s.member_of ? s.member_of[cn] : 0);
+                const cplx *n2 = unit_ptr(NBUF - 1, tn, cn);
+                if (n2) fill(H, s, q + NBUF - 1, n2, tn, s.member_of ? s.member_of[cn] : 0);
             }
             __syncwarp();
-            mbar_wait(&s.bars[q % 3], (q / 3) & 1);
-            const Buf cur = buffer(s, q % 3);
+            mbar_wait(&s.bars[q % NBUF], (q / NBUF) & 1);
+            const Buf cur = buffer(s, q % NBUF);
             if (tile >= H.top_tile) body<false>(H, s, cur, x, tile, pre, post);
             else body<true>(H, s, cur, x, tile, pre, post);
             __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&s.bars[3 + q % 3]);
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&s.bars[3 + q % NBUF]);
             s.loaded = unit_ptr(1, tn, cn);
             s.q = q + 1;
             return;
@@ -1542,7 +1580,21 @@ __device__ __forceinline__ void heom_save(const HeomPropArgs &a, int it) {
 }
 
 template <int METHOD, class Tile>
-__global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagate_kernel(HeomPropArgs a) {
+__device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a);
+
+template <int METHOD, class Tile>
+__global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_propagate_kernel(const __grid_constant__ HeomPropArgs a) {
+    heom_propagate_impl<METHOD, Tile>(a);
+}
+// the same kernel under an explicit register cap (two 7-warp CTAs per SM fit 144 registers per
+// thread; __launch_bounds__(224, 2) rounds down to 128)
+template <int METHOD, class Tile, int NREG>
+__global__ void __maxnreg__(NREG) heom_propagate_kernel_r(const __grid_constant__ HeomPropArgs a) {
+    heom_propagate_impl<METHOD, Tile>(a);
+}
+
+template <int METHOD, class Tile>
+__device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     TileSmem s;
@@ -2084,6 +2136,13 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
         d.e_off = h->e_off.p; d.e_stride = h->e_stride.p;
     }
     d.HR = h->HR.p; d.HC = h->HC.p; d.dterm = h->dterm.p; d.lbin = h->lbin.p;
+    d.dbg = 0;
+    d.linear = (!cfg->modified && !cfg->heisenberg) ? 1 : 0;
+    d.const_h = (cfg->n_members == 1 && nr == 7 && nc == 7) ? 1 : 0;
+    for (int i = 0; i < 49; ++i) {
+        d.hRc[i] = d.const_h ? HR[i].y : 0.0;
+        d.hCc[i] = d.const_h ? HC[i].y : 0.0;
+    }
     d.gu = h->gu.p; d.gd = h->gd.p; d.su = h->su.p; d.sd = h->sd.p;
     size_t offs[14];
     int dev = 0, smem_limit = 0;
@@ -2171,10 +2230,14 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     else if (ee7 && d.real_h && vsel == 'c') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
     else if (ee7 && d.real_h && vsel == '2') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
 #endif
+#ifndef QSX_HEOM_MINIMAL
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 56>)
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.linear) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 40>)
     else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P' || vsel == 'Q')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 8>)
     else if (ee7 && d.real_h && !d.heis && (vsel == 'm' || vsel == 'A')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2>)
     else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
     else if (ee7 && !d.real_h && vsel != 'g') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
+#endif
     else QSX_APPLY(TileGeneric)
 #undef QSX_APPLY
     heom_from_internal<<<sms * 4, 256, 0, stream>>>(yi.p, (cplx *)dy_dev, n_columns, d.n_ado, d.n_tiles, d.M,
@@ -2293,6 +2356,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     a.flags = flags.p; a.ynorm = ynorm.p; a.stats = stats.p;
 
     const bool taylor = args->method == QSX_METHOD_TAYLOR;
+    a.H.dbg = getenv("QSX_HEOM_DBG") ? atoi(getenv("QSX_HEOM_DBG")) : 0;
     const void *kernel;
     int threads;
     const char *variant = getenv("QSX_HEOM_VARIANT");
@@ -2305,6 +2369,13 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;                      \
         kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>           \
                         : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;             \
+    }
+#define QSX_PICK_R(TILE, NREG)                                                                \
+    {                                                                                         \
+        typedef TILE T;                                                                       \
+        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;                      \
+        kernel = taylor ? (const void *)heom_propagate_kernel_r<QSX_METHOD_TAYLOR, T, NREG>   \
+                        : (const void *)heom_propagate_kernel_r<QSX_METHOD_RK4, T, NREG>;     \
     }
     const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
     // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
@@ -2331,13 +2402,21 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     else if (use_warp_tile(d) && vsel == 'w') QSX_PICK(TileWarp<7 COMMA 7 COMMA 4 COMMA 7>)
     else if (use_warp_tile(d) && d.K1 == 2 && vsel == 'f') QSX_PICK(TileFixed<7 COMMA 7 COMMA 4 COMMA 2 COMMA 0 COMMA 3>)
 #endif
+    else if (ee7 && d.real_h && !d.heis && vsel == 'R' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 2 COMMA 57>, 144)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'S' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 3 COMMA 121>, 96)
+#ifndef QSX_HEOM_MINIMAL
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 25>)
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 41>)
     else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 9>)
     else if (ee7 && d.real_h && !d.heis && vsel == 'Q') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 11>)
     else if (ee7 && d.real_h && !d.heis && vsel == 'A') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 1>)
     else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
     else if (ee7 && !d.real_h && vsel != 'g' && vsel != 'f' && vsel != 'w') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
+#endif
     else QSX_PICK(TileGeneric)
 #undef QSX_PICK
+#undef QSX_PICK_R
     int dev = 0, sms = 0, per_sm = 0;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
