@@ -2402,8 +2402,12 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     else if (use_warp_tile(d) && vsel == 'w') QSX_PICK(TileWarp<7 COMMA 7 COMMA 4 COMMA 7>)
     else if (use_warp_tile(d) && d.K1 == 2 && vsel == 'f') QSX_PICK(TileFixed<7 COMMA 7 COMMA 4 COMMA 2 COMMA 0 COMMA 3>)
 #endif
+#ifdef QSX_HEOM_EXPERIMENTS
+    // register-cap experiments: 144 registers only fit one CTA per SM (warps are allocated in
+    // fours: 138 us per RHS), 96 registers with two buffers still two CTAs and 570 B of spills (124 us)
     else if (ee7 && d.real_h && !d.heis && vsel == 'R' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 2 COMMA 57>, 144)
     else if (ee7 && d.real_h && !d.heis && vsel == 'S' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 3 COMMA 121>, 96)
+#endif
 #ifndef QSX_HEOM_MINIMAL
     else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
     else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 25>)
