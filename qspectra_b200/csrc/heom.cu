@@ -1028,6 +1028,12 @@ struct TileLean {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(s.pf + gbase + (long long)b * NS * TL));
         }
         cplx acc[NS];
+#ifdef QSX_HEOM_DBG_FLAGS
+        if (H.dbg & 16) {
+#pragma unroll
+            for (int b = 0; b < NS; ++b) acc[b] = cmake(0, 0);
+        } else
+#endif
         {
             // diagonal terms and - rho Hs_C from the own row (A_C stored transposed)
             cplx own[NS];
@@ -1125,6 +1131,12 @@ struct TileLean {
             }
         }
         const double wscale = cur.sh[TL + lane];
+#ifdef QSX_HEOM_DBG_FLAGS
+        if (H.dbg & 8) {
+            if (acc[0].x == 1.2345e300) post(gbase, acc[0], acc[1], acc[2], wscale);   // keep the arithmetic alive
+            return;
+        }
+#endif
         if (OPT & 1) {
             cplx pv[NS];
 #pragma unroll
@@ -1707,6 +1719,9 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                             int failed = *((volatile int *)&a.flags[fslot]);
                             fslot = (fslot + 1) % 3;
                             nslot = (nslot + 1) % 3;
+#ifdef QSX_HEOM_DBG_FLAGS
+                            if ((a.H.dbg & 32) && k < 12) failed = 1;      // fixed number of terms for timing experiments
+#endif
                             if (!failed) { done = true; break; }
                         }
                     }
@@ -2408,8 +2423,9 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     else if (ee7 && d.real_h && !d.heis && vsel == 'R' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 2 COMMA 57>, 144)
     else if (ee7 && d.real_h && !d.heis && vsel == 'S' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 3 COMMA 121>, 96)
 #endif
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 313>)
 #ifndef QSX_HEOM_MINIMAL
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
+    else if (ee7 && d.real_h && !d.heis && vsel == 'O' && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
     else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 25>)
     else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 41>)
     else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 9>)

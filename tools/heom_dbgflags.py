@@ -8,6 +8,7 @@ from qspectra_b200 import systems
 depth = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 flags = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '0,1,2,4,6').split(',')]
 model = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=qb.CM_FS, level_cutoff=depth, K=1)
+variant = os.environ.get("QSX_HEOM_VARIANT", " ")
 eom = model.equation_of_motion('ee')
 y0 = model.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
 y0 = torch.from_numpy(y0).cuda().reshape(1, -1)
