@@ -2423,9 +2423,8 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     else if (ee7 && d.real_h && !d.heis && vsel == 'R' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 2 COMMA 57>, 144)
     else if (ee7 && d.real_h && !d.heis && vsel == 'S' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 3 COMMA 121>, 96)
 #endif
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 313>)
+    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
 #ifndef QSX_HEOM_MINIMAL
-    else if (ee7 && d.real_h && !d.heis && vsel == 'O' && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
     else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 25>)
     else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 41>)
     else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 9>)
