@@ -108,6 +108,8 @@ struct TileSmem {
     int cur_col, next_col;
     long long next_tile;
     long long w, wstride, total;   // work index of the current tile, CTA stride, number of (column, tile) units
+    int u_tile, u_sdiv, u_smod;    // tile of the current unit; wstride / n_tiles and wstride % n_tiles (no 64-bit
+                                   // divisions per tile: a sweep advances (column, tile) incrementally)
     uint64_t *bars;          // mbarriers of the bulk-copy tile pipeline (TileLean OPT 8)
     int q;                   // number of tiles this CTA has processed so far (pipeline sequence number)
     const int *member_of;    // generator of each column (nullptr: member 0), for tiles staged ahead
@@ -116,6 +118,28 @@ struct TileSmem {
     int buf;
     double t_eval;           // time at which the pulse envelopes are evaluated
 };
+
+// (column, tile) of the unit `ahead` places after the current one in this CTA's strided sweep
+__device__ __forceinline__ void unit_ahead(const TileSmem &s, long long n_tiles, int ahead, int &col, int &tile) {
+    col = s.cur_col; tile = s.u_tile;
+    for (int i = 0; i < ahead; ++i) {
+        tile += s.u_smod; col += s.u_sdiv;
+        if (tile >= n_tiles) { tile -= (int)n_tiles; ++col; }
+    }
+}
+// bookkeeping of the unit a sweep is about to process (general form: two 64-bit divisions)
+__device__ __forceinline__ void unit_set(TileSmem &s, long long w, long long wstride, long long total, long long n_tiles) {
+    s.w = w; s.wstride = wstride; s.total = total;
+    s.cur_col = (int)(w / n_tiles); s.u_tile = (int)(w % n_tiles);
+    s.u_sdiv = (int)(wstride / n_tiles); s.u_smod = (int)(wstride % n_tiles);
+    if (w + wstride < total) {
+        int c, t;
+        unit_ahead(s, n_tiles, 1, c, t);
+        s.next_tile = t; s.next_col = c;
+    } else {
+        s.next_tile = -1; s.next_col = 0;
+    }
+}
 
 __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -1163,10 +1187,10 @@ struct TileLean {
         const cplx *x0 = x - (size_t)s.cur_col * Dp;          // column 0 of the source
         // source tile of the unit `ahead` places further down this CTA's work list (nullptr: none)
         auto unit_ptr = [&](int ahead, long long &t, int &col) -> const cplx * {
-            const long long wn = s.w + ahead * s.wstride;
-            if (wn >= s.total) return nullptr;
-            t = wn % H.n_tiles;
-            col = (int)(wn / H.n_tiles);
+            if (s.w + ahead * s.wstride >= s.total) return nullptr;
+            int ti;
+            unit_ahead(s, H.n_tiles, ahead, col, ti);
+            t = ti;
             return x0 + (size_t)col * Dp + (size_t)t * M * TL;
         };
         long long tn = 0;
@@ -1524,7 +1548,7 @@ __global__ void __launch_bounds__(Tile::THREADS, Tile::MIN_BLOCKS) heom_apply_ke
     for (long long w = w0; w < total; w += wstride) {
         int b = (int)(w / a.H.n_tiles);
         long long tile = w % a.H.n_tiles;
-        { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % a.H.n_tiles : -1; s.next_col = wn < total ? (int)(wn / a.H.n_tiles) : 0; }
+        unit_set(s, w, wstride, total, a.H.n_tiles);
         int member = a.member_of ? a.member_of[b] : 0;
         cplx *yb = a.y + (size_t)b * Dp;
         Tile::run(a.H, s, a.x + (size_t)b * Dp, tile, member,
@@ -1645,6 +1669,8 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
 
     unsigned long long n_rhs = 0, n_steps = 0;
     int status = 0;
+    const int ub0 = (int)(w0 / n_tiles), ut0 = (int)(w0 % n_tiles);
+    const int usdiv = (int)(wstride / n_tiles), usmod = (int)(wstride % n_tiles);
     s.t_eval = a.t0;
     int fslot = 0;      // flag slot of the current convergence check
     int nslot = 0;      // norm slot that holds the latest reference norms
@@ -1676,10 +1702,15 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                             if (threadIdx.x == 0) a.flags[(fslot + 1) % 3] = 0;
                             for (int b = threadIdx.x; b < B; b += blockDim.x) a.ynorm[((nslot + 2) % 3) * B + b] = 0.0;
                         }
+                        int ub = ub0, ut = ut0;        // (column, tile) of the unit, advanced without divisions
                         for (long long w = w0; w < total; w += wstride) {
-                            const int b = (int)(w / n_tiles);
-                            const long long tile = w % n_tiles;
-                            { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                            const int b = ub;
+                            const long long tile = ut;
+                            s.w = w; s.wstride = wstride; s.total = total; s.cur_col = ub; s.u_tile = ut;
+                            s.u_sdiv = usdiv; s.u_smod = usmod;
+                            ut += usmod; ub += usdiv;
+                            if (ut >= n_tiles) { ut -= (int)n_tiles; ++ub; }
+                            if (w + wstride < total) { s.next_tile = ut; s.next_col = ub; } else { s.next_tile = -1; s.next_col = 0; }
                             const int member = a.member_of ? a.member_of[b] : 0;
                             cplx *db = dst + (size_t)b * Dp;
                             cplx *Yb = a.Y + (size_t)b * Dp;
@@ -1742,7 +1773,7 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                     for (long long w = w0; w < total; w += wstride) {
                         const int b = (int)(w / n_tiles);
                         const long long tile = w % n_tiles;
-                        { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                        unit_set(s, w, wstride, total, n_tiles);
                         const int member = a.member_of ? a.member_of[b] : 0;
                         const size_t o = (size_t)b * Dp;
                         Tile::run(a.H, s, src + o, tile, member, [&](long long) { return cmake(0, 0); },
@@ -1795,7 +1826,7 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                     for (long long w = w0; w < total; w += wstride) {
                         const int b = (int)(w / n_tiles);
                         const long long tile = w % n_tiles;
-                        { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                        unit_set(s, w, wstride, total, n_tiles);
                         const int member = a.member_of ? a.member_of[b] : 0;
                         const size_t o = (size_t)b * Dp;
                         Tile::run(a.H, s, TB + o, tile, member, [&](long long) { return cmake(0, 0); },
@@ -1845,7 +1876,7 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                         for (long long w = w0; w < total; w += wstride) {
                             const int b = (int)(w / n_tiles);
                             const long long tile = w % n_tiles;
-                            { const long long wn = w + wstride; s.w = w; s.wstride = wstride; s.total = total; s.cur_col = b; s.next_tile = wn < total ? wn % n_tiles : -1; s.next_col = wn < total ? (int)(wn / n_tiles) : 0; }
+                            unit_set(s, w, wstride, total, n_tiles);
                             const int member = a.member_of ? a.member_of[b] : 0;
                             const size_t o = (size_t)b * Dp;
                             cplx *Yb = a.Y + o, *Ab = ACC + o, *TAb = TA + o, *TBb = TB + o;
