@@ -58,8 +58,8 @@ struct RedfieldBuildArgs {
 // independent rotations per round.  Called by the whole thread block.
 template <bool WARP>
 __device__ void jacobi_eigh(double *A, double *V, int N, double *work) {
-    // WARP: executed by the first warp alone (small matrices): barriers become __syncwarp
-    const int tid = threadIdx.x, nthr = WARP ? 32 : blockDim.x;
+    // WARP: executed by one warp on its own (small matrices): barriers become __syncwarp
+    const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nthr = WARP ? 32 : blockDim.x;
     auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const int Nn = (N + 1) & ~1, half = Nn / 2;
     double *cs = work, *sn = work + half;
@@ -160,6 +160,36 @@ __device__ __forceinline__ void matsubara_sum(const double *m_nu, const double *
     }
     sr = warp_sum(ar);
     si = warp_sum(ai);
+}
+
+// Eigensystems of small member Hamiltonians, one WARP per member (N <= 16): the cyclic Jacobi
+// sweeps are a chain of dependent rotations that keeps one warp busy; run inside the build
+// kernel they left the other seven warps of the member's CTA at a barrier (45 % of the warp
+// time in the ncu capture).  Here every warp works on its own member.
+__global__ void __launch_bounds__(256) redfield_eig_kernel(int m, int N, int nb, const double *__restrict__ H0,
+                                                           const double *__restrict__ shifts,
+                                                           const double *__restrict__ v,
+                                                           const double *__restrict__ quanta, double rw_freq,
+                                                           double *__restrict__ E_out, cplx *__restrict__ U_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int N2 = N * N, per = 2 * N2 + 2 * (((N + 1) & ~1) + 2);
+    double *A = reinterpret_cast<double *>(smem_raw) + (size_t)warp * per, *V = A + N2, *work = V + N2;
+    for (int mem = blockIdx.x * nwarp + warp; mem < m; mem += gridDim.x * nwarp) {
+        for (int i = lane; i < N2; i += 32) {
+            const int r = i / N, c = i % N;
+            double h = H0[i];
+            if (r == c)
+                for (int j = 0; j < nb; ++j) h += shifts[(size_t)mem * nb + j] * v[j * N + r];
+            A[i] = h;
+        }
+        __syncwarp();
+        jacobi_eigh<true>(A, V, N, work);
+        __syncwarp();
+        for (int i = lane; i < N2; i += 32) U_out[(size_t)mem * N2 + i] = cmake(V[i], 0.0);
+        for (int i = lane; i < N; i += 32) E_out[(size_t)mem * N + i] = A[i * N + i] - quanta[i] * rw_freq;
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArgs a) {
@@ -447,6 +477,20 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem; a.in_place = in_place;
     a.transposed_out = transposed_out;
     a.jacobi = jacobi; a.H0 = d_H0.p; a.shifts = shifts_dev; a.quanta = d_quanta.p; a.rw_freq = rw_freq;
+    DevBuf<double> d_E;
+    DevBuf<cplx> d_U;
+    if (jacobi && N <= 16) {
+        // small systems: eigensystems first, one warp per member, then the build kernel reads them
+        QSX_CUDA(d_E.alloc((size_t)n_members * N));
+        QSX_CUDA(d_U.alloc((size_t)n_members * N2));
+        const int per = 2 * (int)N2 + 2 * (((N + 1) & ~1) + 2);
+        const int egrid = std::min((n_members + 7) / 8, sms * 8);
+        redfield_eig_kernel<<<egrid, 256, (size_t)8 * per * sizeof(double), stream>>>(
+            n_members, N, n_baths, d_H0.p, shifts_dev, d_v.p, d_quanta.p, rw_freq, d_E.p, d_U.p);
+        qsx_launch_counter += 1;
+        QSX_CUDA(cudaGetLastError());
+        a.jacobi = 0; a.E = d_E.p; a.U = d_U.p;
+    }
     QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     redfield_build_kernel<<<grid, 256, smem, stream>>>(a);
     qsx_launch_counter += 1;

@@ -211,6 +211,27 @@ def test_heom_ensemble_members_match_single_runs():
     assert rel_l2(avg, np.mean(singles, axis=0)) < 1e-12
 
 
+def test_heom_lean_tile_ensemble_matches_single_member_launches():
+    """FMO depth 4, 128 disorder members in one launch (2816 staged tiles: the bulk-copy
+    pipeline tile with one Hamiltonian per column) against launches of one member each;
+    regression test for the member-switch race of the staged tiles."""
+    import torch
+    E = 128
+    m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
+                     level_cutoff=4, K=1)
+    eom = m.ensemble_eom(E, False, 'ee')
+    y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+    y0 = torch.from_numpy(y0).cuda().reshape(1, -1).expand(E, -1).contiguous()
+    t = m.time_step * np.arange(6)
+    for _ in range(2):      # twice: the race was timing dependent
+        out = eom.propagate(y0, t, save=('ado0',), generators=np.arange(E),
+                            return_device=True).cpu().numpy()
+        for e in range(0, E, 16):
+            one = eom.propagate(y0[e:e + 1].contiguous(), t, save=('ado0',),
+                                generators=np.array([e]), return_device=True).cpu().numpy()[0]
+            assert rel_l2(out[e], one) < 1e-13
+
+
 # ------------------------------------------------------------------ response
 def test_third_order_response_redfield(golden):
     g = golden('response')
