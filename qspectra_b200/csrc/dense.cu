@@ -264,9 +264,13 @@ dense_map_kernel(DenseKernelArgs a) {
     saver.S = a.S ? a.S + (size_t)(a.grp_save ? a.grp_save[g] : gen) * a.S_stride : nullptr;
     saver.out = a.out + (size_t)col0 * a.nt * a.saved_dim;
     saver(0, xb);
+    // whole-state output of a single column: the lane that holds a finished row writes it to
+    // the trajectory directly (no second pass over shared memory with index divisions)
+    const bool direct = NB == 1 && a.save_mode == QSX_SAVE_STATE && a.saved_dim == M;
     for (int it = 1; it < a.nt; ++it) {
         const cplx *xc = xb + ((it - 1) & 1) * XS;
         cplx *xn = xb + (it & 1) * XS;
+        cplx *orow = saver.out + (size_t)it * M;
         // independent FMA chains (xx, yy, xy, yx products of even / odd terms) keep the
         // dependent chain CQ/2 long; every loaded state element feeds RPT rows
 #pragma unroll
@@ -296,11 +300,14 @@ dense_map_kernel(DenseKernelArgs a) {
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
                 }
                 const int r = rr + h * H;
-                if (q == 0 && rr < H && r < M) xn[r * NB + j] = acc;
+                if (q == 0 && rr < H && r < M) {
+                    xn[r * NB + j] = acc;
+                    if (direct) __stcs(&orow[r], acc);
+                }
             }
         }
         __syncthreads();
-        saver(it, xn);
+        if (!direct) saver(it, xn);
     }
     if (tid == 0) {
         atomicAdd(&a.stats[0], (unsigned long long)(a.nt - 1) * ncol);
