@@ -2250,7 +2250,9 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     long long total = d.n_tiles * n_columns;
     int grid = (int)std::min<long long>(total, (long long)sms * 6);
     const char *variant = getenv("QSX_HEOM_VARIANT");
-    const char vsel = variant ? variant[0] : ' ';
+    char vsel = variant ? variant[0] : ' ';
+    const bool force_lean = vsel == 'L';     // tests: the pipeline tile also for small hierarchies
+    if (force_lean) vsel = ' ';
     int apply_occ = 0;
 #define QSX_APPLY(TILE)                                                                                  \
     {                                                                                                    \
@@ -2267,7 +2269,7 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
     // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
     // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
-    const bool lean_pays = d.n_tiles * (long long)n_columns >= 2048;
+    const bool lean_pays = force_lean || d.n_tiles * (long long)n_columns >= 2048;
     if (false) {}
 #ifdef QSX_HEOM_EXPERIMENTS
     else if (d.layout == 1) QSX_APPLY(TileEEP<7 COMMA 2 COMMA true>)
@@ -2406,7 +2408,9 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     const void *kernel;
     int threads;
     const char *variant = getenv("QSX_HEOM_VARIANT");
-    const char vsel = variant ? variant[0] : ' ';
+    char vsel = variant ? variant[0] : ' ';
+    const bool force_lean = vsel == 'L';     // tests: the pipeline tile also for small hierarchies
+    if (force_lean) vsel = ' ';
     size_t smem;
     int units = 1;
 #define QSX_PICK(TILE)                                                                        \
@@ -2426,7 +2430,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
     // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
     // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
-    const bool lean_pays = d.n_tiles * (long long)B >= 2048;
+    const bool lean_pays = force_lean || d.n_tiles * (long long)B >= 2048;
     if (dopri || args->n_pulses > 0) {
         // time-dependent right-hand sides run on the generic tile (any rectangular block)
         QSX_REQUIRE(d.layout == 0, "pulse-driven propagation needs the element-major layout");

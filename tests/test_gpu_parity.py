@@ -232,6 +232,30 @@ def test_heom_lean_tile_ensemble_matches_single_member_launches():
             assert rel_l2(out[e], one) < 1e-13
 
 
+@pytest.mark.parametrize('modified', [False, True])
+def test_heom_pipeline_tile_variants_match_batch_tile(modified, monkeypatch):
+    """The bulk-copy pipeline tile (default only for >= 2048 tiles) forced onto the depth-4 FMO
+    hierarchy: single-member handles (H through the constant bank; arithmetic link coefficients
+    for the plain hierarchy, tables for modified_HEOM) and the RHS application, against the
+    batch tile that the golden-fixture tests validate."""
+    import torch
+    m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS, level_cutoff=4,
+                     K=1, modified_HEOM=modified, low_temp_corr=True)
+    y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+    t = m.time_step * np.arange(8)
+    rng = np.random.RandomState(3)
+    eom = m.equation_of_motion('ee')
+    y = rng.randn(eom.dim) + 1j * rng.randn(eom.dim)
+    res = {}
+    for variant in ('b', 'L'):      # the tile is chosen per call
+        monkeypatch.setenv('QSX_HEOM_VARIANT', variant)
+        traj = eom.propagate(torch.from_numpy(y0).cuda().reshape(1, -1), t, save=('ado0',),
+                             return_device=True).cpu().numpy()
+        res[variant] = (traj, np.asarray(eom.apply(y[None])))
+    assert rel_l2(res['L'][0], res['b'][0]) < 1e-13
+    assert rel_l2(res['L'][1], res['b'][1]) < 1e-13
+
+
 # ------------------------------------------------------------------ response
 def test_third_order_response_redfield(golden):
     g = golden('response')
