@@ -730,6 +730,135 @@ dense_expm_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm,
     }
 }
 
+// Two-CTAs-per-SM form of the propagator build for wide states (MT = 7: the eight planes of the
+// kernel above fill an SM's shared memory with ONE 7-warp CTA, i.e. 1.75 warps per scheduler).
+// Only the two complex planes that serve as GEMM operands stay in shared memory; the element-wise
+// Horner operands A and A^2 are re-read in the epilogues from global memory / L2 (A is the input
+// generator, A^2 goes to a per-CTA scratch tile written once), and CTAs loop over the members.
+template <int MT, int KS>
+__global__ void __launch_bounds__(32 * MT, 2)
+dense_expm2_kernel(const cplx *__restrict__ Lt, const double *__restrict__ lnorm, int M, double dt, int n_gen,
+                   cplx *__restrict__ Pt_out, cplx *__restrict__ A2_scratch, unsigned long long *__restrict__ status) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *planes = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    cplx *A2g = A2_scratch + (size_t)blockIdx.x * M * M;     // transposed storage like Lt: [c*M + r]
+    unsigned long long gemms = 0;
+
+    for (int gen = blockIdx.x; gen < n_gen; gen += gridDim.x) {
+        double *Xr = planes, *Xi = Xr + MP * LD, *Yr = Xi + MP * LD, *Yi = Yr + MP * LD;
+        const cplx *Lg = Lt + (size_t)gen * M * M;          // transposed storage: Lt[c*M + r]
+        int sq = 0;
+        {
+            double nrm = fabs(dt) * lnorm[gen];
+            while (nrm > 0.5 && sq < 40) { nrm *= 0.5; ++sq; }
+        }
+        const double scale = dt / (double)(1ULL << sq);
+        auto A1 = [&](int r, int c) -> cplx {               // scaled generator element (zero padding)
+            if (r >= M || c >= M) return cmake(0, 0);
+            const cplx v = __ldg(&Lg[c * M + r]);
+            return cmake(scale * v.x, scale * v.y);
+        };
+        auto A2 = [&](int r, int c) -> cplx {
+            if (r >= M || c >= M) return cmake(0, 0);
+            return __ldcg(&A2g[c * M + r]);
+        };
+        double a_re[KS], a_im[KS], a_sum[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const cplx v = A1(rb * 8 + g, ks * 4 + t);
+            a_re[ks] = v.x; a_im[ks] = v.y; a_sum[ks] = v.x + v.y;
+        }
+        __syncthreads();                                    // previous member's output pass is done with the planes
+        for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
+            const cplx v = A1(i / LD, i % LD);
+            Xr[i] = v.x; Xi[i] = v.y;
+        }
+        __syncthreads();
+        auto row_block_gemm = [&](const double *Br, const double *Bi, auto &&epi) {
+#pragma unroll
+            for (int nb = 0; nb < MT; ++nb) {
+                double p10 = 0, p11 = 0, p20 = 0, p21 = 0, p30 = 0, p31 = 0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double br = Br[(ks * 4 + t) * LD + nb * 8 + g];
+                    const double bi = Bi[(ks * 4 + t) * LD + nb * 8 + g];
+                    dmma884(p10, p11, a_re[ks], br);
+                    dmma884(p20, p21, a_im[ks], bi);
+                    dmma884(p30, p31, a_sum[ks], br + bi);
+                }
+                epi(rb * 8 + g, nb * 8 + 2 * t, p10 - p20, p11 - p21, p30 - p10 - p20, p31 - p11 - p21);
+            }
+        };
+        auto load_fragments = [&](const double *Zr, const double *Zi) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                a_re[ks] = Zr[(rb * 8 + g) * LD + ks * 4 + t];
+                a_im[ks] = Zi[(rb * 8 + g) * LD + ks * 4 + t];
+                a_sum[ks] = a_re[ks] + a_im[ks];
+            }
+        };
+        // A^2 = A A -> Y (operand of the next product) and the scratch tile (Horner operand)
+        row_block_gemm(Xr, Xi, [&](int r, int c, double r0, double r1, double i0, double i1) {
+            const int o = r * LD + c;
+            Yr[o] = r0; Yr[o + 1] = r1; Yi[o] = i0; Yi[o + 1] = i1;
+            if (r < M && c < M) A2g[c * M + r] = cmake(r0, i0);
+            if (r < M && c + 1 < M) A2g[(c + 1) * M + r] = cmake(r1, i1);
+        });
+        __syncthreads();
+        // A^3 = A A^2 -> X (A itself is re-read from global memory from here on)
+        row_block_gemm(Yr, Yi, [&](int r, int c, double r0, double r1, double i0, double i1) {
+            const int o = r * LD + c;
+            Xr[o] = r0; Xr[o + 1] = r1; Xi[o] = i0; Xi[o + 1] = i1;
+        });
+        __syncthreads();
+        load_fragments(Xr, Xi);                     // left operand from here on: A^3
+        __syncthreads();                            // X is free again
+        // Horner start: P = B4 = c12 I + c13 A + c14 A^2 -> X   (A^2 still sits in Y)
+        for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
+            const int r = i / LD, c = i % LD;
+            const cplx a1 = A1(r, c);
+            Xr[i] = (r == c ? inv_fact[12] : 0.0) + inv_fact[13] * a1.x + inv_fact[14] * Yr[i];
+            Xi[i] = inv_fact[13] * a1.y + inv_fact[14] * Yi[i];
+        }
+        __syncthreads();
+        double *Pr = Xr, *Pi = Xi, *Ur = Yr, *Ui = Yi;
+#pragma unroll 1
+        for (int blk = 3; blk >= 0; --blk) {
+            const double c0 = inv_fact[3 * blk], c1 = inv_fact[3 * blk + 1], c2 = inv_fact[3 * blk + 2];
+            row_block_gemm(Pr, Pi, [&](int r, int c, double r0, double r1, double i0, double i1) {
+                const int o = r * LD + c;
+                const cplx a10 = A1(r, c), a11 = A1(r, c + 1), a20 = A2(r, c), a21 = A2(r, c + 1);
+                Ur[o] = r0 + c1 * a10.x + c2 * a20.x + (r == c ? c0 : 0.0);
+                Ur[o + 1] = r1 + c1 * a11.x + c2 * a21.x + (r == c + 1 ? c0 : 0.0);
+                Ui[o] = i0 + c1 * a10.y + c2 * a20.y;
+                Ui[o + 1] = i1 + c1 * a11.y + c2 * a21.y;
+            });
+            __syncthreads();
+            { double *x = Pr; Pr = Ur; Ur = x; x = Pi; Pi = Ui; Ui = x; }
+        }
+        for (int q = 0; q < sq; ++q) {
+            load_fragments(Pr, Pi);
+            row_block_gemm(Pr, Pi, [&](int r, int c, double r0, double r1, double i0, double i1) {
+                const int o = r * LD + c;
+                Ur[o] = r0; Ur[o + 1] = r1; Ui[o] = i0; Ui[o + 1] = i1;
+            });
+            __syncthreads();
+            { double *x = Pr; Pr = Ur; Ur = x; x = Pi; Pi = Ui; Ui = x; }
+        }
+        cplx *Pg = Pt_out + (size_t)gen * M * M;
+        for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+            int c = i / M, r = i % M;
+            Pg[i] = cmake(Pr[r * LD + c], Pi[r * LD + c]);        // transposed storage
+        }
+        gemms += 6 + sq;
+    }
+    if (threadIdx.x == 0) atomicAdd(&status[1], gemms);
+}
+
 template <int MT, int KS>
 static cudaError_t launch_expm_ks(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
                                   int n_gen, cudaStream_t stream) {
@@ -743,9 +872,45 @@ static cudaError_t launch_expm_ks(const cplx *Lt, const double *lnorm, int M, do
 }
 
 // the contraction dimension is padded to a multiple of 4 only (M = 49: 13 k-steps, not 14)
+template <int MT, int KS>
+static cudaError_t launch_expm2_ks(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
+                                   int n_gen, cudaStream_t stream) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    const size_t smem = (size_t)4 * MP * LD * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(dense_expm2_kernel<MT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_expm2_kernel<MT, KS>, 32 * MT, smem);
+    if (e != cudaSuccess) return e;
+    const int grid = std::min(n_gen, sms * std::max(1, per_sm));
+    // A^2 tiles, one per resident CTA: a process-lifetime buffer (one process per GPU) that only grows
+    static cplx *scratch = nullptr;
+    static size_t scratch_elems = 0;
+    const size_t need = (size_t)grid * M * M;
+    if (need > scratch_elems) {
+        if (scratch) {
+            cudaDeviceSynchronize();             // an earlier launch may still use the old buffer
+            cudaFree(scratch);
+            scratch = nullptr; scratch_elems = 0;
+        }
+        e = cudaMalloc(reinterpret_cast<void **>(&scratch), need * sizeof(cplx));
+        if (e != cudaSuccess) return e;
+        scratch_elems = need;
+    }
+    dense_expm2_kernel<MT, KS><<<grid, 32 * MT, smem, stream>>>(Lt, lnorm, M, dt, n_gen, Pt, scratch, status);
+    return cudaGetLastError();
+}
+
 template <int MT>
 static cudaError_t launch_expm(const cplx *Lt, const double *lnorm, int M, double dt, cplx *Pt, unsigned long long *status,
                                int n_gen, cudaStream_t stream) {
+    if (MT == 7 && !getenv("QSX_EXPM_V1")) {
+        if ((M + 3) / 4 == 2 * MT - 1) return launch_expm2_ks<MT, 2 * MT - 1>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
+        return launch_expm2_ks<MT, 2 * MT>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
+    }
     if ((M + 3) / 4 == 2 * MT - 1) return launch_expm_ks<MT, 2 * MT - 1>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
     return launch_expm_ks<MT, 2 * MT>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
 }
