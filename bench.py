@@ -487,7 +487,7 @@ def run_ours(args):
     k_expm = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': fp64_peak,
               'unit': 'TFLOP/s', 'frac': achieved_tf / fp64_peak,
               'traffic': (ncu_traffic('dense_expm_per_member') or 0) * E or None,
-              'kernel': 'dense_expm_kernel<7> (FP64 DMMA m8n8k4: exp(L dt) per member, '
+              'kernel': 'dense_expm2_kernel<7,13> (FP64 DMMA m8n8k4, three real products per complex one: exp(L dt) per member, '
                         'Paterson-Stockmeyer degree 14 + squarings)',
               'kernel_ms': expm_ms, 'share_of_step': expm_ms / ms_per_step,
               'algorithmic_flops_per_launch': flops_per_launch, 'peak_source': peak_note}
