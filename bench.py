@@ -494,7 +494,7 @@ def run_ours(args):
     k_map = {'bound': 'tensor', 'achieved': map_tf, 'peak': fp64_peak,
              'unit': 'TFLOP/s', 'frac': map_tf / fp64_peak,
              'traffic': (ncu_traffic('dense_map_per_member') or 0) * E or None,
-             'kernel': 'dense_map_kernel<14,1,2> (y <- P y stepping with P in registers; DFMA on '
+             'kernel': 'dense_map_kernel<4,13,1,2> (y <- P y stepping with P in registers; DFMA on '
                        'the FP64 pipe, measured against the same FP64 ceiling as SURVEY 8d asks '
                        'for the dense L.Y contraction)',
              'kernel_ms': kernel_ms, 'share_of_step': kernel_ms / ms_per_step,

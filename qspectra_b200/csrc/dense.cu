@@ -334,7 +334,8 @@ static cudaError_t launch_map_cq(const DenseKernelArgs &a, int groups, cudaStrea
     // wide states: two rows per thread, so that every shared-memory read of the state
     // feeds twice the arithmetic (the one-row mapping is bound by those reads)
     // (eight threads per row with full-width shared-memory wavefronts measured slower: 4.4 vs 3.9 ms)
-    if (NB == 1) return launch_map<4, 14, NB, 2>(a, groups, stream);
+    // M = 49 needs 13 column groups of four, not 14 (52 x 52 instead of 56 x 56 padded work)
+    if (NB == 1) return cq <= 13 ? launch_map<4, 13, NB, 2>(a, groups, stream) : launch_map<4, 14, NB, 2>(a, groups, stream);
     return launch_map<4, 14, NB, 1>(a, groups, stream);
 }
 
