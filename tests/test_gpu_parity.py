@@ -457,6 +457,23 @@ def test_device_redfield_build_restricted_blocks():
         assert rel_l2(Ln, m.ensemble_generators(members, 'fe')[1].T) < 1e-10
 
 
+@pytest.mark.parametrize('M,n_gen', [(8, 3), (24, 3), (41, 2), (48, 2), (50, 600), (52, 3), (56, 3)])
+def test_expm_kernels_all_tile_counts(M, n_gen):
+    """exp(L dt) from the DMMA kernels for every padded size class (one 8-row block per warp,
+    1..7 warps; 49..56 take the two-CTAs-per-SM kernel whose CTAs loop over the generators:
+    600 generators exercise that loop and its per-CTA scratch tile) against scipy's expm."""
+    import scipy.linalg
+    rng = np.random.RandomState(M)
+    L = (rng.randn(n_gen, M, M) + 1j * rng.randn(n_gen, M, M)) / np.sqrt(M)
+    L -= 0.5 * np.eye(M)
+    eom = engine.DenseEOM(L)
+    dt = 0.7
+    prop = eom.propagator(dt)
+    for n in sorted(set([0, n_gen // 2, n_gen - 1])):
+        P = prop.apply(np.eye(M, dtype=complex), generators=np.full(M, n)).T
+        assert rel_l2(P, scipy.linalg.expm(L[n] * dt)) < 1e-13, (M, n)
+
+
 # ------------------------------------------------ tensor-core propagator (expm)
 def test_expm_propagator_matches_reference(fmo_model, golden):
     g = golden('redfield')
