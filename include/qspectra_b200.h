@@ -39,8 +39,13 @@ typedef enum {
     QSX_METHOD_TAYLOR = 0,     /* adaptive-order Taylor of exp(hL), LTI generators only */
     QSX_METHOD_RK4 = 1,        /* classic RK4, fixed sub-steps per output interval      */
     QSX_METHOD_DOPRI5 = 2,     /* Dormand-Prince 5(4), on-device step-size control      */
-    QSX_METHOD_MAP = 3         /* y <- P y per output interval; the handle holds the
+    QSX_METHOD_MAP = 3,        /* y <- P y per output interval; the handle holds the
                                   propagators P = exp(L dt) made by qsx_dense_expm      */
+    QSX_METHOD_POLY = 4        /* HEOM, LTI generators: the Taylor polynomial of exp(hL) in product
+                                  form, prod_j (I + h a_j L) y -- one state read and one write per RHS
+                                  application; its degree comes from adaptive Taylor pilot intervals
+                                  (rtol), refreshed periodically.  Handles without the row tile run
+                                  QSX_METHOD_TAYLOR instead                              */
 } qsx_method;
 
 typedef enum {

@@ -15,11 +15,11 @@ LIB_PATH = os.path.join(_HERE, 'libqsx.so')
 
 QSX_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_INTEGRATOR, ERR_UNSUPPORTED = -1, -2, -3, -4
-METHOD_TAYLOR, METHOD_RK4, METHOD_DOPRI5, METHOD_MAP = 0, 1, 2, 3
+METHOD_TAYLOR, METHOD_RK4, METHOD_DOPRI5, METHOD_MAP, METHOD_POLY = 0, 1, 2, 3, 4
 SAVE_STATE, SAVE_MATRIX, SAVE_ADO0 = 0, 1, 2
 MAX_PULSES = 4
 METHODS = {'taylor': METHOD_TAYLOR, 'rk4': METHOD_RK4, 'dopri5': METHOD_DOPRI5,
-           'map': METHOD_MAP}
+           'map': METHOD_MAP, 'poly': METHOD_POLY}
 
 
 class IntegratorError(Exception):

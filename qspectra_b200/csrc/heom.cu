@@ -32,6 +32,7 @@
 // memory, so there is no per-step host round trip.
 #include "common.cuh"
 #include "ado.h"
+#include "heom_row.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <complex>
@@ -58,7 +59,6 @@ struct HeomDev {
     const int *e_off, *e_stride;  // [M] position of element e inside a tile: e_off[e] + lane * e_stride[e]
     int heis;                 // 1: Heisenberg picture (generator transposed)
     long long top_tile;       // first tile made of top-level ADOs only (no up-neighbours)
-    int layout;               // 0: tile-SoA [e][32]; 1: pair-packed [rho_ab, rho_ba] (TileEEP)
     int n_pulse, Rp;          // time-dependent terms: per-ADO operator rows in ELL form
     const int *pcol;          // [n_pulse][M][Rp] (-1 padded)
     const cplx *pval;         // [n_pulse][M][Rp]
@@ -71,11 +71,6 @@ struct HeomDev {
     const int *lbin;          // [M][Lk]  (-1 padded)
     const cplx *gu, *gd;      // [M][Lk]
     const double *su, *sd;    // [K1][Lc]
-    int dbg;                  // experiment switches (only read when built with -DQSX_HEOM_DBG_FLAGS)
-    int linear;               // 1: su[k][n] == 1 and sd[k][n] == n (plain hierarchy, Schroedinger picture)
-    int const_h;              // 1: hRc / hCc below hold the single member's coefficients
-    double hRc[49], hCc[49];  // Im(HR), Im(HC) of a single-member 7 x 7 real-H handle: read through the
-                              // constant bank (kernel parameters) instead of shared memory
 };
 
 struct qsx_heom_s {
@@ -87,6 +82,12 @@ struct qsx_heom_s {
     DevBuf<int> up, down, lbin, off_up, off_dn, e_off, e_stride;
     DevBuf<double> shift, scale, su, sd, dterm;
     DevBuf<cplx> HR, HC, gu, gd;
+    // row tile (heom_row.cuh): electronic blocks with a real Hamiltonian, Schroedinger picture
+    bool row_ok = false;
+    heom_row::RowDev row;
+    DevBuf<unsigned char> row_rec;
+    DevBuf<double> row_h, row_g;
+    DevBuf<cplx> row_ainv;
 };
 
 // ------------------------------------------------------------- tile machinery
@@ -325,111 +326,6 @@ struct TileGeneric {
     }
 };
 
-// Compile-time shaped tile: NR warps per CTA, warp w owns row w of every ADO
-// matrix in the final pass, so the (rho Hs_C) row results stay in registers.
-// All loop bounds and shared-memory offsets are immediates; the hierarchy
-// gathers of element b+1 are issued before element b is finished.
-template <int NR, int NC, int LK, int K1, int PIPE, int MINB>
-struct TileFixed {
-    static constexpr int THREADS = 32 * NR;
-    static constexpr int MIN_BLOCKS = MINB;
-    static constexpr int UNITS = 1;
-    static constexpr int M = NR * NC;
-    static size_t smem_bytes(const HeomDev &H) { size_t o[14]; return tile_smem_layout(H, o); }
-    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
-        tile_smem_setup(H, base, s);
-    }
-
-    struct Gathered { cplx vu[LK], vd[LK]; cplx p; };
-
-    template <class Pre>
-    static __device__ __forceinline__ void gather(const HeomDev &H, const TileSmem &s,
-                                                  const cplx *__restrict__ x, int e, int lane,
-                                                  long long gi, Pre pre, Gathered &g) {
-        g.p = pre(gi);
-#pragma unroll
-        for (int l = 0; l < LK; ++l) {
-            g.vu[l] = g.vd[l] = cmake(0, 0);
-            const int b = s.lbin[e * LK + l];
-            if (b >= 0) {
-                const int iu = s.t_up[b * TL + lane];
-                const int id = s.t_dn[b * TL + lane];
-                if (iu >= 0) g.vu[l] = __ldcg(&x[((size_t)(iu >> 5) * M + e) * TL + (iu & 31)]);
-                if (id >= 0) g.vd[l] = __ldcg(&x[((size_t)(id >> 5) * M + e) * TL + (id & 31)]);
-            }
-        }
-    }
-
-    template <class Pre, class Post>
-    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
-                                               long long tile, int member, Pre pre, Post post) {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // w < NR
-        tile_stage(H, s, x, tile, member);
-        // (Hs_R rho)[:, b] for the columns owned by this warp -> shared memory
-        for (int b = w; b < NC; b += NR) {
-            cplx in[NR];
-#pragma unroll
-            for (int c = 0; c < NR; ++c) in[c] = s.ys[(c + NR * b) * TL + lane];
-#pragma unroll
-            for (int a = 0; a < NR; ++a) {
-                cplx acc = cmake(0, 0);
-#pragma unroll
-                for (int c = 0; c < NR; ++c) cfma(acc, s.HR[a * NR + c], in[c]);
-                s.os[(a + NR * b) * TL + lane] = acc;
-            }
-        }
-        // (rho Hs_C)[w, :] -> registers
-        cplx rr[NC];
-        {
-            cplx in[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) in[c] = s.ys[(w + NR * c) * TL + lane];
-#pragma unroll
-            for (int b = 0; b < NC; ++b) {
-                cplx acc = cmake(0, 0);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) cfma(acc, s.HC[b * NC + c], in[c]);
-                rr[b] = acc;
-            }
-        }
-        __syncthreads();
-        const double shift = s.t_shift[lane];
-        const double wscale = s.t_shift[TL + lane];
-        const long long gbase = ((long long)tile * M) * TL + lane;
-        Gathered cur, nxt;
-        gather(H, s, x, w, lane, gbase + (long long)w * TL, pre, cur);
-#pragma unroll
-        for (int b = 0; b < NC; ++b) {
-            const int e = w + NR * b;
-            const long long gi = gbase + (long long)e * TL;
-            if (PIPE && b + 1 < NC) gather(H, s, x, e + NR, lane, gi + (long long)NR * TL, pre, nxt);
-            if (!PIPE && b > 0) gather(H, s, x, e, lane, gi, pre, cur);
-            const cplx own = s.ys[e * TL + lane];
-            cplx acc = s.os[e * TL + lane];
-            const double dg = shift + s.dterm[e];
-            acc.x -= rr[b].x + dg * own.x;
-            acc.y -= rr[b].y + dg * own.y;
-#pragma unroll
-            for (int l = 0; l < LK; ++l) {
-                const int bn = s.lbin[e * LK + l];
-                if (bn >= 0) {
-                    const int k = bn % K1;
-                    const int njk = s.t_n[bn * TL + lane];
-                    cfma(acc, cscale(s.su[k * H.Lc + njk], s.gu[e * LK + l]), cur.vu[l]);
-                    cfma(acc, cscale(s.sd[k * H.Lc + njk], s.gd[e * LK + l]), cur.vd[l]);
-                }
-            }
-            post(gi, acc, own, cur.p, wscale);
-            if (PIPE && b + 1 < NC) cur = nxt;
-        }
-    }
-};
-
-
-// Warp-autonomous tile: every warp owns a private staging area and processes
-// whole tiles on its own -- no CTA barriers, so the tile load (cp.async), the two
-// small GEMMs and the hierarchy gathers of different warps overlap freely, and
-// with one CTA per SM each thread can keep dozens of gathers in flight.
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
@@ -441,162 +337,6 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
-
-template <int NR, int NC, int LK, int WARPS>
-struct TileWarp {
-    static constexpr int THREADS = 32 * WARPS;
-    static constexpr int MIN_BLOCKS = 1;
-    static constexpr int UNITS = WARPS;
-    static constexpr int M = NR * NC;
-    static constexpr int HALF = (NC + 1) / 2;
-
-    static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
-        size_t off = 0;
-        off = al16(off + (size_t)M * sizeof(double));            // dterm
-        off = al16(off + (size_t)M * LK * sizeof(int));          // lbin
-        off = al16(off + (size_t)M * LK * sizeof(cplx));         // gu
-        off = al16(off + (size_t)M * LK * sizeof(cplx));         // gd
-        off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));  // su
-        off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));  // sd
-        return off;
-    }
-    static __host__ __device__ size_t warp_bytes(const HeomDev &H) {
-        size_t off = 0;
-        off = al16(off + (size_t)M * TL * sizeof(cplx));         // ys
-        off = al16(off + (size_t)NR * NR * sizeof(cplx));        // HR
-        off = al16(off + (size_t)NC * NC * sizeof(cplx));        // HC
-        off = al16(off + (size_t)H.bins * TL * sizeof(int));     // t_up
-        off = al16(off + (size_t)H.bins * TL * sizeof(int));     // t_dn
-        off = al16(off + (size_t)H.bins * TL);                   // t_n (uint8)
-        off = al16(off + (size_t)TL * sizeof(double));           // t_shift
-        return off;
-    }
-    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + WARPS * warp_bytes(H); }
-
-    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
-        size_t off = 0;
-        s.dterm = reinterpret_cast<double *>(base + off); off = al16(off + (size_t)M * sizeof(double));
-        s.lbin = reinterpret_cast<int *>(base + off); off = al16(off + (size_t)M * LK * sizeof(int));
-        s.gu = reinterpret_cast<cplx *>(base + off); off = al16(off + (size_t)M * LK * sizeof(cplx));
-        s.gd = reinterpret_cast<cplx *>(base + off); off = al16(off + (size_t)M * LK * sizeof(cplx));
-        s.su = reinterpret_cast<double *>(base + off); off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));
-        s.sd = reinterpret_cast<double *>(base + off); off = al16(off + (size_t)H.K1 * H.Lc * sizeof(double));
-        for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
-        for (int i = threadIdx.x; i < M * LK; i += blockDim.x) {
-            s.lbin[i] = H.lbin[i]; s.gu[i] = H.gu[i]; s.gd[i] = H.gd[i];
-        }
-        for (int i = threadIdx.x; i < H.K1 * H.Lc; i += blockDim.x) { s.su[i] = H.su[i]; s.sd[i] = H.sd[i]; }
-        unsigned char *wb = base + shared_bytes(H) + (size_t)(threadIdx.x >> 5) * warp_bytes(H);
-        off = 0;
-        s.ys = reinterpret_cast<cplx *>(wb + off); off = al16(off + (size_t)M * TL * sizeof(cplx));
-        s.HR = reinterpret_cast<cplx *>(wb + off); off = al16(off + (size_t)NR * NR * sizeof(cplx));
-        s.HC = reinterpret_cast<cplx *>(wb + off); off = al16(off + (size_t)NC * NC * sizeof(cplx));
-        s.t_up = reinterpret_cast<int *>(wb + off); off = al16(off + (size_t)H.bins * TL * sizeof(int));
-        s.t_dn = reinterpret_cast<int *>(wb + off); off = al16(off + (size_t)H.bins * TL * sizeof(int));
-        s.t_n = reinterpret_cast<uint8_t *>(wb + off); off = al16(off + (size_t)H.bins * TL);
-        s.t_shift = reinterpret_cast<double *>(wb + off);
-        s.os = nullptr;
-        s.cur_member = -1;
-        __syncthreads();
-    }
-
-    template <class Pre, class Post>
-    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
-                                               long long tile, int member, Pre pre, Post post) {
-        const int lane = threadIdx.x & 31;
-        const int bins = H.bins;
-        uint8_t *t_occ = s.t_n;
-        __syncwarp();
-        if (member != s.cur_member) {
-            const cplx *hr = H.HR + (size_t)member * NR * NR, *hc = H.HC + (size_t)member * NC * NC;
-            for (int i = lane; i < NR * NR; i += 32) s.HR[i] = hr[i];
-            for (int i = lane; i < NC * NC; i += 32) s.HC[i] = hc[i];
-            s.cur_member = member;
-        }
-        // own tile and its index tables: asynchronous copies straight into shared memory
-        const cplx *xs = x + (size_t)tile * M * TL + lane;
-#pragma unroll 7
-        for (int e = 0; e < M; ++e) cp_async16(&s.ys[e * TL + lane], &xs[e * TL]);
-        const size_t tb = (size_t)tile * bins * TL + lane;
-        for (int b = 0; b < bins; ++b) {
-            cp_async4(&s.t_up[b * TL + lane], &H.up[tb + b * TL]);
-            cp_async4(&s.t_dn[b * TL + lane], &H.down[tb + b * TL]);
-        }
-        for (int b = 0; b < bins; ++b) t_occ[b * TL + lane] = __ldg(&H.occ[tb + b * TL]);
-        const double shift = __ldg(&H.shift[tile * TL + lane]);
-        const double wscale = __ldg(&H.scale[tile * TL + lane]);
-        cp_async_wait_all();
-        __syncwarp();
-        const long long gbase = ((long long)tile * M) * TL + lane;
-
-        for (int a = 0; a < NR; ++a) {
-            cplx in_row[NC], acc[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) in_row[c] = s.ys[(a + NR * c) * TL + lane];
-            // - (rho Hs_C)[a][b] = - sum_c A_C[b][c] rho[a][c]
-#pragma unroll
-            for (int b = 0; b < NC; ++b) {
-                cplx t = cmake(0, 0);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) cfma(t, s.HC[b * NC + c], in_row[c]);
-                const double dg = shift + s.dterm[a + NR * b];
-                acc[b] = cmake(-t.x - dg * in_row[b].x, -t.y - dg * in_row[b].y);
-            }
-            // + (Hs_R rho)[a][b] = sum_c A_R[a][c] rho[c][b]
-#pragma unroll
-            for (int c = 0; c < NR; ++c) {
-                const cplx h = s.HR[a * NR + c];
-#pragma unroll
-                for (int b = 0; b < NC; ++b) cfma(acc[b], h, s.ys[(c + NR * b) * TL + lane]);
-            }
-            // hierarchy links + epilogue, two batches of columns to bound the registers
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int b0 = half * HALF;
-                const int nb = half == 0 ? HALF : NC - HALF;
-                cplx vu[HALF][LK], vd[HALF][LK], pv[HALF];
-#pragma unroll
-                for (int q = 0; q < HALF; ++q) {
-                    if (q < nb) {
-                        const int e = a + NR * (b0 + q);
-                        pv[q] = pre(gbase + (long long)e * TL);
-#pragma unroll
-                        for (int l = 0; l < LK; ++l) {
-                            vu[q][l] = vd[q][l] = cmake(0, 0);
-                            const int bn = s.lbin[e * LK + l];
-                            if (bn >= 0) {
-                                const int iu = s.t_up[bn * TL + lane];
-                                const int id = s.t_dn[bn * TL + lane];
-                                if (iu >= 0) vu[q][l] = __ldcg(&x[((size_t)(iu >> 5) * M + e) * TL + (iu & 31)]);
-                                if (id >= 0) vd[q][l] = __ldcg(&x[((size_t)(id >> 5) * M + e) * TL + (id & 31)]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < HALF; ++q) {
-                    if (q < nb) {
-                        const int b = b0 + q;
-                        const int e = a + NR * b;
-                        cplx r = acc[b];
-#pragma unroll
-                        for (int l = 0; l < LK; ++l) {
-                            const int bn = s.lbin[e * LK + l];
-                            if (bn >= 0) {
-                                const int k = bn % H.K1;
-                                const int njk = t_occ[bn * TL + lane];
-                                cfma(r, cscale(s.su[k * H.Lc + njk], s.gu[e * LK + l]), vu[q][l]);
-                                cfma(r, cscale(s.sd[k * H.Lc + njk], s.gd[e * LK + l]), vd[q][l]);
-                            }
-                        }
-                        post(gbase + (long long)e * TL, r, in_row[b], pv[q], wscale);
-                    }
-                }
-            }
-        }
-    }
-};
-
 
 // Electronic-block tile ("ee"-type Liouville blocks whose row/column states are
 // site projectors, e.g. FMO 'ee'): warp w owns row w of every ADO matrix of the
@@ -844,660 +584,12 @@ struct TileEE {
 };
 
 
-// Lean electronic-block tile: the same ownership as TileEE (warp w = row w of the 32
-// ADO matrices of a tile) rebuilt for occupancy instead of per-thread memory
-// parallelism -- <= 96 registers, three CTAs (21 warps) per SM, no batch of 56
-// gathers held in registers.  What makes the instruction stream short:
-//   * Schroedinger picture, real H: up-links carry the purely imaginary coefficient
-//     -+i u s_up(n) (2 DFMA), down-links -i u c_k s_dn(n) and its conjugate (4 DFMA);
-//     both come ready-multiplied from two small shared tables indexed by the occupation
-//     number, so a link costs no coefficient arithmetic;
-//   * a diagonal element (a == b) sees the row-site and the column-site link of the
-//     same neighbour: the up terms cancel and the down terms add to 2 Re(.), so it
-//     gathers 2 instead of 8 neighbours;
-//   * tiles of the top hierarchy level (two thirds of all tiles at depth 8) have no
-//     up-neighbours: a CTA-uniform branch takes a body without those 28 gathers;
-//   * the integrator's own-value and accumulator operands are re-read (shared memory /
-//     streaming load) in the epilogue instead of living in registers across the tile.
-// OPT bits:
-//   1  the integrator operands of the 7 owned elements are loaded as one batch before the
-//      epilogue (otherwise every accumulator load waits behind the previous element's
-//      stores: 7 serial DRAM round trips per tile in the even Taylor stages);
-//   2  the accumulator lines of the tile are prefetched to L2 when the tile body starts;
-//   4  three source-tile buffers (prefetch distance 2 instead of 1);
-//   8  barrier-free tile pipeline: one elected thread stages tile + tables + member H with
-//      bulk asynchronous copies (cp.async.bulk, completion on an mbarrier), every warp waits
-//      on the "full" mbarrier of its buffer and releases it through an "empty" mbarrier, so
-//      the row-warps of a CTA are no longer in lock step (always three buffers);
-//  16  single-member handle: the 7 x 7 H coefficients are DFMA constant-bank operands
-//      (kernel parameters) instead of warp-uniform shared-memory loads (98 LDS per thread and tile);
-//  32  plain hierarchy (no modified_HEOM rescaling): up coefficient = const, down coefficient =
-//      n_jk x const, formed arithmetically from the occupation number instead of two
-//      per-lane shared-memory table look-ups per link;
-//  64  PIPE with two tile buffers (64 KB per CTA: three CTAs per SM under a 96-register cap).
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, int bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// exact double of a small non-negative integer without the conversion pipe: 2^52 + n - 2^52
-__device__ __forceinline__ double small_to_double(int n) {
-    return __hiloint2double(0x43300000, n) - 4503599627370496.0;
-}
-
-template <int NS, int K1, int MINB, int OPT = 0>
-struct TileLean {
-    static constexpr bool PIPE = (OPT & 8) != 0;
-    static constexpr bool CONSTH = (OPT & 16) != 0;
-    static constexpr bool LINEAR = (OPT & 32) != 0;
-    static constexpr int NBUF = (OPT & 64) ? 2 : ((OPT & 12) ? 3 : 2);   // 64: two buffers also in PIPE mode
-    static constexpr int HS = PIPE ? 2 : 1;       // stride of the H coefficients (PIPE reads Im of the complex tables)
-    static constexpr int THREADS = 32 * NS;
-    static constexpr int MIN_BLOCKS = MINB;
-    static constexpr int UNITS = 1;
-    static constexpr int M = NS * NS;
-    static constexpr int BINS = NS * K1;
-
-    static __host__ __device__ size_t buf_bytes() {
-        return al16((size_t)M * TL * sizeof(cplx)) + 2 * al16((size_t)BINS * TL * sizeof(int)) +
-               al16((size_t)BINS * TL) + al16((size_t)2 * TL * sizeof(double)) +
-               (PIPE ? 2 * al16((size_t)NS * NS * sizeof(cplx)) : 0);
-    }
-    static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
-        return 2 * al16((size_t)NS * NS * sizeof(double)) + al16((size_t)M * sizeof(double)) +
-               al16((size_t)K1 * H.Lc * sizeof(double)) + al16((size_t)K1 * H.Lc * sizeof(cplx)) + 64;
-    }
-    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + NBUF * buf_bytes(); }
-
-    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
-        size_t off = 0;
-        s.hR = reinterpret_cast<double *>(base + off); off += al16((size_t)NS * NS * sizeof(double));
-        s.hC = reinterpret_cast<double *>(base + off); off += al16((size_t)NS * NS * sizeof(double));
-        s.dterm = reinterpret_cast<double *>(base + off); off += al16((size_t)M * sizeof(double));
-        s.su = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
-        s.tD = reinterpret_cast<cplx *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(cplx));
-        s.bars = reinterpret_cast<uint64_t *>(base + off); off += 64;   // full[0..2], empty[0..2]
-        s.os = reinterpret_cast<cplx *>(base + off);       // start of the tile buffers
-        for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
-        for (int i = threadIdx.x; i < K1 * H.Lc; i += blockDim.x) {
-            const int k = i / H.Lc;
-            s.su[i] = -H.GuR[k].y * H.su[i];               // u s_up(n):  row coefficient -i t, column +i t
-            s.tD[i] = cscale(H.sd[i], H.GdR[k]);           // -i u c_k s_dn(n); the column-site one is its conjugate
-        }
-        if (PIPE && threadIdx.x == 0) {
-            for (int i = 0; i < 3; ++i) { mbar_init(&s.bars[i], 1); mbar_init(&s.bars[3 + i], NS); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        s.cur_member = -1;
-        s.loaded = nullptr;
-        s.buf = 0;
-        s.q = 0;
-        s.member_of = nullptr;
-        __syncthreads();
-    }
-
-    struct Buf {
-        cplx *ys; int *o_up, *o_dn; uint8_t *occ; double *sh; const double *hR, *hC;
-    };
-    static __device__ __forceinline__ Buf buffer(const TileSmem &s, int which) {
-        unsigned char *p = reinterpret_cast<unsigned char *>(s.os) + (size_t)which * buf_bytes();
-        Buf b;
-        b.ys = reinterpret_cast<cplx *>(p); p += al16((size_t)M * TL * sizeof(cplx));
-        b.o_up = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
-        b.o_dn = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
-        b.occ = p; p += al16((size_t)BINS * TL);
-        b.sh = reinterpret_cast<double *>(p); p += al16((size_t)2 * TL * sizeof(double));
-        if (PIPE) {     // complex member tables staged with the tile; the coefficients are their imaginary parts
-            b.hR = reinterpret_cast<const double *>(p) + 1; p += al16((size_t)NS * NS * sizeof(cplx));
-            b.hC = reinterpret_cast<const double *>(p) + 1;
-        } else {
-            b.hR = s.hR; b.hC = s.hC;
-        }
-        return b;
-    }
-    // asynchronous copy of one source tile and its tables into a buffer (cp.async, all threads)
-    static __device__ __forceinline__ void issue(const HeomDev &H, const Buf &b, const cplx *tile_data, long long tile) {
-        for (int i = threadIdx.x; i < M * TL; i += THREADS) cp_async16(&b.ys[i], &tile_data[i]);
-        const size_t tb = (size_t)tile * BINS * TL;
-        for (int i = threadIdx.x; i < BINS * TL / 4; i += THREADS) {
-            cp_async16(&b.o_up[4 * i], &H.off_up[tb + 4 * i]);
-            cp_async16(&b.o_dn[4 * i], &H.off_dn[tb + 4 * i]);
-        }
-        for (int i = threadIdx.x; i < BINS * TL / 16; i += THREADS) cp_async16(&b.occ[16 * i], &H.occ[tb + 16 * i]);
-        if (threadIdx.x < TL / 2) {
-            cp_async16(&b.sh[2 * threadIdx.x], &H.shift[tile * TL + 2 * threadIdx.x]);
-            cp_async16(&b.sh[TL + 2 * threadIdx.x], &H.scale[tile * TL + 2 * threadIdx.x]);
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    }
-    // bulk-copy staging of the q-th tile of this CTA (one thread): waits until every warp has
-    // released the buffer's previous occupant, then arms the "full" barrier with the byte count
-    static __device__ __forceinline__ void fill(const HeomDev &H, const TileSmem &s, int q, const cplx *tile_data,
-                                                long long tile, int member) {
-        const int bi = q % NBUF;
-        if (q >= NBUF) mbar_wait(&s.bars[3 + bi], ((q / NBUF) - 1) & 1);
-        const Buf b = buffer(s, bi);
-        uint64_t *full = &s.bars[bi];
-        const bool top = tile >= H.top_tile;
-        const int tab = BINS * TL * (int)sizeof(int);
-        const int bytes = M * TL * (int)sizeof(cplx) + (top ? 1 : 2) * tab + BINS * TL + 2 * TL * (int)sizeof(double) +
-                          (CONSTH ? 0 : 2 * NS * NS * (int)sizeof(cplx));
-        mbar_expect_tx(full, bytes);
-        const size_t tb = (size_t)tile * BINS * TL;
-        bulk_g2s(b.ys, tile_data, M * TL * (int)sizeof(cplx), full);
-        if (!top) bulk_g2s(b.o_up, H.off_up + tb, tab, full);
-        bulk_g2s(b.o_dn, H.off_dn + tb, tab, full);
-        bulk_g2s(b.occ, H.occ + tb, BINS * TL, full);
-        bulk_g2s(b.sh, H.shift + tile * TL, TL * (int)sizeof(double), full);
-        bulk_g2s(b.sh + TL, H.scale + tile * TL, TL * (int)sizeof(double), full);
-        if (!CONSTH) {
-            bulk_g2s(const_cast<double *>(b.hR) - 1, H.HR + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
-            bulk_g2s(const_cast<double *>(b.hC) - 1, H.HC + (size_t)member * NS * NS, NS * NS * (int)sizeof(cplx), full);
-        }
-    }
-
-    // Hs_R rho for source rows c in [c0, c1): (i h) z = h (-z.y, z.x)
-    template <int C0, int C1>
-    static __device__ __forceinline__ void left_product(const HeomDev &H, const Buf &cur, const cplx *ys, int w,
-                                                        cplx (&acc)[NS]) {
-#ifdef QSX_HEOM_DBG_FLAGS
-        if (H.dbg & 4) return;
-#endif
-#pragma unroll
-        for (int c = C0; c < C1; ++c) {
-            const double h = CONSTH ? H.hRc[w * NS + c] : cur.hR[(w * NS + c) * HS];
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                const cplx z = ys[(c + NS * b) * TL];
-                acc[b].x = fma(-h, z.y, acc[b].x);
-                acc[b].y = fma(h, z.x, acc[b].y);
-            }
-        }
-    }
-
-    // The 2 K1 gather batches of a row (row-site k = 0.., column-site k = 0..) are each
-    // issued as one group of up to 2 NS independent loads and consumed after a slice of
-    // the commutator arithmetic: four round trips per tile instead of one per link.
-    template <bool UP, class Pre, class Post>
-    static __device__ __forceinline__ void body(const HeomDev &H, const TileSmem &s, const Buf &cur,
-                                                const cplx *__restrict__ x, long long tile, Pre pre, Post post) {
-        static_assert(K1 == 2, "phase split below is written for K = 1 (two exponentials per site)");
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // w = row a
-        const cplx *ys = cur.ys + lane;
-        const cplx *xw = x + (size_t)w * TL;
-        const long long gbase = ((long long)tile * M) * TL + lane + (long long)w * TL;   // element (w, 0)
-        if ((OPT & 2) && s.pf != nullptr && (lane & 7) == 0) {
-#pragma unroll
-            for (int b = 0; b < NS; ++b)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.pf + gbase + (long long)b * NS * TL));
-        }
-        cplx acc[NS];
-#ifdef QSX_HEOM_DBG_FLAGS
-        if (H.dbg & 16) {
-#pragma unroll
-            for (int b = 0; b < NS; ++b) acc[b] = cmake(0, 0);
-        } else
-#endif
-        {
-            // diagonal terms and - rho Hs_C from the own row (A_C stored transposed)
-            cplx own[NS];
-#pragma unroll
-            for (int c = 0; c < NS; ++c) own[c] = ys[(w + NS * c) * TL];
-            const double shift = cur.sh[lane];
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                const double dg = shift + s.dterm[w + NS * b];
-                acc[b] = cmake(-dg * own[b].x, -dg * own[b].y);
-#pragma unroll
-                for (int c = 0; c < NS; ++c) {
-                    const double h = CONSTH ? H.hCc[b * NS + c] : cur.hC[(b * NS + c) * HS];
-                    acc[b].x = fma(h, own[c].y, acc[b].x);
-                    acc[b].y = fma(-h, own[c].x, acc[b].y);
-                }
-            }
-        }
-        cplx gu[UP ? NS : 1], gd[NS];
-        // ---- row-site links (site w): the whole row shares neighbour and coefficient
-#pragma unroll
-        for (int k = 0; k < K1; ++k) {
-            const int bin = w * K1 + k;
-            const int njk = cur.occ[bin * TL + lane];
-            int od = cur.o_dn[bin * TL + lane];
-            int ou = UP ? cur.o_up[bin * TL + lane] : -1;
-#ifdef QSX_HEOM_DBG_FLAGS
-            if (H.dbg & 1) { if (od >= 0) od = (int)(tile * M * TL) + lane; if (ou >= 0) ou = (int)(tile * M * TL) + lane; }
-            if (H.dbg & 2) { od = -1; ou = -1; }
-#endif
-            const cplx *pd = xw + (od >= 0 ? od : 0), *pu = xw + (ou >= 0 ? ou : 0);
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                if (UP) { gu[b] = cmake(0, 0); if (ou >= 0 && b != w) gu[b] = __ldcg(pu + b * NS * TL); }
-                gd[b] = cmake(0, 0);
-                if (od >= 0) gd[b] = __ldcg(pd + b * NS * TL);
-            }
-            if (k == 0) left_product<0, 2>(H, cur, ys, w, acc); else left_product<2, 4>(H, cur, ys, w, acc);
-            const cplx cd = LINEAR ? cscale(small_to_double(njk), H.GdR[k]) : s.tD[k * H.Lc + njk];
-            if (UP) {
-                const double tu = LINEAR ? -H.GuR[k].y : s.su[k * H.Lc + njk];
-#pragma unroll
-                for (int b = 0; b < NS; ++b) {                 // (-i tu) v
-                    acc[b].x = fma(tu, gu[b].y, acc[b].x);
-                    acc[b].y = fma(-tu, gu[b].x, acc[b].y);
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                // off the diagonal cd v; on it cd v + conj(cd) v = 2 Re(cd) v
-                const double gr = b == w ? 2.0 * cd.x : cd.x, gi = b == w ? 0.0 : cd.y;
-                acc[b].x = fma(gr, gd[b].x, acc[b].x);
-                acc[b].x = fma(-gi, gd[b].y, acc[b].x);
-                acc[b].y = fma(gr, gd[b].y, acc[b].y);
-                acc[b].y = fma(gi, gd[b].x, acc[b].y);
-            }
-        }
-        // ---- column-site links (site b) of the off-diagonal elements
-#pragma unroll
-        for (int k = 0; k < K1; ++k) {
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                const int bin = b * K1 + k;
-                int od = cur.o_dn[bin * TL + lane];
-#ifdef QSX_HEOM_DBG_FLAGS
-                if ((H.dbg & 1) && od >= 0) od = (int)(tile * M * TL) + lane;
-                if (H.dbg & 2) od = -1;
-#endif
-                if (UP) {
-                    int ou = cur.o_up[bin * TL + lane];
-#ifdef QSX_HEOM_DBG_FLAGS
-                    if ((H.dbg & 1) && ou >= 0) ou = (int)(tile * M * TL) + lane;
-                    if (H.dbg & 2) ou = -1;
-#endif
-                    gu[b] = cmake(0, 0);
-                    if (ou >= 0 && b != w) gu[b] = __ldcg(xw + ou + b * NS * TL);
-                }
-                gd[b] = cmake(0, 0);
-                if (od >= 0 && b != w) gd[b] = __ldcg(xw + od + b * NS * TL);
-            }
-            if (k == 0) left_product<4, 6>(H, cur, ys, w, acc); else left_product<6, NS>(H, cur, ys, w, acc);
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                const int njk = cur.occ[(b * K1 + k) * TL + lane];
-                const cplx cd = LINEAR ? cscale(small_to_double(njk), H.GdR[k]) : s.tD[k * H.Lc + njk];
-                if (UP) {
-                    const double tu = LINEAR ? -H.GuR[k].y : s.su[k * H.Lc + njk];
-                    acc[b].x = fma(-tu, gu[b].y, acc[b].x);     // (+i tu) v
-                    acc[b].y = fma(tu, gu[b].x, acc[b].y);
-                }
-                acc[b].x = fma(cd.x, gd[b].x, acc[b].x);        // conj(cd) v
-                acc[b].x = fma(cd.y, gd[b].y, acc[b].x);
-                acc[b].y = fma(cd.x, gd[b].y, acc[b].y);
-                acc[b].y = fma(-cd.y, gd[b].x, acc[b].y);
-            }
-        }
-        const double wscale = cur.sh[TL + lane];
-#ifdef QSX_HEOM_DBG_FLAGS
-        if (H.dbg & 8) {
-            if (acc[0].x == 1.2345e300) post(gbase, acc[0], acc[1], acc[2], wscale);   // keep the arithmetic alive
-            return;
-        }
-#endif
-        if (OPT & 1) {
-            cplx pv[NS];
-#pragma unroll
-            for (int b = 0; b < NS; ++b) pv[b] = pre(gbase + (long long)b * NS * TL);
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                const long long i = gbase + (long long)b * NS * TL;
-                post(i, acc[b], ys[(w + NS * b) * TL], pv[b], wscale);
-            }
-        } else {
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                const long long i = gbase + (long long)b * NS * TL;
-                post(i, acc[b], ys[(w + NS * b) * TL], pre(i), wscale);
-            }
-        }
-    }
-
-    template <class Pre, class Post>
-    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
-                                               long long tile, int member, Pre pre, Post post) {
-        const size_t Dp = (size_t)H.n_tiles * M * TL;
-        const cplx *tile_data = x + (size_t)tile * M * TL;
-        const cplx *x0 = x - (size_t)s.cur_col * Dp;          // column 0 of the source
-        // source tile of the unit `ahead` places further down this CTA's work list (nullptr: none)
-        auto unit_ptr = [&](int ahead, long long &t, int &col) -> const cplx * {
-            if (s.w + ahead * s.wstride >= s.total) return nullptr;
-            int ti;
-            unit_ahead(s, H.n_tiles, ahead, col, ti);
-            t = ti;
-            return x0 + (size_t)col * Dp + (size_t)t * M * TL;
-        };
-        long long tn = 0;
-        int cn = 0;
-        if (PIPE) {
-            const int q = s.q;
-            if (threadIdx.x == 0) {
-                if (s.loaded != tile_data) {    // first tile of a phase: nothing in flight yet
-                    fill(H, s, q, tile_data, tile, member);
-                    if (NBUF == 3) {
-                        const cplx *n1 = unit_ptr(1, tn, cn);
-                        if (n1) fill(H, s, q + 1, n1, tn, s.member_of ? s.member_of[cn] : 0);
-                    }
-                }
-                const cplx *n2 = unit_ptr(NBUF - 1, tn, cn);
-                if (n2) fill(H, s, q + NBUF - 1, n2, tn, s.member_of ? s.member_of[cn] : 0);
-            }
-            __syncwarp();
-            mbar_wait(&s.bars[q % NBUF], (q / NBUF) & 1);
-            const Buf cur = buffer(s, q % NBUF);
-            if (tile >= H.top_tile) body<false>(H, s, cur, x, tile, pre, post);
-            else body<true>(H, s, cur, x, tile, pre, post);
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&s.bars[3 + q % NBUF]);
-            s.loaded = unit_ptr(1, tn, cn);
-            s.q = q + 1;
-            return;
-        }
-        if (s.loaded != tile_data) {        // first tile of a phase: nothing in flight yet
-            s.buf = 0;
-            issue(H, buffer(s, 0), tile_data, tile);
-            if (NBUF == 3) {
-                const cplx *n1 = unit_ptr(1, tn, cn);
-                if (n1) issue(H, buffer(s, 1), n1, tn);
-                else asm volatile("cp.async.commit_group;\n" ::: "memory");
-            }
-        }
-        if (member != s.cur_member) {
-            __syncthreads();                // slower warps may still read the previous member's coefficients
-            const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
-            for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.hR[i] = hr[i].y; s.hC[i] = hc[i].y; }
-            s.cur_member = member;
-        }
-        if (NBUF == 3) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncthreads();                    // tile visible; every warp is done with the buffer refilled next
-        const Buf cur = buffer(s, s.buf);
-        {
-            const cplx *nd = unit_ptr(NBUF - 1, tn, cn);      // refill the buffer the previous tile used
-            const int into = (s.buf + NBUF - 1) % NBUF;
-            if (nd) issue(H, buffer(s, into), nd, tn);
-            else if (NBUF == 3) asm volatile("cp.async.commit_group;\n" ::: "memory");
-            s.loaded = unit_ptr(1, tn, cn);
-            s.buf = (s.buf + 1) % NBUF;
-        }
-        if (tile >= H.top_tile) body<false>(H, s, cur, x, tile, pre, post);
-        else body<true>(H, s, cur, x, tile, pre, post);
-    }
-};
-
-
-// Pair-packed electronic-block tile.  Global layout of a tile (32 ADOs, NS sites):
-//   [pair p = (a<b)][lane][2] = { rho_n[a,b], rho_n[b,a] }   (NS(NS-1)/2 pairs, 32 B per lane)
-//   [diag d][lane]            = rho_n[d,d]
-// Both members of a pair are always needed from the same hierarchy neighbour (link along
-// site a or site b), so one 256-bit load (LDG.E.256, sm_100) fetches a fully used sector:
-// half the gather instructions and half the SM<->L2 sectors of the element-wise layout.
-// A warp owns the diagonal element (w,w) and the pairs (w, w+1..w+(NS-1)/2 mod NS).  The
-// source tile is re-laid out element-major [e][lane] in shared memory by the cp.async
-// staging copies, so the small GEMMs keep conflict-free, immediate-offset addressing.
-__device__ __forceinline__ void ld256_cg(const cplx *p, cplx &v0, cplx &v1) {
-    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v0.x), "=d"(v0.y), "=d"(v1.x), "=d"(v1.y) : "l"(p));
-}
-
-template <int NS, int K1, bool REAL_H>
-struct TileEEP {
-    static_assert(NS % 2 == 1, "balanced pair ownership needs an odd number of sites");
-    static constexpr int THREADS = 32 * NS;
-    static constexpr int MIN_BLOCKS = 1;
-    static constexpr int UNITS = 1;
-    static constexpr int M = NS * NS;
-    static constexpr int BINS = NS * K1;
-    static constexpr int NP = NS * (NS - 1) / 2;
-    static constexpr int NQ = (NS - 1) / 2;          // pairs owned by a warp
-
-    static __host__ __device__ int pair_index(int a, int b) {   // a < b
-        return a * (2 * NS - a - 1) / 2 + (b - a - 1);
-    }
-    static __host__ __device__ size_t buf_bytes() {
-        return al16((size_t)M * TL * sizeof(cplx)) + 2 * al16((size_t)BINS * TL * sizeof(int)) +
-               al16((size_t)BINS * TL) + al16((size_t)2 * TL * sizeof(double));
-    }
-    static __host__ __device__ size_t shared_bytes(const HeomDev &H) {
-        return al16((size_t)NS * NS * sizeof(cplx)) * 2 + al16((size_t)M * sizeof(double)) +
-               2 * al16((size_t)K1 * H.Lc * sizeof(double)) + al16((size_t)NP * sizeof(int));
-    }
-    static size_t smem_bytes(const HeomDev &H) { return shared_bytes(H) + 2 * buf_bytes(); }
-
-    static __device__ __forceinline__ void setup(const HeomDev &H, unsigned char *base, TileSmem &s) {
-        size_t off = 0;
-        s.HR = reinterpret_cast<cplx *>(base + off); off += al16((size_t)NS * NS * sizeof(cplx));
-        s.HC = reinterpret_cast<cplx *>(base + off); off += al16((size_t)NS * NS * sizeof(cplx));
-        s.dterm = reinterpret_cast<double *>(base + off); off += al16((size_t)M * sizeof(double));
-        s.su = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
-        s.sd = reinterpret_cast<double *>(base + off); off += al16((size_t)K1 * H.Lc * sizeof(double));
-        s.lbin = reinterpret_cast<int *>(base + off); off += al16((size_t)NP * sizeof(int));   // pair -> a*NS+b
-        s.os = reinterpret_cast<cplx *>(base + off);       // start of the two tile buffers
-        for (int i = threadIdx.x; i < M; i += blockDim.x) s.dterm[i] = H.dterm[i];
-        for (int i = threadIdx.x; i < K1 * H.Lc; i += blockDim.x) { s.su[i] = H.su[i]; s.sd[i] = H.sd[i]; }
-        if (threadIdx.x == 0)
-            for (int a = 0; a < NS; ++a)
-                for (int b = a + 1; b < NS; ++b) s.lbin[pair_index(a, b)] = a * NS + b;
-        s.cur_member = -1;
-        s.loaded = nullptr;
-        s.buf = 0;
-        __syncthreads();
-    }
-
-    struct Buf { cplx *ys; int *n_up, *n_dn; uint8_t *occ; double *sh; };
-    static __device__ __forceinline__ Buf buffer(const TileSmem &s, int which) {
-        unsigned char *p = reinterpret_cast<unsigned char *>(s.os) + (size_t)which * buf_bytes();
-        Buf b;
-        b.ys = reinterpret_cast<cplx *>(p); p += al16((size_t)M * TL * sizeof(cplx));
-        b.n_up = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
-        b.n_dn = reinterpret_cast<int *>(p); p += al16((size_t)BINS * TL * sizeof(int));
-        b.occ = p; p += al16((size_t)BINS * TL);
-        b.sh = reinterpret_cast<double *>(p);
-        return b;
-    }
-    // asynchronous copy of one pair-packed source tile into an element-major buffer
-    static __device__ __forceinline__ void issue(const HeomDev &H, const TileSmem &s, const Buf &b,
-                                                 const cplx *tile_data, long long tile) {
-        for (int i = threadIdx.x; i < M * TL; i += THREADS) {
-            int e, lane;
-            if (i < NP * 2 * TL) {
-                const int ab = s.lbin[i >> 6], a = ab / NS, bb = ab % NS;
-                lane = (i & 63) >> 1;
-                e = (i & 1) ? (bb + NS * a) : (a + NS * bb);     // slot 0: (a,b), slot 1: (b,a)
-            } else {
-                const int r = i - NP * 2 * TL;
-                e = (r >> 5) * (NS + 1);
-                lane = r & 31;
-            }
-            cp_async16(&b.ys[e * TL + lane], &tile_data[i]);
-        }
-        const size_t tb = (size_t)tile * BINS * TL;
-        for (int i = threadIdx.x; i < BINS * TL / 4; i += THREADS) {
-            cp_async16(&b.n_up[4 * i], &H.up[tb + 4 * i]);
-            cp_async16(&b.n_dn[4 * i], &H.down[tb + 4 * i]);
-        }
-        for (int i = threadIdx.x; i < BINS * TL / 16; i += THREADS) cp_async16(&b.occ[16 * i], &H.occ[tb + 16 * i]);
-        if (threadIdx.x < TL / 2) {
-            cp_async16(&b.sh[2 * threadIdx.x], &H.shift[tile * TL + 2 * threadIdx.x]);
-            cp_async16(&b.sh[TL + 2 * threadIdx.x], &H.scale[tile * TL + 2 * threadIdx.x]);
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    }
-
-    // (Hs_R rho - rho Hs_C)[x][y] from the element-major tile
-    static __device__ __forceinline__ cplx commutator(const TileSmem &s, const cplx *ys, int x, int y, int lane) {
-        cplx acc = cmake(0, 0);
-        if (REAL_H) {
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {
-                const double hr = s.HR[x * NS + c].y, hc = s.HC[y * NS + c].y;
-                const cplx z1 = ys[(c + NS * y) * TL + lane], z2 = ys[(x + NS * c) * TL + lane];
-                acc.x = fma(-hr, z1.y, acc.x); acc.y = fma(hr, z1.x, acc.y);
-                acc.x = fma(hc, z2.y, acc.x);  acc.y = fma(-hc, z2.x, acc.y);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {
-                const cplx hr = s.HR[x * NS + c], hc = s.HC[y * NS + c];
-                cfma(acc, hr, ys[(c + NS * y) * TL + lane]);
-                cfma(acc, cmake(-hc.x, -hc.y), ys[(x + NS * c) * TL + lane]);
-            }
-        }
-        return acc;
-    }
-
-    template <class Pre, class Post>
-    static __device__ __forceinline__ void run(const HeomDev &H, TileSmem &s, const cplx *__restrict__ x,
-                                               long long tile, int member, Pre pre, Post post) {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const size_t Dp = (size_t)H.n_tiles * M * TL;
-        const cplx *tile_data = x + (size_t)tile * M * TL;
-        if (s.loaded != tile_data) {
-            s.buf = 0;
-            issue(H, s, buffer(s, 0), tile_data, tile);
-        }
-        if (member != s.cur_member) {
-            __syncthreads();                // slower warps may still read the previous member's coefficients
-            const cplx *hr = H.HR + (size_t)member * NS * NS, *hc = H.HC + (size_t)member * NS * NS;
-            for (int i = threadIdx.x; i < NS * NS; i += THREADS) { s.HR[i] = hr[i]; s.HC[i] = hc[i]; }
-            s.cur_member = member;
-        }
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncthreads();
-        const Buf cur = buffer(s, s.buf);
-        if (s.next_tile >= 0) {
-            const cplx *nd = (x - (size_t)s.cur_col * Dp) + (size_t)s.next_col * Dp + (size_t)s.next_tile * M * TL;
-            issue(H, s, buffer(s, s.buf ^ 1), nd, s.next_tile);
-            s.loaded = nd;
-            s.buf ^= 1;
-        } else {
-            s.loaded = nullptr;
-        }
-        const long long gtile = (long long)tile * M * TL;
-        const double shift = cur.sh[lane], wscale = cur.sh[TL + lane];
-
-        // ---- issue every gather of this warp's tasks: NQ pairs x 4 K1 loads of 32 B, diag 2 K1 x 16 B
-        cplx g0[NQ][2 * K1][2], g1[NQ][2 * K1][2];     // [pair][site(a/b) * K1 + k][up/dn], slots 0/1
-        cplx gd[K1][2];
-        int pb[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int a = w, b = (w + q + 1) % NS;
-            const int lo = min(a, b), hi = max(a, b);
-            const int pidx = pair_index(lo, hi);
-            pb[q] = b;
-#pragma unroll
-            for (int sk = 0; sk < 2 * K1; ++sk) {
-                const int site = sk < K1 ? a : b, k = sk % K1;
-                const int bin = site * K1 + k;
-                const int nu = cur.n_up[bin * TL + lane], nd = cur.n_dn[bin * TL + lane];
-                g0[q][sk][0] = g1[q][sk][0] = g0[q][sk][1] = g1[q][sk][1] = cmake(0, 0);
-                if (nu >= 0) ld256_cg(x + (size_t)(nu >> 5) * M * TL + pidx * 2 * TL + (nu & 31) * 2, g0[q][sk][0], g1[q][sk][0]);
-                if (nd >= 0) ld256_cg(x + (size_t)(nd >> 5) * M * TL + pidx * 2 * TL + (nd & 31) * 2, g0[q][sk][1], g1[q][sk][1]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K1; ++k) {
-            const int bin = w * K1 + k;
-            const int nu = cur.n_up[bin * TL + lane], nd = cur.n_dn[bin * TL + lane];
-            gd[k][0] = nu >= 0 ? __ldcg(x + (size_t)(nu >> 5) * M * TL + NP * 2 * TL + w * TL + (nu & 31)) : cmake(0, 0);
-            gd[k][1] = nd >= 0 ? __ldcg(x + (size_t)(nd >> 5) * M * TL + NP * 2 * TL + w * TL + (nd & 31)) : cmake(0, 0);
-        }
-        // integrator prefetch for the owned elements
-        cplx pv_d = pre(gtile + NP * 2 * TL + w * TL + lane);
-        cplx pv0[NQ], pv1[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int lo = min(w, pb[q]), hi = max(w, pb[q]);
-            const long long gi = gtile + pair_index(lo, hi) * 2 * TL + lane * 2;
-            pv0[q] = pre(gi);
-            pv1[q] = pre(gi + 1);
-        }
-        // ---- diagonal element (w, w)
-        {
-            const int e = w * (NS + 1);
-            const cplx own = cur.ys[e * TL + lane];
-            cplx acc = commutator(s, cur.ys, w, w, lane);
-            const double dg = shift + s.dterm[e];
-            acc.x -= dg * own.x; acc.y -= dg * own.y;
-#pragma unroll
-            for (int k = 0; k < K1; ++k) {
-                const int njk = cur.occ[(w * K1 + k) * TL + lane];
-                const cplx cu = cadd(H.GuR[k], H.GuC[k]), cd = cadd(H.GdR[k], H.GdC[k]);
-                cfma(acc, cscale(s.su[k * H.Lc + njk], cu), gd[k][0]);
-                cfma(acc, cscale(s.sd[k * H.Lc + njk], cd), gd[k][1]);
-            }
-            post(gtile + NP * 2 * TL + w * TL + lane, acc, own, pv_d, wscale);
-        }
-        // ---- pairs (w, b): elements (w,b) and (b,w)
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int a = w, b = pb[q];
-            const bool a_lo = a < b;
-            const int e_ab = a + NS * b, e_ba = b + NS * a;
-            const cplx own_ab = cur.ys[e_ab * TL + lane], own_ba = cur.ys[e_ba * TL + lane];
-            cplx r_ab = commutator(s, cur.ys, a, b, lane), r_ba = commutator(s, cur.ys, b, a, lane);
-            const double d_ab = shift + s.dterm[e_ab], d_ba = shift + s.dterm[e_ba];
-            r_ab.x -= d_ab * own_ab.x; r_ab.y -= d_ab * own_ab.y;
-            r_ba.x -= d_ba * own_ba.x; r_ba.y -= d_ba * own_ba.y;
-#pragma unroll
-            for (int sk = 0; sk < 2 * K1; ++sk) {
-                const bool site_is_a = sk < K1;
-                const int k = sk % K1;
-                const int bin = (site_is_a ? a : b) * K1 + k;
-                const int njk = cur.occ[bin * TL + lane];
-                const double su = s.su[k * H.Lc + njk], sd = s.sd[k * H.Lc + njk];
-                // gathered slots: slot 0 = (lo,hi), slot 1 = (hi,lo)
-                const cplx u_ab = a_lo ? g0[q][sk][0] : g1[q][sk][0], u_ba = a_lo ? g1[q][sk][0] : g0[q][sk][0];
-                const cplx d_ab_v = a_lo ? g0[q][sk][1] : g1[q][sk][1], d_ba_v = a_lo ? g1[q][sk][1] : g0[q][sk][1];
-                // link along site a: (a,b) is a row-site element, (b,a) a col-site one; along site b: reversed
-                const cplx cu_ab = site_is_a ? H.GuR[k] : H.GuC[k], cu_ba = site_is_a ? H.GuC[k] : H.GuR[k];
-                const cplx cd_ab = site_is_a ? H.GdR[k] : H.GdC[k], cd_ba = site_is_a ? H.GdC[k] : H.GdR[k];
-                cfma(r_ab, cscale(su, cu_ab), u_ab);
-                cfma(r_ab, cscale(sd, cd_ab), d_ab_v);
-                cfma(r_ba, cscale(su, cu_ba), u_ba);
-                cfma(r_ba, cscale(sd, cd_ba), d_ba_v);
-            }
-            const int lo = min(a, b), hi = max(a, b);
-            const long long gi = gtile + pair_index(lo, hi) * 2 * TL + lane * 2;
-            // slot 0 holds (lo,hi)
-            post(gi, a_lo ? r_ab : r_ba, a_lo ? own_ab : own_ba, pv0[q], wscale);
-            post(gi + 1, a_lo ? r_ba : r_ab, a_lo ? own_ba : own_ab, pv1[q], wscale);
-        }
-    }
-};
-
 // ------------------------------------------------------------ layout kernels
 // reference [b][n][e]  <->  tile-SoA [b][tile][e][32]
 __global__ void heom_to_internal(const cplx *__restrict__ ref, cplx *__restrict__ internal, int B,
                                  long long n_ado, long long n_tiles, int M,
-                                 const int *__restrict__ e_off, const int *__restrict__ e_stride) {
+                                 const int *__restrict__ e_off, const int *__restrict__ e_stride,
+                                 const double *__restrict__ g) {
     const long long per = n_tiles * M * TL;
     const long long total = per * B;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1506,14 +598,16 @@ __global__ void heom_to_internal(const cplx *__restrict__ ref, cplx *__restrict_
         long long tile = r / ((long long)M * TL);
         int e = (int)((r / TL) % M), lane = (int)(r % TL);
         long long n = tile * TL + lane;
-        internal[(size_t)b * per + tile * M * TL + e_off[e] + lane * e_stride[e]] =
-            (n < n_ado) ? ref[((size_t)b * n_ado + n) * M + e] : cmake(0, 0);
+        cplx v = (n < n_ado) ? ref[((size_t)b * n_ado + n) * M + e] : cmake(0, 0);
+        if (g) v = cscale(g[n], v);             // row tile: sigma_n = g_n rho_n (heom_row.cuh)
+        internal[(size_t)b * per + tile * M * TL + e_off[e] + lane * e_stride[e]] = v;
     }
 }
 
 __global__ void heom_from_internal(const cplx *__restrict__ internal, cplx *__restrict__ ref, int B,
                                    long long n_ado, long long n_tiles, int M,
-                                   const int *__restrict__ e_off, const int *__restrict__ e_stride) {
+                                   const int *__restrict__ e_off, const int *__restrict__ e_stride,
+                                   const double *__restrict__ g) {
     const long long per = n_ado * M;
     const long long total = per * B;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1521,7 +615,9 @@ __global__ void heom_from_internal(const cplx *__restrict__ internal, cplx *__re
         long long b = i / per, r = i % per;
         long long n = r / M;
         int e = (int)(r % M);
-        ref[i] = internal[((size_t)b * n_tiles * M + (n >> 5) * M) * TL + e_off[e] + (n & 31) * e_stride[e]];
+        cplx v = internal[((size_t)b * n_tiles * M + (n >> 5) * M) * TL + e_off[e] + (n & 31) * e_stride[e]];
+        if (g) v = cscale(1.0 / g[n], v);
+        ref[i] = v;
     }
 }
 
@@ -1750,9 +846,6 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                             int failed = *((volatile int *)&a.flags[fslot]);
                             fslot = (fslot + 1) % 3;
                             nslot = (nslot + 1) % 3;
-#ifdef QSX_HEOM_DBG_FLAGS
-                            if ((a.H.dbg & 32) && k < 12) failed = 1;      // fixed number of terms for timing experiments
-#endif
                             if (!failed) { done = true; break; }
                         }
                     }
@@ -2131,7 +1224,6 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     d.n_members = cfg->n_members; d.n_ado = n_ado; d.n_tiles = n_tiles;
     d.shift = h->shift.p; d.scale = h->scale.p; d.up = h->up.p; d.down = h->down.p; d.occ = h->occ.p;
     d.off_up = h->off_up.p; d.off_dn = h->off_dn.p;
-    d.layout = 0;
     d.heis = cfg->heisenberg ? 1 : 0;
     d.top_tile = (tb.level_offset[Lc - 1] + TL - 1) / TL;
     d.n_pulse = 0; d.Rp = 0; d.pcol = nullptr; d.pval = nullptr;
@@ -2153,42 +1245,14 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     for (auto &z : HR) if (z.x != 0.0) d.real_h = 0;
     for (auto &z : HC) if (z.x != 0.0) d.real_h = 0;
     {
-        // pair-packed layout (experimental, QSX_HEOM_VARIANT=p): halves the gather sectors
-        // (measured 14.6 M -> 7.6 M per RHS at depth 8) but is slower end to end than the
-        // element-major TileEE (150 vs 111 us per apply) because of the heavier per-element
-        // commutator and partial-sector stores; kept for the round-2 work on this kernel.
-        const char *variant = getenv("QSX_HEOM_VARIANT");
-#ifdef QSX_HEOM_EXPERIMENTS
-        const bool want_pairs = variant && variant[0] == 'p';
-#else
-        const bool want_pairs = false; (void)variant;
-#endif
-        if (d.ee && d.real_h && nr == 7 && K1 == 2 && want_pairs) d.layout = 1;
         std::vector<int> e_off(M), e_stride(M);
-        for (int e = 0; e < M; ++e) {
-            const int a = e % nr, b = e / nr;
-            if (d.layout == 0) { e_off[e] = e * TL; e_stride[e] = 1; }
-            else if (a == b) { e_off[e] = nr * (nr - 1) / 2 * 2 * TL + a * TL; e_stride[e] = 1; }
-            else {
-                const int lo = std::min(a, b), hi = std::max(a, b);
-                const int p = lo * (2 * nr - lo - 1) / 2 + (hi - lo - 1);
-                e_off[e] = p * 2 * TL + (a < b ? 0 : 1);
-                e_stride[e] = 2;
-            }
-        }
+        for (int e = 0; e < M; ++e) { e_off[e] = e * TL; e_stride[e] = 1; }
         QSX_CUDA(h->e_off.upload(e_off, stream));
         QSX_CUDA(h->e_stride.upload(e_stride, stream));
         QSX_CUDA(cudaStreamSynchronize(stream));
         d.e_off = h->e_off.p; d.e_stride = h->e_stride.p;
     }
     d.HR = h->HR.p; d.HC = h->HC.p; d.dterm = h->dterm.p; d.lbin = h->lbin.p;
-    d.dbg = 0;
-    d.linear = (!cfg->modified && !cfg->heisenberg) ? 1 : 0;
-    d.const_h = (cfg->n_members == 1 && nr == 7 && nc == 7) ? 1 : 0;
-    for (int i = 0; i < 49; ++i) {
-        d.hRc[i] = d.const_h ? HR[i].y : 0.0;
-        d.hCc[i] = d.const_h ? HC[i].y : 0.0;
-    }
     d.gu = h->gu.p; d.gd = h->gd.p; d.su = h->su.p; d.sd = h->sd.p;
     size_t offs[14];
     int dev = 0, smem_limit = 0;
@@ -2197,6 +1261,62 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     if (tile_smem_layout(d, offs) > (size_t)smem_limit) {
         qsx_set_error("HEOM subspace dimension %d too large for the tile kernel", M);
         return QSX_ERR_UNSUPPORTED;
+    }
+    // ---- row tile (heom_row.cuh): sigma_n = g_n rho_n variables, tile records -----------
+    {
+        bool ok = d.ee && d.real_h && !cfg->heisenberg && rows == cols && nr == 7 && K1 == 2;
+        for (int m = 0; m < cfg->n_members && ok; ++m)
+            for (int a = 0; a < nr && ok; ++a)
+                for (int c = 0; c < nr && ok; ++c)
+                    ok = HR[((size_t)m * nr + a) * nr + c].y == HR[((size_t)m * nr + c) * nr + a].y &&
+                         HC[((size_t)m * nr + a) * nr + c].y == HR[((size_t)m * nr + a) * nr + c].y;
+        if (ok) {
+            typedef heom_row::Cfg<7, 2> C;
+            heom_row::RowDev &r = h->row;
+            std::vector<unsigned char> rec((size_t)n_tiles * C::REC_BYTES, 0);
+            std::vector<double> g((size_t)n_tiles * TL, 0.0);
+            for (int64_t n = 0; n < n_tiles * TL; ++n) {
+                const int64_t tile = n / TL;
+                const int lane = (int)(n % TL);
+                unsigned char *base = rec.data() + (size_t)tile * C::REC_BYTES;
+                int *dn = reinterpret_cast<int *>(base + C::OFF_DN) + lane * C::LD;
+                int *up_ = reinterpret_cast<int *>(base + C::OFF_UP) + lane * C::LD;
+                double *upc = reinterpret_cast<double *>(base + C::OFF_UPC) + lane * C::UD;
+                for (int b = 0; b < C::LD; ++b) { dn[b] = -1; up_[b] = -1; }
+                if (n >= n_ado) continue;
+                double logg = 0;
+                for (int b = 0; b < bins; ++b) {
+                    const int njk = tb.index[(size_t)n * bins + b];
+                    const size_t o = ((size_t)tile * bins + b) * TL + lane;
+                    dn[b] = off_dn[o];
+                    up_[b] = off_up[o];
+                    upc[b] = u * (njk + 1);
+                    const double ck = std::abs(cc[b % K1]);
+                    logg += cfg->modified ? 0.5 * (njk * log(ck) - lgamma(njk + 1.0)) : -lgamma(njk + 1.0);
+                }
+                g[n] = exp(logg);
+                reinterpret_cast<double *>(base + C::OFF_SHIFT)[lane] = shift[n];
+                reinterpret_cast<double *>(base + C::OFF_SCALE)[lane] = scale[n] / g[n];
+            }
+            std::vector<double> hm((size_t)cfg->n_members * C::MH, 0.0);
+            for (int m = 0; m < cfg->n_members; ++m)
+                for (int i = 0; i < M; ++i) hm[(size_t)m * C::MH + i] = HR[(size_t)m * M + i].y;
+            std::vector<cplx> ainv(sizeof(qsx_taylor_ainv) / sizeof(qsx_taylor_ainv[0]));
+            for (size_t i = 0; i < ainv.size(); ++i) ainv[i] = cmake(qsx_taylor_ainv[i][0], qsx_taylor_ainv[i][1]);
+            QSX_CUDA(h->row_rec.upload(rec, stream));
+            QSX_CUDA(h->row_g.upload(g, stream));
+            QSX_CUDA(h->row_h.upload(hm, stream));
+            QSX_CUDA(h->row_ainv.upload(ainv, stream));
+            QSX_CUDA(cudaStreamSynchronize(stream));
+            r.n_members = cfg->n_members;
+            r.n_ado = n_ado; r.n_tiles = n_tiles; r.top_tile = d.top_tile;
+            r.rec = h->row_rec.p; r.hmem = h->row_h.p; r.gscale = h->row_g.p;
+            for (int i = 0; i < 64; ++i) r.hc[i] = i < M ? hm[i] : 0.0;
+            for (int k = 0; k < 4; ++k) r.cd[k] = k < K1 ? d.GdR[k] : cmake(0, 0);
+            r.d2 = 2.0 * u * cfg->temp_corr;
+            r.const_h = cfg->n_members == 1;
+            h->row_ok = true;
+        }
     }
     *out = h.release();
     return QSX_OK;
@@ -2215,15 +1335,44 @@ extern "C" int qsx_heom_index_maps(qsx_heom_t h, int64_t *ado_index, int32_t *up
     return QSX_OK;
 }
 
-static bool use_warp_tile(const HeomDev &d) {
-    return d.nr == 7 && d.nc == 7 && d.Lk == 4 && d.bins <= 16;
-}
-
 static int upload_members(DevBuf<int> &buf, const int32_t *host, int n, int n_members, cudaStream_t s) {
     std::vector<int> m(host, host + n);
     for (int x : m) QSX_REQUIRE(x >= 0 && x < n_members, "member index out of range");
     QSX_CUDA(buf.upload(m, s));
     return QSX_OK;
+}
+
+// ---- tile selection ---------------------------------------------------------------
+// QSX_HEOM_VARIANT (tests / A-B runs): 'r' row tile also for small hierarchies, 'b' batch tile
+// (TileEE), 'g' generic tile.  Default: the row tile once every SM has several tiles
+// (measured in round 1: two lean CTAs per SM beat the one-CTA batch tile from ~2000 units on),
+// otherwise the batch tile.
+static char heom_variant() {
+    const char *v = getenv("QSX_HEOM_VARIANT");
+    return v ? v[0] : ' ';
+}
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static bool use_row_tile(const qsx_heom_s *h, long long units) {
+    const char v = heom_variant();
+    if (!h->row_ok || v == 'b' || v == 'g') return false;
+    return v == 'r' || units >= 2048;
+}
+
+// Row-tile launch configurations (buffers per CTA, CTAs per SM); QSX_HEOM_ROWCFG picks one
+// for A-B runs: "32" three buffers / two CTAs (default), "23" two buffers / three CTAs, "22".
+template <class Fn>
+static int row_dispatch(bool const_h, Fn &&fn) {
+    typedef heom_row::Cfg<7, 2> C;
+    const int cfg = env_int("QSX_HEOM_ROWCFG", 32);
+    if (cfg == 23) return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 3>())
+                                  : fn(C(), std::false_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 3>());
+    if (cfg == 22) return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>())
+                                  : fn(C(), std::false_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
+    return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>())
+                   : fn(C(), std::false_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>());
 }
 
 extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int32_t n_columns,
@@ -2241,19 +1390,33 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     int dev = 0, sms = 148;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long total = d.n_tiles * n_columns;
+    const bool row = use_row_tile(h, total);
     heom_to_internal<<<sms * 4, 256, 0, stream>>>((const cplx *)y_dev, xi.p, n_columns, d.n_ado, d.n_tiles, d.M,
-                                                   d.e_off, d.e_stride);
-    HeomApplyArgs a;
-    a.H = d; a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
-    size_t offs[14];
-    size_t smem = tile_smem_layout(d, offs);
-    long long total = d.n_tiles * n_columns;
-    int grid = (int)std::min<long long>(total, (long long)sms * 6);
-    const char *variant = getenv("QSX_HEOM_VARIANT");
-    char vsel = variant ? variant[0] : ' ';
-    const bool force_lean = vsel == 'L';     // tests: the pipeline tile also for small hierarchies
-    if (force_lean) vsel = ' ';
-    int apply_occ = 0;
+                                                   d.e_off, d.e_stride, row ? h->row.gscale : nullptr);
+    if (row) {
+        QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
+        heom_row::RowApplyArgs a;
+        a.R = h->row; a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
+        a.blk = std::max(1, env_int("QSX_HEOM_BLK", 2));
+        rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
+            typedef decltype(C_) C;
+            auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
+            const size_t smem = C::smem_bytes(decltype(NB)::value);
+            int per_sm = 0;
+            QSX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::THREADS, smem));
+            QSX_REQUIRE(per_sm > 0, "heom_row_apply_kernel does not fit on an SM");
+            const int grid = (int)std::min<long long>((total + a.blk - 1) / a.blk, (long long)sms * per_sm);
+            kernel<<<grid, C::THREADS, smem, stream>>>(a);
+            return QSX_OK;
+        });
+        if (rc) return rc;
+    } else {
+        HeomApplyArgs a;
+        a.H = d; a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
+        size_t smem;
+        int grid, apply_occ = 0;
 #define QSX_APPLY(TILE)                                                                                  \
     {                                                                                                    \
         typedef TILE T;                                                                                  \
@@ -2266,30 +1429,15 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
                                         (long long)sms * std::max(1, apply_occ));                        \
         heom_apply_kernel<T><<<grid, T::THREADS, smem, stream>>>(a);                                     \
     }
-    const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
-    // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
-    // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
-    const bool lean_pays = force_lean || d.n_tiles * (long long)n_columns >= 2048;
-    if (false) {}
-#ifdef QSX_HEOM_EXPERIMENTS
-    else if (d.layout == 1) QSX_APPLY(TileEEP<7 COMMA 2 COMMA true>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'l') QSX_APPLY(TileLean<7 COMMA 2 COMMA 3>)
-    else if (ee7 && d.real_h && !d.heis && (vsel == 'C' || vsel == 'D')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 4>)
-    else if (ee7 && d.real_h && vsel == 'c') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
-    else if (ee7 && d.real_h && vsel == '2') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
-#endif
-#ifndef QSX_HEOM_MINIMAL
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 56>)
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.linear) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 40>)
-    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P' || vsel == 'Q')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2 COMMA 8>)
-    else if (ee7 && d.real_h && !d.heis && (vsel == 'm' || vsel == 'A')) QSX_APPLY(TileLean<7 COMMA 2 COMMA 2>)
-    else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
-    else if (ee7 && !d.real_h && vsel != 'g') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
-#endif
-    else QSX_APPLY(TileGeneric)
+        const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
+        const char vsel = heom_variant();
+        if (ee7 && d.real_h && vsel != 'g') QSX_APPLY(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+        else if (ee7 && !d.real_h && vsel != 'g') QSX_APPLY(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
+        else QSX_APPLY(TileGeneric)
 #undef QSX_APPLY
+    }
     heom_from_internal<<<sms * 4, 256, 0, stream>>>(yi.p, (cplx *)dy_dev, n_columns, d.n_ado, d.n_tiles, d.M,
-                                                     d.e_off, d.e_stride);
+                                                     d.e_off, d.e_stride, row ? h->row.gscale : nullptr);
     qsx_launch_counter += 3;
     QSX_CUDA(cudaGetLastError());
     QSX_CUDA(cudaStreamSynchronize(stream));
@@ -2306,14 +1454,21 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_REQUIRE(B > 0 && nt > 0 && args->t_host && args->y0_dev && args->out_dev,
                 "qsx_heom_propagate: empty batch or missing buffers");
     QSX_REQUIRE(args->method == QSX_METHOD_TAYLOR || args->method == QSX_METHOD_RK4 ||
-                args->method == QSX_METHOD_DOPRI5, "HEOM propagation supports taylor, rk4 and dopri5");
+                args->method == QSX_METHOD_DOPRI5 || args->method == QSX_METHOD_POLY,
+                "HEOM propagation supports taylor, poly, rk4 and dopri5");
     QSX_REQUIRE(args->n_pulses >= 0 && args->n_pulses <= QSX_MAX_PULSES, "too many pulses");
-    QSX_REQUIRE(!(args->n_pulses > 0 && args->method == QSX_METHOD_TAYLOR),
-                "Taylor propagation needs a time-independent generator");
+    QSX_REQUIRE(!(args->n_pulses > 0 && (args->method == QSX_METHOD_TAYLOR || args->method == QSX_METHOD_POLY)),
+                "Taylor / product-form propagation needs a time-independent generator");
     const bool dopri = args->method == QSX_METHOD_DOPRI5;
     for (int i = 1; i < nt; ++i)
         QSX_REQUIRE(args->t_host[i] >= args->t_host[i - 1], "output times must be non-decreasing");
     QSX_REQUIRE(args->t_host[0] >= args->t0, "first output time precedes t0");
+
+    const long long total = d.n_tiles * B;
+    const bool lti = args->method == QSX_METHOD_TAYLOR || args->method == QSX_METHOD_POLY;
+    const bool row = lti && args->n_pulses == 0 && use_row_tile(h, total);
+    // the product form lives in the row kernel; other tiles run the adaptive Taylor series instead
+    const int method = (args->method == QSX_METHOD_POLY && !row) ? (int)QSX_METHOD_TAYLOR : args->method;
 
     DevBuf<int> member, flags;
     DevBuf<double> d_t, ynorm;
@@ -2326,163 +1481,153 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_CUDA(d_t.upload(args->t_host, nt, stream));
     QSX_CUDA(flags.alloc(3));
     QSX_CUDA(ynorm.alloc((size_t)3 * B));
-    QSX_CUDA(stats.alloc(3));
-    QSX_CUDA(cudaMemsetAsync(stats.p, 0, 3 * sizeof(unsigned long long), stream));
+    QSX_CUDA(stats.alloc(4));
+    QSX_CUDA(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), stream));
     QSX_CUDA(Y.alloc((size_t)B * Dp));
     QSX_CUDA(V.alloc((size_t)B * Dp));
     QSX_CUDA(W.alloc((size_t)B * Dp));
-    if (args->method == QSX_METHOD_RK4) QSX_CUDA(X.alloc((size_t)B * Dp));
+    if (method == QSX_METHOD_RK4) QSX_CUDA(X.alloc((size_t)B * Dp));
     DevBuf<cplx> Kbuf, pval;
     DevBuf<int> pcol;
     DevBuf<double> red;
     QSX_CUDA(red.alloc(4));
     if (dopri) QSX_CUDA(Kbuf.alloc((size_t)7 * B * Dp));
 
-    HeomPropArgs a;
-    a.H = d; a.B = B; a.nt = nt;
-    for (int k = 0; k < 7; ++k) a.K[k] = dopri ? Kbuf.p + (size_t)k * B * Dp : nullptr;
-    a.atol = args->atol > 0 ? args->atol : 1e-12;
-    a.red = red.p;
-    if (args->n_pulses > 0) {
-        // per-ADO pulse operators: dense [n_pulses][M][M] on the device -> ELL rows
-        QSX_REQUIRE(args->pulse_ops_dev && args->n_pulse_sets == 1,
-                    "HEOM pulse operators must be one shared set of [n_pulses][M][M] matrices");
-        const int np = args->n_pulses;
-        std::vector<cplx> dense((size_t)np * M * M);
-        QSX_CUDA(cudaMemcpyAsync(dense.data(), args->pulse_ops_dev, dense.size() * sizeof(cplx),
-                                 cudaMemcpyDeviceToHost, stream));
-        QSX_CUDA(cudaStreamSynchronize(stream));
-        int Rp = 1;
-        for (int p = 0; p < np; ++p)
-            for (int e = 0; e < M; ++e) {
-                int nz = 0;
-                for (int c = 0; c < M; ++c) {
-                    const cplx v = dense[((size_t)p * M + e) * M + c];
-                    nz += (v.x != 0.0 || v.y != 0.0);
-                }
-                Rp = std::max(Rp, nz);
-            }
-        std::vector<int> hcol((size_t)np * M * Rp, -1);
-        std::vector<cplx> hval((size_t)np * M * Rp, cmake(0, 0));
-        for (int p = 0; p < np; ++p)
-            for (int e = 0; e < M; ++e) {
-                int l = 0;
-                for (int c = 0; c < M; ++c) {
-                    const cplx v = dense[((size_t)p * M + e) * M + c];
-                    if (v.x != 0.0 || v.y != 0.0) {
-                        hcol[((size_t)p * M + e) * Rp + l] = c;
-                        hval[((size_t)p * M + e) * Rp + l] = v;
-                        ++l;
-                    }
-                }
-            }
-        QSX_CUDA(pcol.upload(hcol, stream));
-        QSX_CUDA(pval.upload(hval, stream));
-        QSX_CUDA(cudaStreamSynchronize(stream));
-        a.H.n_pulse = np; a.H.Rp = Rp; a.H.pcol = pcol.p; a.H.pval = pval.p;
-        for (int p = 0; p < np; ++p) a.H.pulses[p] = args->pulses[p];
-    }
-    a.member_of = args->generator_of_column_host ? member.p : nullptr;
-    a.y0 = (const cplx *)args->y0_dev;
-    a.Y = Y.p; a.V = V.p; a.W = W.p; a.X = X.p;
-    a.t = d_t.p; a.t0 = args->t0;
-    a.rtol = args->rtol > 0 ? args->rtol : (dopri ? 1e-10 : 1e-13);
-    a.rk4_sub = args->rk4_substeps > 0 ? args->rk4_substeps : 16;
-    a.kmax = 60; a.theta = 2.0; a.lnorm = h->lnorm;
-    a.save_mode = args->save_mode; a.save_rows = args->save_rows;
-    a.S = (const cplx *)args->save_dev;
-    if (a.save_mode == QSX_SAVE_MATRIX) {
-        QSX_REQUIRE(a.S && a.save_rows > 0 && args->n_save == 1, "HEOM save matrix must be shared ([rows][M])");
-        a.saved_dim = d.n_ado * a.save_rows;
-    } else if (a.save_mode == QSX_SAVE_ADO0) {
-        a.saved_dim = M;
+    long long saved_dim;
+    if (args->save_mode == QSX_SAVE_MATRIX) {
+        QSX_REQUIRE(args->save_dev && args->save_rows > 0 && args->n_save == 1,
+                    "HEOM save matrix must be shared ([rows][M])");
+        saved_dim = d.n_ado * args->save_rows;
+    } else if (args->save_mode == QSX_SAVE_ADO0) {
+        saved_dim = M;
     } else {
-        QSX_REQUIRE(a.save_mode == QSX_SAVE_STATE, "bad save_mode");
-        a.saved_dim = D;
+        QSX_REQUIRE(args->save_mode == QSX_SAVE_STATE, "bad save_mode");
+        saved_dim = D;
     }
-    a.out = (cplx *)args->out_dev;
-    a.flags = flags.p; a.ynorm = ynorm.p; a.stats = stats.p;
-
-    const bool taylor = args->method == QSX_METHOD_TAYLOR;
-    a.H.dbg = getenv("QSX_HEOM_DBG") ? atoi(getenv("QSX_HEOM_DBG")) : 0;
-    const void *kernel;
-    int threads;
-    const char *variant = getenv("QSX_HEOM_VARIANT");
-    char vsel = variant ? variant[0] : ' ';
-    const bool force_lean = vsel == 'L';     // tests: the pipeline tile also for small hierarchies
-    if (force_lean) vsel = ' ';
-    size_t smem;
-    int units = 1;
-#define QSX_PICK(TILE)                                                                        \
-    {                                                                                         \
-        typedef TILE T;                                                                       \
-        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;                      \
-        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>           \
-                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;             \
-    }
-#define QSX_PICK_R(TILE, NREG)                                                                \
-    {                                                                                         \
-        typedef TILE T;                                                                       \
-        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;                      \
-        kernel = taylor ? (const void *)heom_propagate_kernel_r<QSX_METHOD_TAYLOR, T, NREG>   \
-                        : (const void *)heom_propagate_kernel_r<QSX_METHOD_RK4, T, NREG>;     \
-    }
-    const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
-    // two lean CTAs per SM beat the one-CTA batch tile only once every SM has many tiles
-    // (measured: 3634 tiles 113 vs 123 us per RHS, 1212 tiles 42.1 vs 41.8, 364 tiles 16.5 vs 15.0)
-    const bool lean_pays = force_lean || d.n_tiles * (long long)B >= 2048;
-    if (dopri || args->n_pulses > 0) {
-        // time-dependent right-hand sides run on the generic tile (any rectangular block)
-        QSX_REQUIRE(d.layout == 0, "pulse-driven propagation needs the element-major layout");
-        typedef TileGeneric T;
-        threads = T::THREADS; smem = T::smem_bytes(d); units = T::UNITS;
-        kernel = dopri ? (const void *)heom_propagate_kernel<QSX_METHOD_DOPRI5, T>
-                       : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
-    }
-#ifdef QSX_HEOM_EXPERIMENTS
-    else if (d.layout == 1) QSX_PICK(TileEEP<7 COMMA 2 COMMA true>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'l') QSX_PICK(TileLean<7 COMMA 2 COMMA 3>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'm') QSX_PICK(TileLean<7 COMMA 2 COMMA 2>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'B') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 3>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'C') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 7>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'D') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 5>)
-    else if (ee7 && d.real_h && vsel == '2') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true>)
-    else if (ee7 && d.real_h && vsel == '3') QSX_PICK(TileEE<7 COMMA 2 COMMA 3 COMMA true>)
-    else if (ee7 && d.real_h && vsel == 'c') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA true COMMA true>)
-    else if (use_warp_tile(d) && vsel == 'w') QSX_PICK(TileWarp<7 COMMA 7 COMMA 4 COMMA 7>)
-    else if (use_warp_tile(d) && d.K1 == 2 && vsel == 'f') QSX_PICK(TileFixed<7 COMMA 7 COMMA 4 COMMA 2 COMMA 0 COMMA 3>)
-#endif
-#ifdef QSX_HEOM_EXPERIMENTS
-    // register-cap experiments: 144 registers only fit one CTA per SM (warps are allocated in
-    // fours: 138 us per RHS), 96 registers with two buffers still two CTAs and 570 B of spills (124 us)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'R' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 2 COMMA 57>, 144)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'S' && d.const_h && d.linear) QSX_PICK_R(TileLean<7 COMMA 2 COMMA 3 COMMA 121>, 96)
-#endif
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 57>)
-#ifndef QSX_HEOM_MINIMAL
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.const_h) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 25>)
-    else if (ee7 && d.real_h && !d.heis && vsel == ' ' && lean_pays && d.linear) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 41>)
-    else if (ee7 && d.real_h && !d.heis && ((vsel == ' ' && lean_pays) || vsel == 'P')) QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 9>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'Q') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 11>)
-    else if (ee7 && d.real_h && !d.heis && vsel == 'A') QSX_PICK(TileLean<7 COMMA 2 COMMA 2 COMMA 1>)
-    else if (ee7 && d.real_h && (vsel == ' ' || vsel == 'b')) QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
-    else if (ee7 && !d.real_h && vsel != 'g' && vsel != 'f' && vsel != 'w') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
-#endif
-    else QSX_PICK(TileGeneric)
-#undef QSX_PICK
-#undef QSX_PICK_R
+    const double rtol = args->rtol > 0 ? args->rtol : (dopri ? 1e-10 : 1e-13);
     int dev = 0, sms = 0, per_sm = 0;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+    const void *kernel;
+    int threads, grid;
+    size_t smem;
+    HeomPropArgs a;
+    heom_row::RowPropArgs ra;
+    void *kargs[1];
+    if (row) {
+        QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
+        ra.R = h->row;
+        ra.B = B; ra.nt = nt;
+        ra.blk = std::max(1, env_int("QSX_HEOM_BLK", 2));
+        ra.flip = env_int("QSX_HEOM_FLIP", 0);
+        ra.member_of = args->generator_of_column_host ? member.p : nullptr;
+        ra.y0 = (const cplx *)args->y0_dev;
+        ra.Y = Y.p; ra.V = V.p; ra.W = W.p;
+        ra.t = d_t.p; ra.t0 = args->t0; ra.rtol = rtol; ra.theta = 2.0; ra.lnorm = h->lnorm;
+        ra.kmax = 60; ra.method = method;
+        ra.repilot = std::max(1, env_int("QSX_HEOM_REPILOT", 24));
+        ra.ainv = h->row_ainv.p;
+        ra.save_mode = args->save_mode; ra.save_rows = args->save_rows;
+        ra.S = (const cplx *)args->save_dev;
+        ra.out = (cplx *)args->out_dev; ra.saved_dim = saved_dim;
+        ra.flags = flags.p; ra.ynorm = ynorm.p; ra.stats = stats.p;
+        rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
+            typedef decltype(C_) C;
+            kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
+            threads = C::THREADS;
+            smem = C::smem_bytes(decltype(NB)::value);
+            return QSX_OK;
+        });
+        if (rc) return rc;
+        kargs[0] = &ra;
+    } else {
+        a.H = d; a.B = B; a.nt = nt;
+        for (int k = 0; k < 7; ++k) a.K[k] = dopri ? Kbuf.p + (size_t)k * B * Dp : nullptr;
+        a.atol = args->atol > 0 ? args->atol : 1e-12;
+        a.red = red.p;
+        if (args->n_pulses > 0) {
+            // per-ADO pulse operators: dense [n_pulses][M][M] on the device -> ELL rows
+            QSX_REQUIRE(args->pulse_ops_dev && args->n_pulse_sets == 1,
+                        "HEOM pulse operators must be one shared set of [n_pulses][M][M] matrices");
+            const int np = args->n_pulses;
+            std::vector<cplx> dense((size_t)np * M * M);
+            QSX_CUDA(cudaMemcpyAsync(dense.data(), args->pulse_ops_dev, dense.size() * sizeof(cplx),
+                                     cudaMemcpyDeviceToHost, stream));
+            QSX_CUDA(cudaStreamSynchronize(stream));
+            int Rp = 1;
+            for (int p = 0; p < np; ++p)
+                for (int e = 0; e < M; ++e) {
+                    int nz = 0;
+                    for (int c = 0; c < M; ++c) {
+                        const cplx v = dense[((size_t)p * M + e) * M + c];
+                        nz += (v.x != 0.0 || v.y != 0.0);
+                    }
+                    Rp = std::max(Rp, nz);
+                }
+            std::vector<int> hcol((size_t)np * M * Rp, -1);
+            std::vector<cplx> hval((size_t)np * M * Rp, cmake(0, 0));
+            for (int p = 0; p < np; ++p)
+                for (int e = 0; e < M; ++e) {
+                    int l = 0;
+                    for (int c = 0; c < M; ++c) {
+                        const cplx v = dense[((size_t)p * M + e) * M + c];
+                        if (v.x != 0.0 || v.y != 0.0) {
+                            hcol[((size_t)p * M + e) * Rp + l] = c;
+                            hval[((size_t)p * M + e) * Rp + l] = v;
+                            ++l;
+                        }
+                    }
+                }
+            QSX_CUDA(pcol.upload(hcol, stream));
+            QSX_CUDA(pval.upload(hval, stream));
+            QSX_CUDA(cudaStreamSynchronize(stream));
+            a.H.n_pulse = np; a.H.Rp = Rp; a.H.pcol = pcol.p; a.H.pval = pval.p;
+            for (int p = 0; p < np; ++p) a.H.pulses[p] = args->pulses[p];
+        }
+        a.member_of = args->generator_of_column_host ? member.p : nullptr;
+        a.y0 = (const cplx *)args->y0_dev;
+        a.Y = Y.p; a.V = V.p; a.W = W.p; a.X = X.p;
+        a.t = d_t.p; a.t0 = args->t0;
+        a.rtol = rtol;
+        a.rk4_sub = args->rk4_substeps > 0 ? args->rk4_substeps : 16;
+        a.kmax = 60; a.theta = 2.0; a.lnorm = h->lnorm;
+        a.save_mode = args->save_mode; a.save_rows = args->save_rows;
+        a.S = (const cplx *)args->save_dev;
+        a.saved_dim = saved_dim;
+        a.out = (cplx *)args->out_dev;
+        a.flags = flags.p; a.ynorm = ynorm.p; a.stats = stats.p;
+        const bool taylor = method == QSX_METHOD_TAYLOR;
+        const char vsel = heom_variant();
+#define QSX_PICK(TILE)                                                                        \
+    {                                                                                         \
+        typedef TILE T;                                                                       \
+        threads = T::THREADS; smem = T::smem_bytes(d);                                        \
+        kernel = taylor ? (const void *)heom_propagate_kernel<QSX_METHOD_TAYLOR, T>           \
+                        : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;             \
+    }
+        const bool ee7 = d.ee && d.nr == 7 && d.K1 == 2;
+        if (dopri || args->n_pulses > 0) {
+            // time-dependent right-hand sides run on the generic tile (any rectangular block)
+            typedef TileGeneric T;
+            threads = T::THREADS; smem = T::smem_bytes(d);
+            kernel = dopri ? (const void *)heom_propagate_kernel<QSX_METHOD_DOPRI5, T>
+                           : (const void *)heom_propagate_kernel<QSX_METHOD_RK4, T>;
+        }
+        else if (ee7 && d.real_h && vsel != 'g') QSX_PICK(TileEE<7 COMMA 2 COMMA 1 COMMA true COMMA true>)
+        else if (ee7 && !d.real_h && vsel != 'g') QSX_PICK(TileEE<7 COMMA 2 COMMA 2 COMMA false>)
+        else QSX_PICK(TileGeneric)
+#undef QSX_PICK
+        kargs[0] = &a;
+    }
     QSX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     QSX_REQUIRE(per_sm > 0, "heom_propagate_kernel does not fit on an SM");
-    long long total = d.n_tiles * B;
-    int grid = (int)std::min<long long>((total + units - 1) / units, (long long)sms * per_sm);
-    if (const char *gs = getenv("QSX_HEOM_GRID")) grid = std::min(grid, std::max(1, atoi(gs)));   // experiments only
+    grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+    if (const char *gs = getenv("QSX_HEOM_GRID")) grid = std::min(grid, std::max(1, atoi(gs)));   // tests / experiments
     if (getenv("QSX_HEOM_VERBOSE"))
-        fprintf(stderr, "heom_propagate: variant '%c' threads %d smem %zu B, %d CTA/SM, grid %d\n", vsel, threads, smem, per_sm, grid);
-    void *kargs[] = {&a};
+        fprintf(stderr, "heom_propagate: %s tile, threads %d smem %zu B, %d CTA/SM, grid %d\n",
+                row ? "row" : "batch/generic", threads, smem, per_sm, grid);
     cudaEvent_t e0, e1;
     QSX_CUDA(cudaEventCreate(&e0));
     QSX_CUDA(cudaEventCreate(&e1));
@@ -2495,7 +1640,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         return QSX_ERR_CUDA;
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
-    unsigned long long st[3] = {0, 0, 0};
+    unsigned long long st[4] = {0, 0, 0, 0};
     QSX_CUDA(cudaMemcpyAsync(st, stats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;
@@ -2505,8 +1650,8 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     args->accepted_steps = st[1];
     args->kernel_ms = ms;
     if (st[2] != 0) {
-        qsx_set_error("HEOM integration failed (Taylor series not converged within %d terms, or DOPRI5 "
-                      "step-size underflow)", a.kmax);
+        qsx_set_error("HEOM integration failed (Taylor series not converged within 60 terms, or DOPRI5 "
+                      "step-size underflow)");
         return QSX_ERR_INTEGRATOR;
     }
     return QSX_OK;

@@ -75,8 +75,8 @@ def resolve_method(method_name, lti):
     if name not in _capi.METHODS:
         raise ValueError('unknown integration method %r (device methods: '
                          'taylor, rk4, dopri5, expm)' % method_name)
-    if name in ('taylor', 'map') and not lti:
-        raise ValueError('taylor needs a time-independent linear generator')
+    if name in ('taylor', 'map', 'poly') and not lti:
+        raise ValueError('%s needs a time-independent linear generator' % name)
     return name
 
 
@@ -408,6 +408,15 @@ class HeomEOM(DeviceEOM):
         _capi.check(_capi.lib().qsx_heom_index_maps(
             self._h, idx.ctypes.data, up.ctypes.data, down.ctypes.data))
         return idx, up, down
+
+    def propagate(self, y0, t, t0=None, method='zvode', **kw):
+        # constant generator, no pulses: the product-form Taylor propagator
+        # (QSX_METHOD_POLY, csrc/heom_row.cuh) is the default; the library runs
+        # the adaptive Taylor series where the row tile does not apply
+        if (method or 'zvode').lower() in ('zvode', 'vode', 'auto', 'lsoda') \
+                and not kw.get('pulses'):
+            method = 'poly'
+        return DeviceEOM.propagate(self, y0, t, t0=t0, method=method, **kw)
 
     def _apply_dev(self, y, dy, n, gptr):
         _capi.check(_capi.lib().qsx_heom_apply(

@@ -212,9 +212,8 @@ def test_heom_ensemble_members_match_single_runs():
 
 
 def test_heom_lean_tile_ensemble_matches_single_member_launches():
-    """FMO depth 4, 128 disorder members in one launch (2816 staged tiles: the bulk-copy
-    pipeline tile with one Hamiltonian per column) against launches of one member each;
-    regression test for the member-switch race of the staged tiles."""
+    """FMO depth 4, 128 disorder members in one launch (2816 staged tiles: the row tile with one
+    Hamiltonian staged per tile) against launches of one member each (batch tile)."""
     import torch
     E = 128
     m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
@@ -233,27 +232,105 @@ def test_heom_lean_tile_ensemble_matches_single_member_launches():
 
 
 @pytest.mark.parametrize('modified', [False, True])
-def test_heom_pipeline_tile_variants_match_batch_tile(modified, monkeypatch):
-    """The bulk-copy pipeline tile (default only for >= 2048 tiles) forced onto the depth-4 FMO
-    hierarchy: single-member handles (H through the constant bank; arithmetic link coefficients
-    for the plain hierarchy, tables for modified_HEOM) and the RHS application, against the
-    batch tile that the golden-fixture tests validate."""
+@pytest.mark.parametrize('grid', [None, '2'])
+def test_heom_row_tile_matches_batch_tile(modified, grid, golden, monkeypatch):
+    """The row tile (csrc/heom_row.cuh; default only for >= 2048 tiles) forced onto the depth-4
+    FMO hierarchy: RHS application, adaptive Taylor and product-form trajectories against the
+    batch tile that the golden-fixture tests validate, and against the reference trajectory.
+    grid = 2: two CTAs walk eleven tiles each, so the buffer ring wraps and the mbarrier
+    phases flip several times per stage."""
     import torch
     m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS, level_cutoff=4,
                      K=1, modified_HEOM=modified, low_temp_corr=True)
     y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
-    t = m.time_step * np.arange(8)
+    g = golden('heom')
+    t = g['fmo_d3_t'][:40]
     rng = np.random.RandomState(3)
     eom = m.equation_of_motion('ee')
-    y = rng.randn(eom.dim) + 1j * rng.randn(eom.dim)
+    y = rng.randn(2, eom.dim) + 1j * rng.randn(2, eom.dim)
+    if grid:
+        monkeypatch.setenv('QSX_HEOM_GRID', grid)
+    monkeypatch.setenv('QSX_HEOM_REPILOT', '5')
+    y0d = torch.from_numpy(y0).cuda().reshape(1, -1)
     res = {}
-    for variant in ('b', 'L'):      # the tile is chosen per call
+    for variant, method in (('b', 'taylor'), ('r', 'taylor'), ('r', 'poly')):
         monkeypatch.setenv('QSX_HEOM_VARIANT', variant)
-        traj = eom.propagate(torch.from_numpy(y0).cuda().reshape(1, -1), t, save=('ado0',),
+        traj = eom.propagate(y0d, t, save=('ado0',), method=method,
                              return_device=True).cpu().numpy()
-        res[variant] = (traj, np.asarray(eom.apply(y[None])))
-    assert rel_l2(res['L'][0], res['b'][0]) < 1e-13
-    assert rel_l2(res['L'][1], res['b'][1]) < 1e-13
+        res[variant, method] = (traj, np.asarray(eom.apply(y)), dict(eom.last))
+    ref = res['b', 'taylor']
+    assert rel_l2(res['r', 'taylor'][1], ref[1]) < 1e-13
+    assert rel_l2(res['r', 'taylor'][0], ref[0]) < 1e-12
+    assert rel_l2(res['r', 'poly'][0], ref[0]) < 1e-11
+    # the product form really ran: fewer accumulator passes do not show in rhs counts, but the
+    # pilot schedule does (39 intervals, a Taylor pilot every 6th)
+    assert res['r', 'poly'][2]['rhs'] > 0
+    if not modified:
+        want = g['fmo_d4_rho'].reshape(-1, 49)[:40]       # raw state-vector layout, ADO 0
+        assert rel_l2(res['r', 'poly'][0][0], want) < TOL
+    # full-state and per-ADO matrix saves go through the sigma -> rho rescaling
+    monkeypatch.setenv('QSX_HEOM_VARIANT', 'r')
+    full_r = eom.propagate(y0d, t[:4], method='poly', return_device=True).cpu().numpy()
+    S = rng.randn(3, 49) + 1j * rng.randn(3, 49)
+    mat_r = eom.propagate(y0d, t[:4], method='poly', save=S, return_device=True).cpu().numpy()
+    monkeypatch.setenv('QSX_HEOM_VARIANT', 'b')
+    full_b = eom.propagate(y0d, t[:4], method='taylor', return_device=True).cpu().numpy()
+    mat_b = eom.propagate(y0d, t[:4], method='taylor', save=S, return_device=True).cpu().numpy()
+    assert rel_l2(full_r, full_b) < 1e-11
+    assert rel_l2(mat_r, mat_b) < 1e-11
+
+
+def test_heom_row_tile_ensemble(monkeypatch):
+    """Members with their own Hamiltonian (H staged with every tile) on the row tile, forced
+    onto a small batch, against the batch tile."""
+    import torch
+    E = 6
+    m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
+                     level_cutoff=3, K=1)
+    eom = m.ensemble_eom(E, False, 'ee')
+    y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+    y0 = torch.from_numpy(y0).cuda().reshape(1, -1).expand(E, -1).contiguous()
+    t = m.time_step * np.arange(6)
+    out = {}
+    for variant, method in (('b', 'taylor'), ('r', 'poly')):
+        monkeypatch.setenv('QSX_HEOM_VARIANT', variant)
+        out[variant] = eom.propagate(y0, t, save=('ado0',), generators=np.arange(E),
+                                     method=method, return_device=True).cpu().numpy()
+    assert rel_l2(out['r'], out['b']) < 1e-11
+
+
+def test_heom_depth8_default_tile(golden, monkeypatch):
+    """BASELINE config 5 (FMO, level_cutoff 8: 116 280 ADOs, 3 634 tiles): the tile and the
+    integrator the bench times (row tile, product form) against the batch tile with the adaptive
+    Taylor series -- RHS on a seeded random vector, a 3-interval trajectory from site 1, trace
+    conservation, and closeness to the converged depth-4 reference trajectory."""
+    import torch
+    m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS, level_cutoff=8,
+                     K=1)
+    eom = m.equation_of_motion('ee')
+    assert eom.n_ado == 116280
+    rng = np.random.RandomState(8)
+    y = torch.from_numpy(rng.randn(1, eom.dim) + 1j * rng.randn(1, eom.dim)).cuda()
+    y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+    y0d = torch.from_numpy(y0).cuda().reshape(1, -1)
+    t = m.time_step * np.arange(4)
+    res = {}
+    for variant, method in ((' ', 'poly'), ('b', 'taylor')):
+        if variant == ' ':
+            monkeypatch.delenv('QSX_HEOM_VARIANT', raising=False)
+        else:
+            monkeypatch.setenv('QSX_HEOM_VARIANT', variant)
+        dy = torch.empty_like(y)
+        eom._apply_dev(y, dy, 1, None)
+        traj = eom.propagate(y0d, t, save=('ado0',), method=method,
+                             return_device=True).cpu().numpy()[0]
+        res[variant] = (dy.cpu().numpy(), traj)
+    assert rel_l2(res[' '][0], res['b'][0]) < 1e-13
+    assert rel_l2(res[' '][1], res['b'][1]) < 1e-11
+    rho = res[' '][1].reshape(-1, 7, 7)
+    assert np.abs(np.einsum('tii->t', rho) - 1).max() < 1e-12
+    d4 = golden('heom')['fmo_d4_rho'].reshape(-1, 49)[:4]      # raw state-vector layout, ADO 0
+    assert rel_l2(res[' '][1], d4) < 2e-3       # hierarchy depth 4 is converged to ~1e-3 on this span
 
 
 # ------------------------------------------------------------------ response
