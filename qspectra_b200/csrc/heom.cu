@@ -1363,16 +1363,16 @@ static bool use_row_tile(const qsx_heom_s *h, long long units) {
 
 // Row-tile launch configurations (buffers per CTA, CTAs per SM); QSX_HEOM_ROWCFG picks one
 // for A-B runs: "32" three buffers / two CTAs (default), "23" two buffers / three CTAs, "22".
+// Row-tile launch configurations for A-B runs: QSX_HEOM_ROWCFG = buffers per CTA x CTAs per SM
+// ("22" default, "32").
 template <class Fn>
 static int row_dispatch(bool const_h, Fn &&fn) {
     typedef heom_row::Cfg<7, 2> C;
-    const int cfg = env_int("QSX_HEOM_ROWCFG", 32);
-    if (cfg == 23) return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 3>())
-                                  : fn(C(), std::false_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 3>());
-    if (cfg == 22) return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>())
-                                  : fn(C(), std::false_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
-    return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>())
-                   : fn(C(), std::false_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>());
+    const int cfg = env_int("QSX_HEOM_ROWCFG", 22);
+    if (cfg == 32) return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>())
+                                  : fn(C(), std::false_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>());
+    return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>())
+                   : fn(C(), std::false_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
 }
 
 extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int32_t n_columns,
@@ -1398,7 +1398,7 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
         QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
         heom_row::RowApplyArgs a;
         a.R = h->row; a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
-        a.blk = std::max(1, env_int("QSX_HEOM_BLK", 2));
+        a.blk = std::max(1, env_int("QSX_HEOM_BLK", 1));
         rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
             typedef decltype(C_) C;
             auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
@@ -1519,7 +1519,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
         ra.R = h->row;
         ra.B = B; ra.nt = nt;
-        ra.blk = std::max(1, env_int("QSX_HEOM_BLK", 2));
+        ra.blk = std::max(1, env_int("QSX_HEOM_BLK", 1));
         ra.flip = env_int("QSX_HEOM_FLIP", 0);
         ra.member_of = args->generator_of_column_host ? member.p : nullptr;
         ra.y0 = (const cplx *)args->y0_dev;
@@ -1536,7 +1536,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
             typedef decltype(C_) C;
             kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
             threads = C::THREADS;
-            smem = C::smem_bytes(decltype(NB)::value);
+            smem = C::smem_bytes(decltype(NB)::value) + (size_t)env_int("QSX_HEOM_PADSMEM", 0);   // experiments: less L1
             return QSX_OK;
         });
         if (rc) return rc;

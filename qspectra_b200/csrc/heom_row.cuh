@@ -12,8 +12,12 @@
 // tiles of the top level (two thirds of all tiles at depth 8) need no occupation data at
 // all.  g is applied where states enter and leave the device layout.
 //
-// Tile = 32 consecutive ADOs (lane = ADO), state layout [tile][element][32] as in heom.cu.
-// A CTA is NS row-warps: warp w owns row w of the 32 ADO matrices.  The source tile, its
+// Tile = 32 consecutive ADOs, state layout [tile][element][32] as in heom.cu.  A CTA is NS
+// warps; a thread owns one row of one ADO matrix.  Rows are paired: a warp holds rows
+// (2p, 2p+1) of 16 ADOs -- lanes 0-15 row 2p, lanes 16-31 row 2p+1 of the same ADOs -- so the
+// shared-memory reads of H sigma (every thread needs the whole matrix of its ADO) are the same
+// address in both half-warps and cost half the wavefronts; an odd last row takes a full warp
+// of 32 ADOs.  (L1TEX wavefronts bound this kernel: 84 % busy before the pairing.)  The source tile, its
 // neighbour-offset record and (ensembles) the member's H are staged by bulk asynchronous
 // copies (cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier; buffers are released
 // through a second mbarrier, so the row-warps never meet at a CTA barrier.  Hierarchy
@@ -33,6 +37,13 @@
 
 namespace heom_row {
 namespace cg = cooperative_groups;
+
+// hierarchy gathers: L2-only loads by default (-DQSX_ROW_LDCA: allocate in L1 as well)
+#ifdef QSX_ROW_LDCA
+#define ROW_LD(p) (*(p))
+#else
+#define ROW_LD(p) __ldcg(p)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -82,7 +93,8 @@ struct Cfg {
     static constexpr int OFF_H = YS_BYTES + REC_BYTES;           // member coefficients behind the record
     static constexpr int BUF_BYTES = OFF_H + MH * 8;
     static constexpr int THREADS = 32 * NS;
-    static __host__ __device__ constexpr size_t smem_bytes(int nbuf) { return 128 + (size_t)nbuf * BUF_BYTES; }
+    static constexpr int HDR_BYTES = 128 + MH * 8;               // mbarriers, coefficients of member 0
+    static __host__ __device__ constexpr size_t smem_bytes(int nbuf) { return HDR_BYTES + (size_t)nbuf * BUF_BYTES; }
 };
 
 struct RowDev {
@@ -124,14 +136,16 @@ struct Walk {
 // ------------------------------------------------------------------------ tile body
 // acc[b] = (L sigma)[w, b] for the ADO of this lane;
 // epi(b, index within the column, value, own, error-norm weight of the ADO).
+// `w` = row and `lane` = ADO (within the tile) of this thread, see row_of() / ado_of().
 template <class C, bool UP, bool CONSTH, class Epi>
-__device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *buf, const cplx *__restrict__ xc,
-                                         int w, int lane, int tile, Epi &&epi) {
+__device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *buf, const double *hs0,
+                                         const cplx *__restrict__ xc, int w, int lane, int tile, Epi &&epi) {
     constexpr int NS = C::NS, K1 = C::K1, LD = C::LD, UD = C::UD, E4 = C::E4, UB = C::UB;
     const cplx *ys = reinterpret_cast<const cplx *>(buf) + lane;            // element e at ys[e * 32]
     const unsigned char *rec = buf + C::YS_BYTES;
     const int *dn = reinterpret_cast<const int *>(rec + C::OFF_DN) + lane * LD;
-    const double *hm = reinterpret_cast<const double *>(buf + C::OFF_H);
+    const double *hm = CONSTH ? hs0 : reinterpret_cast<const double *>(buf + C::OFF_H);
+    const double *hrow = hm + w * NS;      // row w of h: per half-warp, so it comes from shared memory
     const cplx *xw = xc + w * 32;          // element (w, b) of the ADO at offset o: xw[o + b * NS * 32]
     const cplx zero = cmake(0.0, 0.0);
     cplx acc[NS];
@@ -146,7 +160,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         for (int k = 0; k < K1; ++k) {
             const cplx *p = xw + (o[k] >= 0 ? o[k] : 0);
 #pragma unroll
-            for (int b = 0; b < NS; ++b) g[k][b] = o[k] >= 0 ? __ldcg(p + b * NS * 32) : zero;
+            for (int b = 0; b < NS; ++b) g[k][b] = o[k] >= 0 ? ROW_LD(p + b * NS * 32) : zero;
         }
     }
     // ---- slice 1: diagonal terms and - sigma Hs from the own row
@@ -176,7 +190,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     auto left = [&](auto c0, auto c1) {
 #pragma unroll
         for (int c = decltype(c0)::value; c < decltype(c1)::value; ++c) {
-            const double h = CONSTH ? R.hc[w * NS + c] : hm[w * NS + c];
+            const double h = hrow[c];
 #pragma unroll
             for (int b = 0; b < NS; ++b) {
                 const cplx z = ys[(c + NS * b) * 32];
@@ -202,7 +216,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         for (int b = 0; b < NS; ++b)
 #pragma unroll
             for (int k = 0; k < K1; ++k)
-                v[b][k] = o[b * K1 + k] >= 0 ? __ldcg(xw + o[b * K1 + k] + b * NS * 32) : zero;
+                v[b][k] = o[b * K1 + k] >= 0 ? ROW_LD(xw + o[b * K1 + k] + b * NS * 32) : zero;
         left(I0(), IA());
 #pragma unroll
         for (int b = 0; b < NS; ++b)
@@ -221,7 +235,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
             for (int k = 0; k < K1; ++k) {
                 const cplx *p = xw + (o[k] >= 0 ? o[k] : 0);
 #pragma unroll
-                for (int b = 0; b < NS; ++b) g[k][b] = o[k] >= 0 ? __ldcg(p + b * NS * 32) : zero;
+                for (int b = 0; b < NS; ++b) g[k][b] = o[k] >= 0 ? ROW_LD(p + b * NS * 32) : zero;
             }
             left(IA(), IB());
 #pragma unroll
@@ -244,7 +258,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
             for (int b = 0; b < NS; ++b)
 #pragma unroll
                 for (int k = 0; k < K1; ++k)
-                    v[b][k] = o[b * K1 + k] >= 0 ? __ldcg(xw + o[b * K1 + k] + b * NS * 32) : zero;
+                    v[b][k] = o[b * K1 + k] >= 0 ? ROW_LD(xw + o[b * K1 + k] + b * NS * 32) : zero;
             left(IB(), IN());
             double t[UB];
 #pragma unroll
@@ -271,13 +285,16 @@ template <class C, int NBUF>
 struct Pipe {
     uint64_t *full, *empty;
     unsigned char *bufs;
+    double *hs0;             // coefficients of member 0 (single-member handles)
     unsigned q;              // tiles this CTA has staged/consumed so far (same value in every thread)
 
-    __device__ __forceinline__ void init(unsigned char *smem) {
+    __device__ __forceinline__ void init(const RowDev &R, unsigned char *smem) {
         full = reinterpret_cast<uint64_t *>(smem);
         empty = full + NBUF;
-        bufs = smem + 128;
+        hs0 = reinterpret_cast<double *>(smem + 128);
+        bufs = smem + C::HDR_BYTES;
         q = 0;
+        for (int i = threadIdx.x; i < C::MH; i += blockDim.x) hs0[i] = i < C::M ? R.hc[i] : 0.0;
         if (threadIdx.x == 0) {
             for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], C::NS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -306,7 +323,13 @@ struct Pipe {
     template <bool CONSTH, class MakeEpi, class Done>
     __device__ __forceinline__ void sweep(const RowDev &R, const cplx *src, int B, int blk, int rev,
                                           const int *member_of, MakeEpi &&make_epi, Done &&done) {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        // thread -> (row, ADO): warps below 2 P hold the row pair (2p, 2p+1) of 16 ADOs, the odd last row
+        // takes a whole warp
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        constexpr int P = C::NS / 2;
+        const bool paired = wid < 2 * P;
+        const int w = paired ? 2 * (wid % P) + (lane >> 4) : C::NS - 1;
+        const int ado = paired ? 16 * (wid / P) + (lane & 15) : lane;
         const long long Dp = R.n_tiles * C::M * 32;
         const unsigned n_tiles = (unsigned)R.n_tiles;
         Walk it, ahead;
@@ -334,8 +357,8 @@ struct Pipe {
             mbar_wait(&full[q % NBUF], (q / NBUF) & 1);
             const unsigned char *buf = bufs + (size_t)(q % NBUF) * C::BUF_BYTES;
             auto epi = make_epi(col);
-            if (tile >= R.top_tile) row_body<C, false, CONSTH>(R, buf, src + (size_t)col * Dp, w, lane, tile, epi);
-            else row_body<C, true, CONSTH>(R, buf, src + (size_t)col * Dp, w, lane, tile, epi);
+            if (tile >= R.top_tile) row_body<C, false, CONSTH>(R, buf, hs0, src + (size_t)col * Dp, w, ado, tile, epi);
+            else row_body<C, true, CONSTH>(R, buf, hs0, src + (size_t)col * Dp, w, ado, tile, epi);
             done(col);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[q % NBUF]);
@@ -356,7 +379,7 @@ template <class C, bool CONSTH, int NBUF, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_apply_kernel(const __grid_constant__ RowApplyArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Pipe<C, NBUF> pipe;
-    pipe.init(smem_raw);
+    pipe.init(a.R, smem_raw);
     const long long Dp = a.R.n_tiles * C::M * 32;
     pipe.template sweep<CONSTH>(a.R, a.x, a.B, a.blk, 0, a.member_of, [&](int col) {
         cplx *yb = a.y + (size_t)col * Dp;
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     Pipe<C, NBUF> pipe;
-    pipe.init(smem_raw);
+    pipe.init(a.R, smem_raw);
     constexpr int M = C::M;
     const RowDev &R = a.R;
     const long long Dp = R.n_tiles * M * 32;

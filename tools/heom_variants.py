@@ -36,12 +36,10 @@ def run(n, method):
     return best, out
 
 
-KEYS = ('QSX_HEOM_VARIANT', 'QSX_HEOM_ROWCFG', 'QSX_HEOM_BLK', 'QSX_HEOM_FLIP',
-        'QSX_HEOM_REPILOT', 'QSX_HEOM_GRID', 'QSX_HEOM_OPT')
 ref = None
 for spec in specs:
-    for k in KEYS:
-        os.environ.pop(k, None)
+    for k in [k for k in os.environ if k.startswith('QSX_HEOM_')]:
+        os.environ.pop(k)
     method = 'poly'
     for kv in spec.split(','):
         k, v = kv.split('=')
