@@ -20,10 +20,25 @@ FP64 tensor cores and applies it once per interval; `rhs_per_state_step` counts
 the matrix-vector applications of the stepping phase, the propagator build is
 reported under `roofline`).  The CPU arms report grid-steps (one member advanced
 by one output interval at rtol=1e-10), i.e. the same unit.
+
+Extra sub-objects of the JSON line (same run, same box):
+  heom          depth-8 / depth-4 / 512-member depth-4 HEOM legs (HBM roofline of the
+                hierarchy kernel), an end-to-end `simulate_dynamics(HEOMModel)` number and
+                the reference's own HEOM timed beside it;
+  scaling_extra strong scaling of the headline workload (`--members` in total) and the
+                disorder x orientation averaged 2D spectrum (BASELINE configs[3]) sharded
+                over the N ranks, so that the driver's N = 1, 2, 4, 8 lines carry three
+                scaling curves;
+  parity        members {0, E/2 - 1, E - 1} of the timed ensemble against the CPU oracle.
 """
+import os
+
+# BLAS threads of the CPU arms: one per worker process (set before numpy is imported)
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ.setdefault(_v, '1')
+
 import argparse
 import json
-import os
 import subprocess
 import sys
 import threading
@@ -37,6 +52,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'redfield_state_steps_per_sec'
 UNIT = 'state-steps/s'
 DURATION_FS = 1000.0
+TIGHT = dict(rtol=1e-10, atol=1e-12, nsteps=100000)
 
 
 def parse():
@@ -48,9 +64,12 @@ def parse():
     p.add_argument('--members', type=int, default=10000)
     p.add_argument('--e2e-steps', type=int, default=5)
     p.add_argument('--cpu-members', type=int, default=0,
-                   help='members per CPU step (0: sized for ~10-20 s)')
+                   help='members per CPU step (0: 4096 for the reference arm, ~10-20 s of '
+                        'work for the cpu_baseline leg)')
     p.add_argument('--no-heom', action='store_true')
     p.add_argument('--no-cpu', action='store_true')
+    p.add_argument('--no-extra', action='store_true',
+                   help='skip the strong-scaling and 2D-spectra legs')
     return p.parse_args()
 
 
@@ -60,89 +79,176 @@ def workload_config(members, n_gpus):
                         '1 ps / 197 output points' % members,
             'members_per_gpu': members, 'state_dim': 49, 'grid_points': 197,
             'integrator': 'propagator stepping: exp(L dt) per member on the FP64 tensor '
-                          'cores (scaled Taylor series + squarings, on-device truncation '
-                          'control at 1e-17), then y <- P y per output interval; the '
-                          'propagators are rebuilt in every timed step',
+                          'cores (|A| <= 1/2 scaling, fixed degree-14 Taylor polynomial in '
+                          'Paterson-Stockmeyer form, squarings), then y <- P y per output '
+                          'interval; the propagators are rebuilt in every timed step',
             'parallelism': 'ensemble members sharded over %d GPU(s), one NCCL '
                            'reduce' % n_gpus,
             'l2_policy': 'inputs larger than L2 (1e4 generators = 384 MB vs 126 MB L2)'}
 
 
-# --------------------------------------------------------------- CPU baseline
-def _cpu_member_chunk(args):
-    lo, hi, duration = args
-    import oracle
-    import qspectra_b200 as qb
+# --------------------------------------------------------------- CPU arms
+# Each worker process holds one model built once (the reference's own classes when
+# oracle/_ref is present, the oracle port otherwise) and runs the reference's serial
+# per-member path -- model.hamiltonian.sample(n) -> Redfield tensor -> ZVODE at rtol=1e-10 --
+# for a block of members.
+_W = {}
+
+
+def _worker_init(kind):
     from qspectra_b200 import systems
-    model = oracle.OracleRedfield(systems.fmo(), hilbert_subspace='e',
-                                  unit_convert=qb.CM_FS, secular=False)
-    total, rhs = 0, 0
-    for n in range(lo, hi):
-        member = model.__class__.__new__(model.__class__)
-        member.__dict__.update(model.__dict__)
+    if kind == 'reference':
+        from oracle import vendor_ref
+        q = vendor_ref.load()
+        from qspectra.utils import copy_with_new_cache
+        model = q.RedfieldModel(systems.fmo(ns=q), hilbert_subspace='e',
+                                unit_convert=q.CM_FS, secular=False)
+        _W.update(kind=kind, q=q, model=model, copy=copy_with_new_cache)
+    else:
+        import oracle
+        import qspectra_b200 as qb
+        model = oracle.OracleRedfield(systems.fmo(), hilbert_subspace='e',
+                                      unit_convert=qb.CM_FS, secular=False)
+        _W.update(kind=kind, oracle=oracle, model=model)
+
+
+def _member_trajectory(n, duration):
+    """(t, rho[t, 7, 7]) of ensemble member n through the arm's own public API."""
+    model = _W['model']
+    psi0 = np.eye(7)[0]
+    if _W['kind'] == 'reference':
+        member = _W['copy'](model)                      # dynamics/base.py:120-128
         member.hamiltonian = model.hamiltonian.sample(n)
-        f = oracle.counting(member.equation_of_motion('ee'))
-        y0 = member.density_matrix_to_state_vector(
-            np.diag(np.eye(7)[0]).astype(complex), 'ee')
-        t = np.arange(0, duration, member.time_step)
-        states = oracle.integrate(f, y0, t, **oracle.TIGHT)
-        total = total + states
-        rhs += f.calls
-    return total, rhs, len(t)
+        return _W['q'].simulate_dynamics(member, psi0, duration, **TIGHT)
+    oracle = _W['oracle']
+    member = model.__class__.__new__(model.__class__)
+    member.__dict__.update(model.__dict__)
+    member.hamiltonian = model.hamiltonian.sample(n)
+    return oracle.simulate_dynamics(member, psi0, duration, **oracle.TIGHT)
 
 
-def cpu_reference_rate(n_members, duration=DURATION_FS, workers=None):
-    """grid-steps/s of the CPU oracle (port of the reference's scipy path:
-    generator rebuild per member + ZVODE at rtol=1e-10), members spread over
-    all host cores with multiprocessing (the reference itself is serial)."""
-    import multiprocessing as mp
-    workers = workers or os.cpu_count() or 1
-    workers = max(1, min(workers, n_members))
-    bounds = np.linspace(0, n_members, workers + 1).astype(int)
-    jobs = [(int(bounds[i]), int(bounds[i + 1]), duration) for i in range(workers)
-            if bounds[i + 1] > bounds[i]]
-    ctx = mp.get_context('fork')
-    t0 = time.perf_counter()
-    with ctx.Pool(len(jobs)) as pool:
-        results = pool.map(_cpu_member_chunk, jobs)
-    wall = time.perf_counter() - t0
-    nt = results[0][2]
-    rhs = sum(r[1] for r in results)
-    return {'grid_steps_per_s': n_members * (nt - 1) / wall, 'wall_s': wall,
-            'rhs_per_s': rhs / wall, 'workers': len(jobs), 'members': n_members,
-            'grid_points': nt}
+def _worker_chunk(job):
+    lo, hi, duration = job
+    total, nt = 0, 0
+    for n in range(lo, hi):
+        t, rho = _member_trajectory(n, duration)
+        total = total + rho
+        nt = len(t)
+    return total, nt
+
+
+class CpuArm(object):
+    """Persistent pool of worker processes (one BLAS thread each)."""
+
+    def __init__(self, workers=None):
+        import multiprocessing as mp
+        from oracle import vendor_ref
+        self.kind = 'reference' if vendor_ref.load() is not None else 'port'
+        self.workers = workers or os.cpu_count() or 1
+        self.pool = mp.get_context('fork').Pool(self.workers, _worker_init, (self.kind,))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def step(self, n_members, first=0, duration=DURATION_FS):
+        """Ensemble of `n_members` members (first .. first + n - 1): wall seconds, grid points"""
+        chunks = min(n_members, self.workers * 4)          # small chunks balance the workers
+        b = np.linspace(0, n_members, chunks + 1).astype(int)
+        jobs = [(first + int(b[i]), first + int(b[i + 1]), duration) for i in range(chunks)
+                if b[i + 1] > b[i]]
+        t0 = time.perf_counter()
+        res = self.pool.map(_worker_chunk, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        return wall, res[0][1]
+
+    def serial_rate(self, n_members=8, duration=DURATION_FS):
+        """grid-steps/s of ONE worker (the reference itself is serial)"""
+        t0 = time.perf_counter()
+        res = self.pool.map(_worker_chunk, [(0, n_members, duration)], chunksize=1)
+        wall = time.perf_counter() - t0
+        return n_members * (res[0][1] - 1) / wall
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    os.environ.setdefault('OMP_NUM_THREADS', '1')
-    cores = os.cpu_count() or 1
-    n = args.cpu_members or max(cores, 16 * cores)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_rate(max(cores, n // 4))
-    rates, walls = [], []
+    arm = CpuArm()
+    n = args.cpu_members or 4096
+    for _ in range(min(args.warmup, 1)):
+        arm.step(max(arm.workers * 4, n // 8))
+    serial = arm.serial_rate()
+    walls = []
+    nt = 197
     for _ in range(args.steps):
-        r = cpu_reference_rate(n)
-        rates.append(r['grid_steps_per_s'])
-        walls.append(r['wall_s'])
-    value = float(np.sum([n * 196 for _ in rates]) / np.sum(walls))
+        wall, nt = arm.step(n)
+        walls.append(wall)
+    arm.close()
+    value = float(args.steps * n * (nt - 1) / np.sum(walls))
+    what = ('the unmodified reference (oracle/_ref): RedfieldModel + simulate_dynamics per member'
+            if arm.kind == 'reference' else 'oracle port of the reference path')
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * float(np.mean(walls)), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex128',
             'data': 'synthetic', 'config': workload_config(args.members, args.gpus),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': r['workers'],
-                             'kind': 'port',
-                             'sample': '%d members x 196 output intervals per step '
-                                       '(generator rebuild + ZVODE rtol=1e-10 per '
-                                       'member, as the reference does), %d worker '
-                                       'processes' % (n, r['workers'])},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.workers,
+                             'kind': arm.kind,
+                             'sample': '%d members x %d output intervals per step (%s: generator '
+                                       'rebuild + ZVODE rtol=1e-10 per member), %d worker '
+                                       'processes with one BLAS thread each'
+                                       % (n, nt - 1, what, arm.workers),
+                             'serial_value': serial,
+                             'step_spread': float((np.max(walls) - np.min(walls)) / np.mean(walls))},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def heom_cpu_baseline(n_intervals=10):
+    """The reference's own HEOM (config 2: FMO, K = 1, depth 4) on one host core: generator
+    build, RHS applications/s and output intervals/s at rtol = 1e-10."""
+    from oracle import vendor_ref
+    from qspectra_b200 import systems
+    q = vendor_ref.load()
+    out = {'cores': 1}
+    if q is not None:
+        t0 = time.perf_counter()
+        m = q.HEOMModel(systems.fmo(ns=q), hilbert_subspace='e', unit_convert=q.CM_FS,
+                        level_cutoff=4, K=1)
+        f = m.equation_of_motion('ee')
+        out['kind'] = 'reference'
+        y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+        integrate = q.simulate.utils.integrate
+        dt = m.time_step
+    else:
+        import oracle
+        import qspectra_b200 as qb
+        t0 = time.perf_counter()
+        m = oracle.OracleHEOM(systems.fmo(), hilbert_subspace='e', unit_convert=qb.CM_FS,
+                              level_cutoff=4, K=1)
+        f = m.equation_of_motion('ee')
+        out['kind'] = 'port'
+        y0 = m.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+        integrate = oracle.integrate
+        dt = m.time_step
+    out['build_s'] = time.perf_counter() - t0
+    calls = [0]
+
+    def counted(t, y):
+        calls[0] += 1
+        return f(t, y)
+    t = dt * np.arange(n_intervals + 1)
+    t0 = time.perf_counter()
+    integrate(counted, y0, t, **TIGHT)
+    wall = time.perf_counter() - t0
+    out.update(state_steps_per_s=n_intervals / wall, rhs_per_s=calls[0] / wall,
+               rhs_per_state_step=calls[0] / n_intervals, wall_s=wall,
+               sample='FMO HEOM K=1 level_cutoff=4 (680 ADOs x 49), %d output intervals, '
+                      'ZVODE rtol=1e-10, one process' % n_intervals)
+    return out
 
 
 # ------------------------------------------------------------------ clocks
@@ -242,12 +348,25 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
 
 
-def heom_leg(torch, qb, systems, engine):
-    """BASELINE configs[4]/[2]: FMO HEOM K=1 depth 8 (116 280 ADOs x 49), one
-    trajectory: RHS applications/s and HBM roofline of the hierarchy kernel."""
-    out = {}
+def _heom_roofline(rhs_per_s, D, rhs, key):
     peaks, src = measured_peaks()
-    for depth, n_int in ((8, 2), (4, 20)):
+    achieved = rhs_per_s * 32.0 * D / 1e9
+    per_rhs = ncu_traffic(key)
+    return {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': achieved / peaks['hbm_gbs'],
+            'traffic': per_rhs * rhs if per_rhs else None,
+            'traffic_per_rhs': per_rhs,
+            'achieved_is': 'rhs_per_s x 32 D (algorithmic bytes per RHS application)',
+            'peak_source': src, 'algorithmic_bytes_per_rhs': 32 * D}
+
+
+def heom_leg(torch, qb, systems, engine, with_cpu):
+    """BASELINE configs[4]/[2]: FMO HEOM K=1 depth 8 (116 280 ADOs x 49) and depth 4, one
+    trajectory each, and a 512-member depth-4 disorder ensemble: RHS applications/s and HBM
+    roofline of the hierarchy kernel through the default integrator of HEOMModel (product-form
+    Taylor propagator, csrc/heom_row.cuh, where the row tile applies)."""
+    out = {}
+    for depth, n_int in ((8, 12), (4, 40)):
         model = qb.HEOMModel(systems.fmo(), hilbert_subspace='e',
                              unit_convert=qb.CM_FS, level_cutoff=depth, K=1)
         t0 = time.perf_counter()
@@ -265,20 +384,34 @@ def heom_leg(torch, qb, systems, engine):
                 best = dict(eom.last)
         D = eom.dim
         rhs_per_s = best['rhs'] / (best['kernel_ms'] * 1e-3)
-        achieved = rhs_per_s * 32.0 * D / 1e9
         out['depth%d' % depth] = {
             'workload': 'FMO 7-site HEOM K=1 level_cutoff=%d: %d ADOs x 49, D=%d, '
                         'free evolution, %d output intervals' % (depth, eom.n_ado, D, n_int),
+            'integrator': best['method'],
             'rhs_per_s': rhs_per_s,
             'state_steps_per_s': best['steps'] / (best['kernel_ms'] * 1e-3),
             'rhs_per_state_step': best['rhs'] / max(1, best['steps']),
             'kernel_ms': best['kernel_ms'], 'setup_s': build_s,
-            'roofline': {'bound': 'hbm', 'achieved': achieved,
-                         'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                         'frac': achieved / peaks['hbm_gbs'], 'traffic': ((ncu_traffic('heom_depth%d_per_rhs' % depth) or 0) * best['rhs']) or None,
-                         'achieved_is': 'rhs_per_s x 32 D (algorithmic bytes per RHS application)',
-                         'peak_source': src,
-                         'algorithmic_bytes_per_rhs': 32 * D}}
+            'roofline': _heom_roofline(rhs_per_s, D, best['rhs'], 'heom_depth%d_per_rhs' % depth)}
+        if depth == 4:
+            # end to end through the public API: host model and initial state in, host
+            # density matrices out (handle creation included, as in the reference's call)
+            qb.simulate_dynamics(model, np.eye(7)[0], n_int * model.time_step)
+            h0, d0 = _transfer()
+            times = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                qb.simulate_dynamics(model, np.eye(7)[0], n_int * model.time_step)
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            h1, d1 = _transfer()
+            nt = len(np.arange(0, n_int * model.time_step, model.time_step))
+            out['depth4']['e2e'] = {
+                'value': (nt - 1) / float(np.mean(times)), 'unit': UNIT,
+                'seconds_per_call': float(np.mean(times)),
+                'h2d_bytes_per_step': (h1 - h0) // 3, 'd2h_bytes_per_step': (d1 - d0) // 3,
+                'path': 'simulate_dynamics(HEOMModel(level_cutoff=4), psi0, %d intervals) from '
+                        'host objects' % (nt - 1)}
         del eom, model
     # BASELINE configs[2] batched: the depth-4 hierarchy is L2-resident for one trajectory,
     # so the HBM roofline of the hierarchy kernel is measured on a 512-member disorder
@@ -298,20 +431,84 @@ def heom_leg(torch, qb, systems, engine):
         if best is None or eom.last['kernel_ms'] < best['kernel_ms']:
             best = dict(eom.last)
     rhs_per_s = best['rhs'] / (best['kernel_ms'] * 1e-3)
-    achieved = rhs_per_s * 32.0 * eom.dim / 1e9
     out['depth4_ensemble512'] = {
         'workload': 'FMO 7-site HEOM K=1 level_cutoff=4, %d static-disorder members: %d ADOs x 49 '
                     'per member, 10 output intervals' % (E, eom.n_ado),
+        'integrator': best['method'],
         'rhs_per_s': rhs_per_s,
         'state_steps_per_s': best['steps'] / (best['kernel_ms'] * 1e-3),
         'rhs_per_state_step': best['rhs'] / max(1, best['steps']),
         'kernel_ms': best['kernel_ms'], 'setup_s': build_s,
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
-                     'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
-                     'achieved_is': 'rhs_per_s x 32 D (algorithmic bytes per RHS application)',
-                     'peak_source': src, 'algorithmic_bytes_per_rhs': 32 * eom.dim}}
+        'roofline': _heom_roofline(rhs_per_s, eom.dim, best['rhs'], 'heom_depth4_ens512_per_rhs')}
     del eom, model
+    if with_cpu:
+        out['cpu_baseline'] = heom_cpu_baseline()
     return out
+
+
+def _transfer():
+    from qspectra_b200 import _capi
+    return _capi.transfer_bytes()
+
+
+def parity_check(qb, systems, eom, y0, t, members):
+    """Selected members of the timed ensemble, propagated by the same device handle and
+    integrator as the timed step, against the CPU oracle (checker only)."""
+    import oracle
+    from qspectra_b200 import _capi
+    sel = np.asarray(members)
+    y0_dev = _capi.to_device(y0).reshape(1, -1).expand(len(sel), -1).contiguous()
+    got = _capi.to_host(eom.propagate(y0_dev, t, generators=sel, return_device=True))
+    om = oracle.OracleRedfield(systems.fmo(), hilbert_subspace='e', unit_convert=qb.CM_FS,
+                               secular=False)
+    worst = 0.0
+    for i, n in enumerate(sel):
+        member = om.__class__.__new__(om.__class__)
+        member.__dict__.update(om.__dict__)
+        member.hamiltonian = om.hamiltonian.sample(int(n))
+        f = member.equation_of_motion('ee')
+        ref = oracle.integrate(f, y0, t, **oracle.TIGHT)
+        worst = max(worst, float(np.linalg.norm(got[i] - ref) / np.linalg.norm(ref)))
+    return {'members': [int(n) for n in sel], 'rel_l2_max': worst, 'tolerance': 1e-8,
+            'checker': 'oracle (generator + ZVODE rtol=1e-10) on the same members'}
+
+
+def spectra2d_leg(torch, dist, qb, systems, parallel, world, rank, members_per_gpu=32):
+    """BASELINE configs[3]: FMO third-order response / 2D spectrum ('gef', t1 = t3 = 197 points,
+    5 population times), exact isotropic average (21 polarisation configurations) x static
+    disorder, members sharded over the ranks, one NCCL reduce, device Fourier transforms."""
+    model = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef', unit_convert=qb.CM_FS,
+                             secular=False)
+    E = members_per_gpu * world
+    kw = dict(population_times=np.linspace(0, 1000, 5), geometry='-++', polarization='xxxx',
+              exact_isotropic_average=True, dst=0)
+
+    def once():
+        return parallel.two_dimensional_spectra_sharded(model, 1000, E, **kw)
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        (f1, t2, f3), X = once()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    if world > 1:
+        tmax = torch.tensor([sec], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sec = float(tmax.item())
+    n_t = 197
+    # propagated columns per member and configuration, three pathways: t1 stage 1, t2 stage n_t1,
+    # t3 stage 1; each advanced over its grid
+    units = E * 21
+    return {'workload': 'FMO 2D spectrum (gef, 197 x 5 x 197, -++, xxxx, exact isotropic average: '
+                        '21 configurations) x %d disorder members (%d per GPU)' % (E, members_per_gpu),
+            'seconds_per_spectrum': sec,
+            'member_configurations_per_s': units / sec,
+            'scaling': 'weak', 'finite': bool(np.isfinite(X).all()) if rank == 0 else None}
 
 
 def run_ours(args):
@@ -339,71 +536,80 @@ def run_ours(args):
             dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
         return mean_dev
 
-    # ---- device-resident leg: generators already in HBM ----------------------
-    eom = model.ensemble_eom(E, False, 'ee', member0=rank * E)
-    y0_dev = _capi.to_device(y0).reshape(1, -1).expand(E, -1).contiguous()
-    gens = np.arange(E)
+    def timed_resident(n_members, member0, total_members, steps, warmup):
+        """device-resident leg: generators already in HBM; returns (ms per step, stats, result)"""
+        eom = model.ensemble_eom(n_members, False, 'ee', member0=member0)
+        y0_dev = _capi.to_device(y0).reshape(1, -1).expand(n_members, -1).contiguous()
+        gens = np.arange(n_members)
 
-    def resident_step():
-        eom.__dict__.pop('_propagators', None)    # rebuild exp(L dt) every step
-        out = eom.propagate(y0_dev, t, generators=gens, return_device=True)
-        mean = engine.reduce_members(out, 1.0 / (E * world))
-        return reduce_across(mean)
+        def step():
+            eom.__dict__.pop('_propagators', None)    # rebuild exp(L dt) every step
+            out = eom.propagate(y0_dev, t, generators=gens, return_device=True)
+            mean = engine.reduce_members(out, 1.0 / total_members)
+            return reduce_across(mean)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        engine.PropagationStats.reset()
+        l0 = _capi.kernel_launches()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            result = step()
+        e1.record()
+        torch.cuda.synchronize()
+        t_b = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tmax = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+        st = engine.PropagationStats
+        stats = dict(expm_ms=st.expm_ms, expm_gemms=st.expm_gemms, expm_builds=st.expm_builds,
+                     kernel_ms=st.kernel_ms / max(1, st.propagations),
+                     rhs=st.rhs_evaluations / max(1, st.propagations),
+                     steps=st.accepted_steps / max(1, st.propagations),
+                     launches=_capi.kernel_launches() - l0, window=(t_a, t_b))
+        return ms / steps, stats, result, eom, step
 
     # nvidia-smi needs ~0.1-0.2 s before its first sample: start it ahead of the warm-up and keep
     # only the samples that arrive inside the timed window
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        resident_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    engine.PropagationStats.reset()
-    launches0 = _capi.kernel_launches()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    torch.cuda.synchronize()
-    t_a = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        result = resident_step()
-    e1.record()
-    torch.cuda.synchronize()
-    t_b = time.perf_counter()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = _capi.kernel_launches() - launches0
-    stats = engine.PropagationStats
-    stats_expm_ms, stats_expm_gemms, stats_expm_builds = stats.expm_ms, stats.expm_gemms, stats.expm_builds
-    kernel_ms = stats.kernel_ms / max(1, stats.propagations)
-    rhs_per_launch = stats.rhs_evaluations / max(1, stats.propagations)
-    steps_per_launch = stats.accepted_steps / max(1, stats.propagations)
+    ms_per_step, stats, result, eom, step = timed_resident(E, rank * E, E * world,
+                                                           args.steps, args.warmup)
+    t_a, t_b = stats['window']
     clocks_window = 'timed region'
     if rank == 0 and sampler.proc is not None and sampler.count_between(t_a, t_b) < 3:
         # the timed region is shorter than a few sampling periods: keep the identical load
         # running (untimed) until the sampler has seen it at least a few times
         t_end = time.perf_counter() + 0.6
         while time.perf_counter() < t_end:
-            eom.__dict__.pop('_propagators', None)
-            engine.reduce_members(eom.propagate(y0_dev, t, generators=gens, return_device=True), 1.0 / (E * world))
+            step()
             torch.cuda.synchronize()
         t_b = time.perf_counter()
-        clocks_window = 'timed region + 0.6 s of the identical step repeated untimed (timed region shorter than 3 sampling periods)'
+        clocks_window = ('timed region + 0.6 s of the identical step repeated untimed (timed '
+                         'region shorter than 3 sampling periods)')
+    if world > 1:
+        dist.barrier()
     clocks = sampler.stop(t_a, t_b) if rank == 0 else None
     if clocks is not None:
         clocks['window'] = clocks_window
-    if world > 1:
-        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = world * steps_per_launch / (ms_per_step * 1e-3)
-    trace_err = None
+    value = world * stats['steps'] / (ms_per_step * 1e-3)
+    trace_err, parity = None, None
     if rank == 0:
-        rho_dev = result.cpu().numpy().reshape(len(t), 7, 7)
+        rho_dev = _capi.to_host(result).reshape(len(t), 7, 7)
         trace_err = float(np.abs(np.einsum('tii->t', rho_dev) - 1).max())
+        parity = parity_check(qb, systems, eom, y0, t, [0, E // 2 - 1, E - 1])
+    del eom, step
+    torch.cuda.empty_cache()
 
     # ---- end-to-end leg through the public API, host buffers ------------------
     def e2e_once():
@@ -416,18 +622,18 @@ def run_ours(args):
                 model, psi0, DURATION_FS, ensemble_size=E * world, dst=0)
         return rho
 
-    del eom
-    torch.cuda.empty_cache()
     e2e_once()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e2e_times = []
+    h0, d0 = _capi.transfer_bytes()
     for _ in range(args.e2e_steps):
         t0 = time.perf_counter()
-        rho_host = e2e_once()
+        e2e_once()
         torch.cuda.synchronize()
         e2e_times.append(time.perf_counter() - t0)
+    h1, d1 = _capi.transfer_bytes()
     if world > 1:
         dist.barrier()
     e2e_s = float(np.mean(e2e_times))
@@ -436,12 +642,28 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     e2e_value = world * E * (len(t) - 1) / e2e_s
-    # bytes that actually cross PCIe per call: the user's inputs are the model (7x7 H, bath
-    # parameters, seed), psi0 and the time grid -- the members' disorder is replayed from the
-    # seed ON THE DEVICE (as the reference replays it inside the call on the host); plus the
-    # per-launch column tables (3 ints per member) of the propagate entry point
-    h2d = 49 * 16 + E * 4 * 3 + len(t) * 8 + 7 * 7 * 8 + 4 * 7 * 8 + 49 * 8 + 8
-    d2h = len(t) * 49 * 16
+    # bytes that crossed PCIe per call on this rank, counted where the copies are issued
+    # (library: qsx_transfer_bytes; Python side: _capi.to_device / to_host).  The members'
+    # disorder is replayed from the seed ON THE DEVICE, so no per-member array is uploaded.
+    h2d = (h1 - h0) // max(1, args.e2e_steps)
+    d2h = (d1 - d0) // max(1, args.e2e_steps)
+
+    # ---- further scaling curves (same run): strong scaling, 2D spectra ---------
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        first, count = parallel.shard_members(E, rank, world)
+        ms_s, st_s, _, eom_s, step_s = timed_resident(count, first, E, max(3, args.steps // 2), 2)
+        del eom_s, step_s
+        torch.cuda.empty_cache()
+        extra['strong'] = {
+            'workload': 'the headline workload with %d members IN TOTAL split over the ranks' % E,
+            'value': E * (len(t) - 1) / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
+            'members_per_gpu': count, 'scaling': 'strong'}
+        try:
+            extra['spectra2d'] = spectra2d_leg(torch, dist, qb, systems, parallel, world, rank)
+        except Exception as exc:       # keep the headline line if this leg cannot run
+            extra['spectra2d'] = {'error': repr(exc)}
 
     if rank != 0:
         if world > 1:
@@ -452,9 +674,10 @@ def run_ours(args):
     fp64_peak = measure_fp64_peak(torch)
     # dominant kernel of the step: the tensor-core propagator build (dense_expm_kernel);
     # algorithmic flops = complex M x M GEMMs x 8 M^3 (M = 49, padding not counted)
-    expm_ms = stats_expm_ms / max(1, stats_expm_builds)
-    flops_per_launch = 8.0 * 49 ** 3 * stats_expm_gemms / max(1, stats_expm_builds)
+    expm_ms = stats['expm_ms'] / max(1, stats['expm_builds'])
+    flops_per_launch = 8.0 * 49 ** 3 * stats['expm_gemms'] / max(1, stats['expm_builds'])
     achieved_tf = flops_per_launch / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else 0.0
+    kernel_ms, rhs_per_launch = stats['kernel_ms'], stats['rhs']
     map_flops = 8.0 * 49 * 49 * rhs_per_launch
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
@@ -462,19 +685,21 @@ def run_ours(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'complex128', 'data': 'synthetic',
         'config': workload_config(E, world),
-        'rhs_per_state_step': rhs_per_launch / max(1.0, steps_per_launch),
+        'rhs_per_state_step': rhs_per_launch / max(1.0, stats['steps']),
         'rhs_per_s': world * rhs_per_launch / (ms_per_step * 1e-3),
         'grid_steps_per_s': world * E * (len(t) - 1) / (ms_per_step * 1e-3),
         'trace_error': trace_err,
+        'parity': parity,
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'seconds_per_step': e2e_s,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h), 'seconds_per_step': e2e_s,
                 'seconds_each_step': [round(x, 5) for x in e2e_times],
+                'bytes_are': 'counted copies of rank 0 (qsx_transfer_bytes + _capi.to_device/to_host)',
                 'path': 'simulate_dynamics(model, psi0, duration, ensemble_size) from host objects: '
                         'seed -> device replay of the seeded disorder streams -> K5 (Jacobi '
                         'eigensystems + Redfield generators) -> K1\' propagators -> K1/K4 '
                         'stepping -> K6 mean -> D2H of the averaged density matrices'},
-        'gpu_launches': int(launches),
+        'gpu_launches': int(stats['launches']),
         'roofline': None,
     }
     # the step is two kernels of about equal duration: the DMMA propagator build and the
@@ -499,23 +724,31 @@ def run_ours(args):
                        'for the dense L.Y contraction)',
              'kernel_ms': kernel_ms, 'share_of_step': kernel_ms / ms_per_step,
              'algorithmic_flops_per_launch': map_flops, 'peak_source': peak_note}
-    first, second = (k_map, k_expm) if kernel_ms >= expm_ms else (k_expm, k_map)
-    line['roofline'] = first
-    line['other_kernels'] = {second['kernel']: second,
+    first_k, second_k = (k_map, k_expm) if kernel_ms >= expm_ms else (k_expm, k_map)
+    line['roofline'] = first_k
+    line['other_kernels'] = {second_k['kernel']: second_k,
                              'share_note': 'per step: propagator build + stepping + member '
                                            'reduction; see profiles/ for the ncu launch list'}
+    if extra is not None:
+        line['scaling_extra'] = extra
     if world == 1 and not args.no_heom:
-        line['heom'] = heom_leg(torch, qb, systems, engine)
+        line['heom'] = heom_leg(torch, qb, systems, engine, not args.no_cpu)
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        n = args.cpu_members or 160 * cores
-        r = cpu_reference_rate(n)
+        arm = CpuArm()
+        cores = arm.workers
+        arm.step(cores * 2)                                  # warm the workers
+        serial = arm.serial_rate()
+        # about 15 s of all-core work, at most the full ensemble
+        n = args.cpu_members or int(min(E, max(16 * cores, 15.0 * cores * serial / 196.0)))
+        wall, nt = arm.step(n)
+        arm.close()
         line['cpu_baseline'] = {
-            'value': r['grid_steps_per_s'], 'unit': UNIT, 'cores': r['workers'],
-            'kind': 'port',
-            'sample': '%d of %d members x 196 output intervals (oracle: generator '
-                      'rebuild + ZVODE rtol=1e-10 per member), %.1f s on %d worker '
-                      'processes' % (n, E, r['wall_s'], r['workers'])}
+            'value': n * (nt - 1) / wall, 'unit': UNIT, 'cores': cores, 'kind': arm.kind,
+            'serial_value': serial,
+            'sample': '%d of %d members x %d output intervals (%s: generator rebuild + ZVODE '
+                      'rtol=1e-10 per member), %.1f s on %d worker processes, one BLAS thread each'
+                      % (n, E, nt - 1, 'unmodified reference from oracle/_ref'
+                         if arm.kind == 'reference' else 'oracle port', wall, cores)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

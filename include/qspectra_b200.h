@@ -101,6 +101,10 @@ const char *qsx_last_error(void);
 int qsx_version(void);
 /* number of kernels this library has launched since load (bench.py: gpu_launches) */
 uint64_t qsx_kernel_launches(void);
+/* bytes the library itself has copied host->device / device->host since load (handle tables,
+ * per-call column maps, status words); the Python side adds its own tensor copies
+ * (qspectra_b200._capi.transfer_bytes) for bench.py's e2e.h2d/d2h_bytes_per_step */
+void qsx_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
 /* device properties the host side needs: SM count, L2 bytes, max smem per block */
 int qsx_device_info(int32_t *sm_count, int64_t *l2_bytes, int32_t *smem_per_block);
 

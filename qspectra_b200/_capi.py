@@ -78,7 +78,7 @@ class QsxBath(C.Structure):
 BATH_DEBYE_COMPLEX, BATH_DEBYE_REAL = 0, 1
 
 #: every symbol include/qspectra_b200.h declares (checked by the CPU tests)
-EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches',
+EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches', 'qsx_transfer_bytes',
            'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
            'qsx_dense_propagate', 'qsx_dense_expm', 'qsx_dense_wrap', 'qsx_dense_build_stats',
            'qsx_dense_destroy', 'qsx_heom_create',
@@ -106,6 +106,8 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.qsx_last_error.restype = C.c_char_p
     L.qsx_kernel_launches.restype = C.c_uint64
+    L.qsx_transfer_bytes.restype = None
+    L.qsx_transfer_bytes.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.qsx_ado_count.restype = C.c_int64
     L.qsx_ado_count.argtypes = [C.c_int32, C.c_int32]
     L.qsx_heom_ado_count.restype = C.c_int64
@@ -190,6 +192,26 @@ def kernel_launches():
     return int(lib().qsx_kernel_launches())
 
 
+#: bytes moved by the Python side of the engine (tensor uploads in to_device, downloads in to_host)
+_py_h2d = 0
+_py_d2h = 0
+
+
+def transfer_bytes():
+    """(host->device, device->host) bytes moved so far by the library and by this module."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    lib().qsx_transfer_bytes(C.byref(a), C.byref(b))
+    return int(a.value) + _py_h2d, int(b.value) + _py_d2h
+
+
+def to_host(tensor):
+    """CUDA tensor -> numpy array (counted device->host copy)."""
+    global _py_d2h
+    if tensor.is_cuda:
+        _py_d2h += tensor.numel() * tensor.element_size()
+    return tensor.cpu().numpy()
+
+
 def ado_enumerate(bins, level_cutoff):
     """(ado_index int64 [n, bins], up int32, down int32) from the closed-form
     enumeration -- host only, no GPU needed."""
@@ -222,16 +244,20 @@ def current_stream_ptr():
 
 def to_device(array, dtype=None):
     """numpy / torch -> contiguous CUDA tensor (complex128 by default)."""
+    global _py_h2d
     torch = torch_cuda()
     if isinstance(array, torch.Tensor):
         t = array
         if dtype is not None and t.dtype != dtype:
             t = t.to(dtype)
+        if not t.is_cuda:
+            _py_h2d += t.numel() * t.element_size()
         return t.cuda().contiguous()
     a = np.ascontiguousarray(array, dtype=np.complex128 if dtype is None else None)
     t = torch.from_numpy(a)
     if dtype is not None:
         t = t.to(dtype)
+    _py_h2d += t.numel() * t.element_size()
     # pinned staging makes a large H2D copy a real DMA transfer
     if t.numel() > (1 << 16):
         return t.pin_memory().cuda(non_blocking=True)

@@ -14,6 +14,7 @@
 
 static thread_local char g_error[1024] = "";
 std::atomic<uint64_t> qsx_launch_counter{0};
+std::atomic<uint64_t> qsx_h2d_counter{0}, qsx_d2h_counter{0};
 
 void qsx_set_error(const char *fmt, ...) {
     va_list ap;
@@ -78,6 +79,10 @@ void qsx_pool_free(void *ptr) {
 extern "C" const char *qsx_last_error(void) { return g_error; }
 extern "C" int qsx_version(void) { return 100; }
 extern "C" uint64_t qsx_kernel_launches(void) { return qsx_launch_counter.load(); }
+extern "C" void qsx_transfer_bytes(uint64_t *h2d, uint64_t *d2h) {
+    if (h2d) *h2d = qsx_h2d_counter.load();
+    if (d2h) *d2h = qsx_d2h_counter.load();
+}
 
 extern "C" int qsx_device_info(int32_t *sm_count, int64_t *l2_bytes, int32_t *smem_per_block) {
     int dev = 0;

@@ -88,6 +88,8 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
 // ---- host side ----------------------------------------------------------
 void qsx_set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> qsx_launch_counter;
+// bytes this library has moved across PCIe since load (bench.py: e2e.h2d/d2h_bytes_per_step)
+extern std::atomic<uint64_t> qsx_h2d_counter, qsx_d2h_counter;
 
 #define QSX_CUDA(call)                                                        \
     do {                                                                      \
@@ -128,6 +130,7 @@ struct DevBuf {
     cudaError_t upload(const T *src, size_t count, cudaStream_t s) {
         cudaError_t e = alloc(count);
         if (e != cudaSuccess || count == 0) return e;
+        qsx_h2d_counter += count * sizeof(T);
         return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
     }
     cudaError_t upload(const std::vector<T> &v, cudaStream_t s) { return upload(v.data(), v.size(), s); }

@@ -572,6 +572,7 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
     unsigned long long stats[3] = {0, 0, 0};
+    qsx_d2h_counter += sizeof(stats);
     QSX_CUDA(cudaMemcpyAsync(stats, d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;
@@ -979,6 +980,7 @@ extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnor
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
     unsigned long long st[2] = {0, 0};
+    qsx_d2h_counter += sizeof(st);
     QSX_CUDA(cudaMemcpyAsync(st, status.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;

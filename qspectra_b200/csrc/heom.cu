@@ -1552,6 +1552,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
                         "HEOM pulse operators must be one shared set of [n_pulses][M][M] matrices");
             const int np = args->n_pulses;
             std::vector<cplx> dense((size_t)np * M * M);
+            qsx_d2h_counter += dense.size() * sizeof(cplx);
             QSX_CUDA(cudaMemcpyAsync(dense.data(), args->pulse_ops_dev, dense.size() * sizeof(cplx),
                                      cudaMemcpyDeviceToHost, stream));
             QSX_CUDA(cudaStreamSynchronize(stream));
@@ -1641,6 +1642,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
     unsigned long long st[4] = {0, 0, 0, 0};
+    qsx_d2h_counter += sizeof(st);
     QSX_CUDA(cudaMemcpyAsync(st, stats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;

@@ -409,6 +409,7 @@ extern "C" int qsx_zofe_propagate(qsx_zofe_t h, qsx_propagate_args *args, void *
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
     unsigned long long st[3] = {0, 0, 0};
+    qsx_d2h_counter += sizeof(st);
     QSX_CUDA(cudaMemcpyAsync(st, stats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;

@@ -193,8 +193,12 @@ class RedfieldModel(LiouvilleSpaceModel):
                 heisenberg_picture, member0)
         bath = ham.bath
         if self.evolve_basis == 'eigen':
-            # the eigenbasis ordering/sign gauge is LAPACK's: keep the host eigh
-            E, U = self.ensemble_eigensystems(ensemble_size, member0)
+            # the eigenvector sign / degenerate-subspace gauge must be the one the members'
+            # own dipole operators and states are expressed in (Hamiltonian.eig, scipy's
+            # driver): take the eigensystems from the member Hamiltonians themselves
+            members = [ham.sample(member0 + n) for n in range(ensemble_size)]
+            E = np.array([m.E(ss) for m in members])
+            U = np.array([m.U(ss) for m in members])
             number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
             kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
                     else _capi.BATH_DEBYE_COMPLEX)

@@ -98,7 +98,7 @@ class DeviceEOM(object):
         dy = torch.empty_like(y_dev)
         _, gptr = _capi.int32_ptr(generators)
         self._apply_dev(y_dev, dy, y_dev.shape[0], gptr)
-        return dy.cpu().numpy()
+        return _capi.to_host(dy)
 
     def propagate(self, y0, t, t0=None, method='zvode', save=None,
                   generators=None, pulses=None, pulse_ops=None, rtol=None,
@@ -173,7 +173,7 @@ class DeviceEOM(object):
         self.last = dict(rhs=int(args.rhs_evaluations),
                          steps=int(args.accepted_steps),
                          kernel_ms=float(args.kernel_ms), method=method)
-        return out if return_device else out.cpu().numpy()
+        return out if return_device else _capi.to_host(out)
 
     def _configure_save(self, args, save, keep):
         if save is None:

@@ -88,11 +88,18 @@ def simulate_dynamics_sharded(dynamical_model, initial_state, duration=None,
         part = ensemble_mean(eom, y0, t, count, save, return_device=True,
                              scale=1.0 / ensemble_size, **integrate_kwargs)
     else:
+        # more ranks than members: contribute zeros of the saved width ('ado0' keeps the
+        # density-matrix part of a HEOM / ZOFE state: one entry per subspace element)
         torch_ = _capi.torch_cuda()
-        dim = y0.size if save is None else None
+        if save is None:
+            dim = y0.size
+        elif hasattr(dynamical_model, 'lspace_model'):
+            dim = dynamical_model.lspace_model.liouville_subspace_index(liouville_subspace).size
+        else:
+            dim = dynamical_model.hamiltonian.n_states(dynamical_model.hilbert_subspace) ** 2
         part = torch_.zeros((len(t), dim), dtype=torch_.complex128, device='cuda')
     total = reduce_sum(part, dst)
-    states = total.cpu().numpy()
+    states = _capi.to_host(total)
     return t, dynamical_model.saved_states_to_density_matrix(states)
 
 
@@ -144,7 +151,8 @@ def third_order_response_sharded(dynamical_model, coherence_time_max,
         if count == 0:
             part = torch.zeros_like(part)
         total = reduce_sum(part, dst)
-        return ticks, (total / ensemble_size).cpu().numpy()
+        from . import _capi
+        return ticks, _capi.to_host(total / ensemble_size)
 
     def one(member):
         return third_order_response(
@@ -186,4 +194,5 @@ def two_dimensional_spectra_sharded(dynamical_model, coherence_time_max,
     rw_freq, unit_convert = dynamical_model.rw_freq, dynamical_model.unit_convert
     f1, X = fourier_transform(t1, X, 0, rw_freq=rw_freq, sign=-1, unit_convert=unit_convert)
     f3, X = fourier_transform(t3, X, 2, rw_freq=rw_freq, unit_convert=unit_convert)
-    return (f1, t2, f3), (X.cpu().numpy() if not isinstance(X, np.ndarray) else X)
+    from . import _capi
+    return (f1, t2, f3), (_capi.to_host(X) if not isinstance(X, np.ndarray) else X)

@@ -69,7 +69,7 @@ def ensemble_mean(eom, y0, t, ensemble_size, save, return_device=False,
     mean = engine.reduce_members(out, (1.0 / ensemble_size) if scale is None else scale)
     if return_device:
         return mean
-    res = mean.cpu().numpy()
+    res = _capi.to_host(mean)
     if isinstance(save, LinearMap) and save.matrix.ndim == 1:
         res = res[..., 0]
     return res

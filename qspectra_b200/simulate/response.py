@@ -18,6 +18,7 @@ from .decorators import (optional_ensemble_average,
                          optional_4th_order_isotropic_average)
 from .utils import integrate, fourier_transform
 from ..utils import ZeroArray
+from .. import _capi
 
 
 @optional_ensemble_average
@@ -233,8 +234,12 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
     for lo in range(0, n_members, chunk):
         E = min(chunk, n_members - lo)
         first = member_offset + lo
-        dip = ([model.sample(first + n, True) for n in range(E)]
-               if random_orientations and not single else [model])
+        # dipole operators per member when the members differ in them: random orientations,
+        # or evolution in each member's own eigenbasis (reference decorators.py:55-60 builds
+        # every member's operators from the sampled model)
+        own_basis = getattr(model, 'evolve_basis', 'site') == 'eigen'
+        dip = ([model.sample(first + n, random_orientations) for n in range(E)]
+               if (random_orientations or own_basis) and not single else [model])
         nm = len(dip)
         gens = np.repeat(np.arange(E), nv)                  # generator of unit (e, v)
         sidx = (np.arange(E * nv) if nm == E else np.tile(np.arange(nv), E))
@@ -307,7 +312,7 @@ def third_order_response(dynamical_model, coherence_time_max,
             ensemble_size, ensemble_random_orientations,
             integrate_kwargs.pop('member_offset', 0), True,
             exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
-        return ticks, total.cpu().numpy()
+        return ticks, _capi.to_host(total)
     return _third_order_response(
         dynamical_model, coherence_time_max, population_time_max,
         population_times, geometry, polarization, include_signal,
@@ -348,5 +353,5 @@ def two_dimensional_spectra(dynamical_model, coherence_time_max,
     f3, X_ftf = fourier_transform(t3, X_ftt, 2, rw_freq=rw_freq,
                                   unit_convert=unit_convert)
     if not isinstance(X_ftf, np.ndarray):
-        X_ftf = X_ftf.cpu().numpy()
+        X_ftf = _capi.to_host(X_ftf)
     return (f1, t2, f3), X_ftf

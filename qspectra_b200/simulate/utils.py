@@ -10,6 +10,7 @@ Contract: reference ``qspectra/simulate/utils.py`` -- ``integrate`` :53-109
 """
 import numpy as np
 
+from .. import _capi
 from ..engine import DeviceEOM, LinearMap, IntegratorError  # noqa: F401
 
 
@@ -139,7 +140,7 @@ def fourier_transform(t, x, axis=-1, rw_freq=0, unit_convert=1, sign=1,
     if on_device and _dft_grid(t):
         return _fourier_transform_device(t, x, axis, rw_freq, unit_convert, sign,
                                          convention)
-    x = x.cpu().numpy() if on_device else np.asarray(x)
+    x = _capi.to_host(x) if on_device else np.asarray(x)
     if t.ndim != 1:
         raise ValueError('t must be one dimensional')
     if t.size != x.shape[axis]:

@@ -260,7 +260,58 @@ def response():
     save('response', **out)
 
 
+def round2():
+    """Round-2 additions: the depth-8 ADO table (hash + sampled rows), FMO 'gef' Redfield
+    generator blocks of a sampled member, FMO third-order response per pathway, and an
+    eigen-basis disorder ensemble of third-order responses."""
+    import hashlib
+    out = {}
+    # ---- BASELINE config 5: ADO_mappings(7, 1, 8), 116 280 ADOs
+    ind_to_mat, mat_to_ind = ADO_mappings(7, 1, 8)
+    table = np.array([m.ravel() for m in ind_to_mat], dtype=np.int64)
+    out['ado8_shape'] = np.array(table.shape)
+    out['ado8_sha256'] = np.array(hashlib.sha256(np.ascontiguousarray(table).tobytes()).hexdigest())
+    rng = np.random.RandomState(8)
+    rows = np.sort(rng.choice(len(table), 1000, replace=False))
+    up = -np.ones((len(rows), table.shape[1]), dtype=np.int64)
+    down = -np.ones((len(rows), table.shape[1]), dtype=np.int64)
+    for i, n in enumerate(rows):
+        m = ind_to_mat[n]
+        for b in range(table.shape[1]):
+            e = np.zeros(table.shape[1], dtype=int)
+            e[b] = 1
+            e = e.reshape(m.shape)
+            p, q = mat_to_ind(m + e), mat_to_ind(m - e)
+            up[i, b] = -1 if p is None else p
+            down[i, b] = -1 if q is None else q
+    out['ado8_rows'], out['ado8_index'] = rows, table[rows]
+    out['ado8_up'], out['ado8_down'] = up, down
+    # ---- FMO 'gef' non-secular Redfield: generator blocks of disorder member 3
+    fmo = systems.fmo(qs)
+    m = qs.RedfieldModel(fmo, hilbert_subspace='gef', unit_convert=CM_FS, secular=False)
+    member = list(m.sample_ensemble(4))[3]
+    L = member.evolution_super_operator
+    for ss in ('fe', 'eg', 'ee'):
+        idx = member.liouville_subspace_index(ss)
+        out['fmo_gef_member3_L_%s' % ss] = L[np.ix_(idx, idx)]
+    # ---- FMO third-order response, one pathway each (400 fs coherence times, 3 waiting times)
+    t2 = np.array([0., 100., 300.])
+    for sig in ('GSB', 'ESE', 'ESA'):
+        (t1, _, t3), S = qs.third_order_response(m, 400, population_times=t2,
+                                                 include_signal=sig, **TIGHT)
+        out['fmo_gef_%s' % sig] = S
+    out['fmo_gef_t1'], out['fmo_gef_t2'] = t1, t2
+    # ---- eigen-basis model with disorder: members have their own eigenbases
+    dham = systems.dimer(qs, disorder=80)
+    de = qs.RedfieldModel(dham, hilbert_subspace='gef', unit_convert=CM_FS,
+                          discard_imag_corr=True, evolve_basis='eigen')
+    (_, _, _), S = qs.third_order_response(de, 300, population_times=np.linspace(0, 200, 3),
+                                           ensemble_size=3, **TIGHT)
+    out['dimer_eigen_ens3'] = S
+    save('round2', **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['maps', 'redfield', 'heom', 'zofe', 'response']
+    which = sys.argv[1:] or ['maps', 'redfield', 'heom', 'zofe', 'response', 'round2']
     for name in which:
         globals()[name]()

@@ -736,3 +736,42 @@ def test_wide_state_propagator_stepping():
     a = ens.propagate(y0, t, generators=np.arange(3))
     b = ens.propagate(y0, t, generators=np.arange(3), method='taylor')
     assert ens.last['method'] == 'taylor' and rel_l2(a, b) < 1e-10
+
+
+# ------------------------------------------------------------ round-2 fixtures
+def test_fmo_gef_third_order_pathways(golden):
+    """FMO 'gef' third-order response, one pathway class at a time (GSB: gg/eg stages, ESE:
+    49-dimensional 'ee' stage, ESA: the 147-dimensional 'fe' stage -- the wide-state
+    propagator path) against the reference."""
+    g = golden('round2')
+    m = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef', unit_convert=CM_FS,
+                         secular=False)
+    for sig in ('GSB', 'ESE', 'ESA'):
+        (t1, t2, t3), S = qb.third_order_response(m, 400, population_times=g['fmo_gef_t2'],
+                                                  include_signal=sig)
+        assert np.array_equal(t1, g['fmo_gef_t1'])
+        assert rel_l2(S, g['fmo_gef_%s' % sig]) < TOL, sig
+
+
+def test_fmo_gef_device_generator_blocks(golden):
+    """K5 on the 'gef' manifold of FMO (36 states): the blocks the third-order pathways use,
+    disorder member 3, against the reference's evolution_super_operator."""
+    g = golden('round2')
+    m = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef', unit_convert=CM_FS,
+                         secular=False)
+    for ss in ('fe', 'eg', 'ee'):
+        eom = m.ensemble_eom(1, False, ss, member0=3)
+        M = eom.dim
+        L = eom.apply(np.eye(M, dtype=complex), generators=np.zeros(M, dtype=int)).T
+        assert rel_l2(L, g['fmo_gef_member3_L_%s' % ss]) < 1e-10, ss
+
+
+def test_eigen_basis_ensemble_third_order(golden):
+    """evolve_basis='eigen' with static disorder: every member has its own eigenbasis, so dipole
+    operators and the thermal state must be the member's (reference decorators.py:55-60)."""
+    g = golden('round2')
+    de = qb.RedfieldModel(systems.dimer(disorder=80), hilbert_subspace='gef',
+                          unit_convert=CM_FS, discard_imag_corr=True, evolve_basis='eigen')
+    (_, _, _), S = qb.third_order_response(de, 300, population_times=np.linspace(0, 200, 3),
+                                           ensemble_size=3)
+    assert rel_l2(S, g['dimer_eigen_ens3']) < TOL

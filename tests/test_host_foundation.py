@@ -208,3 +208,20 @@ def test_no_cpu_fallback_without_gpu():
         m.equation_of_motion('ee')
     with pytest.raises(TypeError):
         qb.integrate(lambda t, y: y, np.zeros(2, complex), np.array([0., 1.]))
+
+
+def test_depth8_ado_table_matches_reference(golden):
+    """BASELINE config 5: the closed-form enumeration (csrc/ado.h) for 14 bins, level_cutoff 8
+    against the reference's ADO_mappings(7, 1, 8) (heom.py:92-152): SHA-256 of the whole
+    116 280 x 14 table and the neighbour maps of 1 000 sampled rows, bit-exact."""
+    import hashlib
+    from qspectra_b200 import _capi
+    g = golden('round2')
+    idx, up, down = _capi.ado_enumerate(14, 8)
+    assert idx.shape == tuple(g['ado8_shape'])
+    assert hashlib.sha256(np.ascontiguousarray(idx.astype(np.int64)).tobytes()).hexdigest() \
+        == str(g['ado8_sha256'])
+    rows = g['ado8_rows']
+    assert np.array_equal(idx[rows], g['ado8_index'])
+    assert np.array_equal(up[rows], g['ado8_up'])
+    assert np.array_equal(down[rows], g['ado8_down'])

@@ -217,3 +217,20 @@ def test_response(golden):
                                         time_extra=200, **TIGHT)
     assert np.array_equal(t, g['pump_t'])
     assert rel_l2(st, g['pump_states']) < 1e-11
+
+
+def test_oracle_round2_fixtures(golden):
+    """FMO 'gef' generator blocks of a sampled member and per-pathway third-order responses
+    (reference outputs, tests/golden/make_golden.py: round2)."""
+    g = golden('round2')
+    ham = systems.fmo()
+    m = oracle.OracleRedfield(ham, hilbert_subspace='gef', unit_convert=CM_FS, secular=False)
+    member = m.__class__.__new__(m.__class__)
+    member.__dict__.update(m.__dict__)
+    member.hamiltonian = m.hamiltonian.sample(3)
+    for ss in ('fe', 'eg', 'ee'):
+        assert rel_l2(member.generator(ss), g['fmo_gef_member3_L_%s' % ss]) < 1e-12, ss
+    (t1, _, _), S = oracle.third_order_response(m, 400, population_times=g['fmo_gef_t2'],
+                                                include_signal='ESE', **TIGHT)
+    assert np.array_equal(t1, g['fmo_gef_t1'])
+    assert rel_l2(S, g['fmo_gef_ESE']) < 1e-8
