@@ -130,7 +130,8 @@ int qsx_dense_apply(qsx_dense_t h, const void *y_dev, void *dy_dev,
                     void *stream);
 int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void *stream);
 /* New handle holding P_g = exp(L_g * dt) for every generator of `h`, computed on the FP64
- * tensor cores (scaled Taylor series + squarings, on-device truncation control).  Use it
+ * tensor cores (|A| <= 1/2 scaling, degree-14 Taylor polynomial in Paterson-Stockmeyer form,
+ * squarings; one CTA per generator up to M = 56, tiled GEMM launches up to M = 1024).  Use it
  * with QSX_METHOD_MAP on a uniform output grid of spacing dt: the exact counterpart of the
  * reference's ZVODE loop for a constant generator (simulate/utils.py:45-49). */
 int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnorm_dev,
@@ -276,6 +277,20 @@ int qsx_redfield_build_sampled(int32_t n_members, int32_t N, const double *H0_ho
  * ---------------------------------------------------------------------- */
 int qsx_reduce_members(const void *in_dev, int32_t n_members, int64_t n,
                        double scale, void *out_dev, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K6 (signal contraction of the third-order response):
+ *   S[ab][c] += sum_u w[u] * sum_i X[u][ab][i] * Y[u][c][i]        (complex128, no conjugation)
+ * X: [n_units][n_ab][K] = V_rho2 of every unit (ensemble member x polarisation configuration),
+ * ab = (t1, t2) flattened; Y: [n_units][n_c][K] = the Heisenberg-propagated detection vectors
+ * over t3; w: [n_units] complex weights (isotropic-average weight of the unit's configuration).
+ * Replaces `np.einsum('ci,abi', V_Gt3, V_rho2)` (simulate/response.py:336) and the weighted
+ * sums around it (decorators.py:55-61, 86-92) with one tensor-core GEMM launch whose CTAs walk
+ * all units (deterministic summation order).
+ * ---------------------------------------------------------------------- */
+int qsx_response_contract(const void *x_dev, const void *y_dev, const void *w_dev,
+                          int32_t n_units, int64_t n_ab, int32_t n_c, int32_t K,
+                          void *s_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * K7: Fourier transform of a response function sampled on t = 0, dt, ..., (n-1) dt,

@@ -950,9 +950,23 @@ extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnor
     QSX_REQUIRE(h && out && Pt_dev && lnorm_dev, "qsx_dense_expm: null argument");
     const int M = h->M;
     if (M > 56) {
-        qsx_set_error("qsx_dense_expm: state dimension %d > 56 is not supported by the tensor-core "
-                      "propagator kernel", M);
-        return QSX_ERR_UNSUPPORTED;
+        // wide states: the same series, one tiled tensor-core GEMM launch per product (dense_wide.cu)
+        QSX_REQUIRE(M <= 1024, "qsx_dense_expm: state dimension above 1024");
+        cudaEvent_t w0, w1;
+        QSX_CUDA(cudaEventCreate(&w0));
+        QSX_CUDA(cudaEventCreate(&w1));
+        QSX_CUDA(cudaEventRecord(w0, stream));
+        unsigned long long ng = 0;
+        int rcw = qsx_dense_expm_wide(h->Lt.p, M, h->n_gen, h->lnorm.p, dt, (cplx *)Pt_dev, &ng, stream);
+        QSX_CUDA(cudaEventRecord(w1, stream));
+        QSX_CUDA(cudaStreamSynchronize(stream));
+        float wms = 0;
+        cudaEventElapsedTime(&wms, w0, w1);
+        cudaEventDestroy(w0); cudaEventDestroy(w1);
+        if (rcw) return rcw;
+        rcw = qsx_dense_wrap(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_);
+        if (rcw == QSX_OK) { (*out)->build_ms = wms; (*out)->build_gemms = ng; }
+        return rcw;
     }
     DevBuf<unsigned long long> status;
     QSX_CUDA(status.alloc(2));

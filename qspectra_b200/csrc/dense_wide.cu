@@ -1,0 +1,246 @@
+// Tiled complex FP64 GEMM on the FP64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA) and the two
+// users it has on the propagation path:
+//
+//   * qsx_dense_expm_wide -- exp(L dt) for state dimensions above the single-CTA kernel of
+//     dense.cu (57 .. 1024; FMO 'fe' = 147, 'gg,ge,eg,ee' = 64): the same algorithm
+//     (|A|_inf <= 1/2 scaling, degree-14 Taylor polynomial in Paterson-Stockmeyer form,
+//     squarings), each matrix product one launch of the GEMM below over all generators.
+//     Replaces the ZVODE loop for a constant generator on a uniform grid (reference
+//     simulate/utils.py:45-49, liouville_space.py:316-341) where round 1 called
+//     torch.linalg.matrix_exp.
+//   * qsx_response_contract -- K6, the signal contraction of the third-order response,
+//       S[ab][c] += sum_u w_u sum_i X_u[ab][i] Y_u[c][i]
+//     (reference response.py:336, `np.einsum('ci,abi', V_Gt3, V_rho2)`, summed over ensemble
+//     members and polarisation configurations u with their weights; decorators.py:55-61,
+//     86-92), where round 1 called torch.einsum.  One CTA owns an output tile and walks all
+//     units, so the sum over u is deterministic and needs no atomics.
+//
+// Tile: 32 x 32 complex outputs per CTA, four warps (8 rows x 32 columns each), K in chunks
+// of 16 through planar (re / im) shared-memory tiles whose leading dimensions (4 mod 16
+// doubles) make the A- and B-fragment loads of a half-warp bank-conflict free.  A complex
+// product is three real DMMA products (Gauss), as in dense.cu.
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+__device__ __forceinline__ void dmma884w(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int BM = 32, BN = 32, KC = 16;
+constexpr int LDA = 20;      // doubles per row of the A tile [BM][KC]      (4 mod 16)
+constexpr int LDB = 36;      // doubles per row of the B tile [KC][BN]      (4 mod 16)
+constexpr int LDT = 20;      // doubles per row of the transposed B tile [BN][KC]
+
+struct ZgemmArgs {
+    // C_u = A_u B_u (+ epilogue), or with `reduce`: C += sum_u w_u A_u op(B_u)
+    const cplx *A, *B;
+    cplx *C;
+    int M, N, K;                    // C is M x N, contraction length K
+    int lda, ldb, ldc;              // row strides (elements)
+    long long sA, sB, sC;           // strides between units
+    int n_units;
+    int b_transposed;               // 1: B_u is stored [N][K] (C = A B^T)
+    int reduce;                     // 1: one output, summed over the units with weights w
+    const cplx *w;                  // [n_units] or null (= 1)
+    // epilogue of the unit-wise form: C = AB + c0 I + c1 X + c2 Y  (X, Y like C)
+    const cplx *X, *Y;
+    double c0, c1, c2;
+};
+
+__global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
+    __shared__ __align__(16) double Ar[BM * LDA], Ai[BM * LDA];
+    constexpr int BSZ = KC * LDB > BN * LDT ? KC * LDB : BN * LDT;
+    __shared__ __align__(16) double Br[BSZ], Bi[BSZ];                // [KC][LDB] or [BN][LDT]
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    const int u_begin = a.reduce ? 0 : blockIdx.z, u_end = a.reduce ? a.n_units : blockIdx.z + 1;
+
+    // final accumulators (re, im for the two columns a thread owns in each of the 4 column blocks)
+    double fr[4][2], fi[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) { fr[nb][0] = fr[nb][1] = fi[nb][0] = fi[nb][1] = 0.0; }
+
+    for (int u = u_begin; u < u_end; ++u) {
+        const cplx *Au = a.A + (size_t)u * a.sA, *Bu = a.B + (size_t)u * a.sB;
+        double p1[4][2], p2[4][2], p3[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { p1[nb][0] = p1[nb][1] = p2[nb][0] = p2[nb][1] = p3[nb][0] = p3[nb][1] = 0.0; }
+        for (int k0 = 0; k0 < a.K; k0 += KC) {
+            __syncthreads();
+            // A tile: [BM][KC], k fastest in global memory
+            for (int i = threadIdx.x; i < BM * KC; i += 128) {
+                const int r = i / KC, k = i % KC;
+                cplx v = cmake(0, 0);
+                if (row0 + r < a.M && k0 + k < a.K) v = __ldg(&Au[(size_t)(row0 + r) * a.lda + k0 + k]);
+                Ar[r * LDA + k] = v.x; Ai[r * LDA + k] = v.y;
+            }
+            if (a.b_transposed) {
+                // B stored [N][K]: tile [BN][KC], k fastest
+                for (int i = threadIdx.x; i < BN * KC; i += 128) {
+                    const int c = i / KC, k = i % KC;
+                    cplx v = cmake(0, 0);
+                    if (col0 + c < a.N && k0 + k < a.K) v = __ldg(&Bu[(size_t)(col0 + c) * a.ldb + k0 + k]);
+                    Br[c * LDT + k] = v.x; Bi[c * LDT + k] = v.y;
+                }
+            } else {
+                // B stored [K][N]: tile [KC][BN], column fastest
+                for (int i = threadIdx.x; i < KC * BN; i += 128) {
+                    const int k = i / BN, c = i % BN;
+                    cplx v = cmake(0, 0);
+                    if (k0 + k < a.K && col0 + c < a.N) v = __ldg(&Bu[(size_t)(k0 + k) * a.ldb + col0 + c]);
+                    Br[k * LDB + c] = v.x; Bi[k * LDB + c] = v.y;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ks = 0; ks < KC / 4; ++ks) {
+                const double ar = Ar[(8 * wrp + g) * LDA + 4 * ks + t];
+                const double ai = Ai[(8 * wrp + g) * LDA + 4 * ks + t];
+                const double as = ar + ai;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int o = a.b_transposed ? (8 * nb + g) * LDT + 4 * ks + t : (4 * ks + t) * LDB + 8 * nb + g;
+                    const double br = Br[o], bi = Bi[o];
+                    dmma884w(p1[nb][0], p1[nb][1], ar, br);
+                    dmma884w(p2[nb][0], p2[nb][1], ai, bi);
+                    dmma884w(p3[nb][0], p3[nb][1], as, br + bi);
+                }
+            }
+        }
+        const cplx wu = (a.reduce && a.w) ? __ldg(&a.w[u]) : cmake(1.0, 0.0);
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double re = p1[nb][j] - p2[nb][j], im = p3[nb][j] - p1[nb][j] - p2[nb][j];
+                fr[nb][j] += wu.x * re - wu.y * im;
+                fi[nb][j] += wu.x * im + wu.y * re;
+            }
+    }
+    const int r = row0 + 8 * wrp + g;
+    if (r >= a.M) return;
+    cplx *Cu = a.C + (a.reduce ? 0 : (size_t)blockIdx.z * a.sC);
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = col0 + 8 * nb + 2 * t + j;
+            if (c >= a.N) continue;
+            const size_t o = (size_t)r * a.ldc + c;
+            cplx v = cmake(fr[nb][j], fi[nb][j]);
+            if (a.reduce) {
+                const cplx old = Cu[o];
+                v.x += old.x; v.y += old.y;
+            } else {
+                if (a.X) { const cplx x = a.X[(size_t)blockIdx.z * a.sC + o]; v.x += a.c1 * x.x; v.y += a.c1 * x.y; }
+                if (a.Y) { const cplx y = a.Y[(size_t)blockIdx.z * a.sC + o]; v.x += a.c2 * y.x; v.y += a.c2 * y.y; }
+                if (r == c) v.x += a.c0;
+            }
+            Cu[o] = v;
+        }
+}
+
+// out[g] = s_g * in[g] with s_g = dt / 2^sq (uniform sq), and B4 = c12 I + c13 A + c14 A^2
+__global__ void wide_scale_kernel(const cplx *__restrict__ in, cplx *__restrict__ out, size_t n, double s) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = cscale(s, in[i]);
+}
+__global__ void wide_poly2_kernel(const cplx *__restrict__ A, const cplx *__restrict__ A2, cplx *__restrict__ out,
+                                  int M, size_t n, double c0, double c1, double c2) {
+    const size_t mm = (size_t)M * M;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i % mm;
+        cplx v = cmake(c1 * A[i].x + c2 * A2[i].x, c1 * A[i].y + c2 * A2[i].y);
+        if (e / M == e % M) v.x += c0;
+        out[i] = v;
+    }
+}
+
+int launch_zgemm(const ZgemmArgs &a, cudaStream_t stream) {
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.reduce ? 1 : a.n_units);
+    zgemm_dmma_kernel<<<grid, 128, 0, stream>>>(a);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+}  // namespace
+
+// exp(L_g dt) for every generator, transposed storage in and out (exp commutes with the
+// transpose).  lnorm_host: inf-norms of the generators.  Returns the number of complex GEMMs
+// per generator in *gemms.
+int qsx_dense_expm_wide(const cplx *Lt, int M, int n_gen, const double *lnorm_dev, double dt, cplx *Pt,
+                        unsigned long long *gemms, cudaStream_t stream) {
+    std::vector<double> nrm(n_gen);
+    qsx_d2h_counter += n_gen * sizeof(double);
+    QSX_CUDA(cudaMemcpyAsync(nrm.data(), lnorm_dev, n_gen * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    QSX_CUDA(cudaStreamSynchronize(stream));
+    double worst = 0;
+    for (double x : nrm) {
+        QSX_REQUIRE(x == x && x < 1e300, "qsx_dense_expm: non-finite generator");
+        worst = std::max(worst, fabs(dt) * x);
+    }
+    int sq = 0;
+    while (worst > 0.5 && sq < 60) { worst *= 0.5; ++sq; }
+    const double scale = dt / (double)(1ULL << sq);
+    const size_t mm = (size_t)M * M, n = mm * n_gen;
+    DevBuf<cplx> A, A2, A3, U;
+    QSX_CUDA(A.alloc(n)); QSX_CUDA(A2.alloc(n)); QSX_CUDA(A3.alloc(n)); QSX_CUDA(U.alloc(n));
+    static const double inv_fact[15] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040,
+                                        1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
+                                        1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0};
+    const int eb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    wide_scale_kernel<<<eb, 256, 0, stream>>>(Lt, A.p, n, scale);
+    qsx_launch_counter += 1;
+    ZgemmArgs g;
+    g.M = g.N = g.K = M; g.lda = g.ldb = g.ldc = M; g.sA = g.sB = g.sC = (long long)mm;
+    g.n_units = n_gen; g.b_transposed = 0; g.reduce = 0; g.w = nullptr;
+    g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
+    int rc;
+    // all factors are polynomials in A, so the order of the products is immaterial
+    g.A = A.p; g.B = A.p; g.C = A2.p;
+    if ((rc = launch_zgemm(g, stream))) return rc;                     // A^2
+    g.A = A2.p; g.B = A.p; g.C = A3.p;
+    if ((rc = launch_zgemm(g, stream))) return rc;                     // A^3
+    // p(A) = B0 + A^3 (B1 + A^3 (B2 + A^3 (B3 + A^3 B4))),  B_i = c_3i I + c_3i+1 A + c_3i+2 A^2
+    cplx *P = Pt, *Q = U.p;
+    wide_poly2_kernel<<<eb, 256, 0, stream>>>(A.p, A2.p, P, M, n, inv_fact[12], inv_fact[13], inv_fact[14]);
+    qsx_launch_counter += 1;
+    for (int blk = 3; blk >= 0; --blk) {
+        g.A = A3.p; g.B = P; g.C = Q; g.X = A.p; g.Y = A2.p;
+        g.c0 = inv_fact[3 * blk]; g.c1 = inv_fact[3 * blk + 1]; g.c2 = inv_fact[3 * blk + 2];
+        if ((rc = launch_zgemm(g, stream))) return rc;
+        std::swap(P, Q);
+    }
+    g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
+    for (int q = 0; q < sq; ++q) {
+        g.A = P; g.B = P; g.C = Q;
+        if ((rc = launch_zgemm(g, stream))) return rc;
+        std::swap(P, Q);
+    }
+    if (P != Pt) QSX_CUDA(cudaMemcpyAsync(Pt, P, n * sizeof(cplx), cudaMemcpyDeviceToDevice, stream));
+    QSX_CUDA(cudaStreamSynchronize(stream));       // the work buffers go back to the pool
+    if (gemms) *gemms = (unsigned long long)(6 + sq) * n_gen;
+    return QSX_OK;
+}
+
+extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const void *w_dev, int32_t n_units,
+                                     int64_t n_ab, int32_t n_c, int32_t K, void *s_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(x_dev && y_dev && s_dev && n_units > 0 && n_ab > 0 && n_c > 0 && K > 0,
+                "qsx_response_contract: bad arguments");
+    QSX_REQUIRE(n_ab < ((int64_t)1 << 31) / 64, "qsx_response_contract: signal too large");
+    ZgemmArgs g;
+    g.A = (const cplx *)x_dev; g.B = (const cplx *)y_dev; g.C = (cplx *)s_dev;
+    g.M = (int)n_ab; g.N = n_c; g.K = K;
+    g.lda = K; g.ldb = K; g.ldc = n_c;
+    g.sA = (long long)n_ab * K; g.sB = (long long)n_c * K; g.sC = 0;
+    g.n_units = n_units; g.b_transposed = 1; g.reduce = 1; g.w = (const cplx *)w_dev;
+    g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
+    return launch_zgemm(g, stream);
+}

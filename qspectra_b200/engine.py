@@ -226,9 +226,6 @@ class DenseEOM(DeviceEOM):
             raise ValueError('generators must have shape (n, M, M)')
         self.n_generators, self.dim = int(shape[0]), int(shape[1])
         self.heisenberg_picture = bool(heisenberg_picture)
-        if self.dim > self.EXPM_MAX_DIM:
-            # kept for the library propagator of wide states (see propagator())
-            self._L_source = Ld if on_device else Lh
         self._h = C.c_void_p()
         _capi.check(lib.qsx_dense_create(C.byref(self._h), self.dim,
                                          self.n_generators, ptr, int(on_device),
@@ -241,36 +238,18 @@ class DenseEOM(DeviceEOM):
             _capi._lib.qsx_dense_destroy(h)
             self._h = None
 
-    #: largest state dimension of the tensor-core propagator kernel
+    #: largest state dimension of the single-CTA tensor-core propagator kernel
     EXPM_MAX_DIM = 56
-    #: wider states (e.g. FMO 'fe', 147) get exp(L dt) from the library
-    #: (torch.linalg.matrix_exp -> cuBLAS batched ZGEMM) and are stepped by the
-    #: CTA-resident kernel with P streamed from L2
-    EXPM_LIBRARY_MAX_DIM = 512
-
-    def _stored_matrices(self):
-        """(n, M, M) CUDA tensor in the engine's storage layout (transposed
-        generator; for the Heisenberg picture that is L itself)."""
-        torch = _capi.torch_cuda()
-        if hasattr(self, '_storage'):
-            return self._storage[0]
-        L = self._L_source
-        Ld = L if isinstance(L, torch.Tensor) else torch.from_numpy(L).cuda()
-        return Ld if self.heisenberg_picture else Ld.transpose(1, 2)
+    #: wider states (e.g. FMO 'fe', 147) get exp(L dt) from the same series with one
+    #: tiled tensor-core GEMM launch per product (csrc/dense_wide.cu) and are stepped by
+    #: the CTA-resident kernel with P streamed from L2
+    EXPM_LIBRARY_MAX_DIM = 1024
 
     def propagator(self, dt):
         """DenseEOM holding P_g = exp(L_g dt) for every generator (FP64 tensor
         cores, csrc/dense.cu: dense_expm_kernel); cached per dt."""
         cache = self.__dict__.setdefault('_propagators', {})
         key = float(dt)
-        if key not in cache and self.dim > self.EXPM_MAX_DIM:
-            torch = _capi.torch_cuda()
-            # exp(G dt) in transposed storage is exp(G^T dt): exponentiate the stored matrices
-            P = torch.linalg.matrix_exp(self._stored_matrices() * key).contiguous()
-            prop = DenseEOM.from_transposed(P)
-            prop.heisenberg_picture = self.heisenberg_picture
-            prop.build_ms, prop.build_gemms = 0.0, 0
-            cache[key] = prop
         if key not in cache:
             torch = _capi.torch_cuda()
             prop = DenseEOM.__new__(DenseEOM)
@@ -532,6 +511,22 @@ def reduce_members(batch_dev, scale=1.0):
         batch_dev.data_ptr(), batch_dev.shape[0], out.numel(), float(scale),
         out.data_ptr(), _capi.current_stream_ptr()))
     return out
+
+
+def response_contract(x_dev, y_dev, weights_dev, total_dev):
+    """Kernel K6: total[ab, c] += sum_u w[u] sum_i x[u, ab, i] y[u, c, i] on the FP64 tensor
+    cores (csrc/dense_wide.cu).  x: (U, n_ab, K), y: (U, n_c, K), w: (U,), total: (n_ab, n_c),
+    all complex128 CUDA tensors."""
+    x_dev, y_dev, weights_dev = x_dev.contiguous(), y_dev.contiguous(), weights_dev.contiguous()
+    U, n_ab, K = x_dev.shape
+    n_c = y_dev.shape[1]
+    if y_dev.shape != (U, n_c, K) or weights_dev.shape != (U,) or \
+            total_dev.numel() != n_ab * n_c or not total_dev.is_contiguous():
+        raise ValueError('inconsistent shapes in response_contract')
+    _capi.check(_capi.lib().qsx_response_contract(
+        x_dev.data_ptr(), y_dev.data_ptr(), weights_dev.data_ptr(), U, n_ab, n_c, K,
+        total_dev.data_ptr(), _capi.current_stream_ptr()))
+    return total_dev
 
 
 def fourier_transform(x_dev, axis, dt, sign):

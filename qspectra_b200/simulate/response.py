@@ -18,7 +18,7 @@ from .decorators import (optional_ensemble_average,
                          optional_4th_order_isotropic_average)
 from .utils import integrate, fourier_transform
 from ..utils import ZeroArray
-from .. import _capi
+from .. import _capi, engine
 
 
 @optional_ensemble_average
@@ -283,9 +283,9 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
                                    return_device=True, **opts)
             out3 = eom_c.propagate(per_unit(lambda v: v[3].bra_vector), t3, method=method,
                                    generators=gens, return_device=True, **opts)
-            total += torch.einsum('v,evabi,evci->abc', wv,
-                                  out2.reshape(E, nv, len(t1), len(t2), -1),
-                                  out3.reshape(E, nv, len(t3), -1))
+            # K6: total[a, b, c] += sum_{e, v} w_v sum_i out2[e, v, a, b, i] out3[e, v, c, i]
+            engine.response_contract(out2.reshape(E * nv, len(t1) * len(t2), -1),
+                                     out3.reshape(E * nv, len(t3), -1), wv.repeat(E), total)
     if normalize and not single:
         total = total / ensemble_size
     return (t1, t2, t3), total

@@ -534,11 +534,13 @@ def test_device_redfield_build_restricted_blocks():
         assert rel_l2(Ln, m.ensemble_generators(members, 'fe')[1].T) < 1e-10
 
 
-@pytest.mark.parametrize('M,n_gen', [(8, 3), (24, 3), (41, 2), (48, 2), (50, 600), (52, 3), (56, 3)])
+@pytest.mark.parametrize('M,n_gen', [(8, 3), (24, 3), (41, 2), (48, 2), (50, 600), (52, 3), (56, 3),
+                                     (57, 2), (64, 5), (147, 3), (200, 2)])
 def test_expm_kernels_all_tile_counts(M, n_gen):
     """exp(L dt) from the DMMA kernels for every padded size class (one 8-row block per warp,
     1..7 warps; 49..56 take the two-CTAs-per-SM kernel whose CTAs loop over the generators:
-    600 generators exercise that loop and its per-CTA scratch tile) against scipy's expm."""
+    600 generators exercise that loop and its per-CTA scratch tile; above 56 the tiled
+    tensor-core GEMM of csrc/dense_wide.cu, one launch per product) against scipy's expm."""
     import scipy.linalg
     rng = np.random.RandomState(M)
     L = (rng.randn(n_gen, M, M) + 1j * rng.randn(n_gen, M, M)) / np.sqrt(M)
@@ -718,8 +720,8 @@ def test_device_disorder_streams_match_numpy():
 
 
 def test_wide_state_propagator_stepping():
-    """state dimensions above the tensor-core kernel's 56 (FMO 'fe', M = 147):
-    library matrix exponential + streamed propagator stepping against Taylor"""
+    """state dimensions above the single-CTA propagator kernel's 56 (FMO 'fe', M = 147): tiled
+    tensor-core propagator build + streamed propagator stepping against Taylor"""
     mf = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef', unit_convert=CM_FS)
     rng = np.random.RandomState(2)
     for heis in (False, True):
@@ -775,3 +777,20 @@ def test_eigen_basis_ensemble_third_order(golden):
     (_, _, _), S = qb.third_order_response(de, 300, population_times=np.linspace(0, 200, 3),
                                            ensemble_size=3)
     assert rel_l2(S, g['dimer_eigen_ens3']) < TOL
+
+
+def test_response_contraction_kernel():
+    """K6 (csrc/dense_wide.cu): S[ab, c] += sum_u w_u sum_i X[u, ab, i] Y[u, c, i] against numpy,
+    ragged sizes (tile edges, K not a multiple of the chunk), accumulation into a non-zero S."""
+    import torch
+    rng = np.random.RandomState(6)
+    for U, n_ab, n_c, K in [(1, 5, 3, 2), (7, 70, 45, 7), (3, 197 * 2, 197, 49), (2, 33, 65, 147)]:
+        X = rng.randn(U, n_ab, K) + 1j * rng.randn(U, n_ab, K)
+        Y = rng.randn(U, n_c, K) + 1j * rng.randn(U, n_c, K)
+        w = rng.randn(U) + 1j * rng.randn(U)
+        S0 = rng.randn(n_ab, n_c) + 1j * rng.randn(n_ab, n_c)
+        S = torch.from_numpy(S0.copy()).cuda()
+        engine.response_contract(torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda(),
+                                 torch.from_numpy(w).cuda(), S)
+        want = S0 + np.einsum('u,uai,uci->ac', w, X, Y)
+        assert rel_l2(S.cpu().numpy(), want) < 1e-13, (U, n_ab, n_c, K)
