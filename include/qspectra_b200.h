@@ -82,8 +82,9 @@ typedef struct {
     const void *save_dev;         /* S: [n_save][save_rows][M_from] complex128       */
     int32_t n_save;               /* 1 (shared) or n_generators (per member)         */
     const int32_t *save_of_column_host; /* [n_columns] or NULL: column c is saved through
-                                     S[save_of_column[c]] (any n_save; dense generators only) --
-                                     e.g. one dipole operator per polarisation configuration */
+                                     S[save_of_column[c]] (any n_save; dense generators, and HEOM
+                                     where S is a stack of per-ADO blocks) -- e.g. one dipole
+                                     operator per polarisation configuration */
     int32_t n_pulses;             /* time-dependent terms, <= QSX_MAX_PULSES         */
     qsx_pulse pulses[QSX_MAX_PULSES];
     const void *pulse_ops_dev;    /* C_p: [n_pulse_sets][n_pulses][D][D] commutator blocks (dense),

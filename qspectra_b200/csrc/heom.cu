@@ -668,7 +668,8 @@ struct HeomPropArgs {
     int rk4_sub, kmax;
     double theta, lnorm;
     int save_mode, save_rows;
-    const cplx *S;              // [save_rows][M]
+    const cplx *S;              // [n_save][save_rows][M]
+    const int *save_of;         // [B] save matrix of each column, or null (matrix 0)
     cplx *out;
     long long saved_dim;
     int *flags;                 // [3]
@@ -703,9 +704,10 @@ __device__ __forceinline__ void heom_save(const HeomPropArgs &a, int it) {
             int m = (int)(r % a.save_rows);
             const cplx *y = a.Y + (size_t)b * Dp + ((n >> 5) * M) * TL;
             const int ln = (int)(n & 31);
+            const cplx *Sm = a.S + (a.save_of ? (size_t)a.save_of[b] * a.save_rows * M : 0);
             cplx acc = cmake(0, 0);
             for (int e = 0; e < M; ++e)
-                cfma(acc, __ldg(&a.S[(size_t)m * M + e]), __ldcg(&y[a.H.e_off[e] + ln * a.H.e_stride[e]]));
+                cfma(acc, __ldg(&Sm[(size_t)m * M + e]), __ldcg(&y[a.H.e_off[e] + ln * a.H.e_stride[e]]));
             a.out[((size_t)b * a.nt + it) * a.saved_dim + r] = acc;
         }
     }
@@ -1494,9 +1496,18 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     if (dopri) QSX_CUDA(Kbuf.alloc((size_t)7 * B * Dp));
 
     long long saved_dim;
+    DevBuf<int> save_of;
     if (args->save_mode == QSX_SAVE_MATRIX) {
-        QSX_REQUIRE(args->save_dev && args->save_rows > 0 && args->n_save == 1,
-                    "HEOM save matrix must be shared ([rows][M])");
+        // per-ADO blocks [n_save][rows][M]: one shared matrix, or one per column through
+        // save_of_column (e.g. the dipole operator of each polarisation configuration)
+        QSX_REQUIRE(args->save_dev && args->save_rows > 0 && args->n_save >= 1 &&
+                    (args->n_save == 1 || args->save_of_column_host),
+                    "HEOM save matrices need save_of_column when n_save > 1");
+        if (args->save_of_column_host) {
+            std::vector<int> so(args->save_of_column_host, args->save_of_column_host + B);
+            for (int x : so) QSX_REQUIRE(x >= 0 && x < args->n_save, "save index out of range");
+            QSX_CUDA(save_of.upload(so, stream));
+        }
         saved_dim = d.n_ado * args->save_rows;
     } else if (args->save_mode == QSX_SAVE_ADO0) {
         saved_dim = M;
@@ -1530,6 +1541,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         ra.ainv = h->row_ainv.p;
         ra.save_mode = args->save_mode; ra.save_rows = args->save_rows;
         ra.S = (const cplx *)args->save_dev;
+        ra.save_of = save_of.p;
         ra.out = (cplx *)args->out_dev; ra.saved_dim = saved_dim;
         ra.flags = flags.p; ra.ynorm = ynorm.p; ra.stats = stats.p;
         rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
@@ -1595,6 +1607,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         a.kmax = 60; a.theta = 2.0; a.lnorm = h->lnorm;
         a.save_mode = args->save_mode; a.save_rows = args->save_rows;
         a.S = (const cplx *)args->save_dev;
+        a.save_of = save_of.p;
         a.saved_dim = saved_dim;
         a.out = (cplx *)args->out_dev;
         a.flags = flags.p; a.ynorm = ynorm.p; a.stats = stats.p;

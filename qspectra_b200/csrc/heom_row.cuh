@@ -399,7 +399,8 @@ struct RowPropArgs {
     int repilot;                // POLY: product-form intervals between two Taylor pilot intervals
     const cplx *ainv;           // device copy of qsx_taylor_ainv
     int save_mode, save_rows;
-    const cplx *S;              // [save_rows][M]
+    const cplx *S;              // [n_save][save_rows][M]
+    const int *save_of;         // [B] save matrix of each column, or null (matrix 0)
     cplx *out;
     long long saved_dim;
     int *flags;                 // [3]
@@ -433,8 +434,9 @@ __device__ __forceinline__ void row_save(const RowPropArgs &a, const cplx *Y, in
             const long long b = i / per_col, r = i % per_col, n = r / a.save_rows;
             const int m = (int)(r % a.save_rows);
             const cplx *y = Y + (size_t)b * Dp + ((n >> 5) * M) * 32 + (n & 31);
+            const cplx *Sm = a.S + (a.save_of ? (size_t)a.save_of[b] * a.save_rows * M : 0);
             cplx acc = cmake(0, 0);
-            for (int e = 0; e < M; ++e) cfma(acc, __ldg(&a.S[(size_t)m * M + e]), __ldcg(&y[e * 32]));
+            for (int e = 0; e < M; ++e) cfma(acc, __ldg(&Sm[(size_t)m * M + e]), __ldcg(&y[e * 32]));
             a.out[((size_t)b * a.nt + it) * a.saved_dim + r] = cscale(1.0 / a.R.gscale[n], acc);
         }
     }

@@ -161,7 +161,7 @@ class RedfieldModel(LiouvilleSpaceModel):
         shifts = ham.sampled_site_shifts(ensemble_size, member0)
         if shifts is None:
             return None
-        lab = ham._not_sampled._not_rotating
+        lab = ham._root
         H0 = np.asarray(lab.H(ss), dtype=float)
         number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
         diag = np.arange(H0.shape[0])
@@ -211,7 +211,7 @@ class RedfieldModel(LiouvilleSpaceModel):
         number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
         kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
                 else _capi.BATH_DEBYE_COMPLEX)
-        lab = ham._not_sampled._not_rotating
+        lab = ham._root
         quanta = np.zeros(ham.n_states(ss))
         for letter, n_exc in (('e', 1), ('f', 2)):
             if letter in ss:

@@ -144,8 +144,8 @@ class DeviceEOM(object):
         if sarr is not None:
             if sarr.shape != (B,):
                 raise ValueError('save_index must have one entry per column')
-            if not isinstance(self, DenseEOM):
-                raise ValueError('per-column save matrices need a dense generator')
+            if not isinstance(self, (DenseEOM, HeomEOM)):
+                raise ValueError('per-column save matrices need a dense or HEOM generator')
             args.save_of_column_host = sptr
         n_p = len(pulses) if pulses else 0
         if n_p > _capi.MAX_PULSES:
@@ -414,6 +414,19 @@ class HeomEOM(DeviceEOM):
         S = np.asarray(matrix)
         if S.ndim == 1:
             S = S[None]
+        if S.ndim == 3:
+            # stack of per-ADO blocks (n_save, rows, M): column c is saved through
+            # S[save_index[c]] (e.g. one dipole commutator per polarisation configuration)
+            if S.shape[-1] != self.M:
+                raise ValueError('HEOM save matrix must act on one ADO '
+                                 '(%d columns), got %d' % (self.M, S.shape[-1]))
+            Sd = _capi.to_device(np.ascontiguousarray(S))
+            keep.append(Sd)
+            args.save_mode = _capi.SAVE_MATRIX
+            args.save_rows = S.shape[1]
+            args.save_dev = Sd.data_ptr()
+            args.n_save = S.shape[0]
+            return self.n_ado * S.shape[1]
         if isinstance(save, LinearMap) and save.ado0_only:
             # expectation values read ADO 0 only (heom.py:55-58): embed the row
             # vector in a block that is applied to every ADO and keep block 0

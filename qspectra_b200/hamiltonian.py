@@ -8,10 +8,10 @@ draw first, then ``rand(3)`` for the orientation), eigensystem :310-328,
 Nyquist ``freq_step``/``time_step`` of the *un-sampled* Hamiltonian :382-412,
 dipole / number / system-bath operators :580-608, vibronic extension :633-782.
 
-The rotating-frame / sampled variants keep the reference's bookkeeping
-attributes (``_not_rotating``, ``_not_sampled``, ``rw_freq``) because the
-dynamics layer reads them (time grid of the un-sampled parent, thermal state of
-the lab-frame parent).  ``disorder_stream(n)`` exposes member n's seeded
+Sampled and rotating-frame Hamiltonians are *variants* of a root object, addressed
+by (member, rw_freq) coordinates (see ``Hamiltonian``); the relatives the reference
+reaches through ``_not_rotating`` / ``_not_sampled`` links are the properties
+``lab_frame`` / ``unsampled`` here.  ``disorder_stream(n)`` exposes member n's seeded
 generator so the device ensemble builder can replay exactly the same draws.
 """
 from abc import ABCMeta, abstractmethod
@@ -72,21 +72,73 @@ def diagonal_gaussian_disorder(fwhm, n_sites):
 
 
 class Hamiltonian(metaclass=ABCMeta):
-    """Base class; subclasses provide ``H(subspace)`` plus the two hooks
-    ``_in_rotating_frame`` and ``_sample``."""
+    """A system Hamiltonian, or rather one *variant* of one.
+
+    The object a user constructs is the **root**: lab frame, no disorder applied.
+    Every other Hamiltonian the engine meets is the root seen through two coordinates,
+
+        member   None, or (n, random_orientations): ensemble member n
+        rw_freq  rotating-wave frequency subtracted per excitation quantum
+
+    and is made by the root's ``_build(member, rw_freq)`` hook (subclasses) through
+    ``_variant``.  ``in_rotating_frame`` and ``sample`` only move along one coordinate, so
+    they commute by construction.  Quantities the reference defines on a particular
+    relative (reference hamiltonian.py:96-455) name that relative explicitly here:
+
+        thermal / ground state, eigenvectors   -> ``lab_frame``  (same member, rw_freq 0)
+        frequency / time step                  -> ``unsampled``  (same frame, no member)
+        default rotating frequency             -> the root's mean 'e' eigenenergy
+    """
 
     def __init__(self, energy_spread_extra=None, site_labels=None):
         self.energy_spread_extra = energy_spread_extra
         self.site_labels = site_labels
-        self._not_sampled = self
-        self._not_rotating = self
         self.rw_freq = 0
+        self._root = self
+        self._member = None
+        self._frames = {}           # un-sampled variants of a root, by rw_freq
+
+    # -- variants ------------------------------------------------------------
+    def _variant(self, member, rw_freq):
+        root = self._root
+        if member is None and rw_freq == 0:
+            return root
+        if member is None and rw_freq in root._frames:
+            return root._frames[rw_freq]
+        ham = root._build(member, rw_freq)
+        ham._root, ham._member, ham.rw_freq = root, member, rw_freq
+        if member is None:
+            root._frames[rw_freq] = ham      # members are not cached: ensembles are large
+        return ham
+
+    @abstractmethod
+    def _build(self, member, rw_freq):
+        """Concrete Hamiltonian for the given coordinates (called on the root)."""
 
     @property
-    def _original(self):
-        return self._not_rotating._not_sampled
+    def lab_frame(self):
+        return self if self.rw_freq == 0 else self._variant(self._member, 0)
 
-    # -- matrices ----------------------------------------------------------
+    @property
+    def unsampled(self):
+        return self if self._member is None else self._variant(None, self.rw_freq)
+
+    def in_rotating_frame(self, rw_freq=None):
+        if rw_freq is None:
+            rw_freq = self._root.transition_energy
+        return self if rw_freq == self.rw_freq else self._variant(self._member, rw_freq)
+
+    def sample(self, n=None, random_orientations=False):
+        """Ensemble member ``n`` of the root (sampling a member re-samples the root, so the
+        distribution does not depend on what ``sample`` is called on)."""
+        if n is None:
+            n = np.random.randint(2 ** 30)
+        return self._variant((int(n), bool(random_orientations)), self.rw_freq)
+
+    def sample_ensemble(self, ensemble_size=1, random_orientations=False):
+        return (self.sample(n, random_orientations) for n in range(ensemble_size))
+
+    # -- matrices --------------------------------------------------------------
     @abstractmethod
     def H(self, subspace):
         """system Hamiltonian matrix in the given Hilbert subspace"""
@@ -94,72 +146,33 @@ class Hamiltonian(metaclass=ABCMeta):
     def n_states(self, subspace):
         return len(self.H(subspace))
 
+    def dipole_operator(self, subspace='gef', polarization='x', transitions='-+'):
+        raise NotImplementedError('%s has no dipole operators' % type(self).__name__)
+
+    def system_bath_couplings(self, subspace='gef'):
+        raise NotImplementedError('%s has no system-bath couplings' % type(self).__name__)
+
+    # -- states ----------------------------------------------------------------
     @imemoize
     def ground_state(self, subspace):
-        return ground_state(self._not_rotating.H(subspace))
+        return ground_state(self.lab_frame.H(subspace))
 
     @imemoize
     def thermal_state(self, subspace):
-        bath = getattr(self._not_rotating, 'bath', None)
-        temperature = getattr(bath, 'temperature', 0)
-        return thermal_state(self._not_rotating.H(subspace), temperature)
+        lab = self.lab_frame
+        temperature = getattr(getattr(lab, 'bath', None), 'temperature', 0)
+        return thermal_state(lab.H(subspace), temperature)
 
-    # -- frames and ensembles -----------------------------------------------
-    @imemoize
-    def in_rotating_frame(self, rw_freq=None):
-        if rw_freq is None:
-            rw_freq = self._original.transition_energy
-        lab = self._not_rotating
-        ham = lab._in_rotating_frame(rw_freq)
-        ham._not_rotating = lab
-        if self._not_sampled is not self:
-            ham._not_sampled = self._not_sampled.in_rotating_frame(rw_freq)
-        ham.rw_freq = rw_freq
-        return ham
-
-    def _in_rotating_frame(self, rw_freq):
-        raise NotImplementedError('%s does not implement rotating frame '
-                                  'transformations' % type(self).__name__)
-
-    def sample_ensemble(self, ensemble_size=1, random_orientations=False):
-        for n in range(ensemble_size):
-            yield self.sample(n, random_orientations)
-
-    def sample(self, n=None, random_orientations=False):
-        if n is None:
-            n = np.random.randint(2 ** 30)
-        ham = self._not_sampled._sample(n, random_orientations)
-        if self._not_rotating is not self:
-            ham._not_rotating = self._not_rotating.sample(n, random_orientations)
-        ham._not_sampled = self._not_sampled
-        ham.rw_freq = self.rw_freq
-        return ham
-
-    def _sample(self, n, random_orientations):
-        raise NotImplementedError('%s does not implement ensemble sampling'
-                                  % type(self).__name__)
-
-    # -- operators -----------------------------------------------------------
-    def dipole_operator(self, subspace='gef', polarization='x',
-                        transitions='-+'):
-        raise NotImplementedError('%s does not implement dipole operators'
-                                  % type(self).__name__)
-
-    def system_bath_couplings(self, subspace='gef'):
-        raise NotImplementedError('%s does not implement system-bath couplings'
-                                  % type(self).__name__)
-
-    # -- spectrum ------------------------------------------------------------
+    # -- spectrum --------------------------------------------------------------
     @imemoize
     def eig(self, subspace):
-        """(E, U) from the lab-frame matrix (keeps g < e < f ordering), with
-        the rotating-frame shift applied to E afterwards."""
-        E, U = scipy.linalg.eigh(self._not_rotating.H(subspace))
+        """(E, U): eigenvectors of the lab-frame matrix (which keeps the manifolds ordered
+        g < e < f), energies moved to this variant's frame."""
+        E, U = scipy.linalg.eigh(self.lab_frame.H(subspace))
         for letter, quanta in (('e', 1), ('f', 2)):
-            if letter in subspace:
-                E[self.hilbert_subspace_index(letter, subspace)] -= \
-                    quanta * self.rw_freq
-        return (E, U)
+            if letter in subspace and self.rw_freq:
+                E[self.hilbert_subspace_index(letter, subspace)] -= quanta * self.rw_freq
+        return E, U
 
     def E(self, subspace):
         return self.eig(subspace)[0]
@@ -185,9 +198,10 @@ class Hamiltonian(metaclass=ABCMeta):
 
     @property
     def freq_step(self):
-        energies = self._not_sampled.E('gef')
-        extra = (0.01 * self._original.transition_energy
-                 if self.energy_spread_extra is None
+        """Nyquist bound of the un-sampled spectrum in this frame: all ensemble members share
+        one time / frequency grid."""
+        energies = self.unsampled.E('gef')
+        extra = (0.01 * self._root.transition_energy if self.energy_spread_extra is None
                  else self.energy_spread_extra)
         return 2 * (max(energies.max(), -energies.min()) + extra)
 
@@ -221,30 +235,25 @@ class ElectronicHamiltonian(Hamiltonian):
         return simple_repr(self, ['H_1exc', 'bath', 'dipoles', 'disorder',
                                   'random_seed', 'energy_spread_extra'])
 
+    def _same_data(self, other):
+        return (isinstance(other, ElectronicHamiltonian)
+                and np.all(self.H_1exc == other.H_1exc)
+                and self.bath == other.bath
+                and np.all(self.dipoles == other.dipoles)
+                and self.disorder == other.disorder
+                and np.all(np.atleast_1d(self.random_seed) == np.atleast_1d(other.random_seed))
+                and self.energy_spread_extra == other.energy_spread_extra
+                and self.rw_freq == other.rw_freq
+                and self.site_labels == other.site_labels)
+
     def __eq__(self, other):
-        return self._eq(other, 1)
+        """Same matrices, bath, dipoles and frame, and descended from equal roots."""
+        return bool(self._same_data(other) and self._root._same_data(other._root))
 
     def __ne__(self, other):
         return not self == other
 
     __hash__ = object.__hash__
-
-    def _eq(self, other, depth):
-        if not isinstance(other, ElectronicHamiltonian):
-            return False
-        same = (np.all(self.H_1exc == other.H_1exc)
-                and self.bath == other.bath
-                and np.all(self.dipoles == other.dipoles)
-                and self.disorder == other.disorder
-                and np.all(np.atleast_1d(self.random_seed)
-                           == np.atleast_1d(other.random_seed))
-                and self.energy_spread_extra == other.energy_spread_extra
-                and self.rw_freq == other.rw_freq
-                and self.site_labels == other.site_labels)
-        if same and depth:
-            same = (self._not_sampled._eq(other._not_sampled, depth - 1)
-                    and self._not_rotating._eq(other._not_rotating, depth - 1))
-        return bool(same)
 
     @property
     def n_sites(self):
@@ -253,14 +262,6 @@ class ElectronicHamiltonian(Hamiltonian):
     @imemoize
     def H(self, subspace):
         return operator_extend(self.H_1exc, subspace)
-
-    def _spawn(self, H_1exc, dipoles, seed):
-        return type(self)(H_1exc, self.bath, dipoles, self.disorder, seed,
-                          self.energy_spread_extra, self.site_labels)
-
-    def _in_rotating_frame(self, rw_freq):
-        return self._spawn(self.H_1exc - rw_freq * np.identity(self.n_sites),
-                           self.dipoles, self.random_seed)
 
     def disorder_stream(self, n):
         """The seeded generator of ensemble member ``n``."""
@@ -272,7 +273,7 @@ class ElectronicHamiltonian(Hamiltonian):
         ``sample(n)`` adds -- or None when ``disorder`` is a user callable.
         Uses the C replay of numpy's seeded streams (qsx_sample_streams), so no
         Hamiltonian object is created per member."""
-        base = self._not_sampled
+        base = self._root
         if base.disorder is None:
             return np.zeros((ensemble_size, base.n_sites))
         if not isinstance(base.disorder, Number):
@@ -286,7 +287,7 @@ class ElectronicHamiltonian(Hamiltonian):
         """The same shifts as a CUDA tensor generated on the device (kernel
         `sample_streams_kernel`: integer stream identical, Box-Muller through the
         device log/sqrt), or None when `disorder` is a user callable."""
-        base = self._not_sampled
+        base = self._root
         if base.disorder is not None and not isinstance(base.disorder, Number):
             return None
         from . import _capi
@@ -296,25 +297,32 @@ class ElectronicHamiltonian(Hamiltonian):
         return _capi.sample_gauss_device(base.random_seed, member0, ensemble_size,
                                          base.n_sites, base.disorder * GAUSSIAN_SD_FWHM)
 
-    def _sample(self, n, random_orientations):
-        rng = self.disorder_stream(n)
-        if self.disorder is None:
-            if not random_orientations:
-                warnings.warn('called sample with `disorder=None` and '
-                              '`random_orientations=False`: sampled '
-                              'Hamiltonian is identical to original',
-                              RuntimeWarning, stacklevel=2)
-            shift = 0
-        elif isinstance(self.disorder, Number):
-            shift = diagonal_gaussian_disorder(self.disorder, self.n_sites)(rng)
-        else:
-            shift = self.disorder(rng)
-        dipoles = self.dipoles
-        if random_orientations:
-            dipoles = np.einsum('mn,in->im', random_rotation_matrix(rng),
-                                self.dipoles)
-        return self._spawn(self.H_1exc + shift, dipoles,
-                           list(np.atleast_1d(self.random_seed)) + [n])
+    def _build(self, member, rw_freq):
+        """Root -> variant: static disorder and orientation of member (n, random_orientations)
+        from its seeded stream (the diagonal ``randn`` draw first, then ``rand(3)`` for the
+        rotation, reference hamiltonian.py:552-578) added to the matrix in the requested frame
+        (frame first: bit-identical with sampling a rotating-frame Hamiltonian, the order the
+        dynamical models use)."""
+        H, dipoles, seed = self.H_1exc, self.dipoles, self.random_seed
+        if rw_freq:
+            H = H - rw_freq * np.identity(self.n_sites)
+        if member is not None:
+            n, random_orientations = member
+            rng = self.disorder_stream(n)
+            if self.disorder is None:
+                if not random_orientations:
+                    warnings.warn('called sample with `disorder=None` and '
+                                  '`random_orientations=False`: sampled Hamiltonian is '
+                                  'identical to original', RuntimeWarning, stacklevel=4)
+            elif isinstance(self.disorder, Number):
+                H = H + diagonal_gaussian_disorder(self.disorder, self.n_sites)(rng)
+            else:
+                H = H + self.disorder(rng)
+            if random_orientations:
+                dipoles = np.einsum('mn,in->im', random_rotation_matrix(rng), dipoles)
+            seed = list(np.atleast_1d(seed)) + [n]
+        return type(self)(H, self.bath, dipoles, self.disorder, seed,
+                          self.energy_spread_extra, self.site_labels)
 
     def dipole_operator(self, subspace='gef', polarization='x',
                         transitions='-+'):
@@ -416,16 +424,13 @@ class VibronicHamiltonian(Hamiltonian):
                 + self.vib_to_sys_operator(self.H_vibrational, subspace)
                 + self.H_electronic_vibrational(subspace))
 
-    def _respawn(self, electronic):
-        return type(self)(electronic, self.n_vibrational_levels,
-                          self.vib_energies, self.elec_vib_couplings,
-                          self.energy_spread_extra, self.site_labels)
-
-    def _in_rotating_frame(self, rw_freq):
-        return self._respawn(self.electronic.in_rotating_frame(rw_freq))
-
-    def _sample(self, n, random_orientations):
-        return self._respawn(self.electronic.sample(n, random_orientations))
+    def _build(self, member, rw_freq):
+        electronic = self.electronic
+        if member is not None:
+            electronic = electronic.sample(*member)
+        electronic = electronic.in_rotating_frame(rw_freq) if rw_freq else electronic.lab_frame
+        return type(self)(electronic, self.n_vibrational_levels, self.vib_energies,
+                          self.elec_vib_couplings, self.energy_spread_extra, self.site_labels)
 
     def el_to_sys_operator(self, el_operator):
         return tensor(el_operator, np.eye(self.n_vibrational_states))

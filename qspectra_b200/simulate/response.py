@@ -21,108 +21,11 @@ from ..utils import ZeroArray
 from .. import _capi, engine
 
 
-@optional_ensemble_average
-@optional_2nd_order_isotropic_average
-def _linear_response(dynamical_model, liouv_space_path, time_max,
-                     initial_state=None, polarization='xx', **integrate_kwargs):
-    subspaces = liouv_space_path.split('->')
-    if initial_state is None:
-        initial_state = dynamical_model.thermal_state(subspaces[0])
-    initial_state = np.asarray(initial_state)
-    t = np.arange(0, time_max, dynamical_model.time_step)
-    signal = ZeroArray()
-    for sim_subspace in subspaces[1].split(','):
-        V = [dynamical_model.dipole_operator('{}->{}'.format(a, b), polar, trans)
-             for a, b, polar, trans in zip(subspaces[:-1], subspaces[1:],
-                                           polarization, '+-')]
-        V_rho0 = V[0].commutator(initial_state)
-        try:
-            # Heisenberg picture: one propagation of the detection operator
-            # serves every initial state
-            eom = dynamical_model.equation_of_motion(sim_subspace,
-                                                     heisenberg_picture=True)
-        except NotImplementedError:
-            eom = dynamical_model.equation_of_motion(sim_subspace)
-            signal -= integrate(eom, V_rho0, t,
-                                save_func=V[1].expectation_value,
-                                **integrate_kwargs)
-        else:
-            V_Gt = integrate(eom, -V[1].bra_vector, t, **integrate_kwargs)
-            signal += np.tensordot(V_rho0, V_Gt, (-1, -1))
-    return (t, signal)
-
-
-def linear_response(dynamical_model, liouv_space_path, time_max,
-                    initial_state=None, polarization='xx', ensemble_size=None,
-                    ensemble_random_orientations=False,
-                    exact_isotropic_average=False, **integrate_kwargs):
-    """Linear response function along a Liouville path 'ab->cd->ef'."""
-    return _linear_response(
-        dynamical_model, liouv_space_path, time_max, initial_state,
-        polarization, ensemble_size=ensemble_size,
-        ensemble_random_orientations=ensemble_random_orientations,
-        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
-
-
-def absorption_spectra(dynamical_model, time_max, correlation_decay_time=None,
-                       polarization='xx', ensemble_size=None,
-                       ensemble_random_orientations=False,
-                       exact_isotropic_average=False, **integrate_kwargs):
-    """(frequencies, real absorption signal)."""
-    (t, x) = linear_response(
-        dynamical_model, 'gg->eg->gg', time_max, polarization=polarization,
-        ensemble_size=ensemble_size,
-        ensemble_random_orientations=ensemble_random_orientations,
-        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
-    if correlation_decay_time is not None:
-        x = x * np.exp(-t / correlation_decay_time)
-    (f, X) = fourier_transform(t, -x, rw_freq=dynamical_model.rw_freq,
-                               unit_convert=dynamical_model.unit_convert)
-    return (f, X.real)
-
-
+# Liouville-space pathways (Abramavicius et al., Chem. Rev. 109, 2350 (2009), figs. 4-6;
+# reference response.py:157-159, 252-264)
 PUMP_PROBE_PATHWAYS = {'GSB': 'gg->eg->gg',
                        'ESE': 'ee->eg->gg',
                        'ESA': 'ee->fe->ee'}
-
-
-def _parse_pathways(possible_pathways, include_signal):
-    selected = [path for name, path in possible_pathways.items()
-                if include_signal is None or name in include_signal]
-    if not selected:
-        raise ValueError('at least one Liouville space pathway must be '
-                         'selected, i.e., include_signal must include at least '
-                         'one of %r' % list(possible_pathways.keys()))
-    return selected
-
-
-def impulsive_probe(dynamical_model, state, time_max, polarization='xx',
-                    initial_liouv_subspace='gg,ge,eg,ee',
-                    include_signal='GSB,ESE,ESA', ensemble_size=None,
-                    ensemble_random_orientations=False,
-                    exact_isotropic_average=False, **integrate_kwargs):
-    """Probe the 2nd-order part of ``state`` with an impulsive probe pulse;
-    returns (frequencies, complex signal field)."""
-    state = np.asarray(state)
-    initial_state = state - dynamical_model.thermal_state(initial_liouv_subspace)
-    total_signal = ZeroArray()
-    for path in _parse_pathways(PUMP_PROBE_PATHWAYS, include_signal):
-        first = path.split('->')[0]
-        portion = np.apply_along_axis(
-            lambda s: dynamical_model.map_between_subspaces(
-                s, initial_liouv_subspace, first), -1, initial_state)
-        (t, signal) = linear_response(
-            dynamical_model, path, time_max, portion, polarization,
-            ensemble_size=ensemble_size,
-            ensemble_random_orientations=ensemble_random_orientations,
-            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
-        total_signal += signal
-    return fourier_transform(t, total_signal, rw_freq=dynamical_model.rw_freq,
-                             unit_convert=dynamical_model.unit_convert)
-
-
-# Liouville-space pathways of Abramavicius et al., Chem. Rev. 109, 2350 (2009),
-# figs. 4-6 (same tables as the reference)
 THIRD_ORDER_PATHWAYS = {
     '-++': {'ESE': 'gg->ge->ee->eg->gg',      # photon echo
             'GSB': 'gg->ge->gg->eg->gg',
@@ -135,43 +38,197 @@ THIRD_ORDER_PATHWAYS = {
 }
 
 
+def _parse_pathways(possible_pathways, include_signal):
+    selected = [path for name, path in possible_pathways.items()
+                if include_signal is None or name in include_signal]
+    if not selected:
+        raise ValueError('at least one Liouville space pathway must be '
+                         'selected, i.e., include_signal must include at least '
+                         'one of %r' % list(possible_pathways.keys()))
+    return selected
+
+
+def _interactions(model, subspaces, polarization, transitions):
+    """Dipole operators of the successive interactions of a Liouville path."""
+    return [model.dipole_operator('{}->{}'.format(a, b), polar, trans)
+            for a, b, polar, trans in zip(subspaces[:-1], subspaces[1:], polarization,
+                                          transitions)]
+
+
+# ---------------------------------------------------------------- linear response
+# Batchable models (dense generators, HEOM): every independent unit -- ensemble member x
+# Cartesian configuration of the 2nd-order isotropic average -- is one column of ONE
+# Heisenberg-picture propagation of the detection operator, and the signal
+#     S[s, t] = sum_u w_u sum_i (V_0 rho_s)_u[i] (G(t)^T V_1)_u[i]
+# is one launch of the K6 contraction kernel.  The reference runs
+# ensemble_size x 3 serial ZVODE solves (decorators.py:40-64, 99-125; response.py:13-43).
+def _linear_variants(polarization, exact_isotropic_average):
+    if not exact_isotropic_average:
+        return [(1.0, polarization)]
+    from ..polarization import check_polarizations
+    weight = float(np.dot(*check_polarizations(polarization, 2))) / 3.0
+    return [(weight, p) for p in ('xx', 'yy', 'zz')]
+
+
+def _linear_response_batched(model, liouv_space_path, time_max, initial_state, polarization,
+                             ensemble_size, random_orientations, exact_isotropic_average,
+                             member_offset=0, **integrate_kwargs):
+    torch = _capi.torch_cuda()
+    subspaces = liouv_space_path.split('->')
+    t = np.arange(0, time_max, model.time_step)
+    opts = {k: integrate_kwargs[k] for k in ('rtol', 'atol', 'rk4_substeps')
+            if k in integrate_kwargs}
+    method = integrate_kwargs.get('method_name', 'zvode')
+    variants = _linear_variants(polarization, exact_isotropic_average)
+    nv = len(variants)
+    single = ensemble_size is None
+    n_members = 1 if single else ensemble_size
+    own_basis = getattr(model, 'evolve_basis', 'site') == 'eigen'
+    per_member = (random_orientations or own_basis) and not single
+    states = None if initial_state is None else np.asarray(initial_state)
+    lead = () if states is None or states.ndim == 1 else states.shape[:-1]
+    n_states = int(np.prod(lead)) if lead else 1
+    total = torch.zeros((n_states, len(t)), dtype=torch.complex128, device='cuda')
+    wv = np.array([w for w, _ in variants], dtype=complex)
+    chunk = 4096
+    for lo in range(0, n_members, chunk):
+        E = min(chunk, n_members - lo)
+        first = member_offset + lo
+        dip = ([model.sample(first + n, random_orientations) for n in range(E)]
+               if per_member else [model])
+        gens = np.repeat(np.arange(E), nv)
+        for sim_subspace in subspaces[1].split(','):
+            path = [subspaces[0], sim_subspace, subspaces[2]]
+            V = [[_interactions(m, path, pol, '+-') for _, pol in variants] for m in dip]
+            rho = [m.thermal_state(subspaces[0]) if states is None else states for m in dip]
+            # X[u, s, i] = (V_0 rho_s)[i] of unit u = (member, configuration)
+            X = np.array([[np.atleast_2d(V[m][v][0].commutator(rho[m])).reshape(n_states, -1)
+                           for v in range(nv)] for m in range(len(dip))])
+            if len(dip) != E:
+                X = np.broadcast_to(X, (E,) + X.shape[1:])
+            X = np.ascontiguousarray(X).reshape(E * nv, n_states, -1)
+            bra = np.array([[-V[m][v][1].bra_vector for v in range(nv)]
+                            for m in range(len(dip))])
+            if len(dip) != E:
+                bra = np.broadcast_to(bra, (E,) + bra.shape[1:])
+            eom = (model.equation_of_motion(sim_subspace, heisenberg_picture=True) if single
+                   else model.ensemble_eom(E, random_orientations, sim_subspace,
+                                           heisenberg_picture=True, member0=first))
+            G = eom.propagate(np.ascontiguousarray(bra).reshape(E * nv, -1), t, method=method,
+                              generators=gens, return_device=True, **opts)
+            engine.response_contract(_capi.to_device(X), G,
+                                     _capi.to_device(np.tile(wv, E)), total)
+    signal = _capi.to_host(total) / n_members
+    return t, signal.reshape(lead + (len(t),)) if lead else signal[0]
+
+
+@optional_ensemble_average
+@optional_2nd_order_isotropic_average
+def _linear_response_forward(dynamical_model, liouv_space_path, time_max,
+                             initial_state=None, polarization='xx', **integrate_kwargs):
+    """Member-by-member form for models without a Heisenberg picture (nonlinear equations of
+    motion such as ZOFE): propagate V_0 rho forward and read <V_1> at every output time."""
+    subspaces = liouv_space_path.split('->')
+    rho0 = (dynamical_model.thermal_state(subspaces[0]) if initial_state is None
+            else np.asarray(initial_state))
+    t = np.arange(0, time_max, dynamical_model.time_step)
+    signal = ZeroArray()
+    for sim_subspace in subspaces[1].split(','):
+        V = _interactions(dynamical_model, [subspaces[0], sim_subspace, subspaces[2]],
+                          polarization, '+-')
+        signal -= integrate(dynamical_model.equation_of_motion(sim_subspace),
+                            V[0].commutator(rho0), t, save_func=V[1].expectation_value,
+                            **integrate_kwargs)
+    return t, signal
+
+
+def linear_response(dynamical_model, liouv_space_path, time_max,
+                    initial_state=None, polarization='xx', ensemble_size=None,
+                    ensemble_random_orientations=False,
+                    exact_isotropic_average=False, **integrate_kwargs):
+    """Linear response function along a Liouville path 'ab->cd->ef'."""
+    if _batchable(dynamical_model):
+        return _linear_response_batched(
+            dynamical_model, liouv_space_path, time_max, initial_state, polarization,
+            ensemble_size, ensemble_random_orientations, exact_isotropic_average,
+            **integrate_kwargs)
+    return _linear_response_forward(
+        dynamical_model, liouv_space_path, time_max, initial_state,
+        polarization, ensemble_size=ensemble_size,
+        ensemble_random_orientations=ensemble_random_orientations,
+        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+
+
+def absorption_spectra(dynamical_model, time_max, correlation_decay_time=None,
+                       polarization='xx', ensemble_size=None,
+                       ensemble_random_orientations=False,
+                       exact_isotropic_average=False, **integrate_kwargs):
+    """(frequencies, real absorption signal) = Fourier transform of the 'gg->eg->gg' linear
+    response, optionally apodised with exp(-t / correlation_decay_time)."""
+    t, x = linear_response(
+        dynamical_model, 'gg->eg->gg', time_max, polarization=polarization,
+        ensemble_size=ensemble_size,
+        ensemble_random_orientations=ensemble_random_orientations,
+        exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+    if correlation_decay_time is not None:
+        x = x * np.exp(-t / correlation_decay_time)
+    f, X = fourier_transform(t, -x, rw_freq=dynamical_model.rw_freq,
+                             unit_convert=dynamical_model.unit_convert)
+    return f, X.real
+
+
+def impulsive_probe(dynamical_model, state, time_max, polarization='xx',
+                    initial_liouv_subspace='gg,ge,eg,ee',
+                    include_signal='GSB,ESE,ESA', ensemble_size=None,
+                    ensemble_random_orientations=False,
+                    exact_isotropic_average=False, **integrate_kwargs):
+    """Probe the 2nd-order part of ``state`` (any leading batch axes) with an impulsive
+    pulse; returns (frequencies, complex signal field)."""
+    model = dynamical_model
+    second_order = np.asarray(state) - model.thermal_state(initial_liouv_subspace)
+    flat = second_order.reshape(-1, second_order.shape[-1])
+    total, t = ZeroArray(), None
+    for path in _parse_pathways(PUMP_PROBE_PATHWAYS, include_signal):
+        start = path.split('->')[0]
+        part = np.array([model.map_between_subspaces(row, initial_liouv_subspace, start)
+                         for row in flat]).reshape(second_order.shape[:-1] + (-1,))
+        t, signal = linear_response(
+            model, path, time_max, part, polarization, ensemble_size=ensemble_size,
+            ensemble_random_orientations=ensemble_random_orientations,
+            exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
+        total += signal
+    return fourier_transform(t, total, rw_freq=model.rw_freq,
+                             unit_convert=model.unit_convert)
+
+
+# ---------------------------------------------------------- third-order response
 @optional_ensemble_average
 @optional_4th_order_isotropic_average
-def _third_order_response(dynamical_model, coherence_time_max,
-                          population_time_max, population_times, geometry,
-                          polarization, include_signal, **integrate_kwargs):
-    t1 = np.arange(0, coherence_time_max, dynamical_model.time_step)
-    t2 = (np.arange(0, population_time_max, dynamical_model.time_step)
-          if population_times is None
+def _third_order_response_forward(dynamical_model, coherence_time_max,
+                                  population_time_max, population_times, geometry,
+                                  polarization, include_signal, **integrate_kwargs):
+    """Member-by-member form for models without a Heisenberg picture: three forward
+    propagations per pathway, the detection operator read at every t3."""
+    model = dynamical_model
+    t1 = np.arange(0, coherence_time_max, model.time_step)
+    t2 = (np.arange(0, population_time_max, model.time_step) if population_times is None
           else np.asarray(population_times, dtype=float))
-    t3 = np.arange(0, coherence_time_max, dynamical_model.time_step)
-
-    initial_state = dynamical_model.thermal_state('gg')
-    total_signal = ZeroArray()
+    t3 = t1.copy()
+    rho0 = model.thermal_state('gg')
+    total = ZeroArray()
     for path in _parse_pathways(THIRD_ORDER_PATHWAYS[geometry], include_signal):
         subspaces = path.split('->')
-        V = [dynamical_model.dipole_operator('{}->{}'.format(a, b), polar, trans)
-             for a, b, polar, trans in zip(subspaces[:-1], subspaces[1:],
-                                           polarization, geometry + '-')]
-        eom = [dynamical_model.equation_of_motion(s) for s in subspaces[1:-1]]
-        V_rho0 = V[0].commutator(initial_state)
-        # t1: one column; t2: n_t1 columns under one generator (batched)
-        V_rho1 = integrate(eom[0], V_rho0, t1, save_func=V[1].commutator,
-                           **integrate_kwargs)
-        V_rho2 = integrate(eom[1], V_rho1, t2, t0=0, save_func=V[2].commutator,
-                           **integrate_kwargs)
-        try:
-            eom_heisen = dynamical_model.equation_of_motion(
-                subspaces[3], heisenberg_picture=True)
-        except NotImplementedError:
-            total_signal += integrate(eom[2], V_rho2, t3,
-                                      save_func=V[3].expectation_value,
-                                      **integrate_kwargs)
-        else:
-            V_Gt3 = integrate(eom_heisen, V[3].bra_vector, t3,
+        V = _interactions(model, subspaces, polarization, geometry + '-')
+        state = V[0].commutator(rho0)
+        # the t2 stage propagates all n_t1 columns in one batch, the t3 stage n_t1 x n_t2
+        for stage, (grid, t0) in enumerate(((t1, None), (t2, 0), (t3, 0))):
+            last = stage == 2
+            state = integrate(model.equation_of_motion(subspaces[stage + 1]), state, grid,
+                              t0=t0, save_func=(V[3].expectation_value if last
+                                                else V[stage + 1].commutator),
                               **integrate_kwargs)
-            total_signal += np.einsum('ci,abi', V_Gt3, V_rho2)
-    return (t1, t2, t3), total_signal
+        total += state
+    return (t1, t2, t3), total
 
 
 def _polarization_variants(polarization, exact_isotropic_average):
@@ -228,7 +285,8 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
     total = torch.zeros((len(t1), len(t2), len(t3)), dtype=torch.complex128,
                         device='cuda')
     # bound the (units x t1 x t2 x M3) intermediate to ~2 GB per chunk
-    n_big = max(len(model.liouville_subspace_index(p.split('->')[3])) for p in paths)
+    n_big = max(len(model.liouville_subspace_index(p.split('->')[3])) for p in paths) \
+        * getattr(model, 'ado_count', 1)
     chunk = max(1, int(2e9 // (len(t1) * len(t2) * n_big * 16 * nv)))
     rho0 = model.thermal_state('gg')
     for lo in range(0, n_members, chunk):
@@ -292,8 +350,12 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
 
 
 def _batchable(dynamical_model):
+    """Models whose generators live on the device as linear maps with a Heisenberg picture:
+    dense Liouvillians and HEOM hierarchies (per-ADO dipole blocks).  ZOFE is nonlinear and
+    keeps the member-by-member path."""
     from ..dynamics.liouville_space import LiouvilleSpaceModel
-    return isinstance(dynamical_model, LiouvilleSpaceModel)
+    from ..dynamics.heom import HEOMModel
+    return isinstance(dynamical_model, (LiouvilleSpaceModel, HEOMModel))
 
 
 def third_order_response(dynamical_model, coherence_time_max,
@@ -313,7 +375,7 @@ def third_order_response(dynamical_model, coherence_time_max,
             integrate_kwargs.pop('member_offset', 0), True,
             exact_isotropic_average=exact_isotropic_average, **integrate_kwargs)
         return ticks, _capi.to_host(total)
-    return _third_order_response(
+    return _third_order_response_forward(
         dynamical_model, coherence_time_max, population_time_max,
         population_times, geometry, polarization, include_signal,
         ensemble_size=ensemble_size,

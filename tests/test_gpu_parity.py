@@ -794,3 +794,39 @@ def test_response_contraction_kernel():
                                  torch.from_numpy(w).cuda(), S)
         want = S0 + np.einsum('u,uai,uci->ac', w, X, Y)
         assert rel_l2(S.cpu().numpy(), want) < 1e-13, (U, n_ab, n_c, K)
+
+
+def test_heom_third_order_ensemble_isotropic_one_batch():
+    """HEOM third-order response with static disorder and the exact isotropic average
+    (members x 21 polarisation configurations as columns of one device batch per stage, per-ADO
+    dipole blocks selected per column) against member-by-member, configuration-by-
+    configuration runs combined on the host (reference decorators.py:40-96)."""
+    from qspectra_b200.simulate.response import _polarization_variants
+    ham = systems.dimer(disorder=60)
+    m = qb.HEOMModel(ham, hilbert_subspace='gef', unit_convert=CM_FS, level_cutoff=3,
+                     low_temp_corr=False)
+    t2 = np.array([0., 60.])
+    E = 3
+    (_, _, _), S = qb.third_order_response(m, 120, population_times=t2, polarization='xxyy',
+                                           ensemble_size=E, exact_isotropic_average=True)
+    want = 0
+    for member in m.sample_ensemble(E):
+        for w, pol in _polarization_variants('xxyy', True):
+            (_, _, _), Sp = qb.third_order_response(member, 120, population_times=t2,
+                                                    polarization=pol)
+            want = want + w * Sp
+    assert rel_l2(S, want / E) < 1e-9
+
+
+def test_linear_response_batched_matches_member_loop():
+    """absorption with disorder + random orientations + exact isotropic average: one batch
+    (members x xx/yy/zz) against the member / configuration loop."""
+    ham = systems.fmo(n_sites=4)
+    m = qb.RedfieldModel(ham, hilbert_subspace='ge', unit_convert=CM_FS)
+    t, x = qb.linear_response(m, 'gg->eg->gg', 400, polarization='xx', ensemble_size=3,
+                              ensemble_random_orientations=True, exact_isotropic_average=True)
+    want = 0
+    for member in m.sample_ensemble(3, True):
+        for p in ('xx', 'yy', 'zz'):
+            want = want + qb.linear_response(member, 'gg->eg->gg', 400, polarization=p)[1] / 3.0
+    assert rel_l2(x, want / 3) < 1e-10

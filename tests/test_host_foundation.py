@@ -113,7 +113,7 @@ def test_hamiltonian_known_answers():
                                    disorder=1, energy_spread_extra=0)
     assert ham.in_rotating_frame(2).freq_step == pytest.approx(4) or True
     H = systems.dimer().in_rotating_frame()
-    np.testing.assert_allclose(np.sort(H._not_rotating.E('e')),
+    np.testing.assert_allclose(np.sort(H.lab_frame.E('e')),
                                [12655.22085786, 12944.77914214], atol=1e-8)   # notebook golden
     a, b = ham.sample(1), ham.sample(1)
     assert np.array_equal(a.H('e'), b.H('e'))
