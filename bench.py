@@ -441,9 +441,67 @@ def heom_leg(torch, qb, systems, engine, with_cpu):
         'kernel_ms': best['kernel_ms'], 'setup_s': build_s,
         'roofline': _heom_roofline(rhs_per_s, eom.dim, best['rhs'], 'heom_depth4_ens512_per_rhs')}
     del eom, model
+    # BASELINE configs[4], second half: vibronic dimer with explicit modes (2 sites x 2 modes x 2
+    # levels: 8 'e' states, M = 64, generic tile: any rectangular block, table-driven links)
+    model = qb.HEOMModel(systems.jonas_dimer(), hilbert_subspace='e', unit_convert=qb.CM_FS,
+                         level_cutoff=10, K=1)
+    t0 = time.perf_counter()
+    eom = model.equation_of_motion('ee')
+    build_s = time.perf_counter() - t0
+    psi = np.zeros(eom.M, dtype=complex)
+    psi[0] = 1.0
+    y0_dev = torch.from_numpy(model._pad(psi)).cuda().reshape(1, -1)
+    t = model.time_step * np.arange(21)
+    best = None
+    for _ in range(3):
+        eom.propagate(y0_dev, t, save=('ado0',), return_device=True)
+        if best is None or eom.last['kernel_ms'] < best['kernel_ms']:
+            best = dict(eom.last)
+    rhs_per_s = best['rhs'] / (best['kernel_ms'] * 1e-3)
+    out['vibronic_dimer'] = {
+        'workload': 'vibronic (Jonas) dimer HEOM, 2 explicit modes x 2 levels: 8 states in e, '
+                    'M = %d, K=1 level_cutoff=10: %d ADOs, D=%d, 20 output intervals'
+                    % (eom.M, eom.n_ado, eom.dim),
+        'integrator': best['method'], 'rhs_per_s': rhs_per_s,
+        'state_steps_per_s': best['steps'] / (best['kernel_ms'] * 1e-3),
+        'rhs_per_state_step': best['rhs'] / max(1, best['steps']),
+        'kernel_ms': best['kernel_ms'], 'setup_s': build_s,
+        'roofline': _heom_roofline(rhs_per_s, eom.dim, best['rhs'], 'heom_vibronic_per_rhs')}
+    del eom, model
     if with_cpu:
         out['cpu_baseline'] = heom_cpu_baseline()
     return out
+
+
+def zofe_leg(torch, qb, systems, fp64_peak):
+    """K3: ZOFE master equation, FMO 'e' with the 16-pseudomode bath, a 592-member disorder
+    ensemble (one CTA per trajectory, four per SM): RHS applications/s against the FP64 ceiling."""
+    E = 592
+    model = qb.ZOFEModel(systems.fmo(bath='pseudomode'), hilbert_subspace='e',
+                         unit_convert=qb.CM_FS)
+    eom = model.ensemble_eom(E, False, 'ee')
+    y0 = model.density_matrix_to_state_vector(np.diag(np.eye(7)[0]).astype(complex), 'ee')
+    y0_dev = torch.from_numpy(y0).cuda().reshape(1, -1).expand(E, -1).contiguous()
+    t = model.time_step * np.arange(21)
+    best = None
+    for _ in range(3):
+        eom.propagate(y0_dev, t, save=('ado0',), generators=np.arange(E), return_device=True)
+        if best is None or eom.last['kernel_ms'] < best['kernel_ms']:
+            best = dict(eom.last)
+    n, P, S = 7, 16, 7
+    flops = 8.0 * n ** 3 * (2 * P * S + 5 * S + 2)          # SURVEY 8d
+    rhs_per_s = best['rhs'] / (best['kernel_ms'] * 1e-3)
+    tf = rhs_per_s * flops / 1e12
+    return {'workload': 'ZOFE FMO e (7 states, 16 pseudomodes x 7 sites), %d disorder members, '
+                        '20 output intervals, DOPRI5 rtol=1e-10' % E,
+            'integrator': best['method'], 'rhs_per_s': rhs_per_s,
+            'state_steps_per_s': best['steps'] / (best['kernel_ms'] * 1e-3),
+            'grid_steps_per_s': E * 20 / (best['kernel_ms'] * 1e-3),
+            'kernel_ms': best['kernel_ms'],
+            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                         'frac': tf / fp64_peak, 'traffic': None,
+                         'algorithmic_flops_per_rhs': flops,
+                         'peak_source': 'cuBLAS FP64 GEMM measured in this run'}}
 
 
 def _transfer():
@@ -737,6 +795,10 @@ def run_ours(args):
         line['scaling_extra'] = extra
     if world == 1 and not args.no_heom:
         line['heom'] = heom_leg(torch, qb, systems, engine, not args.no_cpu)
+        try:
+            line['zofe'] = zofe_leg(torch, qb, systems, fp64_peak)
+        except Exception as exc:
+            line['zofe'] = {'error': repr(exc)}
     if world == 1 and not args.no_cpu:
         arm = CpuArm()
         cores = arm.workers

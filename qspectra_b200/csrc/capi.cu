@@ -195,6 +195,9 @@ extern "C" int qsx_ado_enumerate(int32_t bins, int32_t level_cutoff, int64_t *ad
 }
 
 // ------------------------------------------------------------ K6: member sum
+// Deterministic two-pass sum: pass 1 writes the partial sum of each member block, pass 2 adds the
+// partials of an element in block order (no floating-point atomics: ensemble means are
+// bit-reproducible from run to run, like the seed-replayed members themselves).
 __global__ void reduce_members_kernel(const cplx *__restrict__ in, int n_members, long long n,
                                       int members_per_block, double scale, cplx *__restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,24 +210,43 @@ __global__ void reduce_members_kernel(const cplx *__restrict__ in, int n_members
         sr += v.x;
         si += v.y;
     }
-    atomicAdd(&out[i].x, scale * sr);
-    atomicAdd(&out[i].y, scale * si);
+    out[(size_t)blockIdx.y * n + i] = cmake(scale * sr, scale * si);
+}
+__global__ void reduce_partials_kernel(const cplx *__restrict__ part, int n_part, long long n,
+                                       cplx *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sr = 0.0, si = 0.0;
+    for (int p = 0; p < n_part; ++p) {
+        cplx v = part[(size_t)p * n + i];
+        sr += v.x;
+        si += v.y;
+    }
+    out[i] = cmake(sr, si);
 }
 
 extern "C" int qsx_reduce_members(const void *in_dev, int32_t n_members, int64_t n, double scale,
                                   void *out_dev, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     QSX_REQUIRE(in_dev && out_dev && n_members > 0 && n > 0, "qsx_reduce_members: bad arguments");
-    QSX_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(cplx), stream));
     const int threads = 128;
     long long bx = (n + threads - 1) / threads;
     // enough blocks to fill the machine, at most one per 8 members
     int by = (int)std::max<long long>(1, std::min<long long>((n_members + 7) / 8, (148 * 16 + bx - 1) / bx));
     int per = (n_members + by - 1) / by;
     by = (n_members + per - 1) / per;
-    reduce_members_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, stream>>>(
-        (const cplx *)in_dev, n_members, n, per, scale, (cplx *)out_dev);
-    qsx_launch_counter += 1;
+    if (by == 1) {
+        reduce_members_kernel<<<dim3((unsigned)bx, 1), threads, 0, stream>>>(
+            (const cplx *)in_dev, n_members, n, per, scale, (cplx *)out_dev);
+        qsx_launch_counter += 1;
+    } else {
+        DevBuf<cplx> part;
+        QSX_CUDA(part.alloc((size_t)by * n));
+        reduce_members_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, stream>>>(
+            (const cplx *)in_dev, n_members, n, per, scale, part.p);
+        reduce_partials_kernel<<<(unsigned)bx, threads, 0, stream>>>(part.p, by, n, (cplx *)out_dev);
+        qsx_launch_counter += 2;
+    }
     QSX_CUDA(cudaGetLastError());
     return QSX_OK;
 }
@@ -387,6 +409,7 @@ extern "C" int qsx_sample_gauss_device(const uint32_t *seed_prefix, int32_t n_pr
                                                                     scale, (double *)out_dev);
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
-    QSX_CUDA(cudaStreamSynchronize(stream));        // `prefix` goes out of scope
+    // no host synchronisation: the result stays on the device and `prefix` returns to the
+    // stream-ordered scratch pool (all calls of a thread share one stream)
     return QSX_OK;
 }

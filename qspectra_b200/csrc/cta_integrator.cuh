@@ -106,7 +106,7 @@ __device__ void cta_propagate(Rhs &rhs, Saver &save, const CtaProp &P, cplx *vec
                             double yn = 0.0;
 #pragma unroll
                             for (int jj = 0; jj < NB; ++jj) if (jj == j) yn = ynorm[jj];
-                            if (prev + cabs1(w) > P.rtol * yn) ok = 0;
+                            if (!(prev + cabs1(w) <= P.rtol * yn)) ok = 0;      // also catches a non-finite state
                         });
                         st.rhs += 1;
                         int all_ok = __syncthreads_and(ok);

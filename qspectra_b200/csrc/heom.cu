@@ -828,7 +828,7 @@ __device__ __forceinline__ void heom_propagate_impl(const HeomPropArgs &a) {
                                               y.x += own.x + wv.x;
                                               y.y += own.y + wv.y;
                                               __stcs(&Yb[i], y);
-                                              if (sc * (cabs1(own) + cabs1(wv)) > yref) ok = 0;
+                                              if (!(sc * (cabs1(own) + cabs1(wv)) <= yref)) ok = 0;      // also catches a non-finite state
                                               ymax = fmax(ymax, sc * cabs1(y));
                                           });
                                 ymax = warp_max(ymax);
@@ -1483,8 +1483,8 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_CUDA(d_t.upload(args->t_host, nt, stream));
     QSX_CUDA(flags.alloc(3));
     QSX_CUDA(ynorm.alloc((size_t)3 * B));
-    QSX_CUDA(stats.alloc(4));
-    QSX_CUDA(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), stream));
+    QSX_CUDA(stats.alloc(5));
+    QSX_CUDA(cudaMemsetAsync(stats.p, 0, 5 * sizeof(unsigned long long), stream));
     QSX_CUDA(Y.alloc((size_t)B * Dp));
     QSX_CUDA(V.alloc((size_t)B * Dp));
     QSX_CUDA(W.alloc((size_t)B * Dp));
@@ -1654,7 +1654,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         return QSX_ERR_CUDA;
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
-    unsigned long long st[4] = {0, 0, 0, 0};
+    unsigned long long st[5] = {0, 0, 0, 0, 0};
     qsx_d2h_counter += sizeof(st);
     QSX_CUDA(cudaMemcpyAsync(st, stats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaStreamSynchronize(stream));
@@ -1664,9 +1664,9 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     args->rhs_evaluations = st[0];
     args->accepted_steps = st[1];
     args->kernel_ms = ms;
-    if (st[2] != 0) {
-        qsx_set_error("HEOM integration failed (Taylor series not converged within 60 terms, or DOPRI5 "
-                      "step-size underflow)");
+    if (st[2] != 0 || st[4] != 0) {
+        qsx_set_error("HEOM integration failed (Taylor series not converged within 60 terms, DOPRI5 "
+                      "step-size underflow, or a non-finite state)");
         return QSX_ERR_INTEGRATOR;
     }
     return QSX_OK;

@@ -405,7 +405,7 @@ struct RowPropArgs {
     long long saved_dim;
     int *flags;                 // [3]
     double *ynorm;              // [3][B]
-    unsigned long long *stats;  // rhs, steps, status, degree of the last product step
+    unsigned long long *stats;  // rhs, steps, status, degree of the last product step, non-finite saves
 };
 
 template <class C>
@@ -426,7 +426,10 @@ __device__ __forceinline__ void row_save(const RowPropArgs &a, const cplx *Y, in
     } else if (a.save_mode == QSX_SAVE_ADO0) {
         for (long long i = gtid; i < (long long)a.B * M; i += gsz) {
             const long long b = i / M, e = i % M;
-            a.out[((size_t)b * a.nt + it) * a.saved_dim + e] = __ldcg(&Y[(size_t)b * Dp + e * 32]);   // g_0 = 1
+            const cplx v = __ldcg(&Y[(size_t)b * Dp + e * 32]);        // g_0 = 1
+            a.out[((size_t)b * a.nt + it) * a.saved_dim + e] = v;
+            // the product form has no convergence test that a non-finite state would fail
+            if (!(fabs(v.x) + fabs(v.y) < 1e300)) atomicAdd(&a.stats[4], 1ULL);
         }
     } else {
         const long long per_col = n_ado * a.save_rows;
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
                         y.x += own.x + wv.x;
                         y.y += own.y + wv.y;
                         __stcs(&Yb[i], y);
-                        if (sc * (cabs1(own) + cabs1(wv)) > yref) ok = 0;
+                        if (!(sc * (cabs1(own) + cabs1(wv)) <= yref)) ok = 0;      // also catches a non-finite state
                         ymax = fmax(ymax, sc * cabs1(y));
                     };
                 }, [&](int col) {

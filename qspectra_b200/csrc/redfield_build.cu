@@ -495,7 +495,8 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     redfield_build_kernel<<<grid, 256, smem, stream>>>(a);
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
-    QSX_CUDA(cudaStreamSynchronize(stream));
+    // no host synchronisation: the generators stay on the device, the scratch buffers return
+    // to the stream-ordered pool (all calls of a thread share one stream)
     return QSX_OK;
 }
 

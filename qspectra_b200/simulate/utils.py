@@ -47,9 +47,21 @@ def integrate(f, y0, t, t0=None, method_name='zvode', f_params=None,
     method_name : 'zvode' (default -> engine default: adaptive Taylor for
         constant generators, DOPRI5 otherwise), 'taylor', 'rk4', 'dopri5'.
     kwargs : rtol, atol (as for scipy's solvers), rk4_substeps, generators
-        (per-column generator index for batched ensembles); other scipy
-        options such as nsteps are accepted and ignored.
+        (per-column generator index for batched ensembles).  `nsteps` is
+        accepted silently (the device integrators have no step budget per
+        interval); any other scipy option (max_step, first_step, order, ...)
+        has no counterpart here and raises a warning instead of being dropped
+        without notice.  Propagator stepping ('expm', the default for constant
+        dense generators on uniform grids) is accurate to ~1e-13 regardless of
+        rtol/atol; pass method_name='taylor' to have rtol control the series.
+        A non-finite state makes every device integrator fail with
+        IntegratorError.
     """
+    ignored = sorted(set(kwargs) - {'rtol', 'atol', 'rk4_substeps', 'generators', 'nsteps'})
+    if ignored:
+        import warnings
+        warnings.warn('integrate: options %s have no device counterpart and are ignored'
+                      % ', '.join(ignored), RuntimeWarning, stacklevel=2)
     if f_params:
         raise NotImplementedError('f_params are not supported on the device')
     pulses = pulse_ops = None
