@@ -88,6 +88,7 @@ struct qsx_heom_s {
     DevBuf<unsigned char> row_rec;
     DevBuf<double> row_h, row_g;
     DevBuf<cplx> row_ainv;
+    DevBuf<int> row_dep;         // [n_tiles] last tile linked to a tile (flow scheduling, heom_row.cuh)
 };
 
 // ------------------------------------------------------------- tile machinery
@@ -1300,6 +1301,19 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
                 reinterpret_cast<double *>(base + C::OFF_SHIFT)[lane] = shift[n];
                 reinterpret_cast<double *>(base + C::OFF_SCALE)[lane] = scale[n] / g[n];
             }
+            // last tile any ADO of a tile links to (links are symmetric: it is also the last tile that reads it)
+            std::vector<int> dep((size_t)n_tiles);
+            for (int64_t tile = 0; tile < n_tiles; ++tile) {
+                int hi = (int)tile;
+                for (int b = 0; b < bins; ++b)
+                    for (int lane = 0; lane < TL; ++lane) {
+                        const size_t o = ((size_t)tile * bins + b) * TL + lane;
+                        if (off_dn[o] >= 0) hi = std::max(hi, (int)(off_dn[o] / (M * TL)));
+                        if (off_up[o] >= 0) hi = std::max(hi, (int)(off_up[o] / (M * TL)));
+                    }
+                dep[tile] = hi;
+            }
+            QSX_CUDA(h->row_dep.upload(dep, stream));
             std::vector<double> hm((size_t)cfg->n_members * C::MH, 0.0);
             for (int m = 0; m < cfg->n_members; ++m)
                 for (int i = 0; i < M; ++i) hm[(size_t)m * C::MH + i] = HR[(size_t)m * M + i].y;
@@ -1367,14 +1381,19 @@ static bool use_row_tile(const qsx_heom_s *h, long long units) {
 // for A-B runs: "32" three buffers / two CTAs (default), "23" two buffers / three CTAs, "22".
 // Row-tile launch configurations for A-B runs: QSX_HEOM_ROWCFG = buffers per CTA x CTAs per SM
 // ("22" default, "32").
+// "122": two buffers / two CTAs with the exchange form of the commutator (heom_row.cuh, XCH; A-B runs).
 template <class Fn>
 static int row_dispatch(bool const_h, Fn &&fn) {
     typedef heom_row::Cfg<7, 2> C;
+    typedef std::integral_constant<int, 2> I2;
+    typedef std::integral_constant<int, 3> I3;
     const int cfg = env_int("QSX_HEOM_ROWCFG", 22);
-    if (cfg == 32) return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>())
-                                  : fn(C(), std::false_type(), std::integral_constant<int, 3>(), std::integral_constant<int, 2>());
-    return const_h ? fn(C(), std::true_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>())
-                   : fn(C(), std::false_type(), std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
+    if (cfg == 32) return const_h ? fn(C(), std::true_type(), I3(), I2(), std::false_type())
+                                  : fn(C(), std::false_type(), I3(), I2(), std::false_type());
+    if (cfg == 22) return const_h ? fn(C(), std::true_type(), I2(), I2(), std::false_type())
+                                  : fn(C(), std::false_type(), I2(), I2(), std::false_type());
+    return const_h ? fn(C(), std::true_type(), I2(), I2(), std::true_type())
+                   : fn(C(), std::false_type(), I2(), I2(), std::true_type());
 }
 
 extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int32_t n_columns,
@@ -1399,18 +1418,31 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
     if (row) {
         QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
         heom_row::RowApplyArgs a;
-        a.R = h->row; a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
-        a.blk = std::max(1, env_int("QSX_HEOM_BLK", 1));
-        rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
+        a.R = h->row; a.R.dbg = env_int("QSX_ROW_DBGMASK", 0); a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
+        rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB, auto XC) -> int {
             typedef decltype(C_) C;
-            auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
-            const size_t smem = C::smem_bytes(decltype(NB)::value);
+            auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value, decltype(XC)::value>;
+            const size_t smem = C::smem_bytes(decltype(NB)::value, decltype(XC)::value);
             int per_sm = 0;
             QSX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::THREADS, smem));
             QSX_REQUIRE(per_sm > 0, "heom_row_apply_kernel does not fit on an SM");
-            const int grid = (int)std::min<long long>((total + a.blk - 1) / a.blk, (long long)sms * per_sm);
+            int grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+            if (const char *gs = getenv("QSX_HEOM_GRID")) grid = std::min(grid, std::max(1, atoi(gs)));   // tests / experiments
             kernel<<<grid, C::THREADS, smem, stream>>>(a);
+            if (const int reps = env_int("QSX_HEOM_TIME", 0)) {      // diagnostics: mean time of the bare kernel
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, stream);
+                for (int r = 0; r < reps; ++r) kernel<<<grid, C::THREADS, smem, stream>>>(a);
+                cudaEventRecord(e1, stream);
+                cudaEventSynchronize(e1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e0, e1);
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                fprintf(stderr, "heom_row_apply: grid %d, %d CTA/SM, smem %zu: %.2f us per launch\n", grid, per_sm, smem,
+                        1e3 * ms / reps);
+            }
             return QSX_OK;
         });
         if (rc) return rc;
@@ -1528,10 +1560,9 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     void *kargs[1];
     if (row) {
         QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
-        ra.R = h->row;
+        ra.R = h->row; ra.R.dbg = 0;
         ra.B = B; ra.nt = nt;
-        ra.blk = std::max(1, env_int("QSX_HEOM_BLK", 1));
-        ra.flip = env_int("QSX_HEOM_FLIP", 0);
+        ra.use_flow = env_int("QSX_HEOM_FLOW", 1);
         ra.member_of = args->generator_of_column_host ? member.p : nullptr;
         ra.y0 = (const cplx *)args->y0_dev;
         ra.Y = Y.p; ra.V = V.p; ra.W = W.p;
@@ -1544,11 +1575,11 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         ra.save_of = save_of.p;
         ra.out = (cplx *)args->out_dev; ra.saved_dim = saved_dim;
         ra.flags = flags.p; ra.ynorm = ynorm.p; ra.stats = stats.p;
-        rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
+        rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB, auto XC) -> int {
             typedef decltype(C_) C;
-            kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
+            kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value, decltype(XC)::value>;
             threads = C::THREADS;
-            smem = C::smem_bytes(decltype(NB)::value) + (size_t)env_int("QSX_HEOM_PADSMEM", 0);   // experiments: less L1
+            smem = C::smem_bytes(decltype(NB)::value, decltype(XC)::value) + (size_t)env_int("QSX_HEOM_PADSMEM", 0);   // experiments: less L1
             return QSX_OK;
         });
         if (rc) return rc;
@@ -1639,6 +1670,16 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_REQUIRE(per_sm > 0, "heom_propagate_kernel does not fit on an SM");
     grid = (int)std::min<long long>(total, (long long)sms * per_sm);
     if (const char *gs = getenv("QSX_HEOM_GRID")) grid = std::min(grid, std::max(1, atoi(gs)));   // tests / experiments
+    DevBuf<unsigned> flow_cnt;
+    if (row) {
+        // completion counters of the barrier-free product-form stages, one per round of `grid` units
+        const size_t rounds = (size_t)((total + grid - 1) / grid);
+        QSX_CUDA(flow_cnt.alloc(rounds + 1));
+        QSX_CUDA(cudaMemsetAsync(flow_cnt.p, 0, (rounds + 1) * sizeof(unsigned), stream));
+        ra.F.cnt = flow_cnt.p;
+        ra.F.dep_hi = h->row_dep.p;
+        ra.F.rot = (unsigned)(total % grid);      // the short last round moves on by its own length every stage
+    }
     if (getenv("QSX_HEOM_VERBOSE"))
         fprintf(stderr, "heom_propagate: %s tile, threads %d smem %zu B, %d CTA/SM, grid %d\n",
                 row ? "row" : "batch/generic", threads, smem, per_sm, grid);

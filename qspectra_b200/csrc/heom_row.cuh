@@ -92,9 +92,12 @@ struct Cfg {
     static constexpr int YS_BYTES = M * 32 * 16;
     static constexpr int OFF_H = YS_BYTES + REC_BYTES;           // member coefficients behind the record
     static constexpr int BUF_BYTES = OFF_H + MH * 8;
-    static constexpr int THREADS = 32 * NS;
+    static constexpr int THREADS = 32 * (NS + 1);                 // NS row-warps + the producer warp
     static constexpr int HDR_BYTES = 128 + MH * 8;               // mbarriers, coefficients of member 0
-    static __host__ __device__ constexpr size_t smem_bytes(int nbuf) { return HDR_BYTES + (size_t)nbuf * BUF_BYTES; }
+    // xch: one more tile-sized buffer through which the row-warps exchange H sigma (see row_body)
+    static __host__ __device__ constexpr size_t smem_bytes(int nbuf, bool xch = false) {
+        return HDR_BYTES + (size_t)nbuf * BUF_BYTES + (xch ? YS_BYTES : 0);
+    }
 };
 
 struct RowDev {
@@ -107,39 +110,26 @@ struct RowDev {
     cplx cd[4];                             // -i u c_k
     double d2;                              // u * temp_corr * 2: Ishizaki-Tanimura term of off-diagonal elements
     int const_h;
-};
-
-// Work order of a sweep: units u = column * n_tiles + tile are taken in blocks of `blk`
-// consecutive units, block j by CTA j % grid (adjacent tiles share gather lines in L1/L2,
-// and all CTAs move through the hierarchy levels together).  `rev` walks the units backwards
-// so that a stage starts on what the previous stage wrote last (still in L2).
-struct Walk {
-    unsigned total, u;
-    int blk, r, stride, rev;
-    __device__ __forceinline__ void start(unsigned total_, int blk_, int rev_) {
-        total = total_; blk = blk_; rev = rev_;
-        u = blockIdx.x * (unsigned)blk; r = 0;
-        stride = (int)(gridDim.x - 1) * blk + 1;
-    }
-    __device__ __forceinline__ bool valid() const { return u < total; }
-    __device__ __forceinline__ void next() {
-        if (++r == blk) { r = 0; u += stride; } else u += 1;
-    }
-    __device__ __forceinline__ void where(unsigned n_tiles, int &col, int &tile) const {
-        const unsigned e = rev ? total - 1 - u : u;
-        const unsigned c = e / n_tiles;
-        col = (int)c;
-        tile = (int)(e - c * n_tiles);
-    }
+    int dbg;                                // diagnostics (QSX_ROW_DBG builds): 1 no gathers, 2 gathers from the own tile, 4 no stores
 };
 
 // ------------------------------------------------------------------------ tile body
 // acc[b] = (L sigma)[w, b] for the ADO of this lane;
 // epi(b, index within the column, value, own, error-norm weight of the ADO).
 // `w` = row and `lane` = ADO (within the tile) of this thread, see row_of() / ado_of().
-template <class C, bool UP, bool CONSTH, class Epi>
+//
+// XCH (exchange form of the commutator).  Without it every thread reads the whole matrix of its
+// ADO from shared memory to form row w of H sigma: 49 of the 66 shared-memory loads of a thread,
+// and a 16-byte load costs four L1TEX wavefronts per warp whatever the lanes share -- the L1TEX
+// data pipe was the busiest unit of the kernel (74 %).  With XCH thread (w, ADO) forms COLUMN w
+// of H sigma from column w of sigma (7 loads), leaves it in the exchange buffer `xs`, and picks up
+// row w of H sigma (7 loads) once all NS row-warps have delivered theirs (mbarrier xbar[0];
+// xbar[1] hands the buffer back for the next tile): 28 instead of 56 wide shared-memory accesses
+// per thread, and the 7-warp CTA still never meets at a CTA barrier.
+template <class C, bool UP, bool CONSTH, bool XCH, class Epi>
 __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *buf, const double *hs0,
-                                         const cplx *__restrict__ xc, int w, int lane, int tile, Epi &&epi) {
+                                         const cplx *__restrict__ xc, int w, int lane, int tile,
+                                         cplx *xs, uint64_t *xbar, unsigned q, Epi &&epi) {
     constexpr int NS = C::NS, K1 = C::K1, LD = C::LD, UD = C::UD, E4 = C::E4, UB = C::UB;
     const cplx *ys = reinterpret_cast<const cplx *>(buf) + lane;            // element e at ys[e * 32]
     const unsigned char *rec = buf + C::YS_BYTES;
@@ -149,13 +139,39 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     const cplx *xw = xc + w * 32;          // element (w, b) of the ADO at offset o: xw[o + b * NS * 32]
     const cplx zero = cmake(0.0, 0.0);
     cplx acc[NS];
+#ifdef QSX_ROW_DBG
+    auto dbg_off = [&](int o) { return (R.dbg & 1) ? -1 : ((R.dbg & 2) && o >= 0) ? tile * C::M * 32 + lane : o; };
+#else
+    auto dbg_off = [&](int o) { return o; };
+#endif
 
+    if constexpr (XCH) {
+        // ---- column w of Hs sigma: (i h) z = h (-z.y, z.x)
+        cplx P[NS];
+#pragma unroll
+        for (int r = 0; r < NS; ++r) P[r] = zero;
+#pragma unroll
+        for (int c = 0; c < NS; ++c) {
+            const cplx z = ys[(c + NS * w) * 32];
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                const double h = CONSTH ? R.hc[r * NS + c] : hm[r * NS + c];
+                P[r].x = fma(-h, z.y, P[r].x);
+                P[r].y = fma(h, z.x, P[r].y);
+            }
+        }
+        if (q) mbar_wait(&xbar[1], (q - 1) & 1);      // every warp has picked up the previous tile's rows
+#pragma unroll
+        for (int r = 0; r < NS; ++r) xs[(r + NS * w) * 32 + lane] = P[r];
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&xbar[0]);
+    }
     // ---- batch 1: row-site down-links (the whole row shares neighbour and coefficient)
     cplx g[K1][NS];
     {
         int o[K1];
 #pragma unroll
-        for (int k = 0; k < K1; ++k) o[k] = dn[w * K1 + k];
+        for (int k = 0; k < K1; ++k) o[k] = dbg_off(dn[w * K1 + k]);
 #pragma unroll
         for (int k = 0; k < K1; ++k) {
             const cplx *p = xw + (o[k] >= 0 ? o[k] : 0);
@@ -188,6 +204,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
 
     // Hs sigma for source rows [c0, c1): (i h) z = h (-z.y, z.x)
     auto left = [&](auto c0, auto c1) {
+        if constexpr (XCH) return;
 #pragma unroll
         for (int c = decltype(c0)::value; c < decltype(c1)::value; ++c) {
             const double h = hrow[c];
@@ -211,6 +228,10 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         int o[E4];
 #pragma unroll
         for (int j = 0; j < E4 / 4; ++j) *reinterpret_cast<int4 *>(&o[4 * j]) = reinterpret_cast<const int4 *>(dn)[j];
+#ifdef QSX_ROW_DBG
+#pragma unroll
+        for (int j = 0; j < E4; ++j) o[j] = dbg_off(o[j]);
+#endif
         cplx v[NS][K1];
 #pragma unroll
         for (int b = 0; b < NS; ++b)
@@ -230,7 +251,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         {
             int o[K1];
 #pragma unroll
-            for (int k = 0; k < K1; ++k) o[k] = up[w * K1 + k];
+            for (int k = 0; k < K1; ++k) o[k] = dbg_off(up[w * K1 + k]);
 #pragma unroll
             for (int k = 0; k < K1; ++k) {
                 const cplx *p = xw + (o[k] >= 0 ? o[k] : 0);
@@ -253,6 +274,10 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
             int o[E4];
 #pragma unroll
             for (int j = 0; j < E4 / 4; ++j) *reinterpret_cast<int4 *>(&o[4 * j]) = reinterpret_cast<const int4 *>(up)[j];
+#ifdef QSX_ROW_DBG
+#pragma unroll
+            for (int j = 0; j < E4; ++j) o[j] = dbg_off(o[j]);
+#endif
             cplx v[NS][K1];
 #pragma unroll
             for (int b = 0; b < NS; ++b)
@@ -274,40 +299,100 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     } else {
         left(IA(), IN());
     }
+    if constexpr (XCH) {
+        // ---- row w of Hs sigma from the exchange buffer
+        mbar_wait(&xbar[0], q & 1);
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+            const cplx p = xs[(w + NS * b) * 32 + lane];
+            acc[b].x += p.x;
+            acc[b].y += p.y;
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&xbar[1]);
+    }
     const int base = (tile * C::M + w) * 32 + lane;
     const double sc = reinterpret_cast<const double *>(rec + C::OFF_SCALE)[lane];
 #pragma unroll
     for (int b = 0; b < NS; ++b) epi(b, base + b * NS * 32, acc[b], ys[(w + NS * b) * 32], sc);
 }
 
-// ------------------------------------------------------------------ pipelined sweep
-template <class C, int NBUF>
+// ------------------------------------------------------------------ tile pipeline
+// A CTA is NS row-warps plus one producer warp (its lane 0 stages tiles; the register
+// allocation of a 7-warp CTA is that of 8 warps anyway).  Work units u = column * n_tiles +
+// tile are dealt out round by round: round r = units [r G, (r + 1) G), one per CTA.
+//
+// sweep(): one stage behind a grid barrier (RHS application, the adaptive Taylor pilot).
+//
+// flow(): a run of product-form stages WITHOUT grid barriers between them.  Stage S reads what
+// stage S - 1 wrote, but only from the neighbourhood of a tile: the producer stages unit u of
+// stage S as soon as every unit up to dep_hi(u) -- the last tile any ADO of the tile links to --
+// has been completed in stage S - 1 (per-round completion counters in global memory, published
+// by the producers, cumulative over the stages of a launch; by symmetry of the links the same
+// condition covers the tiles of stage S - 1 that still read what the unit overwrites).  The
+// row-warps only ever wait for their tile's mbarrier, so a CTA that finishes a stage early
+// runs on into the low hierarchy levels of the next one: no pipeline drain, no barrier
+// latency, and the uneven last round (3634 tiles over 296 CTAs) is spread by rotating the
+// unit -> CTA assignment from stage to stage.
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, int parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct FlowDev {
+    unsigned *cnt;           // [rounds] units of a round completed, cumulative over flow stages
+    const int *dep_hi;       // [n_tiles] last tile linked to a tile
+    unsigned rot;            // units the CTA assignment advances per stage
+};
+
+template <class C, int NBUF, bool XCH = false>
 struct Pipe {
-    uint64_t *full, *empty;
+    uint64_t *full, *empty, *xbar;
+    cplx *xs;                // exchange buffer (XCH)
     unsigned char *bufs;
     double *hs0;             // coefficients of member 0 (single-member handles)
     unsigned q;              // tiles this CTA has staged/consumed so far (same value in every thread)
+    int lane, wid, w, ado;   // thread -> (row, ADO): warps below 2 P hold the row pair (2p, 2p+1) of 16 ADOs,
+                             // the odd last row takes a whole warp; warp NS is the producer
 
     __device__ __forceinline__ void init(const RowDev &R, unsigned char *smem) {
         full = reinterpret_cast<uint64_t *>(smem);
         empty = full + NBUF;
+        xbar = empty + NBUF;
         hs0 = reinterpret_cast<double *>(smem + 128);
         bufs = smem + C::HDR_BYTES;
+        xs = reinterpret_cast<cplx *>(bufs + (size_t)NBUF * C::BUF_BYTES);
         q = 0;
+        lane = threadIdx.x & 31; wid = threadIdx.x >> 5;
+        constexpr int P = C::NS / 2;
+        const bool paired = wid < 2 * P;
+        w = paired ? 2 * (wid % P) + (lane >> 4) : C::NS - 1;
+        ado = paired ? 16 * (wid / P) + (lane & 15) : lane;
         for (int i = threadIdx.x; i < C::MH; i += blockDim.x) hs0[i] = i < C::M ? R.hc[i] : 0.0;
         if (threadIdx.x == 0) {
             for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], C::NS); }
+            mbar_init(&xbar[0], C::NS);
+            mbar_init(&xbar[1], C::NS);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncthreads();
     }
-    // one thread: stage (column, tile) of `src` as the qq-th tile of this CTA
+    __device__ __forceinline__ bool producer() const { return wid == C::NS; }
+    // producer: stage (column, tile) of `src` as the qq-th tile of this CTA (its buffer is free)
     template <bool CONSTH>
     __device__ __forceinline__ void fill(const RowDev &R, unsigned qq, const cplx *src, long long Dp, int col, int tile,
                                          const int *member_of) {
         const int bi = qq % NBUF;
-        if (qq >= NBUF) mbar_wait(&empty[bi], ((qq / NBUF) - 1) & 1);
         unsigned char *b = bufs + (size_t)bi * C::BUF_BYTES;
         const int recb = tile >= R.top_tile ? C::TOP_BYTES : C::REC_BYTES;
         mbar_expect_tx(&full[bi], C::YS_BYTES + recb + (CONSTH ? 0 : C::MH * 8));
@@ -318,50 +403,131 @@ struct Pipe {
             bulk_g2s(b + C::OFF_H, R.hmem + (size_t)m * C::MH, C::MH * 8, &full[bi]);
         }
     }
+    // row-warps: one staged tile
+    template <bool CONSTH, class Epi>
+    __device__ __forceinline__ void tile_body(const RowDev &R, const cplx *srcb, int tile, Epi &&epi) {
+        mbar_wait(&full[q % NBUF], (q / NBUF) & 1);
+        const unsigned char *buf = bufs + (size_t)(q % NBUF) * C::BUF_BYTES;
+        if (tile >= R.top_tile) row_body<C, false, CONSTH, XCH>(R, buf, hs0, srcb, w, ado, tile, xs, xbar, q, epi);
+        else row_body<C, true, CONSTH, XCH>(R, buf, hs0, srcb, w, ado, tile, xs, xbar, q, epi);
+    }
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[q % NBUF]);
+    }
+
     // All threads.  make_epi(col) returns the epilogue functor of a column; done(col) runs
-    // after every tile.
+    // after every tile.  Callers separate sweeps by grid barriers.
     template <bool CONSTH, class MakeEpi, class Done>
-    __device__ __forceinline__ void sweep(const RowDev &R, const cplx *src, int B, int blk, int rev,
-                                          const int *member_of, MakeEpi &&make_epi, Done &&done) {
-        // thread -> (row, ADO): warps below 2 P hold the row pair (2p, 2p+1) of 16 ADOs, the odd last row
-        // takes a whole warp
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        constexpr int P = C::NS / 2;
-        const bool paired = wid < 2 * P;
-        const int w = paired ? 2 * (wid % P) + (lane >> 4) : C::NS - 1;
-        const int ado = paired ? 16 * (wid / P) + (lane & 15) : lane;
+    __device__ __forceinline__ void sweep(const RowDev &R, const cplx *src, int B, const int *member_of,
+                                          MakeEpi &&make_epi, Done &&done) {
         const long long Dp = R.n_tiles * C::M * 32;
-        const unsigned n_tiles = (unsigned)R.n_tiles;
-        Walk it, ahead;
-        it.start(n_tiles * (unsigned)B, blk, rev);
-        ahead = it;
-        if (threadIdx.x == 0) {
-            // writes of other CTAs (previous stage, generic proxy) before the bulk reads below
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            for (int i = 0; i < NBUF - 1 && ahead.valid(); ++i, ahead.next()) {
-                int col, tile;
-                ahead.where(n_tiles, col, tile);
-                fill<CONSTH>(R, q + i, src, Dp, col, tile, member_of);
+        const unsigned n_tiles = (unsigned)R.n_tiles, total = n_tiles * (unsigned)B, G = gridDim.x;
+        if (producer()) {
+            unsigned qq = q;
+            if (lane == 0) {
+                // writes of other CTAs (previous stage, generic proxy) before the bulk reads below
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                for (unsigned u = blockIdx.x; u < total; u += G, ++qq) {
+                    if (qq >= NBUF) mbar_wait(&empty[qq % NBUF], ((qq / NBUF) - 1) & 1);
+                    const unsigned c = u / n_tiles;
+                    fill<CONSTH>(R, qq, src, Dp, (int)c, (int)(u - c * n_tiles), member_of);
+                }
             }
+            if (blockIdx.x < total) q += (total - 1 - blockIdx.x) / G + 1;
+            return;
         }
-        for (; it.valid(); it.next(), ++q) {
-            if (threadIdx.x == 0 && ahead.valid()) {
-                int col, tile;
-                ahead.where(n_tiles, col, tile);
-                fill<CONSTH>(R, q + NBUF - 1, src, Dp, col, tile, member_of);
-                ahead.next();
-            }
-            __syncwarp();
-            int col, tile;
-            it.where(n_tiles, col, tile);
-            mbar_wait(&full[q % NBUF], (q / NBUF) & 1);
-            const unsigned char *buf = bufs + (size_t)(q % NBUF) * C::BUF_BYTES;
+        for (unsigned u = blockIdx.x; u < total; u += G, ++q) {
+            const unsigned c = u / n_tiles;
+            const int col = (int)c, tile = (int)(u - c * n_tiles);
             auto epi = make_epi(col);
-            if (tile >= R.top_tile) row_body<C, false, CONSTH>(R, buf, hs0, src + (size_t)col * Dp, w, ado, tile, epi);
-            else row_body<C, true, CONSTH>(R, buf, hs0, src + (size_t)col * Dp, w, ado, tile, epi);
+            tile_body<CONSTH>(R, src + (size_t)col * Dp, tile, epi);
             done(col);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[q % NBUF]);
+            release();
+        }
+    }
+
+    // All threads: stages S0 .. S0 + n_stages - 1 (cumulative flow-stage numbers of the launch),
+    // stage j reads X[j & 1] and writes X[(j & 1) ^ 1]; make_stage(j)(col) returns the epilogue.
+    // The caller puts a grid barrier before and after the run.
+    template <bool CONSTH, class MakeEpi>
+    __device__ __forceinline__ void flow(const RowDev &R, const FlowDev &F, cplx *X0, cplx *X1, int B, const int *member_of,
+                                         unsigned S0, int n_stages, MakeEpi &&make_stage) {
+        const long long Dp = R.n_tiles * C::M * 32;
+        const unsigned n_tiles = (unsigned)R.n_tiles, total = n_tiles * (unsigned)B, G = gridDim.x;
+        auto first = [&](unsigned S) { return (unsigned)((blockIdx.x + (unsigned long long)S * F.rot) % G); };
+        if (producer()) {
+            unsigned n_mine = 0;
+            for (int j = 0; j < n_stages; ++j) {
+                const unsigned f = first(S0 + j);
+                if (f < total) n_mine += (total - 1 - f) / G + 1;
+            }
+            if (lane == 0) {
+                // fill cursor (jf, uf, kf) and publish cursor (jp, up, kp) over the units of this CTA
+                int jf = 0, jp = 0;
+                unsigned uf = first(S0), up = uf, kf = 0, kp = 0;
+                unsigned frontier = 0;      // rounds [0, frontier) of stage S0 + jf - 1 are known to be complete
+                auto skip = [&](int &j, unsigned &u) {      // move the cursor to its next existing unit
+                    while (j < n_stages && u >= total) { ++j; u = first(S0 + j); }
+                };
+                skip(jf, uf);
+                skip(jp, up);
+                int spins = 0;
+                while (kp < n_mine) {
+                    if (kp < kf) {
+                        uint64_t *eb = &empty[(q + kp) % NBUF];
+                        const int par = ((q + kp) / NBUF) & 1;
+                        bool left;
+                        if (kf - kp == NBUF || kf == n_mine) { mbar_wait(eb, par); left = true; }   // nothing else to do
+                        else left = mbar_test(eb, par);
+                        if (left) {
+                            // every row-warp has left unit kp: make its stores visible, then count it
+                            __threadfence();
+                            atomicAdd(&F.cnt[up / G], 1u);
+                            ++kp;
+                            up += G;
+                            if (up >= total) { ++jp; up = first(S0 + jp); skip(jp, up); }
+                        }
+                    }
+                    if (kf < n_mine && kf - kp < NBUF) {
+                        const unsigned c = uf / n_tiles, tile = uf - c * n_tiles;
+                        bool ok = true;
+                        if (jf > 0) {
+                            const unsigned need = (c * n_tiles + (unsigned)__ldg(&F.dep_hi[tile])) / G + 1;   // rounds of the previous stage
+                            const unsigned S = S0 + jf;            // completed stages a full counter shows
+                            while (frontier < need) {
+                                const unsigned in_round = min(G, total - frontier * G);
+                                if (ld_acquire(&F.cnt[frontier]) >= S * in_round) ++frontier;
+                                else { ok = false; break; }
+                            }
+                        }
+                        if (ok) {
+                            asm volatile("fence.proxy.async.global;" ::: "memory");
+                            fill<CONSTH>(R, q + kf, (jf & 1) ? X1 : X0, Dp, (int)c, (int)tile, member_of);
+                            ++kf;
+                            uf += G;
+                            if (uf >= total) { ++jf; uf = first(S0 + jf); frontier = 0; skip(jf, uf); }
+                            spins = 0;
+                        } else {
+                            __nanosleep(200);
+                            if (++spins > (1 << 23)) __trap();      // seconds: a broken dependency table must not hang the GPU
+                        }
+                    }
+                }
+            }
+            q += n_mine;
+            return;
+        }
+        for (int j = 0; j < n_stages; ++j) {
+            const cplx *src = (j & 1) ? X1 : X0;
+            auto make_epi = make_stage(j);
+            for (unsigned u = first(S0 + j); u < total; u += G, ++q) {
+                const unsigned c = u / n_tiles;
+                const int col = (int)c, tile = (int)(u - c * n_tiles);
+                auto epi = make_epi(col);
+                tile_body<CONSTH>(R, src + (size_t)col * Dp, tile, epi);
+                release();
+            }
         }
     }
 };
@@ -372,24 +538,31 @@ struct RowApplyArgs {
     const cplx *x;          // internal layout, sigma variables
     cplx *y;
     const int *member_of;   // [B] or null
-    int B, blk;
+    int B;
 };
 
-template <class C, bool CONSTH, int NBUF, int MINB>
+template <class C, bool CONSTH, int NBUF, int MINB, bool XCH>
 __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_apply_kernel(const __grid_constant__ RowApplyArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Pipe<C, NBUF> pipe;
+    Pipe<C, NBUF, XCH> pipe;
     pipe.init(a.R, smem_raw);
     const long long Dp = a.R.n_tiles * C::M * 32;
-    pipe.template sweep<CONSTH>(a.R, a.x, a.B, a.blk, 0, a.member_of, [&](int col) {
+    pipe.template sweep<CONSTH>(a.R, a.x, a.B, a.member_of, [&](int col) {
         cplx *yb = a.y + (size_t)col * Dp;
+#ifdef QSX_ROW_DBG
+        const bool nost = a.R.dbg & 4;
+        return [=](int, int i, cplx f, cplx, double) { if (!nost || f.x == 1.2345e-300) __stcs(&yb[i], f); };
+#else
         return [=](int, int i, cplx f, cplx, double) { __stcs(&yb[i], f); };
+#endif
     }, [](int) {});
 }
 
 struct RowPropArgs {
     RowDev R;
-    int B, nt, blk, flip;       // flip: walk odd stages backwards
+    FlowDev F;
+    int B, nt;
+    int use_flow;               // product-form stages without grid barriers (flow())
     const int *member_of;
     const cplx *y0;             // reference layout [B][n_ado][M]
     cplx *Y, *V, *W;            // work vectors, internal layout [B][Dp]
@@ -445,11 +618,11 @@ __device__ __forceinline__ void row_save(const RowPropArgs &a, const cplx *Y, in
     }
 }
 
-template <class C, bool CONSTH, int NBUF, int MINB>
+template <class C, bool CONSTH, int NBUF, int MINB, bool XCH>
 __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(const __grid_constant__ RowPropArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
-    Pipe<C, NBUF> pipe;
+    Pipe<C, NBUF, XCH> pipe;
     pipe.init(a.R, smem_raw);
     constexpr int M = C::M;
     const RowDev &R = a.R;
@@ -487,7 +660,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
     cplx *cur = a.Y;        // vector that holds the state
     int degree = 0;         // POLY: degree found by the last pilot (0: none yet, -1: series too long for the table)
     int since_pilot = 0;
-    unsigned stage_no = 0;  // parity selects the walking direction when a.flip is set
+    unsigned flow_stage = 0;    // flow stages completed so far in this launch
 
     // adaptive Taylor interval: cur <- exp(h L) cur; the other two vectors hold the terms.
     // Returns the number of terms used (even), or -1 if not converged within kmax.
@@ -505,15 +678,14 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
                 if (threadIdx.x == 0) a.flags[(fslot + 1) % 3] = 0;
                 for (int b = threadIdx.x; b < B; b += blockDim.x) a.ynorm[((nslot + 2) % 3) * B + b] = 0.0;
             }
-            const int rev = a.flip ? (int)(stage_no & 1) : 0;
             if (!even) {
-                pipe.template sweep<CONSTH>(R, src, B, a.blk, rev, a.member_of, [&](int col) {
+                pipe.template sweep<CONSTH>(R, src, B, a.member_of, [&](int col) {
                     cplx *db = dst + (size_t)col * Dp;
                     return [=](int, int i, cplx f, cplx, double) { __stcs(&db[i], cscale(fac, f)); };
                 }, [](int) {});
             } else {
                 double ymax = 0.0;
-                pipe.template sweep<CONSTH>(R, src, B, a.blk, rev, a.member_of, [&](int col) {
+                pipe.template sweep<CONSTH>(R, src, B, a.member_of, [&](int col) {
                     cplx *db = dst + (size_t)col * Dp;
                     cplx *Yb = Yv + (size_t)col * Dp;
                     const double yref = a.rtol * __ldcg(&a.ynorm[nslot * B + col]);
@@ -533,7 +705,6 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
                     ymax = 0.0;
                 });
             }
-            ++stage_no;
             n_rhs += 1;
             if (even) {
                 const int all_ok = __syncthreads_and(ok);
@@ -552,27 +723,45 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
         return -1;
     };
 
-    // product-form interval of degree m: cur <- prod_j (I + h a_j L) cur, ping-pong with one other vector
-    auto poly_step = [&](double h, int m) {
+    // nsub product-form steps of degree m: cur <- [prod_j (I + h a_j L)]^nsub cur, ping-pong with one
+    // other vector; a grid barrier precedes and follows the run
+    auto poly_run = [&](double h, int m, int nsub) {
         const cplx *tab = a.ainv + (size_t)m * (m - 1) / 2;
         cplx *other = (cur == a.Y) ? a.V : a.Y;
-        for (int j = 0; j < m; ++j) {
-            const cplx al = cscale(h, __ldg(&tab[j]));
-            const int rev = a.flip ? (int)(stage_no & 1) : 0;
-            cplx *dst = other;
-            pipe.template sweep<CONSTH>(R, cur, B, a.blk, rev, a.member_of, [&](int col) {
-                cplx *db = dst + (size_t)col * Dp;
-                return [=](int, int i, cplx f, cplx own, double) {
-                    cfma(own, al, f);
-                    db[i] = own;
+        const int n_stages = m * nsub;
+        if (a.use_flow) {
+            cplx *X0 = cur, *X1 = other;
+            pipe.template flow<CONSTH>(R, a.F, X0, X1, B, a.member_of, flow_stage, n_stages, [&](int j) {
+                const cplx al = cscale(h, __ldg(&tab[j % m]));
+                cplx *dst = (j & 1) ? X0 : X1;
+                return [=](int col) {
+                    cplx *db = dst + (size_t)col * Dp;
+                    return [=](int, int i, cplx f, cplx own, double) {
+                        cfma(own, al, f);
+                        db[i] = own;
+                    };
                 };
-            }, [](int) {});
-            ++stage_no;
-            n_rhs += 1;
+            });
+            flow_stage += (unsigned)n_stages;
+            if (n_stages & 1) cur = other;
             grid.sync();
-            other = cur;
-            cur = dst;
+        } else {
+            for (int j = 0; j < n_stages; ++j) {
+                const cplx al = cscale(h, __ldg(&tab[j % m]));
+                cplx *dst = other;
+                pipe.template sweep<CONSTH>(R, cur, B, a.member_of, [&](int col) {
+                    cplx *db = dst + (size_t)col * Dp;
+                    return [=](int, int i, cplx f, cplx own, double) {
+                        cfma(own, al, f);
+                        db[i] = own;
+                    };
+                }, [](int) {});
+                grid.sync();
+                other = cur;
+                cur = dst;
+            }
         }
+        n_rhs += (unsigned long long)n_stages;
     };
 
     for (int it = 0; it < a.nt; ++it) {
@@ -582,24 +771,32 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
             int nsub = (int)ceil(fabs(span) * a.lnorm / a.theta);
             if (nsub < 1) nsub = 1;
             const double h = span / nsub;
-            for (int sub = 0; sub < nsub; ++sub) {
+            int sub = 0;
+            while (sub < nsub) {
                 const bool pilot = a.method == QSX_METHOD_TAYLOR || degree <= 0 || since_pilot >= a.repilot;
                 if (pilot) {
                     const int k = taylor_step(h);
                     if (k < 0) status = QSX_ERR_INTEGRATOR;
                     degree = (k > 0 && k <= QSX_POLY_MMAX) ? k : -1;
                     since_pilot = 0;
+                    sub += 1;
+                    n_steps += 1;
                 } else {
-                    poly_step(h, degree);
-                    ++since_pilot;
+                    // all remaining steps of the interval up to the next pilot in one run
+                    const int n = min(nsub - sub, a.repilot - since_pilot);
+                    poly_run(h, degree, n);
+                    since_pilot += n;
+                    sub += n;
+                    n_steps += (unsigned long long)n;
                 }
-                n_steps += 1;
             }
             tcur = target;
         }
         row_save<C>(a, cur, it);
         // the next stage that writes `cur` is separated from this read by >= 1 grid barrier
-        // (Taylor: first write of the accumulator at k = 2; product form: second stage)
+        // (Taylor: first write of the accumulator at k = 2; product form: the dependency counters
+        // of stage 2 require stage 1 complete, which follows this save in every CTA -- see below)
+        if (a.use_flow) grid.sync();
     }
     if (gtid == 0) {
         a.stats[0] = n_rhs * (unsigned long long)B;
