@@ -64,6 +64,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// the same with the L2 evict_first priority: lines nobody reads again (top-level tiles of the source)
+__device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, int bytes, uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 pol;\n\t"
+                 "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], pol;\n\t}"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, int bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -115,7 +122,8 @@ struct RowDev {
 
 // ------------------------------------------------------------------------ tile body
 // acc[b] = (L sigma)[w, b] for the ADO of this lane;
-// epi(b, index within the column, value, own, error-norm weight of the ADO).
+// epi(integral_constant<bool, UP> (false: top-level tile), index within the column, value, own,
+// error-norm weight of the ADO).
 // `w` = row and `lane` = ADO (within the tile) of this thread, see row_of() / ado_of().
 //
 // XCH (exchange form of the commutator).  Without it every thread reads the whole matrix of its
@@ -314,7 +322,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     const int base = (tile * C::M + w) * 32 + lane;
     const double sc = reinterpret_cast<const double *>(rec + C::OFF_SCALE)[lane];
 #pragma unroll
-    for (int b = 0; b < NS; ++b) epi(b, base + b * NS * 32, acc[b], ys[(w + NS * b) * 32], sc);
+    for (int b = 0; b < NS; ++b) epi(std::integral_constant<bool, UP>(), base + b * NS * 32, acc[b], ys[(w + NS * b) * 32], sc);
 }
 
 // ------------------------------------------------------------------ tile pipeline
@@ -396,8 +404,11 @@ struct Pipe {
         unsigned char *b = bufs + (size_t)bi * C::BUF_BYTES;
         const int recb = tile >= R.top_tile ? C::TOP_BYTES : C::REC_BYTES;
         mbar_expect_tx(&full[bi], C::YS_BYTES + recb + (CONSTH ? 0 : C::MH * 8));
-        bulk_g2s(b, src + (size_t)col * Dp + (size_t)tile * C::M * 32, C::YS_BYTES, &full[bi]);
-        bulk_g2s(b + C::YS_BYTES, R.rec + (size_t)tile * C::REC_BYTES, recb, &full[bi]);
+        // a top-level tile is read once per stage (nothing links down into it from above, and the
+        // up-links of the level below were served earlier in the stage)
+        if (tile >= R.top_tile) bulk_g2s_stream(b, src + (size_t)col * Dp + (size_t)tile * C::M * 32, C::YS_BYTES, &full[bi]);
+        else bulk_g2s(b, src + (size_t)col * Dp + (size_t)tile * C::M * 32, C::YS_BYTES, &full[bi]);
+        bulk_g2s_stream(b + C::YS_BYTES, R.rec + (size_t)tile * C::REC_BYTES, recb, &full[bi]);     // re-read a whole stage later
         if (!CONSTH) {
             const int m = member_of ? member_of[col] : 0;
             bulk_g2s(b + C::OFF_H, R.hmem + (size_t)m * C::MH, C::MH * 8, &full[bi]);
@@ -551,9 +562,9 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_apply_kernel(const 
         cplx *yb = a.y + (size_t)col * Dp;
 #ifdef QSX_ROW_DBG
         const bool nost = a.R.dbg & 4;
-        return [=](int, int i, cplx f, cplx, double) { if (!nost || f.x == 1.2345e-300) __stcs(&yb[i], f); };
+        return [=](auto, int i, cplx f, cplx, double) { if (!nost || f.x == 1.2345e-300) __stcs(&yb[i], f); };
 #else
-        return [=](int, int i, cplx f, cplx, double) { __stcs(&yb[i], f); };
+        return [=](auto, int i, cplx f, cplx, double) { __stcs(&yb[i], f); };
 #endif
     }, [](int) {});
 }
@@ -681,7 +692,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
             if (!even) {
                 pipe.template sweep<CONSTH>(R, src, B, a.member_of, [&](int col) {
                     cplx *db = dst + (size_t)col * Dp;
-                    return [=](int, int i, cplx f, cplx, double) { __stcs(&db[i], cscale(fac, f)); };
+                    return [=](auto, int i, cplx f, cplx, double) { __stcs(&db[i], cscale(fac, f)); };
                 }, [](int) {});
             } else {
                 double ymax = 0.0;
@@ -689,7 +700,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
                     cplx *db = dst + (size_t)col * Dp;
                     cplx *Yb = Yv + (size_t)col * Dp;
                     const double yref = a.rtol * __ldcg(&a.ynorm[nslot * B + col]);
-                    return [&ok, &ymax, db, Yb, yref, fac](int, int i, cplx f, cplx own, double sc) {
+                    return [&ok, &ymax, db, Yb, yref, fac](auto, int i, cplx f, cplx own, double sc) {
                         const cplx wv = cscale(fac, f);
                         __stcs(&db[i], wv);
                         cplx y = __ldcs(&Yb[i]);
@@ -736,7 +747,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
                 cplx *dst = (j & 1) ? X0 : X1;
                 return [=](int col) {
                     cplx *db = dst + (size_t)col * Dp;
-                    return [=](int, int i, cplx f, cplx own, double) {
+                    return [=](auto, int i, cplx f, cplx own, double) {
                         cfma(own, al, f);
                         db[i] = own;
                     };
@@ -751,7 +762,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(co
                 cplx *dst = other;
                 pipe.template sweep<CONSTH>(R, cur, B, a.member_of, [&](int col) {
                     cplx *db = dst + (size_t)col * Dp;
-                    return [=](int, int i, cplx f, cplx own, double) {
+                    return [=](auto, int i, cplx f, cplx own, double) {
                         cfma(own, al, f);
                         db[i] = own;
                     };
