@@ -1377,23 +1377,13 @@ static bool use_row_tile(const qsx_heom_s *h, long long units) {
     return v == 'r' || units >= 2048;
 }
 
-// Row-tile launch configurations (buffers per CTA, CTAs per SM); QSX_HEOM_ROWCFG picks one
-// for A-B runs: "32" three buffers / two CTAs (default), "23" two buffers / three CTAs, "22".
-// Row-tile launch configurations for A-B runs: QSX_HEOM_ROWCFG = buffers per CTA x CTAs per SM
-// ("22" default, "32").
-// "122": two buffers / two CTAs with the exchange form of the commutator (heom_row.cuh, XCH; A-B runs).
+// Row-tile launch configuration: two tile buffers per CTA, two CTAs per SM (three buffers leave
+// too little L1 for the local-memory traffic and ran 25 % slower; three CTAs do not fit 128 registers).
 template <class Fn>
 static int row_dispatch(bool const_h, Fn &&fn) {
     typedef heom_row::Cfg<7, 2> C;
     typedef std::integral_constant<int, 2> I2;
-    typedef std::integral_constant<int, 3> I3;
-    const int cfg = env_int("QSX_HEOM_ROWCFG", 22);
-    if (cfg == 32) return const_h ? fn(C(), std::true_type(), I3(), I2(), std::false_type())
-                                  : fn(C(), std::false_type(), I3(), I2(), std::false_type());
-    if (cfg == 22) return const_h ? fn(C(), std::true_type(), I2(), I2(), std::false_type())
-                                  : fn(C(), std::false_type(), I2(), I2(), std::false_type());
-    return const_h ? fn(C(), std::true_type(), I2(), I2(), std::true_type())
-                   : fn(C(), std::false_type(), I2(), I2(), std::true_type());
+    return const_h ? fn(C(), std::true_type(), I2(), I2()) : fn(C(), std::false_type(), I2(), I2());
 }
 
 extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int32_t n_columns,
@@ -1419,10 +1409,10 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
         QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
         heom_row::RowApplyArgs a;
         a.R = h->row; a.R.dbg = env_int("QSX_ROW_DBGMASK", 0); a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
-        rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB, auto XC) -> int {
+        rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
             typedef decltype(C_) C;
-            auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value, decltype(XC)::value>;
-            const size_t smem = C::smem_bytes(decltype(NB)::value, decltype(XC)::value);
+            auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
+            const size_t smem = C::smem_bytes(decltype(NB)::value);
             int per_sm = 0;
             QSX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::THREADS, smem));
@@ -1575,11 +1565,11 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         ra.save_of = save_of.p;
         ra.out = (cplx *)args->out_dev; ra.saved_dim = saved_dim;
         ra.flags = flags.p; ra.ynorm = ynorm.p; ra.stats = stats.p;
-        rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB, auto XC) -> int {
+        rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
             typedef decltype(C_) C;
-            kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value, decltype(XC)::value>;
+            kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
             threads = C::THREADS;
-            smem = C::smem_bytes(decltype(NB)::value, decltype(XC)::value) + (size_t)env_int("QSX_HEOM_PADSMEM", 0);   // experiments: less L1
+            smem = C::smem_bytes(decltype(NB)::value) + (size_t)env_int("QSX_HEOM_PADSMEM", 0);   // experiments: less L1
             return QSX_OK;
         });
         if (rc) return rc;

@@ -101,10 +101,7 @@ struct Cfg {
     static constexpr int BUF_BYTES = OFF_H + MH * 8;
     static constexpr int THREADS = 32 * (NS + 1);                 // NS row-warps + the producer warp
     static constexpr int HDR_BYTES = 128 + MH * 8;               // mbarriers, coefficients of member 0
-    // xch: one more tile-sized buffer through which the row-warps exchange H sigma (see row_body)
-    static __host__ __device__ constexpr size_t smem_bytes(int nbuf, bool xch = false) {
-        return HDR_BYTES + (size_t)nbuf * BUF_BYTES + (xch ? YS_BYTES : 0);
-    }
+    static __host__ __device__ constexpr size_t smem_bytes(int nbuf) { return HDR_BYTES + (size_t)nbuf * BUF_BYTES; }
 };
 
 struct RowDev {
@@ -125,19 +122,9 @@ struct RowDev {
 // epi(integral_constant<bool, UP> (false: top-level tile), index within the column, value, own,
 // error-norm weight of the ADO).
 // `w` = row and `lane` = ADO (within the tile) of this thread, see row_of() / ado_of().
-//
-// XCH (exchange form of the commutator).  Without it every thread reads the whole matrix of its
-// ADO from shared memory to form row w of H sigma: 49 of the 66 shared-memory loads of a thread,
-// and a 16-byte load costs four L1TEX wavefronts per warp whatever the lanes share -- the L1TEX
-// data pipe was the busiest unit of the kernel (74 %).  With XCH thread (w, ADO) forms COLUMN w
-// of H sigma from column w of sigma (7 loads), leaves it in the exchange buffer `xs`, and picks up
-// row w of H sigma (7 loads) once all NS row-warps have delivered theirs (mbarrier xbar[0];
-// xbar[1] hands the buffer back for the next tile): 28 instead of 56 wide shared-memory accesses
-// per thread, and the 7-warp CTA still never meets at a CTA barrier.
-template <class C, bool UP, bool CONSTH, bool XCH, class Epi>
+template <class C, bool UP, bool CONSTH, class Epi>
 __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *buf, const double *hs0,
-                                         const cplx *__restrict__ xc, int w, int lane, int tile,
-                                         cplx *xs, uint64_t *xbar, unsigned q, Epi &&epi) {
+                                         const cplx *__restrict__ xc, int w, int lane, int tile, Epi &&epi) {
     constexpr int NS = C::NS, K1 = C::K1, LD = C::LD, UD = C::UD, E4 = C::E4, UB = C::UB;
     const cplx *ys = reinterpret_cast<const cplx *>(buf) + lane;            // element e at ys[e * 32]
     const unsigned char *rec = buf + C::YS_BYTES;
@@ -153,27 +140,6 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     auto dbg_off = [&](int o) { return o; };
 #endif
 
-    if constexpr (XCH) {
-        // ---- column w of Hs sigma: (i h) z = h (-z.y, z.x)
-        cplx P[NS];
-#pragma unroll
-        for (int r = 0; r < NS; ++r) P[r] = zero;
-#pragma unroll
-        for (int c = 0; c < NS; ++c) {
-            const cplx z = ys[(c + NS * w) * 32];
-#pragma unroll
-            for (int r = 0; r < NS; ++r) {
-                const double h = CONSTH ? R.hc[r * NS + c] : hm[r * NS + c];
-                P[r].x = fma(-h, z.y, P[r].x);
-                P[r].y = fma(h, z.x, P[r].y);
-            }
-        }
-        if (q) mbar_wait(&xbar[1], (q - 1) & 1);      // every warp has picked up the previous tile's rows
-#pragma unroll
-        for (int r = 0; r < NS; ++r) xs[(r + NS * w) * 32 + lane] = P[r];
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&xbar[0]);
-    }
     // ---- batch 1: row-site down-links (the whole row shares neighbour and coefficient)
     cplx g[K1][NS];
     {
@@ -212,7 +178,6 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
 
     // Hs sigma for source rows [c0, c1): (i h) z = h (-z.y, z.x)
     auto left = [&](auto c0, auto c1) {
-        if constexpr (XCH) return;
 #pragma unroll
         for (int c = decltype(c0)::value; c < decltype(c1)::value; ++c) {
             const double h = hrow[c];
@@ -307,18 +272,6 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     } else {
         left(IA(), IN());
     }
-    if constexpr (XCH) {
-        // ---- row w of Hs sigma from the exchange buffer
-        mbar_wait(&xbar[0], q & 1);
-#pragma unroll
-        for (int b = 0; b < NS; ++b) {
-            const cplx p = xs[(w + NS * b) * 32 + lane];
-            acc[b].x += p.x;
-            acc[b].y += p.y;
-        }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&xbar[1]);
-    }
     const int base = (tile * C::M + w) * 32 + lane;
     const double sc = reinterpret_cast<const double *>(rec + C::OFF_SCALE)[lane];
 #pragma unroll
@@ -362,10 +315,9 @@ struct FlowDev {
     unsigned rot;            // units the CTA assignment advances per stage
 };
 
-template <class C, int NBUF, bool XCH = false>
+template <class C, int NBUF>
 struct Pipe {
-    uint64_t *full, *empty, *xbar;
-    cplx *xs;                // exchange buffer (XCH)
+    uint64_t *full, *empty;
     unsigned char *bufs;
     double *hs0;             // coefficients of member 0 (single-member handles)
     unsigned q;              // tiles this CTA has staged/consumed so far (same value in every thread)
@@ -375,10 +327,8 @@ struct Pipe {
     __device__ __forceinline__ void init(const RowDev &R, unsigned char *smem) {
         full = reinterpret_cast<uint64_t *>(smem);
         empty = full + NBUF;
-        xbar = empty + NBUF;
         hs0 = reinterpret_cast<double *>(smem + 128);
         bufs = smem + C::HDR_BYTES;
-        xs = reinterpret_cast<cplx *>(bufs + (size_t)NBUF * C::BUF_BYTES);
         q = 0;
         lane = threadIdx.x & 31; wid = threadIdx.x >> 5;
         constexpr int P = C::NS / 2;
@@ -388,8 +338,6 @@ struct Pipe {
         for (int i = threadIdx.x; i < C::MH; i += blockDim.x) hs0[i] = i < C::M ? R.hc[i] : 0.0;
         if (threadIdx.x == 0) {
             for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], C::NS); }
-            mbar_init(&xbar[0], C::NS);
-            mbar_init(&xbar[1], C::NS);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -419,8 +367,8 @@ struct Pipe {
     __device__ __forceinline__ void tile_body(const RowDev &R, const cplx *srcb, int tile, Epi &&epi) {
         mbar_wait(&full[q % NBUF], (q / NBUF) & 1);
         const unsigned char *buf = bufs + (size_t)(q % NBUF) * C::BUF_BYTES;
-        if (tile >= R.top_tile) row_body<C, false, CONSTH, XCH>(R, buf, hs0, srcb, w, ado, tile, xs, xbar, q, epi);
-        else row_body<C, true, CONSTH, XCH>(R, buf, hs0, srcb, w, ado, tile, xs, xbar, q, epi);
+        if (tile >= R.top_tile) row_body<C, false, CONSTH>(R, buf, hs0, srcb, w, ado, tile, epi);
+        else row_body<C, true, CONSTH>(R, buf, hs0, srcb, w, ado, tile, epi);
     }
     __device__ __forceinline__ void release() {
         __syncwarp();
@@ -552,10 +500,10 @@ struct RowApplyArgs {
     int B;
 };
 
-template <class C, bool CONSTH, int NBUF, int MINB, bool XCH>
+template <class C, bool CONSTH, int NBUF, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_apply_kernel(const __grid_constant__ RowApplyArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Pipe<C, NBUF, XCH> pipe;
+    Pipe<C, NBUF> pipe;
     pipe.init(a.R, smem_raw);
     const long long Dp = a.R.n_tiles * C::M * 32;
     pipe.template sweep<CONSTH>(a.R, a.x, a.B, a.member_of, [&](int col) {
@@ -629,11 +577,11 @@ __device__ __forceinline__ void row_save(const RowPropArgs &a, const cplx *Y, in
     }
 }
 
-template <class C, bool CONSTH, int NBUF, int MINB, bool XCH>
+template <class C, bool CONSTH, int NBUF, int MINB>
 __global__ void __launch_bounds__(C::THREADS, MINB) heom_row_propagate_kernel(const __grid_constant__ RowPropArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
-    Pipe<C, NBUF, XCH> pipe;
+    Pipe<C, NBUF> pipe;
     pipe.init(a.R, smem_raw);
     constexpr int M = C::M;
     const RowDev &R = a.R;

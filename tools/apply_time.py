@@ -5,7 +5,7 @@ sys.path.insert(0, '.')
 import torch, qspectra_b200 as qb
 from qspectra_b200 import systems
 depth = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-specs = sys.argv[2:] or ['QSX_HEOM_ROWCFG=22', 'QSX_HEOM_ROWCFG=122']
+specs = sys.argv[2:] or ['QSX_HEOM_GRID=296', 'QSX_HEOM_GRID=148']
 model = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=qb.CM_FS, level_cutoff=depth, K=1)
 eom = model.equation_of_motion('ee')
 rng = np.random.RandomState(0)

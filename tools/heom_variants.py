@@ -3,9 +3,9 @@ configurations in one process, with a cross-check of the trajectories against th
 
 usage: python tools/heom_variants.py [depth] [spec spec ...]
 spec = comma-separated KEY=VALUE settings, e.g.
-    method=poly,QSX_HEOM_ROWCFG=32,QSX_HEOM_BLK=2,QSX_HEOM_FLIP=1
+    method=poly,QSX_HEOM_FLOW=0,QSX_HEOM_GRID=148
 `method` picks the integrator (poly | taylor); every other key is exported to the
-environment (QSX_HEOM_VARIANT, QSX_HEOM_ROWCFG, QSX_HEOM_BLK, QSX_HEOM_FLIP, ...)."""
+environment (QSX_HEOM_VARIANT, QSX_HEOM_FLOW, QSX_HEOM_GRID, ...)."""
 import os
 import sys
 
