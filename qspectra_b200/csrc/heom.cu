@@ -1660,12 +1660,12 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
     QSX_REQUIRE(per_sm > 0, "heom_propagate_kernel does not fit on an SM");
     grid = (int)std::min<long long>(total, (long long)sms * per_sm);
     if (const char *gs = getenv("QSX_HEOM_GRID")) grid = std::min(grid, std::max(1, atoi(gs)));   // tests / experiments
-    DevBuf<unsigned> flow_cnt;
+    DevBuf<unsigned long long> flow_cnt;
     if (row) {
         // completion counters of the barrier-free product-form stages, one per round of `grid` units
         const size_t rounds = (size_t)((total + grid - 1) / grid);
         QSX_CUDA(flow_cnt.alloc(rounds + 1));
-        QSX_CUDA(cudaMemsetAsync(flow_cnt.p, 0, (rounds + 1) * sizeof(unsigned), stream));
+        QSX_CUDA(cudaMemsetAsync(flow_cnt.p, 0, (rounds + 1) * sizeof(unsigned long long), stream));
         ra.F.cnt = flow_cnt.p;
         ra.F.dep_hi = h->row_dep.p;
         ra.F.rot = (unsigned)(total % grid);      // the short last round moves on by its own length every stage

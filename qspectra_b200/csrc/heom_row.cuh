@@ -303,14 +303,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, int parity) {
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
 struct FlowDev {
-    unsigned *cnt;           // [rounds] units of a round completed, cumulative over flow stages
+    unsigned long long *cnt; // [rounds] units of a round completed, cumulative over flow stages
     const int *dep_hi;       // [n_tiles] last tile linked to a tile
     unsigned rot;            // units the CTA assignment advances per stage
 };
@@ -442,7 +442,7 @@ struct Pipe {
                         if (left) {
                             // every row-warp has left unit kp: make its stores visible, then count it
                             __threadfence();
-                            atomicAdd(&F.cnt[up / G], 1u);
+                            atomicAdd(&F.cnt[up / G], 1ULL);
                             ++kp;
                             up += G;
                             if (up >= total) { ++jp; up = first(S0 + jp); skip(jp, up); }
@@ -456,7 +456,7 @@ struct Pipe {
                             const unsigned S = S0 + jf;            // completed stages a full counter shows
                             while (frontier < need) {
                                 const unsigned in_round = min(G, total - frontier * G);
-                                if (ld_acquire(&F.cnt[frontier]) >= S * in_round) ++frontier;
+                                if (ld_acquire(&F.cnt[frontier]) >= (unsigned long long)S * in_round) ++frontier;
                                 else { ok = false; break; }
                             }
                         }
