@@ -153,6 +153,16 @@ class RedfieldModel(LiouvilleSpaceModel):
                 and type(ham.bath) is DebyeBath
                 and not np.iscomplexobj(ham.H_1exc))
 
+    def _tensor_device_buildable(self):
+        """K5 with host-supplied eigensystems: any Hamiltonian class (vibronic, complex)
+        with a Drude-Lorentz bath and diagonal system-bath operators, up to 64 states."""
+        ham, ss = self.hamiltonian, self.hilbert_subspace
+        if type(ham.bath) is not DebyeBath or ham.n_states(ss) > 64:
+            return False
+        V = np.asarray(ham.system_bath_couplings(ss))
+        diag = np.einsum('jaa->ja', V)
+        return bool(np.all(V == diag[:, :, None] * np.eye(V.shape[1])[None]))
+
     def ensemble_eigensystems(self, ensemble_size, member0=0):
         """(E, U) of the members in the rotating frame, computed from the
         lab-frame matrices like Hamiltonian.eig (hamiltonian.py:310-328), with
@@ -184,27 +194,28 @@ class RedfieldModel(LiouvilleSpaceModel):
         # as well (nothing but the seed crosses PCIe); the eigenbasis path below needs
         # them on the host for LAPACK's eigenvector gauge
         on_device = self._device_buildable() and self.evolve_basis != 'eigen'
-        shifts = (ham.sampled_site_shifts_device(ensemble_size, member0) if on_device
-                  else ham.sampled_site_shifts(ensemble_size, member0)
-                  if self._device_buildable() else None)
-        if shifts is None:
-            return super(RedfieldModel, self).ensemble_eom(
-                ensemble_size, random_orientations, liouville_subspace,
-                heisenberg_picture, member0)
+        shifts = ham.sampled_site_shifts_device(ensemble_size, member0) if on_device else None
         bath = ham.bath
-        if self.evolve_basis == 'eigen':
-            # the eigenvector sign / degenerate-subspace gauge must be the one the members'
-            # own dipole operators and states are expressed in (Hamiltonian.eig, scipy's
-            # driver): take the eigensystems from the member Hamiltonians themselves
+        if shifts is None:
+            if not self._tensor_device_buildable():
+                return super(RedfieldModel, self).ensemble_eom(
+                    ensemble_size, random_orientations, liouville_subspace,
+                    heisenberg_picture, member0)
+            # Eigensystems from the member Hamiltonians themselves (Hamiltonian.eig, scipy's
+            # driver: for eigen-basis evolution the eigenvector sign / degenerate-subspace gauge
+            # must be the one the members' own dipole operators and states are expressed in;
+            # vibronic and complex Hamiltonians have no device eigensolver), Redfield tensors
+            # and the basis transform on the device.
             members = [ham.sample(member0 + n) for n in range(ensemble_size)]
             E = np.array([m.E(ss) for m in members])
             U = np.array([m.U(ss) for m in members])
-            number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
+            number = np.einsum('jaa->ja', ham.system_bath_couplings(ss)).real
             kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
                     else _capi.BATH_DEBYE_COMPLEX)
             L = engine.redfield_build(
                 E, U, number, kind, bath.temperature, bath.reorg_energy,
-                bath.cutoff_freq, self.secular, True, self.unit_convert,
+                bath.cutoff_freq, self.secular, self.evolve_basis == 'eigen',
+                self.unit_convert,
                 self.liouville_subspace_index(liouville_subspace),
                 transposed=not heisenberg_picture)
             return engine.DenseEOM.from_transposed(L)

@@ -512,6 +512,33 @@ def test_device_redfield_build_variants(secular, dic, basis):
                 assert rel_l2(np.abs(Ln), np.abs(ref[n])) < 1e-10, (ss, n)
 
 
+@pytest.mark.parametrize('basis', ['site', 'eigen'])
+def test_device_redfield_build_vibronic(basis):
+    """Vibronic dimer (2 sites x one explicit two-level mode each: 1 + 8 states in 'ge') with
+    static disorder: the members' eigensystems come from the host (Hamiltonian.eig), Redfield
+    tensors and basis transform from K5 -- against the host builder that the golden
+    fixtures pin, and an ensemble-averaged trajectory against per-member runs."""
+    ham = systems.jonas_dimer(disorder=60)
+    m = qb.RedfieldModel(ham, hilbert_subspace='ge', unit_convert=CM_FS, secular=False,
+                         evolve_basis=basis)
+    assert not m._device_buildable() and m._tensor_device_buildable()
+    members = list(m.sample_ensemble(3))
+    for ss in ('ee', 'eg'):
+        ref = m.ensemble_generators(members, ss)
+        eom = m.ensemble_eom(3, False, ss)
+        M = ref.shape[-1]
+        for n in range(3):
+            Ln = eom.apply(np.eye(M, dtype=complex), generators=np.full(M, n)).T
+            assert rel_l2(Ln, ref[n]) < 1e-10, (ss, n)
+    psi0 = np.zeros(8)
+    psi0[0] = 1
+    me = qb.RedfieldModel(ham, hilbert_subspace='e', unit_convert=CM_FS, secular=False,
+                          evolve_basis=basis)
+    t, avg = qb.simulate_dynamics(me, psi0, 200, ensemble_size=3)
+    singles = [qb.simulate_dynamics(mm, psi0, 200)[1] for mm in me.sample_ensemble(3)]
+    assert rel_l2(avg, np.mean(singles, axis=0)) < 1e-10
+
+
 def test_device_redfield_build_restricted_blocks():
     """4-site 'gef' (1 + 4 + 6 states): the builder forms only the ket x bra
     block each Liouville subspace touches; mixed subspaces and the non-secular
