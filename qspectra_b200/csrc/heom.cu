@@ -84,6 +84,7 @@ struct qsx_heom_s {
     DevBuf<cplx> HR, HC, gu, gd;
     // row tile (heom_row.cuh): electronic blocks with a real Hamiltonian, Schroedinger picture
     bool row_ok = false;
+    int row_cfg = 0;             // 1: Cfg<7,2> (FMO-like electronic block), 2: Cfg<8,2,4> (vibronic dimer, 4 states per site)
     heom_row::RowDev row;
     DevBuf<unsigned char> row_rec;
     DevBuf<double> row_h, row_g;
@@ -1267,14 +1268,23 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
     }
     // ---- row tile (heom_row.cuh): sigma_n = g_n rho_n variables, tile records -----------
     {
-        bool ok = d.ee && d.real_h && !cfg->heisenberg && rows == cols && nr == 7 && K1 == 2;
+        // block structure: both sides of the block are the same `nr` states, grouped per site
+        // (vib states each: 1 for an electronic block, > 1 for a vibronic one), every coupling
+        // operator the projector onto its site's states; real symmetric H
+        const int vib = (cfg->n_sites > 0 && nr % cfg->n_sites == 0) ? nr / cfg->n_sites : 0;
+        bool ok = vib > 0 && d.real_h && !cfg->heisenberg && nr == nc && K1 == 2 &&
+                  (int64_t)n_tiles * M * TL < ((int64_t)1 << 31);
+        for (int a = 0; a < nr && ok; ++a) ok = rows[a] == cols[a];
+        for (int j = 0; j < cfg->n_sites && ok; ++j)
+            for (int a = 0; a < nr && ok; ++a) ok = v[j * N + rows[a]] == (a / vib == j ? 1.0 : 0.0);
         for (int m = 0; m < cfg->n_members && ok; ++m)
             for (int a = 0; a < nr && ok; ++a)
                 for (int c = 0; c < nr && ok; ++c)
                     ok = HR[((size_t)m * nr + a) * nr + c].y == HR[((size_t)m * nr + c) * nr + a].y &&
                          HC[((size_t)m * nr + a) * nr + c].y == HR[((size_t)m * nr + a) * nr + c].y;
-        if (ok) {
-            typedef heom_row::Cfg<7, 2> C;
+        auto build_row = [&](auto C_) -> int {
+            typedef decltype(C_) C;
+            static_assert(C::M <= 64, "RowDev::hc holds 64 coefficients");
             heom_row::RowDev &r = h->row;
             std::vector<unsigned char> rec((size_t)n_tiles * C::REC_BYTES, 0);
             std::vector<double> g((size_t)n_tiles * TL, 0.0);
@@ -1331,8 +1341,14 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
             for (int k = 0; k < 4; ++k) r.cd[k] = k < K1 ? d.GdR[k] : cmake(0, 0);
             r.d2 = 2.0 * u * cfg->temp_corr;
             r.const_h = cfg->n_members == 1;
-            h->row_ok = true;
-        }
+            r.dbg = 0;
+            return QSX_OK;
+        };
+        int rc_row = QSX_OK;
+        if (ok && nr == 7 && vib == 1) { rc_row = build_row(heom_row::Cfg<7, 2>()); h->row_cfg = 1; }
+        else if (ok && nr == 8 && vib == 4) { rc_row = build_row(heom_row::Cfg<8, 2, 4>()); h->row_cfg = 2; }
+        if (rc_row) return rc_row;
+        h->row_ok = h->row_cfg != 0;
     }
     *out = h.release();
     return QSX_OK;
@@ -1374,15 +1390,23 @@ static int env_int(const char *name, int dflt) {
 static bool use_row_tile(const qsx_heom_s *h, long long units) {
     const char v = heom_variant();
     if (!h->row_ok || v == 'b' || v == 'g') return false;
-    return v == 'r' || units >= 2048;
+    // the vibronic block has no batch tile: its alternative is the table-driven generic tile
+    return v == 'r' || units >= 2048 || h->row_cfg == 2;
 }
 
-// Row-tile launch configuration: two tile buffers per CTA, two CTAs per SM (three buffers leave
-// too little L1 for the local-memory traffic and ran 25 % slower; three CTAs do not fit 128 registers).
+// Row-tile launch configurations.  FMO-like blocks: two tile buffers per CTA, two CTAs per SM at
+// 128 registers (three buffers leave too little L1 for the local-memory traffic and ran 25 % slower;
+// three CTAs do not fit 128 registers).  Vibronic-dimer blocks (8 x 8 matrices: 16 more registers
+// per gather batch) run one CTA per SM without a register cap.
 template <class Fn>
-static int row_dispatch(bool const_h, Fn &&fn) {
-    typedef heom_row::Cfg<7, 2> C;
+static int row_dispatch(const qsx_heom_s *h, bool const_h, Fn &&fn) {
+    typedef std::integral_constant<int, 1> I1;
     typedef std::integral_constant<int, 2> I2;
+    if (h->row_cfg == 2) {
+        typedef heom_row::Cfg<8, 2, 4> C;
+        return const_h ? fn(C(), std::true_type(), I2(), I1()) : fn(C(), std::false_type(), I2(), I1());
+    }
+    typedef heom_row::Cfg<7, 2> C;
     return const_h ? fn(C(), std::true_type(), I2(), I2()) : fn(C(), std::false_type(), I2(), I2());
 }
 
@@ -1409,7 +1433,7 @@ extern "C" int qsx_heom_apply(qsx_heom_t h, const void *y_dev, void *dy_dev, int
         QSX_REQUIRE(total < ((long long)1 << 31), "too many (column, tile) units");
         heom_row::RowApplyArgs a;
         a.R = h->row; a.R.dbg = env_int("QSX_ROW_DBGMASK", 0); a.x = xi.p; a.y = yi.p; a.member_of = member_host ? member.p : nullptr; a.B = n_columns;
-        rc = row_dispatch(h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
+        rc = row_dispatch(h, h->row.const_h && !member_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
             typedef decltype(C_) C;
             auto kernel = heom_row::heom_row_apply_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
             const size_t smem = C::smem_bytes(decltype(NB)::value);
@@ -1565,7 +1589,7 @@ extern "C" int qsx_heom_propagate(qsx_heom_t h, qsx_propagate_args *args, void *
         ra.save_of = save_of.p;
         ra.out = (cplx *)args->out_dev; ra.saved_dim = saved_dim;
         ra.flags = flags.p; ra.ynorm = ynorm.p; ra.stats = stats.p;
-        rc = row_dispatch(h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
+        rc = row_dispatch(h, h->row.const_h && !args->generator_of_column_host, [&](auto C_, auto CH, auto NB, auto MB) -> int {
             typedef decltype(C_) C;
             kernel = (const void *)heom_row::heom_row_propagate_kernel<C, decltype(CH)::value, decltype(NB)::value, decltype(MB)::value>;
             threads = C::THREADS;

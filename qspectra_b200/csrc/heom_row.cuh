@@ -77,10 +77,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, int bytes, 
 }
 
 // ---------------------------------------------------------------- compile-time layout
-template <int NS_, int K1_>
+// NS states per side of the block, K1 exponentials per site, VIB states per site (1: electronic
+// block, state = site; > 1: vibronic block, state a belongs to site a / VIB).
+template <int NS_, int K1_, int VIB_ = 1>
 struct Cfg {
-    static constexpr int NS = NS_, K1 = K1_;
-    static constexpr int M = NS * NS, BINS = NS * K1;
+    static constexpr int NS = NS_, K1 = K1_, VIB = VIB_;
+    static constexpr int M = NS * NS, BINS = (NS / VIB) * K1;
     static constexpr int E4 = (BINS + 3) / 4 * 4;
     // int32 words per lane of an offset table: 16-byte rows whose quarter-warp reads
     // (LDS.128) fall into distinct banks need an odd number of 16-byte units
@@ -125,7 +127,8 @@ struct RowDev {
 template <class C, bool UP, bool CONSTH, class Epi>
 __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *buf, const double *hs0,
                                          const cplx *__restrict__ xc, int w, int lane, int tile, Epi &&epi) {
-    constexpr int NS = C::NS, K1 = C::K1, LD = C::LD, UD = C::UD, E4 = C::E4, UB = C::UB;
+    constexpr int NS = C::NS, K1 = C::K1, LD = C::LD, UD = C::UD, E4 = C::E4, UB = C::UB, VIB = C::VIB;
+    const int ws = w / VIB;                // site of the row state
     const cplx *ys = reinterpret_cast<const cplx *>(buf) + lane;            // element e at ys[e * 32]
     const unsigned char *rec = buf + C::YS_BYTES;
     const int *dn = reinterpret_cast<const int *>(rec + C::OFF_DN) + lane * LD;
@@ -145,7 +148,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
     {
         int o[K1];
 #pragma unroll
-        for (int k = 0; k < K1; ++k) o[k] = dbg_off(dn[w * K1 + k]);
+        for (int k = 0; k < K1; ++k) o[k] = dbg_off(dn[ws * K1 + k]);
 #pragma unroll
         for (int k = 0; k < K1; ++k) {
             const cplx *p = xw + (o[k] >= 0 ? o[k] : 0);
@@ -161,7 +164,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         const double shift = reinterpret_cast<const double *>(rec + C::OFF_SHIFT)[lane];
 #pragma unroll
         for (int b = 0; b < NS; ++b) {
-            const double dg = shift + (b == w ? 0.0 : R.d2);
+            const double dg = shift + (b / VIB == ws ? 0.0 : R.d2);
             acc[b] = cmake(-dg * own[b].x, -dg * own[b].y);
 #pragma unroll
             for (int c = 0; c < NS; ++c) {
@@ -210,7 +213,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         for (int b = 0; b < NS; ++b)
 #pragma unroll
             for (int k = 0; k < K1; ++k)
-                v[b][k] = o[b * K1 + k] >= 0 ? ROW_LD(xw + o[b * K1 + k] + b * NS * 32) : zero;
+                v[b][k] = o[(b / VIB) * K1 + k] >= 0 ? ROW_LD(xw + o[(b / VIB) * K1 + k] + b * NS * 32) : zero;
         left(I0(), IA());
 #pragma unroll
         for (int b = 0; b < NS; ++b)
@@ -224,7 +227,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
         {
             int o[K1];
 #pragma unroll
-            for (int k = 0; k < K1; ++k) o[k] = dbg_off(up[w * K1 + k]);
+            for (int k = 0; k < K1; ++k) o[k] = dbg_off(up[ws * K1 + k]);
 #pragma unroll
             for (int k = 0; k < K1; ++k) {
                 const cplx *p = xw + (o[k] >= 0 ? o[k] : 0);
@@ -234,7 +237,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
             left(IA(), IB());
 #pragma unroll
             for (int k = 0; k < K1; ++k) {
-                const double t = upc[w * K1 + k];
+                const double t = upc[ws * K1 + k];
 #pragma unroll
                 for (int b = 0; b < NS; ++b) {
                     acc[b].x = fma(t, g[k][b].y, acc[b].x);
@@ -256,7 +259,7 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
             for (int b = 0; b < NS; ++b)
 #pragma unroll
                 for (int k = 0; k < K1; ++k)
-                    v[b][k] = o[b * K1 + k] >= 0 ? ROW_LD(xw + o[b * K1 + k] + b * NS * 32) : zero;
+                    v[b][k] = o[(b / VIB) * K1 + k] >= 0 ? ROW_LD(xw + o[(b / VIB) * K1 + k] + b * NS * 32) : zero;
             left(IB(), IN());
             double t[UB];
 #pragma unroll
@@ -265,8 +268,8 @@ __device__ __forceinline__ void row_body(const RowDev &R, const unsigned char *b
             for (int b = 0; b < NS; ++b)
 #pragma unroll
                 for (int k = 0; k < K1; ++k) {
-                    acc[b].x = fma(-t[b * K1 + k], v[b][k].y, acc[b].x);
-                    acc[b].y = fma(t[b * K1 + k], v[b][k].x, acc[b].y);
+                    acc[b].x = fma(-t[(b / VIB) * K1 + k], v[b][k].y, acc[b].x);
+                    acc[b].y = fma(t[(b / VIB) * K1 + k], v[b][k].x, acc[b].y);
                 }
         }
     } else {

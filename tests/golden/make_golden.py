@@ -311,7 +311,30 @@ def round2():
     save('round2', **out)
 
 
+def vibronic():
+    """BASELINE config 5, second half: HEOM of the vibronic (Jonas) dimer with explicit modes --
+    trajectory of the system density matrix from the lowest vibronic 'e' state (plain and
+    modified hierarchy) and the RHS on a seeded vector in the 'e' Hilbert subspace."""
+    out = {}
+    vib = systems.jonas_dimer(qs)
+    for tag, kw in (('plain', {}), ('mod', dict(modified_HEOM=True))):
+        m = qs.HEOMModel(vib, hilbert_subspace='e', unit_convert=CM_FS, level_cutoff=5, K=1, **kw)
+        eom = m.equation_of_motion('ee')
+        psi = np.zeros(8, dtype=complex)
+        psi[0] = 1.0
+        y0 = m.density_matrix_to_state_vector(np.outer(psi, psi.conj()), 'ee')
+        t = np.arange(0, 300, m.time_step)
+        traj = qs.integrate(eom, y0, t, **TIGHT)
+        out['vib_%s_t' % tag] = t
+        out['vib_%s_rho' % tag] = np.array(traj)[:, :64]
+        rng = np.random.RandomState(21)
+        y = rng.randn(y0.size) + 1j * rng.randn(y0.size)
+        out['vib_%s_y' % tag] = y
+        out['vib_%s_Ly' % tag] = eom(0, y)
+    save('vibronic', **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['maps', 'redfield', 'heom', 'zofe', 'response', 'round2']
+    which = sys.argv[1:] or ['maps', 'redfield', 'heom', 'zofe', 'response', 'round2', 'vibronic']
     for name in which:
         globals()[name]()

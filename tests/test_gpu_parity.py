@@ -299,6 +299,57 @@ def test_heom_row_tile_ensemble(monkeypatch):
     assert rel_l2(out['r'], out['b']) < 1e-11
 
 
+@pytest.mark.parametrize('modified', [False, True])
+def test_heom_vibronic_row_tile(modified, golden, monkeypatch):
+    """BASELINE config 5, second half: vibronic dimer with explicit modes (2 sites x 4 vibrational
+    states = 8 states in 'e', bins = 2 sites x 2 exponentials).  The shaped row tile
+    Cfg<8, 2, 4> (states grouped per site) against the table-driven generic tile: RHS on a
+    seeded vector, product-form and adaptive-Taylor trajectories, a 3-member batch; the RHS is
+    also pinned to the reference through test_heom_apply_vs_reference_rhs."""
+    import torch
+    m = qb.HEOMModel(systems.jonas_dimer(), hilbert_subspace='e', unit_convert=CM_FS,
+                     level_cutoff=6, K=1, modified_HEOM=modified)
+    eom = m.equation_of_motion('ee')
+    rng = np.random.RandomState(11)
+    y = rng.randn(2, eom.dim) + 1j * rng.randn(2, eom.dim)
+    psi = np.zeros(8, dtype=complex)
+    psi[0] = 1.0
+    y0 = m.density_matrix_to_state_vector(np.outer(psi, psi.conj()), 'ee')
+    y0d = torch.from_numpy(y0).cuda().reshape(1, -1).expand(3, -1).contiguous()
+    t = m.time_step * np.arange(12)
+    monkeypatch.setenv('QSX_HEOM_REPILOT', '4')
+    res = {}
+    for variant, method in ((' ', 'poly'), (' ', 'taylor'), ('g', 'taylor')):
+        if variant == ' ':
+            monkeypatch.delenv('QSX_HEOM_VARIANT', raising=False)
+        else:
+            monkeypatch.setenv('QSX_HEOM_VARIANT', variant)
+        traj = eom.propagate(y0d, t, save=('ado0',), method=method,
+                             return_device=True).cpu().numpy()
+        full = eom.propagate(y0d[:1], t[:3], method=method, return_device=True).cpu().numpy()
+        res[variant, method] = (np.asarray(eom.apply(y)), traj, full)
+    ref = res['g', 'taylor']
+    for key in ((' ', 'poly'), (' ', 'taylor')):
+        assert rel_l2(res[key][0], ref[0]) < 1e-13, key
+        assert rel_l2(res[key][1], ref[1]) < 1e-11, key
+        assert rel_l2(res[key][2], ref[2]) < 1e-11, key
+    rho = res[' ', 'poly'][1][0].reshape(-1, 8, 8)
+    assert np.abs(np.einsum('tii->t', rho) - 1).max() < 1e-12
+    # the reference itself: RHS and a 300 fs trajectory at level_cutoff 5
+    tag = 'mod' if modified else 'plain'
+    g = golden('vibronic')
+    monkeypatch.delenv('QSX_HEOM_VARIANT', raising=False)
+    m5 = qb.HEOMModel(systems.jonas_dimer(), hilbert_subspace='e', unit_convert=CM_FS,
+                      level_cutoff=5, K=1, modified_HEOM=modified)
+    eom5 = m5.equation_of_motion('ee')
+    assert rel_l2(eom5(0, g['vib_%s_y' % tag]), g['vib_%s_Ly' % tag]) < 1e-13
+    for method in ('poly', 'taylor'):
+        traj = eom5.propagate(torch.from_numpy(y0[:eom5.dim].copy()).cuda().reshape(1, -1),
+                              g['vib_%s_t' % tag], save=('ado0',), method=method,
+                              return_device=True).cpu().numpy()[0]
+        assert rel_l2(traj, g['vib_%s_rho' % tag]) < TOL, method
+
+
 def test_heom_depth8_default_tile(golden, monkeypatch):
     """BASELINE config 5 (FMO, level_cutoff 8: 116 280 ADOs, 3 634 tiles): the tile and the
     integrator the bench times (row tile, product form) against the batch tile with the adaptive

@@ -169,6 +169,15 @@ def test_heom_generator_and_rhs(golden):
         assert rel_l2(mf.generator('ee') @ y, g['fmo_d%d_Ly' % depth]) < 1e-14
 
 
+def test_heom_vibronic_dimer(golden):
+    """vibronic (Jonas) dimer HEOM with explicit modes: oracle generator against the reference's RHS"""
+    g = golden('vibronic')
+    for tag, kw in (('plain', {}), ('mod', dict(modified_HEOM=True))):
+        mv = oracle.OracleHEOM(systems.jonas_dimer(), hilbert_subspace='e',
+                               unit_convert=CM_FS, level_cutoff=5, K=1, **kw)
+        assert rel_l2(mv.generator('ee') @ g['vib_%s_y' % tag], g['vib_%s_Ly' % tag]) < 1e-14
+
+
 def test_heom_trajectory(golden):
     g = golden('heom')
     m = oracle.OracleHEOM(systems.dimer(), hilbert_subspace='gef',
