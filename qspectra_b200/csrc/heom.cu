@@ -1375,10 +1375,10 @@ static int upload_members(DevBuf<int> &buf, const int32_t *host, int n, int n_me
 }
 
 // ---- tile selection ---------------------------------------------------------------
-// QSX_HEOM_VARIANT (tests / A-B runs): 'r' row tile also for small hierarchies, 'b' batch tile
-// (TileEE), 'g' generic tile.  Default: the row tile once every SM has several tiles
-// (measured in round 1: two lean CTAs per SM beat the one-CTA batch tile from ~2000 units on),
-// otherwise the batch tile.
+// QSX_HEOM_VARIANT (tests / A-B runs): 'r' row tile also for the smallest hierarchies, 'b' batch tile
+// (TileEE), 'g' generic tile.  Default: the row tile from 64 (column, tile) units on -- measured on
+// FMO 'ee' (us per RHS, batch tile vs row tile): depth 4 (22 tiles) 6.5 / 6.2, depth 6 (364) 14.9 / 10.3,
+// depth 7 (1212) 41.2 / 20.8 -- otherwise the batch tile.
 static char heom_variant() {
     const char *v = getenv("QSX_HEOM_VARIANT");
     return v ? v[0] : ' ';
@@ -1391,7 +1391,7 @@ static bool use_row_tile(const qsx_heom_s *h, long long units) {
     const char v = heom_variant();
     if (!h->row_ok || v == 'b' || v == 'g') return false;
     // the vibronic block has no batch tile: its alternative is the table-driven generic tile
-    return v == 'r' || units >= 2048 || h->row_cfg == 2;
+    return v == 'r' || units >= 64 || h->row_cfg == 2;
 }
 
 // Row-tile launch configurations.  FMO-like blocks: two tile buffers per CTA, two CTAs per SM at

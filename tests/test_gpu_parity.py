@@ -234,7 +234,7 @@ def test_heom_lean_tile_ensemble_matches_single_member_launches():
 @pytest.mark.parametrize('modified', [False, True])
 @pytest.mark.parametrize('grid', [None, '2'])
 def test_heom_row_tile_matches_batch_tile(modified, grid, golden, monkeypatch):
-    """The row tile (csrc/heom_row.cuh; default only for >= 2048 tiles) forced onto the depth-4
+    """The row tile (csrc/heom_row.cuh; default from 64 (column, tile) units on) forced onto the depth-4
     FMO hierarchy: RHS application, adaptive Taylor and product-form trajectories against the
     batch tile that the golden-fixture tests validate, and against the reference trajectory.
     grid = 2: two CTAs walk eleven tiles each, so the buffer ring wraps and the mbarrier
