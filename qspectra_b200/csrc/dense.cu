@@ -24,6 +24,8 @@ struct qsx_dense_s {
     // statistics of the kernel that produced this handle (qsx_dense_expm)
     double build_ms = 0.0;
     unsigned long long build_gemms = 0;
+    // the handle holds propagators exp(L dt): only QSX_METHOD_MAP applies, no norms are kept
+    bool is_propagator = false;
 };
 
 // ------------------------------------------------------------------ kernels
@@ -430,6 +432,8 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
                 "qsx_dense_propagate: empty batch or missing buffers");
     QSX_REQUIRE(args->method >= QSX_METHOD_TAYLOR && args->method <= QSX_METHOD_MAP,
                 "qsx_dense_propagate: unknown method %d", args->method);
+    QSX_REQUIRE(!h->is_propagator || args->method == QSX_METHOD_MAP,
+                "a propagator handle (qsx_dense_expm) can only be stepped with QSX_METHOD_MAP");
     if (args->method == QSX_METHOD_MAP) {
         // the handle holds propagators exp(L dt): the grid must be uniform and start at t0
         QSX_REQUIRE(args->n_pulses == 0, "propagator stepping needs a time-independent generator");
@@ -924,16 +928,21 @@ extern "C" int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t 
     return QSX_OK;
 }
 
-extern "C" int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_dev,
-                              void *lnorm_dev, void *stream_) {
+static int dense_wrap_impl(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_dev,
+                           void *lnorm_dev, void *stream_, bool propagator) {
     cudaStream_t stream = (cudaStream_t)stream_;
     QSX_REQUIRE(out && Lt_dev && lnorm_dev && M > 0 && n_generators > 0, "qsx_dense_wrap: bad arguments");
     qsx_dense_s *h = new qsx_dense_s();
     h->M = M; h->n_gen = n_generators;
     h->Lt.p = (cplx *)Lt_dev;
     h->lnorm.p = (double *)lnorm_dev;
-    dense_norm_kernel<<<n_generators, 64, 0, stream>>>(h->Lt.p, h->lnorm.p, M);
-    qsx_launch_counter += 1;
+    h->is_propagator = propagator;
+    // generators: inf-norms for sub-step sizes and the propagator scaling; propagators are
+    // only ever stepped (y <- P y), which needs none
+    if (!propagator) {
+        dense_norm_kernel<<<n_generators, 64, 0, stream>>>(h->Lt.p, h->lnorm.p, M);
+        qsx_launch_counter += 1;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         delete h;
@@ -942,6 +951,11 @@ extern "C" int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators,
     }
     *out = h;
     return QSX_OK;
+}
+
+extern "C" int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_dev,
+                              void *lnorm_dev, void *stream_) {
+    return dense_wrap_impl(out, M, n_generators, Lt_dev, lnorm_dev, stream_, false);
 }
 
 extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnorm_dev, qsx_dense_t *out,
@@ -964,7 +978,7 @@ extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnor
         cudaEventElapsedTime(&wms, w0, w1);
         cudaEventDestroy(w0); cudaEventDestroy(w1);
         if (rcw) return rcw;
-        rcw = qsx_dense_wrap(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_);
+        rcw = dense_wrap_impl(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_, true);
         if (rcw == QSX_OK) { (*out)->build_ms = wms; (*out)->build_gemms = ng; }
         return rcw;
     }
@@ -1004,7 +1018,7 @@ extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnor
         qsx_set_error("qsx_dense_expm: Taylor series of the propagator did not converge for %llu generator(s)", st[0]);
         return QSX_ERR_INTEGRATOR;
     }
-    int rc = qsx_dense_wrap(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_);
+    int rc = dense_wrap_impl(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_, true);
     if (rc == QSX_OK) { (*out)->build_ms = ms; (*out)->build_gemms = st[1]; }
     return rc;
 }

@@ -26,7 +26,15 @@ struct ZofeDev {
     const cplx *Gamma, *w;      // [P][S]
     double u;
     int ham_hermit, rho_hermit;
+    // the auxiliary operators of a stage input are copied to shared memory once per RHS
+    // (every O' element reads 2 n of them) when they fit next to the n x n operators
+    int stage_O;
+    unsigned mP, mS;            // 2^32 / P + 1, 2^32 / S + 1: division by multiplication (0: plain division)
 };
+
+__device__ __forceinline__ unsigned zofe_div(unsigned i, int d, unsigned m) {
+    return m ? __umulhi(i, m) : i / (unsigned)d;
+}
 
 struct qsx_zofe_s {
     ZofeDev d;
@@ -40,29 +48,54 @@ struct ZofeRhs {
     cplx *Sg;               // [S][n][n] shared (row-major per site)
     cplx *bop, *aop, *rho;  // [n][n] shared (row-major)
     cplx *cop;              // [n][n]
+    cplx *Os;               // [P S n n] shared copy of the auxiliary operators (stage_O) or null
     int n_pulse;
     const qsx_pulse *pulses;
     const cplx *Vp;         // [n_pulse][n][n] row-major Hilbert-space dipole operators (global)
 
     template <class Epi>
     __device__ __forceinline__ void apply(const cplx *x, double t, Epi epi) {
-        const int n = Z.n, S = Z.S, P = Z.P, nn = n * n;
+        // compile-time state count for the FMO-sized systems (unrolled n-loops, constant divisions)
+        if (Z.n == 7) apply_impl<7>(x, t, epi);
+        else apply_impl<0>(x, t, epi);
+    }
+
+    template <int NC, class Epi>
+    __device__ __forceinline__ void apply_impl(const cplx *x, double t, Epi epi) {
+        const int n = NC ? NC : Z.n, S = Z.S, P = Z.P, nn = n * n;
         cplx gp[QSX_MAX_PULSES];
         for (int p = 0; p < n_pulse; ++p) gp[p] = pulse_coefficient(pulses[p], t);
         const int tid = threadIdx.x, nthr = blockDim.x;
-        const cplx *O = x + nn;
+        const long long no = (long long)P * S * nn;
         __syncthreads();        // previous users of the shared operators are done
+        const cplx *O = x + nn;
+        if (Os) {
+            for (int i = tid; i < (int)no; i += nthr) Os[i] = O[i];
+            O = Os;
+            __syncthreads();
+        }
         // rho (row-major copy) and Sg_s = sum_p O[p,s]
         for (int i = tid; i < nn; i += nthr) {
             int a = i / n, b = i % n;
             rho[i] = x[a + n * b];
         }
-        for (int i = tid; i < S * nn; i += nthr) {
-            int s = i / nn, ab = i % nn, a = ab / n, b = ab % n;
-            const cplx *col = O + (size_t)P * (s + S * (a + n * b));
+        // sixteen lanes per sum: they read consecutive pseudomodes (contiguous, conflict-free
+        // in shared memory) and meet in four shuffles; the trip count is uniform per warp
+        for (int i0 = (tid >> 5) * 2; i0 < S * nn; i0 += (nthr >> 5) * 2) {
+            const int i = i0 + ((tid >> 4) & 1);
+            const bool live = i < S * nn;
             cplx acc = cmake(0, 0);
-            for (int p = 0; p < P; ++p) acc = cadd(acc, col[p]);
-            Sg[i] = acc;
+            if (live) {
+                int s = i / nn, ab = i % nn, a = ab / n, b = ab % n;
+                const cplx *col = O + P * (s + S * (a + n * b));
+                for (int p = tid & 15; p < P; p += 16) acc = cadd(acc, col[p]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o, 16);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o, 16);
+            }
+            if (live && (tid & 15) == 0) Sg[i] = acc;
         }
         __syncthreads();
         // a[x][y] = sum_s (-v_s[x]) Sg_s[x][y];  b = -i H - a
@@ -142,13 +175,12 @@ struct ZofeRhs {
             epi(xr + n * yc, tot);
         }
         // O' elements; consecutive threads = consecutive pseudomodes (coalesced)
-        const long long no = (long long)P * S * nn;
-        for (long long i = tid; i < no; i += nthr) {
-            int p = (int)(i % P);
-            long long r = i / P;
-            int s = (int)(r % S);
-            r /= S;
-            int xr = (int)(r % n), yc = (int)(r / n);
+        for (unsigned i = tid; i < (unsigned)no; i += nthr) {
+            unsigned r = zofe_div(i, P, Z.mP);
+            const int p = (int)(i - r * P);
+            const unsigned r2 = zofe_div(r, S, Z.mS);
+            const int s = (int)(r - r2 * S);
+            const int xr = (int)(r2 % n), yc = (int)(r2 / n);
             const cplx o = O[i];
             const cplx wv = Z.w[p * S + s];
             cplx acc = cmake(-(wv.x * o.x - wv.y * o.y), -(wv.x * o.y + wv.y * o.x));
@@ -156,8 +188,9 @@ struct ZofeRhs {
                 cplx g = Z.Gamma[p * S + s];
                 rfma(acc, -Z.v[s * n + xr], g);
             }
-            const cplx *Ops = O + p + (size_t)P * s;       // O[p,s,a,b] at Ops[P S (a + n b)]
-            const size_t st = (size_t)P * S;
+            const cplx *Ops = O + p + P * s;               // O[p,s,a,b] at Ops[P S (a + n b)]
+            const int st = P * S;
+#pragma unroll
             for (int z = 0; z < n; ++z) {
                 cfma(acc, bop[xr * n + z], Ops[st * (z + n * yc)]);
                 cplx bz = bop[z * n + yc];
@@ -178,7 +211,7 @@ struct ZofeRhs {
                 }
                 cfma(tot, gp[p], c2);
             }
-            epi((int)(nn + i), tot);
+            epi(nn + (int)i, tot);
         }
     }
 };
@@ -235,11 +268,15 @@ __device__ __forceinline__ void zofe_rhs_setup(const ZofeDev &Z, unsigned char *
     r.bop = p; p += nn;
     r.aop = p; p += nn;
     r.rho = p; p += nn;
-    r.cop = p;
+    r.cop = p; p += nn;
+    r.Os = Z.stage_O ? p : nullptr;
     r.n_pulse = 0; r.pulses = nullptr; r.Vp = nullptr;
 }
 
-__global__ void __launch_bounds__(256) zofe_propagate_kernel(ZofeKernelArgs a) {
+#ifndef QSX_ZOFE_MINB
+#define QSX_ZOFE_MINB 2
+#endif
+__global__ void __launch_bounds__(256, QSX_ZOFE_MINB) zofe_propagate_kernel(ZofeKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int col = blockIdx.x;
     ZofeRhs rhs;
@@ -283,8 +320,9 @@ __global__ void __launch_bounds__(256) zofe_apply_kernel(ZofeApplyArgs a) {
     rhs.apply(a.x + (size_t)col * a.Z.dim, 0.0, [&](int i, cplx v) { yb[i] = v; });
 }
 
+static size_t zofe_smem_base(const ZofeDev &Z) { return (16 + (size_t)(Z.S + 4) * Z.n * Z.n) * sizeof(cplx); }
 static size_t zofe_smem(const ZofeDev &Z) {
-    return (16 + (size_t)(Z.S + 4) * Z.n * Z.n) * sizeof(cplx);
+    return zofe_smem_base(Z) + (Z.stage_O ? (size_t)Z.P * Z.S * Z.n * Z.n * sizeof(cplx) : 0);
 }
 
 extern "C" int qsx_zofe_create(qsx_zofe_t *out, const qsx_zofe_config *cfg, void *stream_) {
@@ -307,6 +345,12 @@ extern "C" int qsx_zofe_create(qsx_zofe_t *out, const qsx_zofe_config *cfg, void
     int dev = 0, smem_limit = 0;
     QSX_CUDA(cudaGetDevice(&dev));
     QSX_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // staged auxiliary operators: two CTAs per SM must still fit
+    d.stage_O = 2 * (zofe_smem_base(d) + (size_t)P * S * n * n * sizeof(cplx) + 1024) <= (size_t)228 * 1024 ? 1 : 0;
+    const unsigned long long no = (unsigned long long)P * S * n * n;
+    const bool magic = no * (unsigned long long)std::max(P, S) < (1ULL << 31);
+    d.mP = magic ? (unsigned)((1ULL << 32) / P + 1) : 0;
+    d.mS = magic ? (unsigned)((1ULL << 32) / S + 1) : 0;
     if (zofe_smem(d) > (size_t)smem_limit || d.dim > 0x7fffffffLL) {
         qsx_set_error("ZOFE system too large for the CTA-resident kernel (n=%d, sites=%d)", n, S);
         return QSX_ERR_UNSUPPORTED;
