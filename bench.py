@@ -490,7 +490,7 @@ def heom_leg(torch, qb, systems, engine, with_cpu):
 
 def zofe_leg(torch, qb, systems, fp64_peak):
     """K3: ZOFE master equation, FMO 'e' with the 16-pseudomode bath, a 592-member disorder
-    ensemble (one CTA per trajectory, four per SM): RHS applications/s against the FP64 ceiling."""
+    ensemble (one CTA per trajectory, two per SM: two full waves): RHS applications/s against the FP64 ceiling."""
     E = 592
     model = qb.ZOFEModel(systems.fmo(bath='pseudomode'), hilbert_subspace='e',
                          unit_convert=qb.CM_FS)
