@@ -192,10 +192,14 @@ __global__ void __launch_bounds__(256) redfield_eig_kernel(int m, int N, int nb,
     }
 }
 
+// NC > 0: compile-time state count for full blocks (N = na = nbb = nb = NC, e.g. FMO 'ee'):
+// the index arithmetic of the tensor loops -- a fifth of the kernel's instructions with
+// run-time divisors -- becomes multiplications by constants and the state loops unroll.
+template <int NC>
 __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = a.N, nb = a.nb, N2 = N * N;
-    const int na = a.na, nbb = a.nbb;
+    const int N = NC ? NC : a.N, nb = NC ? NC : a.nb, N2 = N * N;
+    const int na = NC ? NC : a.na, nbb = NC ? NC : a.nbb;
     const size_t N4 = (size_t)na * nbb * na * nbb;       // entries of the tensor block
     cplx *Us = reinterpret_cast<cplx *>(smem_raw);       // [N][N]
     cplx *Cs = Us + N2;                                  // [N][N]
@@ -491,8 +495,13 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
         QSX_CUDA(cudaGetLastError());
         a.jacobi = 0; a.E = d_E.p; a.U = d_U.p;
     }
-    QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    redfield_build_kernel<<<grid, 256, smem, stream>>>(a);
+    if (N == 7 && na == 7 && nbb == 7 && n_baths == 7) {
+        QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        redfield_build_kernel<7><<<grid, 256, smem, stream>>>(a);
+    } else {
+        QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        redfield_build_kernel<0><<<grid, 256, smem, stream>>>(a);
+    }
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
     // no host synchronisation: the generators stay on the device, the scratch buffers return
