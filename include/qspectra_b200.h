@@ -147,6 +147,10 @@ int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_d
 /* Device time (CUDA events) and number of M x M complex GEMMs of the qsx_dense_expm call
  * that produced `h` (bench.py: FP64 tensor roofline). */
 int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_gemms);
+/* qsx_dense_expm and qsx_dense_propagate with QSX_METHOD_MAP return as soon as their kernel is
+ * queued (no host synchronisation; neither can fail at run time): qsx_dense_build_stats waits for
+ * the build, and a propagation that reports kernel_ms < 0 has its device time collected here. */
+int qsx_dense_last_kernel_ms(qsx_dense_t h, double *kernel_ms);
 void qsx_dense_destroy(qsx_dense_t h);
 
 /* ------------------------------------------------------------------------

@@ -81,6 +81,7 @@ BATH_DEBYE_COMPLEX, BATH_DEBYE_REAL = 0, 1
 EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches', 'qsx_transfer_bytes',
            'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
            'qsx_dense_propagate', 'qsx_dense_expm', 'qsx_dense_wrap', 'qsx_dense_build_stats',
+           'qsx_dense_last_kernel_ms',
            'qsx_dense_destroy', 'qsx_heom_create',
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
@@ -126,6 +127,7 @@ def lib():
                                  C.POINTER(C.c_void_p), C.c_void_p]
     L.qsx_dense_build_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double),
                                         C.POINTER(C.c_uint64)]
+    L.qsx_dense_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qsx_dense_wrap.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p]
     L.qsx_dense_destroy.argtypes = [C.c_void_p]
@@ -254,16 +256,16 @@ def to_device(array, dtype=None):
             t = t.to(dtype)
         if not t.is_cuda:
             _py_h2d += t.numel() * t.element_size()
-        return t.cuda().contiguous()
+            t = t.contiguous().pin_memory().cuda(non_blocking=True)
+        return t.contiguous()
     a = np.ascontiguousarray(array, dtype=np.complex128 if dtype is None else None)
     t = torch.from_numpy(a)
     if dtype is not None:
         t = t.to(dtype)
     _py_h2d += t.numel() * t.element_size()
-    # pinned staging makes a large H2D copy a real DMA transfer
-    if t.numel() > (1 << 16):
-        return t.pin_memory().cuda(non_blocking=True)
-    return t.cuda()
+    # pinned staging (torch's caching host allocator): a large copy becomes a real DMA transfer,
+    # and a small one does not make the host wait for the kernels queued ahead of it
+    return t.pin_memory().cuda(non_blocking=True)
 
 
 def int32_ptr(values):

@@ -26,6 +26,19 @@ struct qsx_dense_s {
     unsigned long long build_gemms = 0;
     // the handle holds propagators exp(L dt): only QSX_METHOD_MAP applies, no norms are kept
     bool is_propagator = false;
+    // Deferred completion: qsx_dense_expm and QSX_METHOD_MAP propagations return as soon as
+    // their kernel is queued (neither can fail at run time); the device time and counters are
+    // collected when qsx_dense_build_stats / qsx_dense_last_kernel_ms ask for them.
+    cudaEvent_t build_ev[2] = {nullptr, nullptr};
+    const unsigned long long *build_status = nullptr;      // pinned host slot the counters are copied to in-stream
+    bool build_pending = false;
+    cudaEvent_t prop_ev[2] = {nullptr, nullptr};
+    bool prop_pending = false;
+    double last_prop_ms = 0.0;
+    ~qsx_dense_s() {
+        for (cudaEvent_t e : build_ev) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : prop_ev) if (e) cudaEventDestroy(e);
+    }
 };
 
 // ------------------------------------------------------------------ kernels
@@ -575,6 +588,17 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
         return QSX_ERR_CUDA;
     }
     QSX_CUDA(cudaEventRecord(e1, stream));
+    if (args->method == QSX_METHOD_MAP) {
+        // propagator stepping cannot fail and its counters are known: return without a host
+        // synchronisation; kernel_ms < 0 tells the caller to ask qsx_dense_last_kernel_ms later
+        if (h->prop_ev[0]) { cudaEventDestroy(h->prop_ev[0]); cudaEventDestroy(h->prop_ev[1]); }
+        h->prop_ev[0] = e0; h->prop_ev[1] = e1;
+        h->prop_pending = true;
+        args->rhs_evaluations = (uint64_t)(nt - 1) * B;
+        args->accepted_steps = (uint64_t)(nt - 1) * B;
+        args->kernel_ms = -1.0;
+        return QSX_OK;
+    }
     unsigned long long stats[3] = {0, 0, 0};
     qsx_d2h_counter += sizeof(stats);
     QSX_CUDA(cudaMemcpyAsync(stats, d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, stream));
@@ -921,8 +945,45 @@ static cudaError_t launch_expm(const cplx *Lt, const double *lnorm, int M, doubl
     return launch_expm_ks<MT, 2 * MT>(Lt, lnorm, M, dt, Pt, status, n_gen, stream);
 }
 
+// Ring of pinned host slots for counters that are read back lazily (a slot is reused after
+// 1024 further propagator builds; by then its handle has been asked or destroyed).
+static unsigned long long *pinned_status_slot() {
+    static unsigned long long *ring = nullptr;
+    static unsigned next = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ring && cudaHostAlloc(reinterpret_cast<void **>(&ring), 1024 * 2 * sizeof(unsigned long long),
+                               cudaHostAllocDefault) != cudaSuccess) {
+        ring = nullptr;
+        return nullptr;
+    }
+    unsigned long long *slot = ring + 2 * (next++ % 1024);
+    return slot;
+}
+
+extern "C" int qsx_dense_last_kernel_ms(qsx_dense_t h, double *kernel_ms) {
+    QSX_REQUIRE(h && kernel_ms, "null argument");
+    if (h->prop_pending) {
+        QSX_CUDA(cudaEventSynchronize(h->prop_ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->prop_ev[0], h->prop_ev[1]);
+        h->last_prop_ms = ms;
+        h->prop_pending = false;
+    }
+    *kernel_ms = h->last_prop_ms;
+    return QSX_OK;
+}
+
 extern "C" int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_gemms) {
     QSX_REQUIRE(h, "null handle");
+    if (h->build_pending) {
+        QSX_CUDA(cudaEventSynchronize(h->build_ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->build_ev[0], h->build_ev[1]);
+        h->build_ms = ms;
+        h->build_gemms = h->build_status[1];                // copied in-stream ahead of the event
+        h->build_pending = false;
+    }
     if (kernel_ms) *kernel_ms = h->build_ms;
     if (complex_gemms) *complex_gemms = h->build_gemms;
     return QSX_OK;
@@ -1006,19 +1067,20 @@ extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnor
         qsx_set_error("qsx_dense_expm: %s", cudaGetErrorString(e));
         return QSX_ERR_CUDA;
     }
+    // no host synchronisation: the fixed-degree series cannot fail; time and GEMM count are
+    // read back by qsx_dense_build_stats (the counters travel to a pinned host slot in-stream)
+    unsigned long long *slot = pinned_status_slot();
+    QSX_REQUIRE(slot, "qsx_dense_expm: no pinned host memory");
+    qsx_d2h_counter += 2 * sizeof(unsigned long long);
+    QSX_CUDA(cudaMemcpyAsync(slot, status.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     QSX_CUDA(cudaEventRecord(e1, stream));
-    unsigned long long st[2] = {0, 0};
-    qsx_d2h_counter += sizeof(st);
-    QSX_CUDA(cudaMemcpyAsync(st, status.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
-    QSX_CUDA(cudaStreamSynchronize(stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (st[0]) {
-        qsx_set_error("qsx_dense_expm: Taylor series of the propagator did not converge for %llu generator(s)", st[0]);
-        return QSX_ERR_INTEGRATOR;
-    }
     int rc = dense_wrap_impl(out, M, h->n_gen, Pt_dev, lnorm_dev, stream_, true);
-    if (rc == QSX_OK) { (*out)->build_ms = ms; (*out)->build_gemms = st[1]; }
+    if (rc != QSX_OK) {
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return rc;
+    }
+    (*out)->build_ev[0] = e0; (*out)->build_ev[1] = e1;
+    (*out)->build_status = slot;
+    (*out)->build_pending = true;
     return rc;
 }

@@ -16,7 +16,10 @@ from ._capi import IntegratorError  # noqa: F401  (re-export)
 
 
 class PropagationStats(object):
-    """Counters of the most recent propagations (bench.py reads these)."""
+    """Counters of the most recent propagations (bench.py reads these after
+    ``flush()``).  Propagator builds and propagator stepping do not synchronise
+    with the host; their device times are collected lazily: ``flush()`` (or reading
+    ``eom.last`` / ``prop.build_ms``) waits for the recorded events."""
     rhs_evaluations = 0
     accepted_steps = 0
     kernel_ms = 0.0
@@ -24,9 +27,12 @@ class PropagationStats(object):
     expm_ms = 0.0
     expm_gemms = 0
     expm_builds = 0
+    _pending = []          # objects with a resolve() that adds their device times
+    MAX_PENDING = 8        # older entries are resolved (their events have long completed)
 
     @classmethod
     def reset(cls):
+        cls.flush()
         cls.rhs_evaluations = 0
         cls.accepted_steps = 0
         cls.kernel_ms = 0.0
@@ -34,6 +40,17 @@ class PropagationStats(object):
         cls.expm_ms = 0.0
         cls.expm_gemms = 0
         cls.expm_builds = 0
+
+    @classmethod
+    def defer(cls, resolve):
+        cls._pending.append(resolve)
+        while len(cls._pending) > cls.MAX_PENDING:
+            cls._pending.pop(0)()
+
+    @classmethod
+    def flush(cls):
+        while cls._pending:
+            cls._pending.pop(0)()
 
 
 class LinearMap(object):
@@ -168,12 +185,42 @@ class DeviceEOM(object):
         self._propagate(args)
         PropagationStats.rhs_evaluations += int(args.rhs_evaluations)
         PropagationStats.accepted_steps += int(args.accepted_steps)
-        PropagationStats.kernel_ms += float(args.kernel_ms)
         PropagationStats.propagations += 1
-        self.last = dict(rhs=int(args.rhs_evaluations),
-                         steps=int(args.accepted_steps),
-                         kernel_ms=float(args.kernel_ms), method=method)
+        info = dict(rhs=int(args.rhs_evaluations), steps=int(args.accepted_steps),
+                    kernel_ms=float(args.kernel_ms), method=method)
+        if info['kernel_ms'] < 0:
+            # queued without a host synchronisation (propagator stepping): the device time
+            # is collected when somebody asks for it
+            info['kernel_ms'] = None
+            PropagationStats.defer(lambda eom=self, info=info: eom._resolve_last(info))
+        else:
+            PropagationStats.kernel_ms += info['kernel_ms']
+        self.last = info
         return out if return_device else _capi.to_host(out)
+
+    def _resolve_last(self, info):
+        if info.get('kernel_ms') is None:
+            info['kernel_ms'] = self._last_kernel_ms()
+            PropagationStats.kernel_ms += info['kernel_ms']
+
+    def _last_kernel_ms(self):
+        raise RuntimeError('%s never defers its statistics' % type(self).__name__)
+
+    @property
+    def last(self):
+        """Statistics of the most recent propagation: rhs, steps, kernel_ms, method."""
+        src = self.__dict__.get('_last_src')
+        if src is not None:
+            return dict(src.last, method='expm')
+        info = self.__dict__.get('_last')
+        if info is not None:
+            self._resolve_last(info)
+        return info
+
+    @last.setter
+    def last(self, info):
+        self.__dict__['_last'] = info
+        self.__dict__['_last_src'] = None
 
     def _configure_save(self, args, save, keep):
         if save is None:
@@ -265,13 +312,9 @@ class DenseEOM(DeviceEOM):
                 self._h, key, prop._storage[0].data_ptr(),
                 prop._storage[1].data_ptr(), C.byref(prop._h),
                 _capi.current_stream_ptr()))
-            ms, gemms = C.c_double(), C.c_uint64()
-            _capi.check(_capi.lib().qsx_dense_build_stats(prop._h, C.byref(ms),
-                                                          C.byref(gemms)))
-            prop.build_ms, prop.build_gemms = ms.value, int(gemms.value)
-            PropagationStats.expm_ms += ms.value
-            PropagationStats.expm_gemms += int(gemms.value)
+            # no host synchronisation: device time and GEMM count are read back lazily
             PropagationStats.expm_builds += 1
+            PropagationStats.defer(prop._resolve_build)
             cache[key] = prop
         return cache[key]
 
@@ -316,7 +359,7 @@ class DenseEOM(DeviceEOM):
                     (name == 'expm' or worth):
                 prop = self.propagator(dt)
                 out = DeviceEOM.propagate(prop, y0, t, t0=t0, method='map', **kw)
-                self.last = dict(prop.last, method='expm')
+                self.__dict__['_last_src'] = prop      # resolved (and relabelled 'expm') on access
                 return out
             if name == 'expm':
                 raise ValueError('expm needs a uniform output grid starting at '
@@ -332,6 +375,29 @@ class DenseEOM(DeviceEOM):
     def _propagate(self, args):
         _capi.check(_capi.lib().qsx_dense_propagate(
             self._h, C.byref(args), _capi.current_stream_ptr()))
+
+    def _last_kernel_ms(self):
+        ms = C.c_double()
+        _capi.check(_capi.lib().qsx_dense_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def _resolve_build(self):
+        """Device time / GEMM count of the qsx_dense_expm call that made this handle."""
+        if '_build' not in self.__dict__ and getattr(self, '_h', None):
+            ms, gemms = C.c_double(), C.c_uint64()
+            _capi.check(_capi.lib().qsx_dense_build_stats(self._h, C.byref(ms), C.byref(gemms)))
+            self.__dict__['_build'] = (ms.value, int(gemms.value))
+            PropagationStats.expm_ms += ms.value
+            PropagationStats.expm_gemms += int(gemms.value)
+        return self.__dict__.get('_build', (0.0, 0))
+
+    @property
+    def build_ms(self):
+        return self._resolve_build()[0]
+
+    @property
+    def build_gemms(self):
+        return self._resolve_build()[1]
 
 
 class HeomEOM(DeviceEOM):
