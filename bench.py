@@ -79,7 +79,7 @@ def workload_config(members, n_gpus):
                         '1 ps / 197 output points' % members,
             'members_per_gpu': members, 'state_dim': 49, 'grid_points': 197,
             'integrator': 'propagator stepping: exp(L dt) per member on the FP64 tensor '
-                          'cores (|A| <= 1/2 scaling, fixed degree-14 Taylor polynomial in '
+                          'cores (|A| <= 1/2 scaling, fixed degree-12 Taylor polynomial in '
                           'Paterson-Stockmeyer form, squarings), then y <- P y per output '
                           'interval; the propagators are rebuilt in every timed step',
             'parallelism': 'ensemble members sharded over %d GPU(s), one NCCL '
@@ -791,7 +791,7 @@ def run_ours(args):
               'unit': 'TFLOP/s', 'frac': achieved_tf / fp64_peak,
               'traffic': (ncu_traffic('dense_expm_per_member') or 0) * E or None,
               'kernel': 'dense_expm2_kernel<7,13> (FP64 DMMA m8n8k4, three real products per complex one: exp(L dt) per member, '
-                        'Paterson-Stockmeyer degree 14 + squarings)',
+                        'Paterson-Stockmeyer degree 12 + squarings)',
               'kernel_ms': expm_ms, 'share_of_step': expm_ms / ms_per_step,
               'algorithmic_flops_per_launch': flops_per_launch, 'peak_source': peak_note}
     k_map = {'bound': 'tensor', 'achieved': map_tf, 'peak': fp64_peak,

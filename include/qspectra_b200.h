@@ -131,7 +131,8 @@ int qsx_dense_apply(qsx_dense_t h, const void *y_dev, void *dy_dev,
                     void *stream);
 int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void *stream);
 /* New handle holding P_g = exp(L_g * dt) for every generator of `h`, computed on the FP64
- * tensor cores (|A| <= 1/2 scaling, degree-14 Taylor polynomial in Paterson-Stockmeyer form,
+ * tensor cores (|A| <= 1/2 scaling, degree-12 Taylor polynomial in Paterson-Stockmeyer form: five
+ * products, remainder < 2e-14; degree 14 in the tiled path for M > 56,
  * squarings; one CTA per generator up to M = 56, tiled GEMM launches up to M = 1024).  Use it
  * with QSX_METHOD_MAP on a uniform output grid of spacing dt: the exact counterpart of the
  * reference's ZVODE loop for a constant generator (simulate/utils.py:45-49). */
