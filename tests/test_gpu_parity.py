@@ -232,13 +232,15 @@ def test_heom_lean_tile_ensemble_matches_single_member_launches():
 
 
 @pytest.mark.parametrize('modified', [False, True])
-@pytest.mark.parametrize('grid', [None, '2'])
+@pytest.mark.parametrize('grid', [None, '2', '3', '5'])
 def test_heom_row_tile_matches_batch_tile(modified, grid, golden, monkeypatch):
     """The row tile (csrc/heom_row.cuh; default from 64 (column, tile) units on) forced onto the depth-4
     FMO hierarchy: RHS application, adaptive Taylor and product-form trajectories against the
     batch tile that the golden-fixture tests validate, and against the reference trajectory.
     grid = 2: two CTAs walk eleven tiles each, so the buffer ring wraps and the mbarrier
-    phases flip several times per stage."""
+    phases flip several times per stage; grid = 3 and 5 leave a short last round (22 = 7 x 3 + 1
+    = 4 x 5 + 2), so the unit -> CTA assignment of the barrier-free stages rotates from stage
+    to stage and CTAs own different numbers of tiles."""
     import torch
     m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS, level_cutoff=4,
                      K=1, modified_HEOM=modified, low_temp_corr=True)
@@ -280,11 +282,15 @@ def test_heom_row_tile_matches_batch_tile(modified, grid, golden, monkeypatch):
     assert rel_l2(mat_r, mat_b) < 1e-11
 
 
-def test_heom_row_tile_ensemble(monkeypatch):
+@pytest.mark.parametrize('grid', [None, '4', '7'])
+def test_heom_row_tile_ensemble(grid, monkeypatch):
     """Members with their own Hamiltonian (H staged with every tile) on the row tile, forced
-    onto a small batch, against the batch tile."""
+    onto a small batch, against the batch tile.  With a capped grid the barrier-free stages
+    run several rounds per stage over six columns (dependencies stay inside a column)."""
     import torch
     E = 6
+    if grid:
+        monkeypatch.setenv('QSX_HEOM_GRID', grid)
     m = qb.HEOMModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS,
                      level_cutoff=3, K=1)
     eom = m.ensemble_eom(E, False, 'ee')
