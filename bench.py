@@ -481,7 +481,7 @@ def heom_leg(torch, qb, systems, engine, with_cpu):
         'integrator': best['method'], 'rhs_per_s': rhs_per_s,
         'state_steps_per_s': best['steps'] / (best['kernel_ms'] * 1e-3),
         'kernel_ms': best['kernel_ms'],
-        'roofline': _heom_roofline(rhs_per_s, eom.dim, best['rhs'], 'heom_vibronic_per_rhs')}
+        'roofline': _heom_roofline(rhs_per_s, eom.dim, best['rhs'], 'heom_vibronic_batch64_per_rhs')}
     del eom, model
     if with_cpu:
         out['cpu_baseline'] = heom_cpu_baseline()
