@@ -354,7 +354,7 @@ def _heom_roofline(rhs_per_s, D, rhs, key):
     per_rhs = ncu_traffic(key)
     return {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
             'frac': achieved / peaks['hbm_gbs'],
-            'traffic': per_rhs * rhs if per_rhs else None,
+            'traffic': per_rhs * rhs if per_rhs is not None else None,
             'traffic_per_rhs': per_rhs,
             'achieved_is': 'rhs_per_s x 32 D (algorithmic bytes per RHS application)',
             'peak_source': src, 'algorithmic_bytes_per_rhs': 32 * D}
