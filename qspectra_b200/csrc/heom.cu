@@ -1342,6 +1342,7 @@ extern "C" int qsx_heom_create(qsx_heom_t *out, const qsx_heom_config *cfg, void
             r.d2 = 2.0 * u * cfg->temp_corr;
             r.const_h = cfg->n_members == 1;
             r.dbg = 0;
+            r.stream_rec = (size_t)n_tiles * C::REC_BYTES >= ((size_t)8 << 20);
             return QSX_OK;
         };
         int rc_row = QSX_OK;

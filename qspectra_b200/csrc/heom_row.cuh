@@ -116,6 +116,7 @@ struct RowDev {
     cplx cd[4];                             // -i u c_k
     double d2;                              // u * temp_corr * 2: Ishizaki-Tanimura term of off-diagonal elements
     int const_h;
+    int stream_rec;                         // large single hierarchy: top-level tiles and tile records are read once per stage (L2 evict_first)
     int dbg;                                // diagnostics (QSX_ROW_DBG builds): 1 no gathers, 2 gathers from the own tile, 4 no stores
 };
 
@@ -355,11 +356,14 @@ struct Pipe {
         unsigned char *b = bufs + (size_t)bi * C::BUF_BYTES;
         const int recb = tile >= R.top_tile ? C::TOP_BYTES : C::REC_BYTES;
         mbar_expect_tx(&full[bi], C::YS_BYTES + recb + (CONSTH ? 0 : C::MH * 8));
-        // a top-level tile is read once per stage (nothing links down into it from above, and the
-        // up-links of the level below were served earlier in the stage)
-        if (tile >= R.top_tile) bulk_g2s_stream(b, src + (size_t)col * Dp + (size_t)tile * C::M * 32, C::YS_BYTES, &full[bi]);
+        // in a large hierarchy a top-level tile is read once per stage (nothing links down into it
+        // from above, and the up-links of the level below were served earlier in the stage); in a
+        // batch of small hierarchies all tiles of a column are in flight together
+        if (R.stream_rec && tile >= R.top_tile) bulk_g2s_stream(b, src + (size_t)col * Dp + (size_t)tile * C::M * 32, C::YS_BYTES, &full[bi]);
         else bulk_g2s(b, src + (size_t)col * Dp + (size_t)tile * C::M * 32, C::YS_BYTES, &full[bi]);
-        bulk_g2s_stream(b + C::YS_BYTES, R.rec + (size_t)tile * C::REC_BYTES, recb, &full[bi]);     // re-read a whole stage later
+        // records: re-read a whole stage later in a large hierarchy, but shared by every column of a batch
+        if (R.stream_rec) bulk_g2s_stream(b + C::YS_BYTES, R.rec + (size_t)tile * C::REC_BYTES, recb, &full[bi]);
+        else bulk_g2s(b + C::YS_BYTES, R.rec + (size_t)tile * C::REC_BYTES, recb, &full[bi]);
         if (!CONSTH) {
             const int m = member_of ? member_of[col] : 0;
             bulk_g2s(b + C::OFF_H, R.hmem + (size_t)m * C::MH, C::MH * 8, &full[bi]);
