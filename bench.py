@@ -630,6 +630,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         engine.PropagationStats.reset()
+        engine.PropagationStats.keep_alive = True      # every timed step's device times are collected
         l0 = _capi.kernel_launches()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         torch.cuda.synchronize()
@@ -649,6 +650,7 @@ def run_ours(args):
             ms = float(tmax.item())
         st = engine.PropagationStats
         st.flush()          # collect the deferred device times of the timed steps
+        st.keep_alive = False
         stats = dict(expm_ms=st.expm_ms, expm_gemms=st.expm_gemms, expm_builds=st.expm_builds,
                      kernel_ms=st.kernel_ms / max(1, st.propagations),
                      rhs=st.rhs_evaluations / max(1, st.propagations),

@@ -152,6 +152,8 @@ int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_ge
  * queued (no host synchronisation; neither can fail at run time): qsx_dense_build_stats waits for
  * the build, and a propagation that reports kernel_ms < 0 has its device time collected here. */
 int qsx_dense_last_kernel_ms(qsx_dense_t h, double *kernel_ms);
+/* 1 when the two calls above would not block (the recorded events have completed). */
+int qsx_dense_events_ready(qsx_dense_t h);
 void qsx_dense_destroy(qsx_dense_t h);
 
 /* ------------------------------------------------------------------------

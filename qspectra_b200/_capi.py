@@ -81,7 +81,7 @@ BATH_DEBYE_COMPLEX, BATH_DEBYE_REAL = 0, 1
 EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches', 'qsx_transfer_bytes',
            'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
            'qsx_dense_propagate', 'qsx_dense_expm', 'qsx_dense_wrap', 'qsx_dense_build_stats',
-           'qsx_dense_last_kernel_ms',
+           'qsx_dense_last_kernel_ms', 'qsx_dense_events_ready',
            'qsx_dense_destroy', 'qsx_heom_create',
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
@@ -128,6 +128,7 @@ def lib():
     L.qsx_dense_build_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double),
                                         C.POINTER(C.c_uint64)]
     L.qsx_dense_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.qsx_dense_events_ready.argtypes = [C.c_void_p]
     L.qsx_dense_wrap.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p]
     L.qsx_dense_destroy.argtypes = [C.c_void_p]

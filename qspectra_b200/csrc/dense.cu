@@ -978,6 +978,13 @@ extern "C" int qsx_dense_last_kernel_ms(qsx_dense_t h, double *kernel_ms) {
     return QSX_OK;
 }
 
+extern "C" int qsx_dense_events_ready(qsx_dense_t h) {
+    if (!h) return 1;
+    if (h->build_pending && cudaEventQuery(h->build_ev[1]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (h->prop_pending && cudaEventQuery(h->prop_ev[1]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return 1;
+}
+
 extern "C" int qsx_dense_build_stats(qsx_dense_t h, double *kernel_ms, uint64_t *complex_gemms) {
     QSX_REQUIRE(h, "null handle");
     if (h->build_pending) {

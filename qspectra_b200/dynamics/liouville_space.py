@@ -16,7 +16,7 @@ from .base import DynamicalModel, SystemOperator
 from ..engine import DenseEOM, LinearMap
 from ..operator_tools import (SubspaceError, n_excitations,
                               full_liouville_subspace)
-from ..utils import imemoize, memoized_property
+from ..utils import _CACHE_ATTR, imemoize, memoized_property
 
 
 # ------------------------------------------------------------- conventions
@@ -205,6 +205,20 @@ class LiouvilleSpaceModel(DynamicalModel):
 
     def dipole_operator(self, liouv_subspace_map, polarization,
                         transitions='-+'):
+        # the response functions ask for the same few operators once per polarisation
+        # configuration and pathway: keep them per model (hashable polarisations only)
+        try:
+            key = ('dipole_operator', liouv_subspace_map, polarization, transitions)
+            # the instance cache of utils.imemoize: dropped by copy_with_new_cache (sampled members)
+            memo = self.__dict__.setdefault(_CACHE_ATTR, {})
+            return memo[key]
+        except KeyError:
+            memo[key] = op = self._dipole_operator(liouv_subspace_map, polarization, transitions)
+            return op
+        except TypeError:           # array-valued polarisation
+            return self._dipole_operator(liouv_subspace_map, polarization, transitions)
+
+    def _dipole_operator(self, liouv_subspace_map, polarization, transitions):
         operator = self.hamiltonian.dipole_operator(self.hilbert_subspace,
                                                     polarization, transitions)
         if self.evolve_basis == 'eigen':

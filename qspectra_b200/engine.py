@@ -27,8 +27,12 @@ class PropagationStats(object):
     expm_ms = 0.0
     expm_gemms = 0
     expm_builds = 0
-    _pending = []          # objects with a resolve() that adds their device times
-    MAX_PENDING = 8        # older entries are resolved (their events have long completed)
+    _pending = []          # (reference to an EOM, method name, argument) whose device times are outstanding
+    MAX_PENDING = 256
+    #: bench.py: keep the objects alive until flush() so that no timing is lost; by default
+    #: only weak references are held (no device memory is retained for statistics) and an
+    #: entry that overflows the list is resolved only if that does not block
+    keep_alive = False
 
     @classmethod
     def reset(cls):
@@ -42,15 +46,26 @@ class PropagationStats(object):
         cls.expm_builds = 0
 
     @classmethod
-    def defer(cls, resolve):
-        cls._pending.append(resolve)
+    def defer(cls, obj, name, arg=None):
+        import weakref
+        cls._pending.append((obj if cls.keep_alive else weakref.ref(obj), not cls.keep_alive, name, arg))
         while len(cls._pending) > cls.MAX_PENDING:
-            cls._pending.pop(0)()
+            cls._resolve(cls._pending.pop(0), False)
+
+    @classmethod
+    def _resolve(cls, entry, blocking):
+        ref, weak, name, arg = entry
+        obj = ref() if weak else ref
+        if obj is None or getattr(obj, '_h', None) is None:
+            return
+        if not blocking and not obj._stats_ready():
+            return
+        getattr(obj, name)(*(() if arg is None else (arg,)))
 
     @classmethod
     def flush(cls):
         while cls._pending:
-            cls._pending.pop(0)()
+            cls._resolve(cls._pending.pop(0), True)
 
 
 class LinearMap(object):
@@ -192,7 +207,7 @@ class DeviceEOM(object):
             # queued without a host synchronisation (propagator stepping): the device time
             # is collected when somebody asks for it
             info['kernel_ms'] = None
-            PropagationStats.defer(lambda eom=self, info=info: eom._resolve_last(info))
+            PropagationStats.defer(self, '_resolve_last', info)
         else:
             PropagationStats.kernel_ms += info['kernel_ms']
         self.last = info
@@ -314,7 +329,7 @@ class DenseEOM(DeviceEOM):
                 _capi.current_stream_ptr()))
             # no host synchronisation: device time and GEMM count are read back lazily
             PropagationStats.expm_builds += 1
-            PropagationStats.defer(prop._resolve_build)
+            PropagationStats.defer(prop, '_resolve_build')
             cache[key] = prop
         return cache[key]
 
@@ -380,6 +395,9 @@ class DenseEOM(DeviceEOM):
         ms = C.c_double()
         _capi.check(_capi.lib().qsx_dense_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def _stats_ready(self):
+        return bool(_capi.lib().qsx_dense_events_ready(self._h))
 
     def _resolve_build(self):
         """Device time / GEMM count of the qsx_dense_expm call that made this handle."""

@@ -333,6 +333,7 @@ class ElectronicHamiltonian(Hamiltonian):
                for n in range(self.n_sites)]
         return np.einsum('nij,n->ij', ops, mu)
 
+    @imemoize
     def number_operator(self, site, subspace='gef'):
         return operator_extend(
             np.diag(unit_vec(site, self.n_sites, dtype=float)), subspace)

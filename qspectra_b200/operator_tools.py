@@ -11,6 +11,8 @@ compared bit-exactly against the reference's golden vectors in
 from functools import reduce
 from itertools import combinations
 
+import functools
+
 import numpy as np
 
 _EXC_ORDER = 'gef'
@@ -95,9 +97,12 @@ def all_states(N, subspace='gef'):
     return states
 
 
+@functools.lru_cache(maxsize=None)
 def _state_masks(N, subspace):
-    return np.array([sum(1 << s for s in st) for st in all_states(N, subspace)],
-                    dtype=np.int64)
+    masks = np.array([sum(1 << s for s in st) for st in all_states(N, subspace)],
+                     dtype=np.int64)
+    masks.setflags(write=False)
+    return masks
 
 
 def operator_1_to_2(operator1):
@@ -132,7 +137,14 @@ def operator_extend(operator1, subspace='gef'):
 
 
 def transition_operator(n, n_sites, subspace='gef', include_transitions='-+'):
-    """0/1 matrix of a+_n ('+') and/or a_n ('-') between the listed states."""
+    """0/1 matrix of a+_n ('+') and/or a_n ('-') between the listed states (a fresh array;
+    the construction is cached: the response functions ask for the same few operators once
+    per polarisation configuration and pathway)."""
+    return _transition_operator(int(n), int(n_sites), str(subspace), str(include_transitions)).copy()
+
+
+@functools.lru_cache(maxsize=4096)
+def _transition_operator(n, n_sites, subspace, include_transitions):
     masks = _state_masks(n_sites, subspace)
     bit = 1 << n
     has = (masks & bit) != 0
