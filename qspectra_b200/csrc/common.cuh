@@ -112,6 +112,9 @@ extern std::atomic<uint64_t> qsx_h2d_counter, qsx_d2h_counter;
 // dense_wide.cu: exp(L dt) for state dimensions above the single-CTA propagator kernel
 int qsx_dense_expm_wide(const cplx *Lt, int M, int n_gen, const double *lnorm_dev, double dt, cplx *Pt,
                         unsigned long long *gemms, cudaStream_t stream);
+int qsx_dense_map_gemm(const cplx *Lt, int M, int n_runs, int R, const int *run_gen_dev, const int *run_save_dev,
+                       const cplx *y0, int nt, const cplx *S, int save_rows, long long S_stride, cplx *out,
+                       cudaStream_t stream);
 
 // Device scratch comes from a small caching pool (power-of-two size classes, blocks up
 // to 64 MB are kept for reuse; larger ones go straight to cudaMalloc/cudaFree): the

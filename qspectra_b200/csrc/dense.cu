@@ -467,6 +467,52 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
         QSX_REQUIRE(args->t_host[i] >= args->t_host[i - 1], "output times must be non-decreasing");
     QSX_REQUIRE(args->t_host[0] >= args->t0, "first output time precedes t0");
 
+    // Many columns per propagator with a save operator (the t2 stage of a response function):
+    // equal-length runs of >= 32 consecutive columns under one propagator and one save matrix go
+    // through the tensor-core GEMM form (dense_wide.cu) instead of one small CTA per four columns,
+    // where the save operator (rows x M, re-read from L2 for every group and time) dominated.
+    if (args->method == QSX_METHOD_MAP && args->save_mode == QSX_SAVE_MATRIX && B >= 4096 && !getenv("QSX_MAP_NO_GEMM")) {
+        QSX_REQUIRE(args->save_dev && args->save_rows > 0, "save matrix missing");
+        const int32_t *gen_of = args->generator_of_column_host, *save_of = args->save_of_column_host;
+        QSX_REQUIRE(save_of || args->n_save == 1 || args->n_save == h->n_gen,
+                    "n_save must be 1 or n_generators unless save_of_column is given");
+        auto gen_at = [&](int c) { return gen_of ? gen_of[c] : 0; };
+        auto save_at = [&](int c) { return save_of ? save_of[c] : (args->n_save > 1 ? gen_at(c) : 0); };
+        int R = 1;
+        while (R < B && gen_at(R) == gen_at(0) && save_at(R) == save_at(0)) ++R;
+        bool uniform = R >= 32 && B % R == 0;
+        std::vector<int> run_gen, run_save;
+        for (int r0 = 0; r0 < B && uniform; r0 += R) {
+            const int g = gen_at(r0), sv = save_at(r0);
+            uniform = g >= 0 && g < h->n_gen && sv >= 0 && sv < std::max(1, args->n_save);
+            for (int c = r0 + 1; c < r0 + R && uniform; ++c) uniform = gen_at(c) == g && save_at(c) == sv;
+            // the next run must differ, or runs would not be maximal -- harmless, but keep R as found
+            run_gen.push_back(g);
+            run_save.push_back(sv);
+        }
+        if (uniform) {
+            DevBuf<int> d_rg, d_rs;
+            int rcu;
+            if ((rcu = upload_ints(d_rg, run_gen, stream)) || (rcu = upload_ints(d_rs, run_save, stream))) return rcu;
+            cudaEvent_t e0, e1;
+            QSX_CUDA(cudaEventCreate(&e0));
+            QSX_CUDA(cudaEventCreate(&e1));
+            QSX_CUDA(cudaEventRecord(e0, stream));
+            const long long S_stride = args->n_save > 1 ? (long long)args->save_rows * M : 0;
+            rcu = qsx_dense_map_gemm(h->Lt.p, M, (int)run_gen.size(), R, d_rg.p, d_rs.p, (const cplx *)args->y0_dev, nt,
+                                     (const cplx *)args->save_dev, args->save_rows, S_stride, (cplx *)args->out_dev,
+                                     stream);
+            if (rcu) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rcu; }
+            QSX_CUDA(cudaEventRecord(e1, stream));
+            if (h->prop_ev[0]) { cudaEventDestroy(h->prop_ev[0]); cudaEventDestroy(h->prop_ev[1]); }
+            h->prop_ev[0] = e0; h->prop_ev[1] = e1;
+            h->prop_pending = true;
+            args->rhs_evaluations = (uint64_t)(nt - 1) * B;
+            args->accepted_steps = (uint64_t)(nt - 1) * B;
+            args->kernel_ms = -1.0;
+            return QSX_OK;
+        }
+    }
     // groups: runs of consecutive columns sharing a generator, at most NB wide
     int max_run = 1, run = 0, prev = -1;
     for (int c = 0; c < B; ++c) {

@@ -42,9 +42,13 @@ struct ZgemmArgs {
     int M, N, K;                    // C is M x N, contraction length K
     int lda, ldb, ldc;              // row strides (elements)
     long long sA, sB, sC;           // strides between units
+    const int *ib;                  // B operand of unit u is B + ib[u] * sB (null: u)
     int n_units;
     int b_transposed;               // 1: B_u is stored [N][K] (C = A B^T)
     int reduce;                     // 1: one output, summed over the units with weights w
+    int n_split;                    // reduce: the units are dealt out to n_split CTAs per output tile; CTA z writes
+                                    // its partial sum to part[z] (deterministic second pass adds them to C)
+    cplx *part;                     // [n_split][M][ldc] (reduce with n_split > 1)
     const cplx *w;                  // [n_units] or null (= 1)
     // epilogue of the unit-wise form: C = AB + c0 I + c1 X + c2 Y  (X, Y like C)
     const cplx *X, *Y;
@@ -58,7 +62,10 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
-    const int u_begin = a.reduce ? 0 : blockIdx.z, u_end = a.reduce ? a.n_units : blockIdx.z + 1;
+    // reduce: contiguous block of units per split
+    const int per = a.reduce ? (a.n_units + a.n_split - 1) / a.n_split : 1;
+    const int u_begin = a.reduce ? (int)blockIdx.z * per : (int)blockIdx.z;
+    const int u_end = a.reduce ? min(a.n_units, u_begin + per) : (int)blockIdx.z + 1;
 
     // final accumulators (re, im for the two columns a thread owns in each of the 4 column blocks)
     double fr[4][2], fi[4][2];
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
     for (int nb = 0; nb < 4; ++nb) { fr[nb][0] = fr[nb][1] = fi[nb][0] = fi[nb][1] = 0.0; }
 
     for (int u = u_begin; u < u_end; ++u) {
-        const cplx *Au = a.A + (size_t)u * a.sA, *Bu = a.B + (size_t)u * a.sB;
+        const cplx *Au = a.A + (size_t)u * a.sA, *Bu = a.B + (size_t)(a.ib ? __ldg(&a.ib[u]) : u) * a.sB;
         double p1[4][2], p2[4][2], p3[4][2];
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) { p1[nb][0] = p1[nb][1] = p2[nb][0] = p2[nb][1] = p3[nb][0] = p3[nb][1] = 0.0; }
@@ -133,6 +140,10 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
             if (c >= a.N) continue;
             const size_t o = (size_t)r * a.ldc + c;
             cplx v = cmake(fr[nb][j], fi[nb][j]);
+            if (a.reduce && a.n_split > 1) {
+                a.part[(size_t)blockIdx.z * a.M * a.ldc + o] = v;
+                continue;
+            }
             if (a.reduce) {
                 const cplx old = Cu[o];
                 v.x += old.x; v.y += old.y;
@@ -161,8 +172,20 @@ __global__ void wide_poly2_kernel(const cplx *__restrict__ A, const cplx *__rest
     }
 }
 
+// C[i] += sum_z part[z][i] in split order
+__global__ void zgemm_add_partials_kernel(const cplx *__restrict__ part, int n_split, size_t n, cplx *__restrict__ C) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        cplx v = C[i];
+        for (int z = 0; z < n_split; ++z) {
+            const cplx p = part[(size_t)z * n + i];
+            v.x += p.x; v.y += p.y;
+        }
+        C[i] = v;
+    }
+}
+
 int launch_zgemm(const ZgemmArgs &a, cudaStream_t stream) {
-    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.reduce ? 1 : a.n_units);
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.reduce ? std::max(1, a.n_split) : a.n_units);
     zgemm_dmma_kernel<<<grid, 128, 0, stream>>>(a);
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
@@ -199,7 +222,7 @@ int qsx_dense_expm_wide(const cplx *Lt, int M, int n_gen, const double *lnorm_de
     qsx_launch_counter += 1;
     ZgemmArgs g;
     g.M = g.N = g.K = M; g.lda = g.ldb = g.ldc = M; g.sA = g.sB = g.sC = (long long)mm;
-    g.n_units = n_gen; g.b_transposed = 0; g.reduce = 0; g.w = nullptr;
+    g.n_units = n_gen; g.b_transposed = 0; g.reduce = 0; g.w = nullptr; g.n_split = 1; g.part = nullptr; g.ib = nullptr;
     g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
     int rc;
     // all factors are polynomials in A, so the order of the products is immaterial
@@ -229,6 +252,67 @@ int qsx_dense_expm_wide(const cplx *Lt, int M, int n_gen, const double *lnorm_de
     return QSX_OK;
 }
 
+// Propagator stepping as tensor-core GEMMs for MANY columns per propagator (the t2 stage of a
+// response function: n_t1 columns per unit under one generator and one save operator; reference
+// simulate/utils.py:103-109 runs them one ZVODE solve at a time).  Columns come in `n_runs` runs
+// of `R` consecutive columns that share a propagator (run_gen) and a save matrix (run_save):
+//   per output time:  out[col][it][:] = S_run Y[col]     (R x M)(M x rows)  per run
+//   between times:    Y[col] <- P_run Y[col]             (R x M)(M x M)     per run
+// Lt is the engine's transposed storage Lt[g][c][r] = P_g[r][c], i.e. exactly the [K][N]
+// operand of Y_new^T = Y^T P^T.  Y ping-pongs between two work buffers.
+int qsx_dense_map_gemm(const cplx *Lt, int M, int n_runs, int R, const int *run_gen_dev, const int *run_save_dev,
+                       const cplx *y0, int nt, const cplx *S, int save_rows, long long S_stride, cplx *out,
+                       cudaStream_t stream) {
+    const size_t n = (size_t)n_runs * R * M;
+    // two state buffers from the stream-ordered allocator (they can be hundreds of MB: the
+    // scratch pool would cudaMalloc / cudaFree them, and cudaFree synchronises the device)
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        int dev = 0;
+        cudaMemPool_t mp;
+        unsigned long long keep = ~0ULL;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_ready = true;
+    }
+    cplx *Ya = nullptr, *Yb = nullptr;
+    QSX_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&Ya), n * sizeof(cplx), stream));
+    cudaError_t eb = cudaMallocAsync(reinterpret_cast<void **>(&Yb), n * sizeof(cplx), stream);
+    if (eb != cudaSuccess) {
+        cudaFreeAsync(Ya, stream);
+        qsx_set_error("qsx_dense_map_gemm: %s", cudaGetErrorString(eb));
+        return QSX_ERR_CUDA;
+    }
+    struct Release {
+        cplx *a, *b; cudaStream_t s;
+        ~Release() { cudaFreeAsync(a, s); cudaFreeAsync(b, s); }
+    } release{Ya, Yb, stream};
+    const cplx *cur = y0;
+    cplx *next = Ya;
+    ZgemmArgs g;
+    g.reduce = 0; g.w = nullptr; g.n_split = 1; g.part = nullptr;
+    g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
+    g.n_units = n_runs;
+    int rc;
+    for (int it = 0; it < nt; ++it) {
+        if (it > 0) {
+            g.A = cur; g.B = Lt; g.C = next; g.ib = run_gen_dev;
+            g.M = R; g.N = M; g.K = M; g.lda = M; g.ldb = M; g.ldc = M;
+            g.sA = (long long)R * M; g.sB = (long long)M * M; g.sC = (long long)R * M;
+            g.b_transposed = 0;
+            if ((rc = launch_zgemm(g, stream))) return rc;
+            cur = next;
+            next = (next == Ya) ? Yb : Ya;
+        }
+        g.A = cur; g.B = S; g.C = out + (size_t)it * save_rows; g.ib = S_stride ? run_save_dev : nullptr;
+        g.M = R; g.N = save_rows; g.K = M; g.lda = M; g.ldb = M; g.ldc = nt * save_rows;
+        g.sA = (long long)R * M; g.sB = S_stride; g.sC = (long long)R * nt * save_rows;
+        g.b_transposed = 1;
+        if ((rc = launch_zgemm(g, stream))) return rc;
+    }
+    return QSX_OK;
+}
+
 extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const void *w_dev, int32_t n_units,
                                      int64_t n_ab, int32_t n_c, int32_t K, void *s_dev, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -240,7 +324,22 @@ extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const
     g.M = (int)n_ab; g.N = n_c; g.K = K;
     g.lda = K; g.ldb = K; g.ldc = n_c;
     g.sA = (long long)n_ab * K; g.sB = (long long)n_c * K; g.sC = 0;
-    g.n_units = n_units; g.b_transposed = 1; g.reduce = 1; g.w = (const cplx *)w_dev;
+    g.n_units = n_units; g.b_transposed = 1; g.reduce = 1; g.w = (const cplx *)w_dev; g.ib = nullptr;
     g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
-    return launch_zgemm(g, stream);
+    // One CTA per output tile walking every unit leaves most SMs idle for a 197 x 5 x 197 signal
+    // (217 tiles): deal the units out to enough CTAs for ~16 resident per SM; the partial sums
+    // are added in split order, so the result does not depend on scheduling.
+    const long long tiles = ((n_ab + BM - 1) / BM) * ((n_c + BN - 1) / BN);
+    int n_split = (int)std::min<long long>(std::min<long long>(n_units, 64), (148LL * 16 + tiles - 1) / tiles);
+    n_split = std::max(1, n_split);
+    DevBuf<cplx> part;
+    if (n_split > 1) QSX_CUDA(part.alloc((size_t)n_split * n_ab * n_c));
+    g.n_split = n_split; g.part = part.p;
+    int rc = launch_zgemm(g, stream);
+    if (rc || n_split == 1) return rc;
+    const size_t n = (size_t)n_ab * n_c;
+    zgemm_add_partials_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(part.p, n_split, n, g.C);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
 }

@@ -745,6 +745,34 @@ def test_batched_third_order_ensemble(golden):
     assert rel_l2(B, np.mean(singles, axis=0)) < 1e-9
 
 
+def test_t2_stage_gemm_path_matches_kernel_path(golden, monkeypatch):
+    """The t2 stage of a batched response function (n_t1 columns per unit under one propagator
+    and one save operator) takes the tensor-core GEMM form of propagator stepping from 4096
+    columns on (csrc/dense_wide.cu: qsx_dense_map_gemm; also the split K6 contraction): against
+    the per-group stepping kernel (QSX_MAP_NO_GEMM=1), for a small state (dimer) and the wide FMO
+    'fe' stage, with shared and per-configuration dipole operators -- and the FMO single-model
+    fixture of the reference stays the anchor of both."""
+    t2 = np.linspace(0, 200, 3)
+    dred = qb.RedfieldModel(systems.dimer(disorder=80), hilbert_subspace='gef',
+                            unit_convert=CM_FS, discard_imag_corr=True)
+    fred = qb.RedfieldModel(systems.fmo(), hilbert_subspace='gef', unit_convert=CM_FS)
+    cases = [(dred, dict(ensemble_size=96)),                                   # 96 x 1 x 52 columns
+             (dred, dict(ensemble_size=8, polarization='xxyy', exact_isotropic_average=True)),
+             (fred, dict(ensemble_size=6, exact_isotropic_average=True,
+                         include_signal='ESA'))]                               # 6 x 21 x 79: 'ee' -> 'fe' save
+    for model, kw in cases:
+        res = {}
+        for flag in ('0', '1'):
+            if flag == '1':
+                monkeypatch.setenv('QSX_MAP_NO_GEMM', '1')
+            else:
+                monkeypatch.delenv('QSX_MAP_NO_GEMM', raising=False)
+            _, res[flag] = qb.third_order_response(model, 400 if model is fred else 500,
+                                                   population_times=t2, **kw)
+        assert rel_l2(res['0'], res['1']) < 1e-12, kw
+    monkeypatch.delenv('QSX_MAP_NO_GEMM', raising=False)
+
+
 # ------------------------------------------------- device Fourier transform (K7)
 @pytest.mark.parametrize('shape,axis,sign', [((103,), 0, 1), ((37, 5, 41), 0, -1),
                                              ((37, 5, 41), 2, 1), ((6, 130, 3), 1, -1),
