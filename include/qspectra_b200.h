@@ -299,6 +299,14 @@ int qsx_reduce_members(const void *in_dev, int32_t n_members, int64_t n,
 int qsx_response_contract(const void *x_dev, const void *y_dev, const void *w_dev,
                           int32_t n_units, int64_t n_ab, int32_t n_c, int32_t K,
                           void *s_dev, void *stream);
+/* The same with units that share their Y operand multiplied once: group g contracts
+ *   X'_g = sum_{j < grp_count[g]} w[grp_first[g] + j] * X[grp_first[g] + j]   (summed while the tile is staged)
+ * with Y[g] -- e.g. the polarisation configurations of the isotropic average that end in the same
+ * detection polarisation (3 products per member instead of 21).  X: [n_x][n_ab][K], Y: [n_groups][n_c][K]. */
+int qsx_response_contract_grouped(const void *x_dev, int32_t n_x, const void *y_dev, const void *w_dev,
+                                  int32_t n_groups, const int32_t *grp_first_host,
+                                  const int32_t *grp_count_host, int64_t n_ab, int32_t n_c, int32_t K,
+                                  void *s_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * K7: Fourier transform of a response function sampled on t = 0, dt, ..., (n-1) dt,

@@ -86,7 +86,7 @@ EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches', 'qsx_transfer
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
            'qsx_ado_enumerate', 'qsx_redfield_build', 'qsx_redfield_build_sampled',
-           'qsx_reduce_members', 'qsx_fourier_transform', 'qsx_response_contract',
+           'qsx_reduce_members', 'qsx_fourier_transform', 'qsx_response_contract', 'qsx_response_contract_grouped',
            'qsx_sample_streams', 'qsx_sample_gauss_device', 'qsx_zofe_create', 'qsx_zofe_state_dim',
            'qsx_zofe_apply', 'qsx_zofe_propagate', 'qsx_zofe_destroy']
 
@@ -159,6 +159,9 @@ def lib():
                                         C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
     L.qsx_response_contract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.qsx_response_contract_grouped.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
+                                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.qsx_zofe_create.argtypes = [C.POINTER(C.c_void_p),
                                   C.POINTER(QsxZofeConfig), C.c_void_p]
     L.qsx_zofe_state_dim.restype = C.c_int64

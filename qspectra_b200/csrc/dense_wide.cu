@@ -43,6 +43,9 @@ struct ZgemmArgs {
     int lda, ldb, ldc;              // row strides (elements)
     long long sA, sB, sC;           // strides between units
     const int *ib;                  // B operand of unit u is B + ib[u] * sB (null: u)
+    // reduce with groups: unit u multiplies A_u = sum_{j < grp_count[u]} w[grp_first[u] + j] A[grp_first[u] + j]
+    // (summed while the A tile is staged) with B_u -- units that share their B operand cost one product
+    const int *grp_first, *grp_count;
     int n_units;
     int b_transposed;               // 1: B_u is stored [N][K] (C = A B^T)
     int reduce;                     // 1: one output, summed over the units with weights w
@@ -80,6 +83,18 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
         for (int k0 = 0; k0 < a.K; k0 += KC) {
             __syncthreads();
             // A tile: [BM][KC], k fastest in global memory
+            if (a.grp_first) {
+                const int first = __ldg(&a.grp_first[u]), count = __ldg(&a.grp_count[u]);
+                for (int i = threadIdx.x; i < BM * KC; i += 128) {
+                    const int r = i / KC, k = i % KC;
+                    cplx v = cmake(0, 0);
+                    if (row0 + r < a.M && k0 + k < a.K) {
+                        const cplx *Aj = a.A + (size_t)first * a.sA + (size_t)(row0 + r) * a.lda + k0 + k;
+                        for (int j = 0; j < count; ++j) cfma(v, __ldg(&a.w[first + j]), __ldg(&Aj[(size_t)j * a.sA]));
+                    }
+                    Ar[r * LDA + k] = v.x; Ai[r * LDA + k] = v.y;
+                }
+            } else
             for (int i = threadIdx.x; i < BM * KC; i += 128) {
                 const int r = i / KC, k = i % KC;
                 cplx v = cmake(0, 0);
@@ -119,7 +134,7 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
                 }
             }
         }
-        const cplx wu = (a.reduce && a.w) ? __ldg(&a.w[u]) : cmake(1.0, 0.0);
+        const cplx wu = (a.reduce && a.w && !a.grp_first) ? __ldg(&a.w[u]) : cmake(1.0, 0.0);
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
@@ -222,7 +237,7 @@ int qsx_dense_expm_wide(const cplx *Lt, int M, int n_gen, const double *lnorm_de
     qsx_launch_counter += 1;
     ZgemmArgs g;
     g.M = g.N = g.K = M; g.lda = g.ldb = g.ldc = M; g.sA = g.sB = g.sC = (long long)mm;
-    g.n_units = n_gen; g.b_transposed = 0; g.reduce = 0; g.w = nullptr; g.n_split = 1; g.part = nullptr; g.ib = nullptr;
+    g.n_units = n_gen; g.b_transposed = 0; g.reduce = 0; g.w = nullptr; g.n_split = 1; g.part = nullptr; g.ib = nullptr; g.grp_first = g.grp_count = nullptr;
     g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
     int rc;
     // all factors are polynomials in A, so the order of the products is immaterial
@@ -290,7 +305,7 @@ int qsx_dense_map_gemm(const cplx *Lt, int M, int n_runs, int R, const int *run_
     const cplx *cur = y0;
     cplx *next = Ya;
     ZgemmArgs g;
-    g.reduce = 0; g.w = nullptr; g.n_split = 1; g.part = nullptr;
+    g.reduce = 0; g.w = nullptr; g.n_split = 1; g.part = nullptr; g.grp_first = g.grp_count = nullptr;
     g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
     g.n_units = n_runs;
     int rc;
@@ -313,9 +328,9 @@ int qsx_dense_map_gemm(const cplx *Lt, int M, int n_runs, int R, const int *run_
     return QSX_OK;
 }
 
-extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const void *w_dev, int32_t n_units,
-                                     int64_t n_ab, int32_t n_c, int32_t K, void *s_dev, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+static int response_contract_impl(const void *x_dev, const void *y_dev, const void *w_dev, int32_t n_units,
+                                  const int32_t *grp_first_host, const int32_t *grp_count_host, int32_t n_x,
+                                  int64_t n_ab, int32_t n_c, int32_t K, void *s_dev, cudaStream_t stream) {
     QSX_REQUIRE(x_dev && y_dev && s_dev && n_units > 0 && n_ab > 0 && n_c > 0 && K > 0,
                 "qsx_response_contract: bad arguments");
     QSX_REQUIRE(n_ab < ((int64_t)1 << 31) / 64, "qsx_response_contract: signal too large");
@@ -326,6 +341,18 @@ extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const
     g.sA = (long long)n_ab * K; g.sB = (long long)n_c * K; g.sC = 0;
     g.n_units = n_units; g.b_transposed = 1; g.reduce = 1; g.w = (const cplx *)w_dev; g.ib = nullptr;
     g.X = g.Y = nullptr; g.c0 = g.c1 = g.c2 = 0.0;
+    g.grp_first = g.grp_count = nullptr;
+    DevBuf<int> d_first, d_count;
+    if (grp_first_host) {
+        QSX_REQUIRE(grp_count_host && w_dev, "qsx_response_contract_grouped: group sizes and weights are required");
+        for (int u = 0; u < n_units; ++u)
+            QSX_REQUIRE(grp_first_host[u] >= 0 && grp_count_host[u] > 0 &&
+                        (long long)grp_first_host[u] + grp_count_host[u] <= n_x,
+                        "qsx_response_contract_grouped: group %d out of range", u);
+        QSX_CUDA(d_first.upload(grp_first_host, n_units, stream));
+        QSX_CUDA(d_count.upload(grp_count_host, n_units, stream));
+        g.grp_first = d_first.p; g.grp_count = d_count.p;
+    }
     // One CTA per output tile walking every unit leaves most SMs idle for a 197 x 5 x 197 signal
     // (217 tiles): deal the units out to enough CTAs for ~16 resident per SM; the partial sums
     // are added in split order, so the result does not depend on scheduling.
@@ -342,4 +369,19 @@ extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
     return QSX_OK;
+}
+
+extern "C" int qsx_response_contract(const void *x_dev, const void *y_dev, const void *w_dev, int32_t n_units,
+                                     int64_t n_ab, int32_t n_c, int32_t K, void *s_dev, void *stream_) {
+    return response_contract_impl(x_dev, y_dev, w_dev, n_units, nullptr, nullptr, n_units, n_ab, n_c, K, s_dev,
+                                  (cudaStream_t)stream_);
+}
+
+extern "C" int qsx_response_contract_grouped(const void *x_dev, int32_t n_x, const void *y_dev, const void *w_dev,
+                                             int32_t n_groups, const int32_t *grp_first_host,
+                                             const int32_t *grp_count_host, int64_t n_ab, int32_t n_c, int32_t K,
+                                             void *s_dev, void *stream_) {
+    QSX_REQUIRE(grp_first_host && grp_count_host, "qsx_response_contract_grouped: null group tables");
+    return response_contract_impl(x_dev, y_dev, w_dev, n_groups, grp_first_host, grp_count_host, n_x, n_ab, n_c, K,
+                                  s_dev, (cudaStream_t)stream_);
 }

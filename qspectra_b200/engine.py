@@ -610,19 +610,33 @@ def reduce_members(batch_dev, scale=1.0):
     return out
 
 
-def response_contract(x_dev, y_dev, weights_dev, total_dev):
+def response_contract(x_dev, y_dev, weights_dev, total_dev, group_first=None, group_count=None):
     """Kernel K6: total[ab, c] += sum_u w[u] sum_i x[u, ab, i] y[u, c, i] on the FP64 tensor
     cores (csrc/dense_wide.cu).  x: (U, n_ab, K), y: (U, n_c, K), w: (U,), total: (n_ab, n_c),
-    all complex128 CUDA tensors."""
+    all complex128 CUDA tensors.  With groups, y is (G, n_c, K) and group g contracts
+    sum_{j < group_count[g]} w[group_first[g] + j] x[group_first[g] + j] with y[g]: units that
+    share their y operand cost one product."""
     x_dev, y_dev, weights_dev = x_dev.contiguous(), y_dev.contiguous(), weights_dev.contiguous()
     U, n_ab, K = x_dev.shape
     n_c = y_dev.shape[1]
-    if y_dev.shape != (U, n_c, K) or weights_dev.shape != (U,) or \
-            total_dev.numel() != n_ab * n_c or not total_dev.is_contiguous():
+    if weights_dev.shape != (U,) or total_dev.numel() != n_ab * n_c or not total_dev.is_contiguous():
         raise ValueError('inconsistent shapes in response_contract')
-    _capi.check(_capi.lib().qsx_response_contract(
-        x_dev.data_ptr(), y_dev.data_ptr(), weights_dev.data_ptr(), U, n_ab, n_c, K,
-        total_dev.data_ptr(), _capi.current_stream_ptr()))
+    if group_first is None:
+        if y_dev.shape != (U, n_c, K):
+            raise ValueError('inconsistent shapes in response_contract')
+        _capi.check(_capi.lib().qsx_response_contract(
+            x_dev.data_ptr(), y_dev.data_ptr(), weights_dev.data_ptr(), U, n_ab, n_c, K,
+            total_dev.data_ptr(), _capi.current_stream_ptr()))
+        return total_dev
+    first = np.ascontiguousarray(group_first, dtype=np.int32)
+    count = np.ascontiguousarray(group_count, dtype=np.int32)
+    G = first.size
+    if count.shape != (G,) or y_dev.shape != (G, n_c, K):
+        raise ValueError('inconsistent group tables in response_contract')
+    _capi.check(_capi.lib().qsx_response_contract_grouped(
+        x_dev.data_ptr(), U, y_dev.data_ptr(), weights_dev.data_ptr(), G,
+        first.ctypes.data_as(C.POINTER(C.c_int32)), count.ctypes.data_as(C.POINTER(C.c_int32)),
+        n_ab, n_c, K, total_dev.data_ptr(), _capi.current_stream_ptr()))
     return total_dev
 
 

@@ -278,7 +278,14 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
     method = integrate_kwargs.get('method_name', 'zvode')
     paths = _parse_pathways(THIRD_ORDER_PATHWAYS[geometry], include_signal)
     variants = _polarization_variants(polarization, exact_isotropic_average)
+    # configurations that end in the same detection polarisation share their t3 stage (the
+    # Heisenberg-propagated detection vector depends on the last field only): order them by it,
+    # so that each member's configurations fall into contiguous groups (at most three)
+    variants.sort(key=lambda wp: str(wp[1][3]))
     nv = len(variants)
+    grp_lo = [v for v in range(nv) if v == 0 or str(variants[v][1][3]) != str(variants[v - 1][1][3])]
+    grp_n = [(grp_lo[i + 1] if i + 1 < len(grp_lo) else nv) - lo for i, lo in enumerate(grp_lo)]
+    ng = len(grp_lo)
     wv = torch.tensor([w for w, _ in variants], dtype=torch.complex128, device='cuda')
     single = ensemble_size is None
     n_members = 1 if single else ensemble_size
@@ -339,11 +346,19 @@ def _third_order_response_batched(dynamical_model, coherence_time_max,
                                    generators=np.repeat(gens, len(t1)),
                                    save_index=np.repeat(sidx, len(t1)),
                                    return_device=True, **opts)
-            out3 = eom_c.propagate(per_unit(lambda v: v[3].bra_vector), t3, method=method,
-                                   generators=gens, return_device=True, **opts)
-            # K6: total[a, b, c] += sum_{e, v} w_v sum_i out2[e, v, a, b, i] out3[e, v, c, i]
+            # t3 stage: one Heisenberg column per member and detection polarisation
+            y3 = np.array([[V[m][lo][3].bra_vector for lo in grp_lo] for m in range(nm)])
+            if nm != E:
+                y3 = np.broadcast_to(y3, (E,) + y3.shape[1:])
+            y3 = np.ascontiguousarray(y3).reshape((E * ng,) + y3.shape[2:])
+            out3 = eom_c.propagate(y3, t3, method=method, generators=np.repeat(np.arange(E), ng),
+                                   return_device=True, **opts)
+            # K6: total[a, b, c] += sum_{e, g} sum_i (sum_{v in g} w_v out2[e, v, a, b, i]) out3[e, g, c, i]
+            g_first = (np.arange(E)[:, None] * nv + np.asarray(grp_lo)[None, :]).ravel()
+            g_count = np.tile(np.asarray(grp_n), E)
             engine.response_contract(out2.reshape(E * nv, len(t1) * len(t2), -1),
-                                     out3.reshape(E * nv, len(t3), -1), wv.repeat(E), total)
+                                     out3.reshape(E * ng, len(t3), -1), wv.repeat(E), total,
+                                     group_first=g_first, group_count=g_count)
     if normalize and not single:
         total = total / ensemble_size
     return (t1, t2, t3), total
