@@ -69,80 +69,95 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
     const int per = a.reduce ? (a.n_units + a.n_split - 1) / a.n_split : 1;
     const int u_begin = a.reduce ? (int)blockIdx.z * per : (int)blockIdx.z;
     const int u_end = a.reduce ? min(a.n_units, u_begin + per) : (int)blockIdx.z + 1;
+    const int nK = (a.K + KC - 1) / KC;
+    const int n_chunks = max(0, u_end - u_begin) * nK;      // (unit, K chunk) pairs of this CTA, in order
 
-    // final accumulators (re, im for the two columns a thread owns in each of the 4 column blocks)
-    double fr[4][2], fi[4][2];
+    // The three real products of the complex one (Gauss); in the reducing form the unit weights are
+    // applied while the A tile is staged, so the accumulators run over all units of the CTA.
+    double p1[4][2], p2[4][2], p3[4][2];
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) { fr[nb][0] = fr[nb][1] = fi[nb][0] = fi[nb][1] = 0.0; }
+    for (int nb = 0; nb < 4; ++nb) { p1[nb][0] = p1[nb][1] = p2[nb][0] = p2[nb][1] = p3[nb][0] = p3[nb][1] = 0.0; }
 
-    for (int u = u_begin; u < u_end; ++u) {
-        const cplx *Au = a.A + (size_t)u * a.sA, *Bu = a.B + (size_t)(a.ib ? __ldg(&a.ib[u]) : u) * a.sB;
-        double p1[4][2], p2[4][2], p3[4][2];
+    // global -> registers for chunk c (four A and four B elements per thread); the loads of the
+    // next chunk are in flight while the tensor cores work on the current one
+    constexpr int EPT = BM * KC / 128;
+    cplx ra[EPT], rb[EPT];
+    auto fetch = [&](int c) {
+        const int u = u_begin + c / nK, k0 = (c % nK) * KC;
+        const cplx *Bu = a.B + (size_t)(a.ib ? __ldg(&a.ib[u]) : u) * a.sB;
+        if (a.grp_first) {
+            const int first = __ldg(&a.grp_first[u]), count = __ldg(&a.grp_count[u]);
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) { p1[nb][0] = p1[nb][1] = p2[nb][0] = p2[nb][1] = p3[nb][0] = p3[nb][1] = 0.0; }
-        for (int k0 = 0; k0 < a.K; k0 += KC) {
-            __syncthreads();
-            // A tile: [BM][KC], k fastest in global memory
-            if (a.grp_first) {
-                const int first = __ldg(&a.grp_first[u]), count = __ldg(&a.grp_count[u]);
-                for (int i = threadIdx.x; i < BM * KC; i += 128) {
-                    const int r = i / KC, k = i % KC;
-                    cplx v = cmake(0, 0);
-                    if (row0 + r < a.M && k0 + k < a.K) {
-                        const cplx *Aj = a.A + (size_t)first * a.sA + (size_t)(row0 + r) * a.lda + k0 + k;
-                        for (int j = 0; j < count; ++j) cfma(v, __ldg(&a.w[first + j]), __ldg(&Aj[(size_t)j * a.sA]));
-                    }
-                    Ar[r * LDA + k] = v.x; Ai[r * LDA + k] = v.y;
+            for (int e = 0; e < EPT; ++e) {
+                const int i = threadIdx.x + 128 * e, r = i / KC, k = i % KC;
+                cplx v = cmake(0, 0);
+                if (row0 + r < a.M && k0 + k < a.K) {
+                    const cplx *Aj = a.A + (size_t)first * a.sA + (size_t)(row0 + r) * a.lda + k0 + k;
+                    for (int j = 0; j < count; ++j) cfma(v, __ldg(&a.w[first + j]), __ldg(&Aj[(size_t)j * a.sA]));
                 }
-            } else
-            for (int i = threadIdx.x; i < BM * KC; i += 128) {
-                const int r = i / KC, k = i % KC;
+                ra[e] = v;
+            }
+        } else {
+            const cplx *Au = a.A + (size_t)u * a.sA;
+            const cplx wu = (a.reduce && a.w) ? __ldg(&a.w[u]) : cmake(1.0, 0.0);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = threadIdx.x + 128 * e, r = i / KC, k = i % KC;
                 cplx v = cmake(0, 0);
                 if (row0 + r < a.M && k0 + k < a.K) v = __ldg(&Au[(size_t)(row0 + r) * a.lda + k0 + k]);
-                Ar[r * LDA + k] = v.x; Ai[r * LDA + k] = v.y;
-            }
-            if (a.b_transposed) {
-                // B stored [N][K]: tile [BN][KC], k fastest
-                for (int i = threadIdx.x; i < BN * KC; i += 128) {
-                    const int c = i / KC, k = i % KC;
-                    cplx v = cmake(0, 0);
-                    if (col0 + c < a.N && k0 + k < a.K) v = __ldg(&Bu[(size_t)(col0 + c) * a.ldb + k0 + k]);
-                    Br[c * LDT + k] = v.x; Bi[c * LDT + k] = v.y;
-                }
-            } else {
-                // B stored [K][N]: tile [KC][BN], column fastest
-                for (int i = threadIdx.x; i < KC * BN; i += 128) {
-                    const int k = i / BN, c = i % BN;
-                    cplx v = cmake(0, 0);
-                    if (k0 + k < a.K && col0 + c < a.N) v = __ldg(&Bu[(size_t)(k0 + k) * a.ldb + col0 + c]);
-                    Br[k * LDB + c] = v.x; Bi[k * LDB + c] = v.y;
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int ks = 0; ks < KC / 4; ++ks) {
-                const double ar = Ar[(8 * wrp + g) * LDA + 4 * ks + t];
-                const double ai = Ai[(8 * wrp + g) * LDA + 4 * ks + t];
-                const double as = ar + ai;
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    const int o = a.b_transposed ? (8 * nb + g) * LDT + 4 * ks + t : (4 * ks + t) * LDB + 8 * nb + g;
-                    const double br = Br[o], bi = Bi[o];
-                    dmma884w(p1[nb][0], p1[nb][1], ar, br);
-                    dmma884w(p2[nb][0], p2[nb][1], ai, bi);
-                    dmma884w(p3[nb][0], p3[nb][1], as, br + bi);
-                }
+                ra[e] = (a.reduce && a.w) ? cmul(wu, v) : v;
             }
         }
-        const cplx wu = (a.reduce && a.w && !a.grp_first) ? __ldg(&a.w[u]) : cmake(1.0, 0.0);
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const double re = p1[nb][j] - p2[nb][j], im = p3[nb][j] - p1[nb][j] - p2[nb][j];
-                fr[nb][j] += wu.x * re - wu.y * im;
-                fi[nb][j] += wu.x * im + wu.y * re;
+        for (int e = 0; e < EPT; ++e) {
+            const int i = threadIdx.x + 128 * e;
+            cplx v = cmake(0, 0);
+            if (a.b_transposed) {       // B stored [N][K]: tile [BN][KC], k fastest
+                const int c2 = i / KC, k = i % KC;
+                if (col0 + c2 < a.N && k0 + k < a.K) v = __ldg(&Bu[(size_t)(col0 + c2) * a.ldb + k0 + k]);
+            } else {                    // B stored [K][N]: tile [KC][BN], column fastest
+                const int k = i / BN, c2 = i % BN;
+                if (k0 + k < a.K && col0 + c2 < a.N) v = __ldg(&Bu[(size_t)(k0 + k) * a.ldb + col0 + c2]);
             }
+            rb[e] = v;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = threadIdx.x + 128 * e;
+            const int r = i / KC, k = i % KC;
+            Ar[r * LDA + k] = ra[e].x; Ai[r * LDA + k] = ra[e].y;
+            if (a.b_transposed) {
+                Br[r * LDT + k] = rb[e].x; Bi[r * LDT + k] = rb[e].y;
+            } else {
+                const int kk = i / BN, cc = i % BN;
+                Br[kk * LDB + cc] = rb[e].x; Bi[kk * LDB + cc] = rb[e].y;
+            }
+        }
+    };
+    static_assert(BM == BN && BM * KC == BN * KC, "one element count for the A and B tiles");
+
+    if (n_chunks > 0) fetch(0);
+    for (int c = 0; c < n_chunks; ++c) {
+        __syncthreads();                    // the previous chunk's fragments have been read
+        stash();
+        __syncthreads();
+        if (c + 1 < n_chunks) fetch(c + 1);
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            const double ar = Ar[(8 * wrp + g) * LDA + 4 * ks + t];
+            const double ai = Ai[(8 * wrp + g) * LDA + 4 * ks + t];
+            const double as = ar + ai;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const int o = a.b_transposed ? (8 * nb + g) * LDT + 4 * ks + t : (4 * ks + t) * LDB + 8 * nb + g;
+                const double br = Br[o], bi = Bi[o];
+                dmma884w(p1[nb][0], p1[nb][1], ar, br);
+                dmma884w(p2[nb][0], p2[nb][1], ai, bi);
+                dmma884w(p3[nb][0], p3[nb][1], as, br + bi);
+            }
+        }
     }
     const int r = row0 + 8 * wrp + g;
     if (r >= a.M) return;
@@ -154,7 +169,7 @@ __global__ void __launch_bounds__(128) zgemm_dmma_kernel(const ZgemmArgs a) {
             const int c = col0 + 8 * nb + 2 * t + j;
             if (c >= a.N) continue;
             const size_t o = (size_t)r * a.ldc + c;
-            cplx v = cmake(fr[nb][j], fi[nb][j]);
+            cplx v = cmake(p1[nb][j] - p2[nb][j], p3[nb][j] - p1[nb][j] - p2[nb][j]);
             if (a.reduce && a.n_split > 1) {
                 a.part[(size_t)blockIdx.z * a.M * a.ldc + o] = v;
                 continue;
