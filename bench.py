@@ -626,6 +626,12 @@ def run_ours(args):
             return reduce_across(local_step())
         for _ in range(warmup):
             step()
+        # untimed rehearsal of the timed block with the same object lifetimes (the propagators of all
+        # K steps stay alive until their device times are collected): the caching allocator grows
+        # here, not inside the timed region (cudaMalloc synchronises the device)
+        engine.PropagationStats.keep_alive = True
+        for _ in range(steps):
+            step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
