@@ -330,6 +330,85 @@ dense_map_kernel(DenseKernelArgs a) {
     }
 }
 
+// Propagator stepping for state dimensions whose row pairs do not fill whole warps in the
+// four-threads-per-row mapping above (M = 49: 26 row pairs x 4 = 104 threads in four warps, a
+// fifth of the FP64 lanes switched off, 52 x 52 padded work).  Here Q threads share RPT rows each
+// (M = 49: Q = 5 column groups x 25 row pairs = 125 of 128 lanes, 50 x 50 padded work, 80
+// registers of P per thread), the Q partial sums of a row meet through shared memory instead of
+// shuffles -- two barriers per output step, hidden by four resident CTAs per SM -- and the
+// finished state is written to the trajectory by consecutive lanes (coalesced 16-byte stores).
+// Single column per generator, whole-state output.
+template <int Q, int CQ, int RP, int RPT>
+__global__ void __launch_bounds__((Q * RP + 31) / 32 * 32, 4)
+dense_map_split_kernel(DenseKernelArgs a) {
+    constexpr int NR = RP * RPT, NC = Q * CQ, NX = NC > NR ? NC : NR;
+    __shared__ __align__(16) cplx x[NX];
+    __shared__ __align__(16) cplx part[Q][NR];
+    const int M = a.M, grp = blockIdx.x, tid = threadIdx.x;
+    const int col0 = a.grp_col0[grp], gen = a.grp_gen[grp];
+    const bool live = tid < Q * RP;
+    const int g = live ? tid / RP : 0, rs = live ? tid % RP : 0;
+    const cplx *Lg = a.Lt + (size_t)gen * M * M;        // transposed storage: Lt[c*M + r]
+    cplx p[RPT][CQ];
+#pragma unroll
+    for (int h = 0; h < RPT; ++h)
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+            const int r = rs + h * RP, c = g + Q * i;
+            p[h][i] = (live && r < M && c < M) ? Lg[c * M + r] : cmake(0, 0);
+        }
+    cplx *out = a.out + (size_t)col0 * a.nt * M;
+    if (tid < NX) {
+        const cplx v = tid < M ? a.y0[(size_t)col0 * M + tid] : cmake(0, 0);
+        x[tid] = v;
+        if (tid < M) __stcs(&out[tid], v);
+    }
+    __syncthreads();
+    for (int it = 1; it < a.nt; ++it) {
+        double sxx[RPT], syy[RPT], sxy[RPT], syx[RPT];
+#pragma unroll
+        for (int h = 0; h < RPT; ++h) sxx[h] = syy[h] = sxy[h] = syx[h] = 0.0;
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+            const cplx v = x[g + Q * i];
+#pragma unroll
+            for (int h = 0; h < RPT; ++h) {
+                sxx[h] = fma(p[h][i].x, v.x, sxx[h]);
+                syy[h] = fma(p[h][i].y, v.y, syy[h]);
+                sxy[h] = fma(p[h][i].x, v.y, sxy[h]);
+                syx[h] = fma(p[h][i].y, v.x, syx[h]);
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int h = 0; h < RPT; ++h) part[g][rs + h * RP] = cmake(sxx[h] - syy[h], sxy[h] + syx[h]);
+        }
+        __syncthreads();
+        if (tid < M) {
+            cplx s = part[0][tid];
+#pragma unroll
+            for (int q = 1; q < Q; ++q) {
+                const cplx w = part[q][tid];
+                s.x += w.x;
+                s.y += w.y;
+            }
+            x[tid] = s;
+            __stcs(&out[(size_t)it * M + tid], s);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        atomicAdd(&a.stats[0], (unsigned long long)(a.nt - 1));
+        atomicAdd(&a.stats[1], (unsigned long long)(a.nt - 1));
+    }
+}
+
+template <int Q, int CQ, int RP, int RPT>
+static cudaError_t launch_map_split(const DenseKernelArgs &a, int groups, cudaStream_t stream) {
+    dense_map_split_kernel<Q, CQ, RP, RPT><<<groups, (Q * RP + 31) / 32 * 32, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <int Q, int CQ, int NB, int RPT>
 static cudaError_t launch_map(const DenseKernelArgs &a, int groups, cudaStream_t stream) {
     const int rows = RPT == 1 ? (a.M + 7) / 8 * 8 : Q * CQ / RPT;
@@ -350,6 +429,12 @@ static cudaError_t launch_map_cq(const DenseKernelArgs &a, int groups, cudaStrea
     // feeds twice the arithmetic (the one-row mapping is bound by those reads)
     // (eight threads per row with full-width shared-memory wavefronts measured slower: 4.4 vs 3.9 ms)
     // M = 49 needs 13 column groups of four, not 14 (52 x 52 instead of 56 x 56 padded work)
+    if (NB == 1 && a.M >= 46 && a.M <= 50 && a.save_mode == QSX_SAVE_STATE && a.saved_dim == a.M) {
+        // QSX_MAP_SPLIT: 0 = four-threads-per-row kernel, 1 = one row per thread (A/B runs)
+        const char *sw = getenv("QSX_MAP_SPLIT");
+        if (!sw || sw[0] == '2') return launch_map_split<5, 10, 25, 2>(a, groups, stream);
+        if (sw[0] == '1') return launch_map_split<5, 10, 50, 1>(a, groups, stream);
+    }
     if (NB == 1) return cq <= 13 ? launch_map<4, 13, NB, 2>(a, groups, stream) : launch_map<4, 14, NB, 2>(a, groups, stream);
     return launch_map<4, 14, NB, 1>(a, groups, stream);
 }
