@@ -157,6 +157,40 @@ int qsx_dense_events_ready(qsx_dense_t h);
 void qsx_dense_destroy(qsx_dense_t h);
 
 /* ------------------------------------------------------------------------
+ * Hermitian-coordinate ("real form") propagation of dense generators.
+ * Every physical generator on a Liouville subspace that is closed under transposition
+ * ('ee', 'gg,ee', ... -- what simulate_dynamics propagates, reference simulate/eom.py:11-26 with
+ * dynamics/liouville_space.py:316-341) commutes with Hermitian conjugation:
+ * L[perm r][perm c] = conj L[r][c], perm[k] = position of the transposed ket-bra pair of element
+ * k.  In the coordinates u_k = rho_k (perm k = k), u_a = Re rho_a, u_b = Im rho_a (pair a < b =
+ * perm a) it is a REAL M x M matrix G and a Hermitian state a real vector, so exp(G dt) costs one
+ * real tensor-core product per complex one and a step u <- P u a quarter of the complex
+ * multiply-adds.  M <= 56.  defect_dev: four float64 the caller zeroes once,
+ * [0] max |Im G|, [1] max |Re G|, [2] max |Im u0|, [3] max |Re u0| -- the caller checks
+ * [0] <= eps [1] and [2] <= eps [3] after its next synchronisation (a generator or state that is
+ * not Hermiticity-compatible must go through qsx_dense_propagate instead).
+ * ---------------------------------------------------------------------- */
+/* Gt_dev [n_generators][M][M] float64, transposed storage like the handle's generators;
+ * gnorm_dev [n_generators] inf-norms of G. */
+int qsx_dense_hermitian_form(qsx_dense_t h, const int32_t *perm_host, void *Gt_dev, void *gnorm_dev,
+                             void *defect_dev, void *stream);
+/* P_dev [n_generators][M][M] float64 row-major = exp(G_g dt), the series of qsx_dense_expm on real
+ * DMMA; gemm_count_dev: one uint64 counter (incremented by the number of M x M real products). */
+int qsx_real_expm(const void *Gt_dev, const void *gnorm_dev, int32_t M, int32_t n_generators, double dt,
+                  void *P_dev, void *gemm_count_dev, void *stream);
+/* out[c][i][:] = P_gen(c)^i u0[c], i < n_times; rows of u0 and out are row_stride >= M float64 apart
+ * (the tail of every output row is zero-filled).  generator_of_column_host == NULL: column c uses
+ * generator c when n_columns == n_generators, else generator 0. */
+int qsx_real_map(const void *P_dev, int32_t M, int32_t n_generators, const int32_t *generator_of_column_host,
+                 int32_t n_columns, const void *u0_dev, int32_t n_times, int32_t row_stride, void *out_dev,
+                 void *stream);
+/* complex128 state vectors y [rows][M] <-> real coordinates u [rows][row_stride] */
+int qsx_hermitian_pack(const void *y_dev, int32_t M, int64_t rows, const int32_t *perm_host, int32_t row_stride,
+                       void *u_dev, void *defect_dev, void *stream);
+int qsx_hermitian_unpack(const void *u_dev, int32_t M, int64_t rows, int32_t row_stride, const int32_t *perm_host,
+                         void *y_dev, void *stream);
+
+/* ------------------------------------------------------------------------
  * HEOM hierarchy (HEOMModel).  Replaces HEOM_tensor + csr_matrix.dot
  * (dynamics/heom.py:228-244, 298-443) with an index-map driven structured
  * apply; no CSR matrix is ever built.

@@ -483,6 +483,14 @@ extern "C" int qsx_dense_create(qsx_dense_t *out, int32_t M, int32_t n_generator
 
 extern "C" void qsx_dense_destroy(qsx_dense_t h) { delete h; }
 
+extern "C" int qsx_dense_hermitian_form(qsx_dense_t h, const int32_t *perm_host, void *Gt_dev, void *gnorm_dev,
+                                        void *defect_dev, void *stream_) {
+    QSX_REQUIRE(h, "qsx_dense_hermitian_form: null handle");
+    QSX_REQUIRE(!h->is_propagator, "qsx_dense_hermitian_form: the handle holds propagators, not generators");
+    return qsx_real_form_launch(h->Lt.p, h->M, h->n_gen, perm_host, (double *)Gt_dev, (double *)gnorm_dev,
+                                (double *)defect_dev, (cudaStream_t)stream_);
+}
+
 static int upload_ints(DevBuf<int> &buf, const std::vector<int> &v, cudaStream_t s) {
     cudaError_t e = buf.upload(v, s);
     if (e != cudaSuccess) {

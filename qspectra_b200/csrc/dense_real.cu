@@ -1,0 +1,541 @@
+// Hermitian-coordinate ("real form") propagation for dense generators that commute with
+// Hermitian conjugation -- every physical Liouvillian on a subspace closed under transposition
+// ('ee', 'gg,ee', ...; reference dynamics/liouville_space.py:316-341 builds them as complex
+// M x M matrices).  With sigma(k) the position of the transposed ket-bra pair of element k,
+// such a generator satisfies L[sigma r][sigma c] = conj L[r][c], so in the coordinates
+//     u_k = rho_k                      (sigma k = k:  populations)
+//     u_a = Re rho_a,  u_b = Im rho_a  (pair a < b = sigma a)
+// it is a REAL M x M matrix G = T L T^-1 and a Hermitian state is a real vector: the
+// propagator build exp(G dt) costs one real DMMA product per complex one (instead of three) and
+// a stepping y <- P y one DFMA per matrix element (instead of four).  The imaginary residual of
+// G and of the packed state is measured on the device (defect[0..3]) and checked by the caller.
+//
+//   hermitian_form_kernel   Lt (complex, transposed) -> Gt (real, transposed), inf-norms, defect
+//   real_expm_kernel        exp(G dt): the degree-12 Paterson-Stockmeyer series of dense.cu on one plane
+//   real_map_kernel         u <- P u per output step, one warp per column, P in registers
+//   hermitian_pack/unpack   complex state vectors <-> real coordinates
+#include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
+
+struct HermPerm { unsigned char s[64]; };
+
+__device__ __forceinline__ void dmma884r(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__constant__ double inv_fact_r[13] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040,
+                                      1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
+                                      1.0 / 479001600};
+
+// ------------------------------------------------------------------ L -> G = T L T^-1
+__global__ void __launch_bounds__(128)
+hermitian_form_kernel(const cplx *__restrict__ Lt, int M, HermPerm perm, double *__restrict__ Gt,
+                      double *__restrict__ gnorm, double *__restrict__ defect) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *Ls = reinterpret_cast<cplx *>(smem_raw);              // Ls[c*M + r] = L[r][c]
+    __shared__ double rowsum[2][64];
+    __shared__ double scratch[32];
+    const int gen = blockIdx.x, tid = threadIdx.x;
+    const cplx *Lg = Lt + (size_t)gen * M * M;
+    for (int i = tid; i < M * M; i += blockDim.x) Ls[i] = Lg[i];
+    __syncthreads();
+    const int R = tid & 63, half = tid >> 6;
+    double rs = 0.0, dmax = 0.0, amax = 0.0;
+    if (R < M) {
+        const int sR = perm.s[R];
+        // (T L)[R][c]
+        auto TL = [&](int c) -> cplx {
+            const cplx x = Ls[c * M + R];
+            if (sR == R) return x;
+            const cplx y = Ls[c * M + sR];
+            if (R < sR) return cmake(0.5 * (x.x + y.x), 0.5 * (x.y + y.y));       // a = R, b = sR
+            return cmake(0.5 * (y.y - x.y), -0.5 * (y.x - x.x));                   // a = sR, b = R: (L_a - L_b) / 2i
+        };
+        double *Gg = Gt + (size_t)gen * M * M;
+        for (int C = half; C < M; C += 2) {
+            const int sC = perm.s[C];
+            cplx z = TL(C);
+            if (sC != C) {
+                const cplx w = TL(sC);
+                if (C < sC) z = cmake(z.x + w.x, z.y + w.y);                      // column a: X_a + X_b
+                else z = cmake(-(w.y - z.y), w.x - z.x);                          // column b: i (X_a - X_b), a = sC
+            }
+            Gg[C * M + R] = z.x;
+            rs += fabs(z.x);
+            dmax = fmax(dmax, fabs(z.y));
+            amax = fmax(amax, fabs(z.x));
+        }
+    }
+    rowsum[half][R] = rs;
+    __syncthreads();
+    const double nrm = block_max(tid < 64 ? rowsum[0][tid] + rowsum[1][tid] : 0.0, scratch);
+    dmax = block_max(dmax, scratch);
+    amax = block_max(amax, scratch);
+    if (tid == 0) {
+        gnorm[gen] = nrm;
+        atomic_max_nonneg(&defect[0], dmax);
+        atomic_max_nonneg(&defect[1], amax);
+    }
+}
+
+// ------------------------------------------------------------------ exp(G dt), real DMMA
+template <int MT, int KS, int NBLK>      // matrix padded to 8*MT rows/cols (4*KS along the contraction); MT warps per CTA, NBLK CTAs per SM
+__global__ void __launch_bounds__(32 * MT, NBLK)
+real_expm_kernel(const double *__restrict__ Gt, const double *__restrict__ gnorm, int M, double dt, int n_gen,
+                 double *__restrict__ P_out, double *__restrict__ A2_scratch, unsigned long long *__restrict__ status) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *planes = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *A2g = A2_scratch + (size_t)blockIdx.x * M * M;       // transposed storage like Gt: [c*M + r]
+    unsigned long long gemms = 0;
+
+    for (int gen = blockIdx.x; gen < n_gen; gen += gridDim.x) {
+        double *X = planes, *Y = X + MP * LD;
+        const double *Gg = Gt + (size_t)gen * M * M;
+        int sq = 0;
+        {
+            double nrm = fabs(dt) * gnorm[gen];
+            while (nrm > 0.5 && sq < 40) { nrm *= 0.5; ++sq; }
+        }
+        const double scale = dt / (double)(1ULL << sq);
+        auto A1 = [&](int r, int c) -> double { return (r < M && c < M) ? scale * __ldg(&Gg[c * M + r]) : 0.0; };
+        auto A2 = [&](int r, int c) -> double { return (r < M && c < M) ? __ldcg(&A2g[c * M + r]) : 0.0; };
+        double a[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) a[ks] = A1(rb * 8 + g, ks * 4 + t);
+        __syncthreads();                                    // previous member's output pass is done with the planes
+        for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) X[i] = A1(i / LD, i % LD);
+        __syncthreads();
+        auto row_block_gemm = [&](const double *B, auto &&epi) {
+#pragma unroll
+            for (int nb = 0; nb < MT; ++nb) {
+                double p0 = 0, p1 = 0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) dmma884r(p0, p1, a[ks], B[(ks * 4 + t) * LD + nb * 8 + g]);
+                epi(rb * 8 + g, nb * 8 + 2 * t, p0, p1);
+            }
+        };
+        auto load_fragments = [&](const double *Z) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) a[ks] = Z[(rb * 8 + g) * LD + ks * 4 + t];
+        };
+        // A^2 -> Y (operand of the next product) and the scratch tile (Horner operand)
+        row_block_gemm(X, [&](int r, int c, double v0, double v1) {
+            Y[r * LD + c] = v0; Y[r * LD + c + 1] = v1;
+            if (r < M && c < M) A2g[c * M + r] = v0;
+            if (r < M && c + 1 < M) A2g[(c + 1) * M + r] = v1;
+        });
+        __syncthreads();
+        // A^3 = A A^2 -> X
+        row_block_gemm(Y, [&](int r, int c, double v0, double v1) { X[r * LD + c] = v0; X[r * LD + c + 1] = v1; });
+        __syncthreads();
+        load_fragments(X);                          // left operand from here on: A^3
+        __syncthreads();
+        // Horner start: P = c9 I + c10 A + c11 A^2 + c12 A^3 -> X, in place (A^3 in X, A^2 in Y)
+        for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
+            const int r = i / LD, c = i % LD;
+            X[i] = (r == c ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1(r, c) + inv_fact_r[11] * Y[i] + inv_fact_r[12] * X[i];
+        }
+        __syncthreads();
+        double *P = X, *U = Y;
+#pragma unroll 1
+        for (int blk = 2; blk >= 0; --blk) {
+            const double c0 = inv_fact_r[3 * blk], c1 = inv_fact_r[3 * blk + 1], c2 = inv_fact_r[3 * blk + 2];
+            row_block_gemm(P, [&](int r, int c, double v0, double v1) {
+                U[r * LD + c] = v0 + c1 * A1(r, c) + c2 * A2(r, c) + (r == c ? c0 : 0.0);
+                U[r * LD + c + 1] = v1 + c1 * A1(r, c + 1) + c2 * A2(r, c + 1) + (r == c + 1 ? c0 : 0.0);
+            });
+            __syncthreads();
+            { double *x = P; P = U; U = x; }
+        }
+        for (int q = 0; q < sq; ++q) {
+            load_fragments(P);
+            row_block_gemm(P, [&](int r, int c, double v0, double v1) { U[r * LD + c] = v0; U[r * LD + c + 1] = v1; });
+            __syncthreads();
+            { double *x = P; P = U; U = x; }
+        }
+        double *Pg = P_out + (size_t)gen * M * M;           // row-major: P[r*M + c]
+        for (int i = threadIdx.x; i < M * M; i += blockDim.x) Pg[i] = P[(i / M) * LD + i % M];
+        gemms += 5 + sq;
+    }
+    if (threadIdx.x == 0) atomicAdd(&status[0], gemms);
+}
+
+template <int MT, int KS, int NBLK>
+static cudaError_t launch_real_expm_ks(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
+                                       unsigned long long *status, cudaStream_t stream) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    const size_t smem = (size_t)2 * MP * LD * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(real_expm_kernel<MT, KS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, real_expm_kernel<MT, KS, NBLK>, 32 * MT, smem);
+    if (e != cudaSuccess) return e;
+    const int grid = std::min(n_gen, sms * std::max(1, per_sm));
+    // A^2 tiles, one per resident CTA: a process-lifetime buffer (one process per GPU) that only grows
+    static double *scratch = nullptr;
+    static size_t scratch_elems = 0;
+    const size_t need = (size_t)grid * M * M;
+    if (need > scratch_elems) {
+        if (scratch) {
+            cudaDeviceSynchronize();
+            cudaFree(scratch);
+            scratch = nullptr; scratch_elems = 0;
+        }
+        e = cudaMalloc(reinterpret_cast<void **>(&scratch), need * sizeof(double));
+        if (e != cudaSuccess) return e;
+        scratch_elems = need;
+    }
+    real_expm_kernel<MT, KS, NBLK><<<grid, 32 * MT, smem, stream>>>(Gt, gnorm, M, dt, n_gen, P, scratch, status);
+    return cudaGetLastError();
+}
+
+template <int MT>
+static cudaError_t launch_real_expm(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
+                                    unsigned long long *status, cudaStream_t stream) {
+    // the contraction dimension is padded to a multiple of 4 only (M = 49: 13 k-steps, not 14)
+    // QSX_REXPM_BLOCKS: register cap for 2 / 3 / 4 resident CTAs per SM (A/B runs; default 3)
+    const char *sw = getenv("QSX_REXPM_BLOCKS");
+    const int nblk = sw ? atoi(sw) : 3;
+    if ((M + 3) / 4 == 2 * MT - 1) {
+        if (nblk == 2) return launch_real_expm_ks<MT, 2 * MT - 1, 2>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+        if (nblk == 4) return launch_real_expm_ks<MT, 2 * MT - 1, 4>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+        return launch_real_expm_ks<MT, 2 * MT - 1, 3>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+    }
+    if (nblk == 2) return launch_real_expm_ks<MT, 2 * MT, 2>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+    if (nblk == 4) return launch_real_expm_ks<MT, 2 * MT, 4>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+    return launch_real_expm_ks<MT, 2 * MT, 3>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+}
+
+// ------------------------------------------------------------------ u <- P u
+// One warp per column: lane (rs, q) = (lane / 4, lane % 4) keeps rows rs + 8h (h < RW) and columns
+// q + 4i (i < CQ) of P in registers; the state lives in two per-warp shared buffers, the four
+// partial sums of a row meet in two shuffles.  No CTA barrier anywhere.
+template <int RW, int CQ>
+__global__ void __launch_bounds__(64)
+real_map_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen_of, int identity, int n_col,
+                const double *__restrict__ u0, int nt, int MS, double *__restrict__ out) {
+    __shared__ double xs[2][2][64];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 2 + w;
+    if (col >= n_col) return;
+    const int q = lane & 3, rs = lane >> 2;
+    const int gen = gen_of ? gen_of[col] : (identity ? col : 0);
+    const double *Pg = P + (size_t)gen * M * M;
+    double p[RW][CQ];
+#pragma unroll
+    for (int h = 0; h < RW; ++h)
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+            const int r = rs + 8 * h, c = q + 4 * i;
+            p[h][i] = (r < M && c < M) ? Pg[r * M + c] : 0.0;
+        }
+    double *orow = out + (size_t)col * nt * MS;
+    for (int i = lane; i < 64; i += 32) {
+        const double v = i < M ? u0[(size_t)col * MS + i] : 0.0;
+        xs[w][0][i] = v;
+        xs[w][1][i] = 0.0;
+        if (i < MS) __stcs(&orow[i], v);
+    }
+    __syncwarp();
+    for (int it = 1; it < nt; ++it) {
+        const double *cur = xs[w][(it - 1) & 1];
+        double *nxt = xs[w][it & 1];
+        orow += MS;
+        double acc[RW];
+#pragma unroll
+        for (int h = 0; h < RW; ++h) acc[h] = 0.0;
+        // all state elements of the lane first: with two warps per scheduler a load issued one
+        // round ahead of its use is not back in time
+        double v[CQ];
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) v[i] = cur[q + 4 * i];
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+#pragma unroll
+            for (int h = 0; h < RW; ++h) acc[h] = fma(p[h][i], v[i], acc[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < RW; ++h) {
+            acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+            acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
+        }
+        // lane q of a row group writes the rows with h = q (mod 4)
+#pragma unroll
+        for (int h = 0; h < RW; ++h) {
+            const int r = rs + 8 * h;
+            if ((h & 3) == q && r < M) {
+                nxt[r] = acc[h];
+                __stcs(&orow[r], acc[h]);
+            }
+        }
+        for (int k = M + lane; k < MS; k += 32) __stcs(&orow[k], 0.0);
+        __syncwarp();
+    }
+}
+
+// Two warps per column (wide states): warp w keeps rows rs + 8h for h = w, w + 2, ... (four and
+// three row groups for M = 49) -- half the registers per thread, twice the resident warps to hide
+// the shared-memory and shuffle round trips; the warps meet at one named barrier per output step.
+template <int NR, int CQ>
+__device__ __forceinline__ void real_map_rows(const double *__restrict__ Pg, int M, int w, int lane, double (*xs)[64],
+                                              int nt, int MS, double *__restrict__ orow) {
+    const int q = lane & 3, rs = lane >> 2;
+    double p[NR][CQ];
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+            const int r = rs + 8 * (w + 2 * j), c = q + 4 * i;
+            p[j][i] = (r < M && c < M) ? Pg[r * M + c] : 0.0;
+        }
+    for (int it = 1; it < nt; ++it) {
+        const double *cur = xs[(it - 1) & 1];
+        double *nxt = xs[it & 1];
+        orow += MS;
+        double acc[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < CQ; ++i) {
+            const double v = cur[q + 4 * i];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] = fma(p[j][i], v, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const int r = rs + 8 * (w + 2 * j);
+            if ((j & 3) == q && r < M) {
+                nxt[r] = acc[j];
+                __stcs(&orow[r], acc[j]);
+            }
+        }
+        if (w == 0)
+            for (int k = M + lane; k < MS; k += 32) __stcs(&orow[k], 0.0);
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+    }
+}
+
+template <int RW, int CQ, int NBLK>
+__global__ void __launch_bounds__(64, NBLK)
+real_map2_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen_of, int identity, int n_col,
+                 const double *__restrict__ u0, int nt, int MS, double *__restrict__ out) {
+    __shared__ double xs[2][64];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x;
+    const int gen = gen_of ? gen_of[col] : (identity ? col : 0);
+    const double *Pg = P + (size_t)gen * M * M;
+    double *orow = out + (size_t)col * nt * MS;
+    {
+        const int i = threadIdx.x;
+        const double v = i < M ? u0[(size_t)col * MS + i] : 0.0;
+        xs[0][i] = v;
+        xs[1][i] = 0.0;
+        if (i < MS) __stcs(&orow[i], v);
+    }
+    __syncthreads();
+    if (w == 0) real_map_rows<(RW + 1) / 2, CQ>(Pg, M, 0, lane, xs, nt, MS, orow);
+    else real_map_rows<RW / 2, CQ>(Pg, M, 1, lane, xs, nt, MS, orow);
+}
+
+template <int RW, int CQ>
+static cudaError_t launch_real_map2(const double *P, int M, const int *gen_of, int identity, int n_col, const double *u0,
+                                    int nt, int MS, double *out, cudaStream_t stream) {
+    // QSX_RMAP_BLOCKS: register cap for 6 / 7 / 8 resident CTAs per SM (A/B runs)
+    const char *sw = getenv("QSX_RMAP_BLOCKS");
+    const int nblk = sw ? atoi(sw) : 7;
+    if (nblk == 6) real_map2_kernel<RW, CQ, 6><<<n_col, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
+    else if (nblk == 8) real_map2_kernel<RW, CQ, 8><<<n_col, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
+    else real_map2_kernel<RW, CQ, 7><<<n_col, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
+    return cudaGetLastError();
+}
+
+template <int RW, int CQ>
+static cudaError_t launch_real_map(const double *P, int M, const int *gen_of, int identity, int n_col, const double *u0,
+                                   int nt, int MS, double *out, cudaStream_t stream) {
+    real_map_kernel<RW, CQ><<<(n_col + 1) / 2, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ pack / unpack
+__global__ void hermitian_pack_kernel(const cplx *__restrict__ y, int M, long long rows, HermPerm perm, int MS,
+                                      double *__restrict__ u, double *__restrict__ defect) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double im = 0.0, re = 0.0;
+    if (i < rows * MS) {
+        const long long row = i / MS;
+        const int k = (int)(i % MS);
+        cplx z = cmake(0, 0);
+        if (k < M) {
+            const int s = perm.s[k];
+            const cplx a = y[row * M + k];
+            if (s == k) z = a;
+            else {
+                const cplx b = y[row * M + s];
+                if (k < s) z = cmake(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+                else z = cmake(0.5 * (b.y - a.y), -0.5 * (b.x - a.x));            // (y_s - y_k) / 2i, s = a of the pair
+            }
+        }
+        u[i] = z.x;
+        re = fabs(z.x);
+        im = fabs(z.y);
+    }
+    re = warp_max(re);
+    im = warp_max(im);
+    if ((threadIdx.x & 31) == 0 && defect) {
+        if (im > 0.0) atomic_max_nonneg(&defect[2], im);
+        if (re > 0.0) atomic_max_nonneg(&defect[3], re);
+    }
+}
+
+__global__ void hermitian_unpack_kernel(const double *__restrict__ u, int M, long long rows, int MS, HermPerm perm,
+                                        cplx *__restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * M) return;
+    const long long row = i / M;
+    const int k = (int)(i % M);
+    const int s = perm.s[k];
+    const double *ur = u + row * MS;
+    y[i] = s == k ? cmake(ur[k], 0.0) : k < s ? cmake(ur[k], ur[s]) : cmake(ur[s], -ur[k]);
+}
+
+// ------------------------------------------------------------------ host
+static int make_perm(HermPerm &p, const int32_t *perm_host, int M) {
+    for (int k = 0; k < M; ++k) {
+        const int s = perm_host[k];
+        if (s < 0 || s >= M || perm_host[s] != k) return 0;          // must be an involution
+        p.s[k] = (unsigned char)s;
+    }
+    return 1;
+}
+
+int qsx_real_form_launch(const cplx *Lt, int M, int n_gen, const int32_t *perm_host, double *Gt, double *gnorm,
+                         double *defect, cudaStream_t stream) {
+    QSX_REQUIRE(Lt && perm_host && Gt && gnorm && defect && M > 0 && M <= 56 && n_gen > 0,
+                "qsx_dense_hermitian_form: bad arguments (state dimension 1..56)");
+    HermPerm p;
+    QSX_REQUIRE(make_perm(p, perm_host, M), "qsx_dense_hermitian_form: perm is not an involution of 0..M-1");
+    const size_t smem = (size_t)M * M * sizeof(cplx);
+    QSX_CUDA(cudaFuncSetAttribute(hermitian_form_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hermitian_form_kernel<<<n_gen, 128, smem, stream>>>(Lt, M, p, Gt, gnorm, defect);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+extern "C" int qsx_real_expm(const void *Gt_dev, const void *gnorm_dev, int32_t M, int32_t n_generators, double dt,
+                             void *P_dev, void *gemm_count_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(Gt_dev && gnorm_dev && P_dev && gemm_count_dev && M > 0 && M <= 56 && n_generators > 0,
+                "qsx_real_expm: bad arguments (state dimension 1..56)");
+    const double *Gt = (const double *)Gt_dev, *gn = (const double *)gnorm_dev;
+    double *P = (double *)P_dev;
+    unsigned long long *st = (unsigned long long *)gemm_count_dev;
+    cudaError_t e;
+    switch ((M + 7) / 8) {
+        case 1: e = launch_real_expm<1>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+        case 2: e = launch_real_expm<2>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+        case 3: e = launch_real_expm<3>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+        case 4: e = launch_real_expm<4>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+        case 5: e = launch_real_expm<5>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+        case 6: e = launch_real_expm<6>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+        default: e = launch_real_expm<7>(Gt, gn, M, dt, n_generators, P, st, stream); break;
+    }
+    qsx_launch_counter += 1;
+    if (e != cudaSuccess) {
+        qsx_set_error("qsx_real_expm: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    return QSX_OK;
+}
+
+extern "C" int qsx_real_map(const void *P_dev, int32_t M, int32_t n_generators, const int32_t *generator_of_column_host,
+                            int32_t n_columns, const void *u0_dev, int32_t n_times, int32_t row_stride, void *out_dev,
+                            void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(P_dev && u0_dev && out_dev && M > 0 && M <= 56 && n_generators > 0 && n_columns > 0 && n_times > 0 &&
+                    row_stride >= M && row_stride <= 64,
+                "qsx_real_map: bad arguments");
+    DevBuf<int> gen;
+    int identity = 0;
+    if (generator_of_column_host) {
+        std::vector<int> g(generator_of_column_host, generator_of_column_host + n_columns);
+        for (int v : g) QSX_REQUIRE(v >= 0 && v < n_generators, "qsx_real_map: generator index out of range");
+        QSX_CUDA(gen.upload(g, stream));
+    } else {
+        identity = n_generators == n_columns;
+    }
+    const double *P = (const double *)P_dev, *u0 = (const double *)u0_dev;
+    double *out = (double *)out_dev;
+    const int rw = (M + 7) / 8;
+    cudaError_t e;
+#define QSX_RMAP(RW, CQ) e = launch_real_map<RW, CQ>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream)
+    switch (rw) {
+        case 1: QSX_RMAP(1, 2); break;
+        case 2: QSX_RMAP(2, 4); break;
+        case 3: QSX_RMAP(3, 6); break;
+        case 4: QSX_RMAP(4, 8); break;
+        case 5: QSX_RMAP(5, 10); break;
+        case 6: QSX_RMAP(6, 12); break;
+        default:
+            // QSX_RMAP_ONE_WARP=1: the one-warp-per-column kernel for wide states too (A/B runs)
+            if (getenv("QSX_RMAP_ONE_WARP")) {
+                if (M <= 52) QSX_RMAP(7, 13);
+                else QSX_RMAP(7, 14);
+            } else if (M <= 52) {
+                e = launch_real_map2<7, 13>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
+            } else {
+                e = launch_real_map2<7, 14>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
+            }
+            break;
+    }
+#undef QSX_RMAP
+    qsx_launch_counter += 1;
+    if (e != cudaSuccess) {
+        qsx_set_error("qsx_real_map: %s", cudaGetErrorString(e));
+        return QSX_ERR_CUDA;
+    }
+    return QSX_OK;
+}
+
+extern "C" int qsx_hermitian_pack(const void *y_dev, int32_t M, int64_t rows, const int32_t *perm_host, int32_t row_stride,
+                                  void *u_dev, void *defect_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(y_dev && u_dev && perm_host && M > 0 && M <= 64 && rows > 0 && row_stride >= M, "qsx_hermitian_pack: bad arguments");
+    HermPerm p;
+    QSX_REQUIRE(make_perm(p, perm_host, M), "qsx_hermitian_pack: perm is not an involution of 0..M-1");
+    const long long n = (long long)rows * row_stride;
+    hermitian_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const cplx *)y_dev, M, rows, p, row_stride,
+                                                                           (double *)u_dev, (double *)defect_dev);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}
+
+extern "C" int qsx_hermitian_unpack(const void *u_dev, int32_t M, int64_t rows, int32_t row_stride, const int32_t *perm_host,
+                                    void *y_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    QSX_REQUIRE(y_dev && u_dev && perm_host && M > 0 && M <= 64 && rows > 0 && row_stride >= M, "qsx_hermitian_unpack: bad arguments");
+    HermPerm p;
+    QSX_REQUIRE(make_perm(p, perm_host, M), "qsx_hermitian_unpack: perm is not an involution of 0..M-1");
+    const long long n = (long long)rows * M;
+    hermitian_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const double *)u_dev, M, rows, row_stride, p,
+                                                                             (cplx *)y_dev);
+    qsx_launch_counter += 1;
+    QSX_CUDA(cudaGetLastError());
+    return QSX_OK;
+}

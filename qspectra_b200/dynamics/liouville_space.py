@@ -63,6 +63,21 @@ def liouville_subspace_index(liouville_subspace, full_subspace, n_sites,
     return np.flatnonzero(keep.reshape(-1, order='F'))
 
 
+def transposition_permutation(index, n_states):
+    """perm[k] = position, inside the sorted flat (column-major) subspace ``index``, of the
+    transposed ket-bra pair of element k; None if the subspace is not closed under
+    transposition ('eg', 'fe', ...).  Physical generators commute with Hermitian conjugation,
+    L[perm r][perm c] = conj L[r][c], which the engine uses to propagate Hermitian states in
+    real coordinates (engine.DenseEOM.hermitian_perm, csrc/dense_real.cu)."""
+    index = np.asarray(index)
+    a, b = index % n_states, index // n_states
+    mirrored = b + n_states * a
+    perm = np.searchsorted(index, mirrored)
+    if np.any(perm >= index.size) or np.any(index[np.minimum(perm, index.size - 1)] != mirrored):
+        return None
+    return perm.astype(np.int32)
+
+
 def tensor_to_super(tensor_operator):
     """R[i, j, k, l] -> S[i + N j, k + N l]"""
     R = np.asarray(tensor_operator)
@@ -241,7 +256,17 @@ class LiouvilleSpaceModel(DynamicalModel):
     def equation_of_motion(self, liouville_subspace, heisenberg_picture=False):
         """DeviceEOM for dy/dt = L y; the Heisenberg picture uses the plain
         transpose L^T (reference liouville_space.py:325-330)."""
-        return DenseEOM(self.generator(liouville_subspace), heisenberg_picture)
+        return self.with_transposition(
+            DenseEOM(self.generator(liouville_subspace), heisenberg_picture),
+            liouville_subspace, heisenberg_picture)
+
+    def with_transposition(self, eom, liouville_subspace, heisenberg_picture=False):
+        """Tell a dense device generator how its subspace transposes (Schroedinger picture only)."""
+        if not heisenberg_picture and isinstance(eom, DenseEOM):
+            eom.hermitian_perm = transposition_permutation(
+                self.liouville_subspace_index(liouville_subspace),
+                self.hamiltonian.n_states(self.hilbert_subspace))
+        return eom
 
     def ensemble_generators(self, members, liouville_subspace):
         """(n_members, M, M) stack of the members' generators."""
@@ -252,5 +277,6 @@ class LiouvilleSpaceModel(DynamicalModel):
         if len(members) == 1:
             return members[0].equation_of_motion(liouville_subspace,
                                                  heisenberg_picture)
-        return DenseEOM(self.ensemble_generators(members, liouville_subspace),
-                        heisenberg_picture)
+        return self.with_transposition(
+            DenseEOM(self.ensemble_generators(members, liouville_subspace), heisenberg_picture),
+            liouville_subspace, heisenberg_picture)

@@ -218,7 +218,8 @@ class RedfieldModel(LiouvilleSpaceModel):
                 self.unit_convert,
                 self.liouville_subspace_index(liouville_subspace),
                 transposed=not heisenberg_picture)
-            return engine.DenseEOM.from_transposed(L)
+            return self.with_transposition(engine.DenseEOM.from_transposed(L),
+                                       liouville_subspace, heisenberg_picture)
         number = np.einsum('jaa->ja', ham.system_bath_couplings(ss))
         kind = (_capi.BATH_DEBYE_REAL if self.discard_imag_corr
                 else _capi.BATH_DEBYE_COMPLEX)
@@ -235,4 +236,5 @@ class RedfieldModel(LiouvilleSpaceModel):
             transposed=not heisenberg_picture)
         # the builder wrote the engine's storage layout directly (the Heisenberg
         # picture L^T in that layout is plain row-major L): no copy, no cudaMalloc
-        return engine.DenseEOM.from_transposed(L)
+        return self.with_transposition(engine.DenseEOM.from_transposed(L),
+                                       liouville_subspace, heisenberg_picture)

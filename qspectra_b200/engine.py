@@ -8,6 +8,7 @@ run the whole ``integrate`` loop (simulate/utils.py:53-109) on the GPU for a
 batch of initial states.  PyTorch is used for device memory and streams only.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -27,6 +28,7 @@ class PropagationStats(object):
     expm_ms = 0.0
     expm_gemms = 0
     expm_builds = 0
+    hermitian_builds = 0       # propagator builds that went through the Hermitian-coordinate (real) form
     _pending = []          # (reference to an EOM, method name, argument) whose device times are outstanding
     MAX_PENDING = 256
     #: bench.py: keep the objects alive until flush() so that no timing is lost; by default
@@ -44,6 +46,7 @@ class PropagationStats(object):
         cls.expm_ms = 0.0
         cls.expm_gemms = 0
         cls.expm_builds = 0
+        cls.hermitian_builds = 0
 
     @classmethod
     def defer(cls, obj, name, arg=None):
@@ -266,6 +269,111 @@ class DeviceEOM(object):
         return S.shape[1]
 
 
+class HermitianTrajectory(object):
+    """Trajectories in Hermitian coordinates (csrc/dense_real.cu): a real CUDA tensor
+    (..., n_times, MS) with MS = dim rounded up to even, the transposition permutation of the
+    subspace and the propagators that produced it (their device-side Hermiticity check is
+    settled when the complex form is read on the host)."""
+
+    def __init__(self, data, perm, dim, source=None):
+        self.data, self.perm, self.dim, self.source = data, perm, dim, source
+
+    def to_complex(self):
+        """complex128 CUDA tensor (..., n_times, dim) in the reference's vectorisation."""
+        torch = _capi.torch_cuda()
+        lead = tuple(self.data.shape[:-1])
+        rows = int(np.prod(lead, dtype=np.int64))
+        out = torch.empty(lead + (self.dim,), dtype=torch.complex128, device=self.data.device)
+        _capi.check(_capi.lib().qsx_hermitian_unpack(
+            self.data.data_ptr(), self.dim, rows, self.data.shape[-1],
+            self.perm.ctypes.data_as(C.POINTER(C.c_int32)), out.data_ptr(),
+            _capi.current_stream_ptr()))
+        return out
+
+
+class HermitianPropagators(object):
+    """exp(G dt) of every generator of a DenseEOM in Hermitian coordinates, where a generator
+    that commutes with Hermitian conjugation is REAL (csrc/dense_real.cu): one real tensor-core
+    product per complex one, a quarter of the multiply-adds per step."""
+    TOLERANCE = 1e-10
+    _h = True           # PropagationStats protocol: "still alive"
+
+    def __init__(self, eom, dt):
+        torch = _capi.torch_cuda()
+        lib, stream = _capi.lib(), _capi.current_stream_ptr()
+        n, M = eom.n_generators, eom.dim
+        self.perm = np.ascontiguousarray(eom.hermitian_perm, dtype=np.int32)
+        self.dim, self.n_generators = M, n
+        self.G = torch.empty((n, M, M), dtype=torch.float64, device='cuda')
+        self.gnorm = torch.empty(n, dtype=torch.float64, device='cuda')
+        self.P = torch.empty((n, M, M), dtype=torch.float64, device='cuda')
+        self.defect = torch.zeros(4, dtype=torch.float64, device='cuda')
+        self.counter = torch.zeros(1, dtype=torch.int64, device='cuda')
+        self.host = torch.zeros(5, dtype=torch.float64).pin_memory()
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.events[0].record()
+        _capi.check(lib.qsx_dense_hermitian_form(
+            eom._h, self.perm.ctypes.data_as(C.POINTER(C.c_int32)), self.G.data_ptr(),
+            self.gnorm.data_ptr(), self.defect.data_ptr(), stream))
+        _capi.check(lib.qsx_real_expm(self.G.data_ptr(), self.gnorm.data_ptr(), M, n, float(dt),
+                                      self.P.data_ptr(), self.counter.data_ptr(), stream))
+        self.events[1].record()
+        self.last_event = self.events[1]
+        PropagationStats.expm_builds += 1
+        PropagationStats.hermitian_builds += 1
+        PropagationStats.defer(self, '_resolve_build')
+
+    def snapshot(self):
+        """queue the copy of the device-side check values to pinned host memory"""
+        torch = _capi.torch_cuda()
+        self.host[:4].copy_(self.defect, non_blocking=True)
+        self.host[4:].copy_(self.counter.to(torch.float64), non_blocking=True)
+        self.events[2].record()
+        self.last_event = self.events[2]
+
+    def _stats_ready(self):
+        return self.last_event.query()
+
+    def ok(self):
+        """after a synchronisation that follows snapshot(): did generators and states pass the
+        Hermiticity check?"""
+        d = self.host.numpy()
+        return bool(d[0] <= self.TOLERANCE * d[1] and d[2] <= self.TOLERANCE * max(d[3], 1e-300))
+
+    def _resolve_build(self):
+        if '_build' not in self.__dict__:
+            self.snapshot()
+            self.last_event.synchronize()
+            ms = self.events[0].elapsed_time(self.events[1])
+            gemms = int(self.host[4].item())
+            self.__dict__['_build'] = (ms, gemms)
+            PropagationStats.expm_ms += ms
+            PropagationStats.expm_gemms += gemms
+            if not self.ok() and not self.__dict__.get('_fallback'):
+                raise RuntimeError(
+                    'Hermitian-coordinate propagation was used for a generator or state that is '
+                    'not compatible with Hermitian conjugation (|Im G| %.3e of %.3e, |Im u0| %.3e '
+                    'of %.3e); set QSX_NO_HERMITIAN_FORM=1' % tuple(self.host[:4].tolist()))
+        return self.__dict__['_build']
+
+
+class _MapTiming(object):
+    """deferred device time of one stepping call in Hermitian coordinates"""
+    _h = True
+
+    def __init__(self, e0, e1, info):
+        self.e0, self.e1, self.info = e0, e1, info
+
+    def _stats_ready(self):
+        return self.e1.query()
+
+    def _resolve(self):
+        if self.info.get('kernel_ms') is None:
+            self.e1.synchronize()
+            self.info['kernel_ms'] = self.e0.elapsed_time(self.e1)
+            PropagationStats.kernel_ms += self.info['kernel_ms']
+
+
 class DenseEOM(DeviceEOM):
     """Batched dense Liouvillians L[g] (n_generators, M, M) staged on the GPU
     (kernel K1/K4, csrc/dense.cu)."""
@@ -359,6 +467,80 @@ class DenseEOM(DeviceEOM):
             return None
         return float(d[0])
 
+    #: transposition permutation of the Liouville subspace (set by the models for subspaces
+    #: closed under transposition, Schroedinger picture): enables Hermitian-coordinate stepping
+    hermitian_perm = None
+    HERMITIAN_MAX_DIM = 56
+
+    def _hermitian_state(self, y0):
+        """True when the host array y0 (..., dim) is Hermitian under the subspace's transposition."""
+        if not isinstance(y0, np.ndarray) or self.hermitian_perm is None:
+            return False
+        y = y0.reshape(-1, self.dim)
+        return bool(np.abs(y[:, self.hermitian_perm] - y.conj()).max() <= 1e-14 * max(np.abs(y).max(), 1e-300))
+
+    def _propagate_hermitian(self, y0, t, dt, generators, return_device, packed):
+        """Propagator stepping of Hermitian states in real coordinates (csrc/dense_real.cu)."""
+        torch = _capi.torch_cuda()
+        lib, stream = _capi.lib(), _capi.current_stream_ptr()
+        M = self.dim
+        MS = M + (M & 1)
+        cache = self.__dict__.setdefault('_propagators', {})
+        key = ('hermitian', float(dt))
+        if key not in cache:
+            cache[key] = HermitianPropagators(self, dt)
+        hp = cache[key]
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y0_dev = _capi.to_device(y0).reshape(-1, M)
+        B = y0_dev.shape[0]
+        garr, gptr = _capi.int32_ptr(generators)
+        if garr is not None:
+            if garr.shape != (B,):
+                raise ValueError('generators must have one entry per column')
+            if B == self.n_generators and np.array_equal(garr, np.arange(B)):
+                gptr = None                 # column c uses generator c: no table upload
+        pptr = hp.perm.ctypes.data_as(C.POINTER(C.c_int32))
+        u0 = torch.empty((B, MS), dtype=torch.float64, device=y0_dev.device)
+        _capi.check(lib.qsx_hermitian_pack(y0_dev.data_ptr(), M, B, pptr, MS, u0.data_ptr(),
+                                           hp.defect.data_ptr(), stream))
+        out = torch.empty((B, t.size, MS), dtype=torch.float64, device=y0_dev.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _capi.check(lib.qsx_real_map(hp.P.data_ptr(), M, self.n_generators, gptr, B, u0.data_ptr(),
+                                     t.size, MS, out.data_ptr(), stream))
+        e1.record()
+        n_rhs = (t.size - 1) * B
+        PropagationStats.rhs_evaluations += n_rhs
+        PropagationStats.accepted_steps += n_rhs
+        PropagationStats.propagations += 1
+        info = dict(rhs=n_rhs, steps=n_rhs, kernel_ms=None, method='expm', hermitian_form=True)
+        timing = _MapTiming(e0, e1, info)
+        info['_timing'] = timing
+        PropagationStats.defer(timing, '_resolve')
+        self.__dict__['_last'] = info
+        self.__dict__['_last_src'] = None
+        traj = HermitianTrajectory(out, hp.perm, M, hp)
+        if packed:
+            return traj
+        res = traj.to_complex()
+        if return_device:
+            return res
+        hp.snapshot()
+        host = _capi.to_host(res)
+        if not hp.ok():
+            # not Hermiticity-compatible after all: the caller falls back to the complex path
+            hp.__dict__['_fallback'] = True
+            self.hermitian_perm = None
+            return None
+        return host
+
+    def _resolve_last(self, info):
+        timing = info.get('_timing')
+        if timing is not None:
+            timing._resolve()
+            return
+        DeviceEOM._resolve_last(self, info)
+
     def propagate(self, y0, t, t0=None, method='zvode', **kw):
         """Adds method 'expm' (propagator stepping: y_{i+1} = exp(L dt) y_i,
         built once per generator on the tensor cores).  It is also what the
@@ -372,6 +554,17 @@ class DenseEOM(DeviceEOM):
             worth = len(t) * max(1, n_cols // self.n_generators) >= 64
             if dt is not None and self.dim <= self.EXPM_LIBRARY_MAX_DIM and \
                     (name == 'expm' or worth):
+                hermitian = kw.pop('hermitian_state', None)
+                packed = kw.pop('packed', False)
+                if (self.hermitian_perm is not None and self.dim <= self.HERMITIAN_MAX_DIM
+                        and not self.heisenberg_picture and kw.get('save') is None
+                        and kw.get('save_index') is None
+                        and not os.environ.get('QSX_NO_HERMITIAN_FORM')
+                        and (self._hermitian_state(y0) if hermitian is None else hermitian)):
+                    out = self._propagate_hermitian(y0, t, dt, kw.get('generators'),
+                                                    kw.get('return_device', False), packed)
+                    if out is not None:
+                        return out
                 prop = self.propagator(dt)
                 out = DeviceEOM.propagate(prop, y0, t, t0=t0, method='map', **kw)
                 self.__dict__['_last_src'] = prop      # resolved (and relabelled 'expm') on access
@@ -380,6 +573,8 @@ class DenseEOM(DeviceEOM):
                 raise ValueError('expm needs a uniform output grid starting at '
                                  't0 and a state dimension <= %d'
                                  % self.EXPM_LIBRARY_MAX_DIM)
+        kw.pop('hermitian_state', None)
+        kw.pop('packed', None)
         return DeviceEOM.propagate(self, y0, t, t0=t0, method=method, **kw)
 
     def _apply_dev(self, y, dy, n, gptr):
@@ -600,6 +795,18 @@ class ZofeEOM(DeviceEOM):
 
 def reduce_members(batch_dev, scale=1.0):
     """out[...] = scale * sum_m batch[m, ...] on the device (kernel K6)."""
+    torch = _capi.torch_cuda()
+    if isinstance(batch_dev, HermitianTrajectory):
+        # the member sum commutes with the (linear) change of coordinates: reduce the real
+        # rows (viewed as complex pairs, MS is even), then unpack the mean only
+        data = batch_dev.data.contiguous()
+        B = data.shape[0]
+        red = reduce_members(torch.view_as_complex(data.reshape(B, -1, 2)), scale)
+        mean = HermitianTrajectory(torch.view_as_real(red).reshape(data.shape[1:]),
+                                   batch_dev.perm, batch_dev.dim, batch_dev.source)
+        if batch_dev.source is not None:
+            batch_dev.source.snapshot()
+        return mean.to_complex()
     torch = _capi.torch_cuda()
     batch_dev = batch_dev.contiguous()
     out = torch.empty(batch_dev.shape[1:], dtype=torch.complex128,

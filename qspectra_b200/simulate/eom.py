@@ -63,6 +63,11 @@ def ensemble_mean(eom, y0, t, ensemble_size, save, return_device=False,
         return states.sum(axis=0) / ensemble_size
     torch = _capi.torch_cuda()
     y0_dev = _capi.to_device(y0).reshape(1, -1).expand(ensemble_size, -1).contiguous()
+    # Hermitian initial state on a subspace closed under transposition: dense generators step it
+    # in real coordinates, and the member sum runs over the real rows (engine.HermitianTrajectory)
+    hermitian = isinstance(eom, engine.DenseEOM) and eom._hermitian_state(np.asarray(y0))
+    if hermitian:
+        opts.update(hermitian_state=True, packed=True)
     out = eom.propagate(y0_dev, t, method=integrate_kwargs.get('method_name', 'zvode'),
                         save=save, generators=np.arange(ensemble_size),
                         return_device=True, **opts)
@@ -70,6 +75,13 @@ def ensemble_mean(eom, y0, t, ensemble_size, save, return_device=False,
     if return_device:
         return mean
     res = _capi.to_host(mean)
+    if isinstance(out, engine.HermitianTrajectory) and not out.source.ok():
+        # the device-side check found a generator that does not commute with Hermitian
+        # conjugation: repeat on the complex path
+        out.source.__dict__['_fallback'] = True
+        eom.hermitian_perm = None
+        return ensemble_mean(eom, y0, t, ensemble_size, save, return_device, scale,
+                             **integrate_kwargs)
     if isinstance(save, LinearMap) and save.matrix.ndim == 1:
         res = res[..., 0]
     return res
