@@ -115,10 +115,19 @@ real_expm_kernel(const double *__restrict__ Gt, const double *__restrict__ gnorm
         auto row_block_gemm = [&](const double *B, auto &&epi) {
 #pragma unroll
             for (int nb = 0; nb < MT; ++nb) {
-                double p0 = 0, p1 = 0;
+                // all B fragments of the column block first (one dependent load -> DMMA pair after the
+                // other leaves the tensor pipe idle for a shared-memory round trip per instruction), then
+                // two independent accumulator chains over the even and odd k-steps
+                double b[KS];
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) dmma884r(p0, p1, a[ks], B[(ks * 4 + t) * LD + nb * 8 + g]);
-                epi(rb * 8 + g, nb * 8 + 2 * t, p0, p1);
+                for (int ks = 0; ks < KS; ++ks) b[ks] = B[(ks * 4 + t) * LD + nb * 8 + g];
+                double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks += 2) {
+                    dmma884r(p0, p1, a[ks], b[ks]);
+                    if (ks + 1 < KS) dmma884r(q0, q1, a[ks + 1], b[ks + 1]);
+                }
+                epi(rb * 8 + g, nb * 8 + 2 * t, p0 + q0, p1 + q1);
             }
         };
         auto load_fragments = [&](const double *Z) {
@@ -246,122 +255,54 @@ real_map_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen
         xs[w][1][i] = 0.0;
         if (i < MS) __stcs(&orow[i], v);
     }
+    // tails of the output rows (row_stride > M), once, outside the stepping loop
+    for (int k = M; k < MS; ++k)
+        for (int it = 1 + lane; it < nt; it += 32) __stcs(&orow[(size_t)it * MS + k], 0.0);
     __syncwarp();
-    for (int it = 1; it < nt; ++it) {
-        const double *cur = xs[w][(it - 1) & 1];
-        double *nxt = xs[w][it & 1];
-        orow += MS;
+    // per-lane base addresses; everything inside a step is a constant offset from them
+    const double *ld_a = &xs[w][0][q], *ld_b = &xs[w][1][q];
+    double *st_a = &xs[w][0][rs], *st_b = &xs[w][1][rs];
+    double *og = orow + rs;
+    const bool writer = q == 0, last_row = rs + 8 * (RW - 1) < M;
+    auto step = [&](const double *__restrict__ ld, double *__restrict__ st) {
         double acc[RW];
 #pragma unroll
         for (int h = 0; h < RW; ++h) acc[h] = 0.0;
-        // all state elements of the lane first: with two warps per scheduler a load issued one
-        // round ahead of its use is not back in time
-        double v[CQ];
-#pragma unroll
-        for (int i = 0; i < CQ; ++i) v[i] = cur[q + 4 * i];
 #pragma unroll
         for (int i = 0; i < CQ; ++i) {
+            const double v = ld[4 * i];
 #pragma unroll
-            for (int h = 0; h < RW; ++h) acc[h] = fma(p[h][i], v[i], acc[h]);
+            for (int h = 0; h < RW; ++h) acc[h] = fma(p[h][i], v, acc[h]);
         }
 #pragma unroll
         for (int h = 0; h < RW; ++h) {
             acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
             acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
         }
-        // lane q of a row group writes the rows with h = q (mod 4)
+        if (writer) {
 #pragma unroll
-        for (int h = 0; h < RW; ++h) {
-            const int r = rs + 8 * h;
-            if ((h & 3) == q && r < M) {
-                nxt[r] = acc[h];
-                __stcs(&orow[r], acc[h]);
+            for (int h = 0; h < RW - 1; ++h) {
+                st[8 * h] = acc[h];
+                __stcs(og + 8 * h, acc[h]);
+            }
+            if (last_row) {
+                st[8 * (RW - 1)] = acc[RW - 1];
+                __stcs(og + 8 * (RW - 1), acc[RW - 1]);
             }
         }
-        for (int k = M + lane; k < MS; k += 32) __stcs(&orow[k], 0.0);
         __syncwarp();
+    };
+    int it = 1;
+    for (; it + 1 < nt; it += 2) {
+        og += MS;
+        step(ld_a, st_b);
+        og += MS;
+        step(ld_b, st_a);
     }
-}
-
-// Two warps per column (wide states): warp w keeps rows rs + 8h for h = w, w + 2, ... (four and
-// three row groups for M = 49) -- half the registers per thread, twice the resident warps to hide
-// the shared-memory and shuffle round trips; the warps meet at one named barrier per output step.
-template <int NR, int CQ>
-__device__ __forceinline__ void real_map_rows(const double *__restrict__ Pg, int M, int w, int lane, double (*xs)[64],
-                                              int nt, int MS, double *__restrict__ orow) {
-    const int q = lane & 3, rs = lane >> 2;
-    double p[NR][CQ];
-#pragma unroll
-    for (int j = 0; j < NR; ++j)
-#pragma unroll
-        for (int i = 0; i < CQ; ++i) {
-            const int r = rs + 8 * (w + 2 * j), c = q + 4 * i;
-            p[j][i] = (r < M && c < M) ? Pg[r * M + c] : 0.0;
-        }
-    for (int it = 1; it < nt; ++it) {
-        const double *cur = xs[(it - 1) & 1];
-        double *nxt = xs[it & 1];
-        orow += MS;
-        double acc[NR];
-#pragma unroll
-        for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-#pragma unroll
-        for (int i = 0; i < CQ; ++i) {
-            const double v = cur[q + 4 * i];
-#pragma unroll
-            for (int j = 0; j < NR; ++j) acc[j] = fma(p[j][i], v, acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
-        }
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            const int r = rs + 8 * (w + 2 * j);
-            if ((j & 3) == q && r < M) {
-                nxt[r] = acc[j];
-                __stcs(&orow[r], acc[j]);
-            }
-        }
-        if (w == 0)
-            for (int k = M + lane; k < MS; k += 32) __stcs(&orow[k], 0.0);
-        asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (it < nt) {
+        og += MS;
+        step(ld_a, st_b);
     }
-}
-
-template <int RW, int CQ, int NBLK>
-__global__ void __launch_bounds__(64, NBLK)
-real_map2_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen_of, int identity, int n_col,
-                 const double *__restrict__ u0, int nt, int MS, double *__restrict__ out) {
-    __shared__ double xs[2][64];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = blockIdx.x;
-    const int gen = gen_of ? gen_of[col] : (identity ? col : 0);
-    const double *Pg = P + (size_t)gen * M * M;
-    double *orow = out + (size_t)col * nt * MS;
-    {
-        const int i = threadIdx.x;
-        const double v = i < M ? u0[(size_t)col * MS + i] : 0.0;
-        xs[0][i] = v;
-        xs[1][i] = 0.0;
-        if (i < MS) __stcs(&orow[i], v);
-    }
-    __syncthreads();
-    if (w == 0) real_map_rows<(RW + 1) / 2, CQ>(Pg, M, 0, lane, xs, nt, MS, orow);
-    else real_map_rows<RW / 2, CQ>(Pg, M, 1, lane, xs, nt, MS, orow);
-}
-
-template <int RW, int CQ>
-static cudaError_t launch_real_map2(const double *P, int M, const int *gen_of, int identity, int n_col, const double *u0,
-                                    int nt, int MS, double *out, cudaStream_t stream) {
-    // QSX_RMAP_BLOCKS: register cap for 6 / 7 / 8 resident CTAs per SM (A/B runs)
-    const char *sw = getenv("QSX_RMAP_BLOCKS");
-    const int nblk = sw ? atoi(sw) : 7;
-    if (nblk == 6) real_map2_kernel<RW, CQ, 6><<<n_col, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
-    else if (nblk == 8) real_map2_kernel<RW, CQ, 8><<<n_col, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
-    else real_map2_kernel<RW, CQ, 7><<<n_col, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
-    return cudaGetLastError();
 }
 
 template <int RW, int CQ>
@@ -492,15 +433,10 @@ extern "C" int qsx_real_map(const void *P_dev, int32_t M, int32_t n_generators, 
         case 5: QSX_RMAP(5, 10); break;
         case 6: QSX_RMAP(6, 12); break;
         default:
-            // QSX_RMAP_ONE_WARP=1: the one-warp-per-column kernel for wide states too (A/B runs)
-            if (getenv("QSX_RMAP_ONE_WARP")) {
-                if (M <= 52) QSX_RMAP(7, 13);
-                else QSX_RMAP(7, 14);
-            } else if (M <= 52) {
-                e = launch_real_map2<7, 13>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
-            } else {
-                e = launch_real_map2<7, 14>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
-            }
+            // (two warps per column -- half the registers, twice the resident warps -- measured slower:
+            // 1.0-1.2 vs 0.8 ms per 1e4 FMO members; the per-step overhead doubles)
+            if (M <= 52) QSX_RMAP(7, 13);
+            else QSX_RMAP(7, 14);
             break;
     }
 #undef QSX_RMAP
