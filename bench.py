@@ -78,10 +78,13 @@ def workload_config(members, n_gpus):
                         "'ee' subspace (M=49), %d static-disorder members per GPU, "
                         '1 ps / 197 output points' % members,
             'members_per_gpu': members, 'state_dim': 49, 'grid_points': 197,
-            'integrator': 'propagator stepping: exp(L dt) per member on the FP64 tensor '
-                          'cores (|A| <= 1/2 scaling, fixed degree-12 Taylor polynomial in '
-                          'Paterson-Stockmeyer form, squarings), then y <- P y per output '
-                          'interval; the propagators are rebuilt in every timed step',
+            'integrator': 'propagator stepping in Hermitian coordinates (populations, Re and Im of '
+                          'the coherences), where the generator of a Hermiticity-preserving master '
+                          'equation is a real 49 x 49 matrix: change of coordinates, exp(G dt) per '
+                          'member on the FP64 tensor cores (|A| <= 1/2 scaling, fixed degree-12 Taylor '
+                          'polynomial in Paterson-Stockmeyer form, squarings), then u <- P u per '
+                          'output interval; coordinates, propagators and trajectories are rebuilt in '
+                          'every timed step (QSX_NO_HERMITIAN_FORM=1: the complex path)',
             'parallelism': 'ensemble members sharded over %d GPU(s), one NCCL '
                            'reduce' % n_gpus,
             'l2_policy': 'inputs larger than L2 (1e4 generators = 384 MB vs 126 MB L2)'}
@@ -619,7 +622,11 @@ def run_ours(args):
 
         def local_step():
             eom.__dict__.pop('_propagators', None)    # rebuild exp(L dt) every step
-            out = eom.propagate(y0_dev, t, generators=gens, return_device=True)
+            # the initial state is a density matrix (Hermitian): dense generators step it in real
+            # coordinates and the member sum runs over the real rows (what simulate_dynamics does
+            # after checking the host state)
+            out = eom.propagate(y0_dev, t, generators=gens, return_device=True,
+                                hermitian_state=True, packed=True)
             return engine.reduce_members(out, 1.0 / total_members)
 
         def step():
@@ -658,6 +665,7 @@ def run_ours(args):
         st.flush()          # collect the deferred device times of the timed steps
         st.keep_alive = False
         stats = dict(expm_ms=st.expm_ms, expm_gemms=st.expm_gemms, expm_builds=st.expm_builds,
+                     form_ms=st.form_ms, hermitian_builds=st.hermitian_builds,
                      kernel_ms=st.kernel_ms / max(1, st.propagations),
                      rhs=st.rhs_evaluations / max(1, st.propagations),
                      steps=st.accepted_steps / max(1, st.propagations),
@@ -758,18 +766,24 @@ def run_ours(args):
 
     peaks, peak_src = measured_peaks()
     fp64_peak = measure_fp64_peak(torch)
-    # dominant kernel of the step: the tensor-core propagator build (dense_expm_kernel);
-    # algorithmic flops = complex M x M GEMMs x 8 M^3 (M = 49, padding not counted)
-    expm_ms = stats['expm_ms'] / max(1, stats['expm_builds'])
-    flops_per_launch = 8.0 * 49 ** 3 * stats['expm_gemms'] / max(1, stats['expm_builds'])
+    # kernels of the step: change of coordinates (Hermitian form), tensor-core propagator build,
+    # stepping, member sum.  Algorithmic flops: in Hermitian coordinates the generators are REAL,
+    # so a product is 2 M^3 and a step 2 M^2 flops (M = 49, padding not counted); on the complex
+    # path (QSX_NO_HERMITIAN_FORM=1) 8 M^3 and 8 M^2.
+    real_form = stats['hermitian_builds'] > 0
+    builds = max(1, stats['expm_builds'])
+    form_ms = stats['form_ms'] / builds
+    expm_ms = stats['expm_ms'] / builds - form_ms
+    flops_per_launch = (2.0 if real_form else 8.0) * 49 ** 3 * stats['expm_gemms'] / builds
     achieved_tf = flops_per_launch / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else 0.0
     kernel_ms, rhs_per_launch = stats['kernel_ms'], stats['rhs']
-    map_flops = 8.0 * 49 * 49 * rhs_per_launch
+    map_flops = (2.0 if real_form else 8.0) * 49 * 49 * rhs_per_launch
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'complex128', 'data': 'synthetic',
+        'dtype': 'float64 (Hermitian coordinates of the complex128 density matrices)' if real_form else 'complex128',
+        'data': 'synthetic',
         'config': workload_config(E, world),
         'rhs_per_state_step': rhs_per_launch / max(1.0, stats['steps']),
         'rhs_per_s': world * rhs_per_launch / (ms_per_step * 1e-3),
@@ -783,8 +797,9 @@ def run_ours(args):
                 'bytes_are': 'counted copies of rank 0 (qsx_transfer_bytes + _capi.to_device/to_host)',
                 'path': 'simulate_dynamics(model, psi0, duration, ensemble_size) from host objects: '
                         'seed -> device replay of the seeded disorder streams -> K5 (Jacobi '
-                        'eigensystems + Redfield generators) -> K1\' propagators -> K1/K4 '
-                        'stepping -> K6 mean -> D2H of the averaged density matrices'},
+                        'eigensystems + Redfield generators) -> Hermitian coordinates -> K1\' real '
+                        'propagators -> K1/K4 stepping -> K6 mean over the real rows -> complex '
+                        'density matrices -> D2H'},
         'gpu_launches': int(stats['launches']),
         'roofline': None,
     }
@@ -795,24 +810,31 @@ def run_ours(args):
     peak_note = ('cuBLAS FP64 GEMM 6144^3 measured in this run (cutlass d884 DMMA kernel; '
                  'FP64 is not in MEASURED_PEAKS.json)')
     map_tf = map_flops / (kernel_ms * 1e-3) / 1e12
+    expm_name = ('real_expm_kernel<7,13,3> (FP64 DMMA m8n8k4 on the real generators in Hermitian coordinates: '
+                 'exp(G dt) per member, Paterson-Stockmeyer degree 12 + squarings)' if real_form else
+                 'dense_expm2_kernel<7,13> (FP64 DMMA m8n8k4, three real products per complex one: exp(L dt) per member, '
+                 'Paterson-Stockmeyer degree 12 + squarings)')
+    map_name = ('real_map_kernel<7,13> (u <- P u stepping in Hermitian coordinates, one warp per member with P in '
+                'registers; DFMA on the FP64 pipe, measured against the same FP64 ceiling)' if real_form else
+                'dense_map_split_kernel<5,10,25,2> (y <- P y stepping with P in registers; DFMA on '
+                'the FP64 pipe, measured against the same FP64 ceiling as SURVEY 8d asks '
+                'for the dense L.Y contraction)')
     k_expm = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': fp64_peak,
               'unit': 'TFLOP/s', 'frac': achieved_tf / fp64_peak,
-              'traffic': (ncu_traffic('dense_expm_per_member') or 0) * E or None,
-              'kernel': 'dense_expm2_kernel<7,13> (FP64 DMMA m8n8k4, three real products per complex one: exp(L dt) per member, '
-                        'Paterson-Stockmeyer degree 12 + squarings)',
+              'traffic': (ncu_traffic('real_expm_per_member' if real_form else 'dense_expm_per_member') or 0) * E or None,
+              'kernel': expm_name,
               'kernel_ms': expm_ms, 'share_of_step': expm_ms / ms_per_step,
               'algorithmic_flops_per_launch': flops_per_launch, 'peak_source': peak_note}
     k_map = {'bound': 'tensor', 'achieved': map_tf, 'peak': fp64_peak,
              'unit': 'TFLOP/s', 'frac': map_tf / fp64_peak,
-             'traffic': (ncu_traffic('dense_map_per_member') or 0) * E or None,
-             'kernel': 'dense_map_kernel<4,13,1,2> (y <- P y stepping with P in registers; DFMA on '
-                       'the FP64 pipe, measured against the same FP64 ceiling as SURVEY 8d asks '
-                       'for the dense L.Y contraction)',
+             'traffic': (ncu_traffic('real_map_per_member' if real_form else 'dense_map_per_member') or 0) * E or None,
+             'kernel': map_name,
              'kernel_ms': kernel_ms, 'share_of_step': kernel_ms / ms_per_step,
              'algorithmic_flops_per_launch': map_flops, 'peak_source': peak_note}
     first_k, second_k = (k_map, k_expm) if kernel_ms >= expm_ms else (k_expm, k_map)
     line['roofline'] = first_k
     line['other_kernels'] = {second_k['kernel']: second_k,
+                             'hermitian_form_kernel_ms': form_ms if real_form else None,
                              'share_note': 'per step: propagator build + stepping + member '
                                            'reduction; see profiles/ for the ncu launch list'}
     if extra is not None:

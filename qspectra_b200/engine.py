@@ -29,6 +29,7 @@ class PropagationStats(object):
     expm_gemms = 0
     expm_builds = 0
     hermitian_builds = 0       # propagator builds that went through the Hermitian-coordinate (real) form
+    form_ms = 0.0              # of expm_ms: the change of coordinates L -> G (hermitian_form_kernel)
     _pending = []          # (reference to an EOM, method name, argument) whose device times are outstanding
     MAX_PENDING = 256
     #: bench.py: keep the objects alive until flush() so that no timing is lost; by default
@@ -47,6 +48,7 @@ class PropagationStats(object):
         cls.expm_gemms = 0
         cls.expm_builds = 0
         cls.hermitian_builds = 0
+        cls.form_ms = 0.0
 
     @classmethod
     def defer(cls, obj, name, arg=None):
@@ -310,11 +312,12 @@ class HermitianPropagators(object):
         self.defect = torch.zeros(4, dtype=torch.float64, device='cuda')
         self.counter = torch.zeros(1, dtype=torch.int64, device='cuda')
         self.host = torch.zeros(5, dtype=torch.float64).pin_memory()
-        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         self.events[0].record()
         _capi.check(lib.qsx_dense_hermitian_form(
             eom._h, self.perm.ctypes.data_as(C.POINTER(C.c_int32)), self.G.data_ptr(),
             self.gnorm.data_ptr(), self.defect.data_ptr(), stream))
+        self.events[3].record()
         _capi.check(lib.qsx_real_expm(self.G.data_ptr(), self.gnorm.data_ptr(), M, n, float(dt),
                                       self.P.data_ptr(), self.counter.data_ptr(), stream))
         self.events[1].record()
@@ -348,6 +351,7 @@ class HermitianPropagators(object):
             gemms = int(self.host[4].item())
             self.__dict__['_build'] = (ms, gemms)
             PropagationStats.expm_ms += ms
+            PropagationStats.form_ms += self.events[0].elapsed_time(self.events[3])
             PropagationStats.expm_gemms += gemms
             if not self.ok() and not self.__dict__.get('_fallback'):
                 raise RuntimeError(
