@@ -176,6 +176,138 @@ real_expm_kernel(const double *__restrict__ Gt, const double *__restrict__ gnorm
     if (threadIdx.x == 0) atomicAdd(&status[0], gemms);
 }
 
+// Register-resident form of the kernel above (default): the element-wise Horner operands A and A^2
+// stay in the registers of the thread that owns the matching accumulator fragment (A is loaded once
+// per member in that ownership, A^2 is the thread's own result of the first product), the planes
+// are filled from those registers, and the start of the Horner recursion is written by the epilogue
+// of the A^3 product into a third plane.  One global read of the generator per member and no
+// scratch tile: the epilogues of the kernel above re-read A and A^2 from global memory / L2 for
+// every product, which was 45 % of its stall samples.  Three planes, two CTAs per SM.
+template <int MT, int KS>
+__global__ void __launch_bounds__(32 * MT, 2)
+real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnorm, int M, double dt, int n_gen,
+                  double *__restrict__ P_out, unsigned long long *__restrict__ status) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *planes = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r = rb * 8 + g;
+    unsigned long long gemms = 0;
+
+    for (int gen = blockIdx.x; gen < n_gen; gen += gridDim.x) {
+        double *X = planes, *Y = X + MP * LD, *Z = Y + MP * LD;
+        const double *Gg = Gt + (size_t)gen * M * M;
+        int sq = 0;
+        {
+            double nrm = fabs(dt) * gnorm[gen];
+            while (nrm > 0.5 && sq < 40) { nrm *= 0.5; ++sq; }
+        }
+        const double scale = dt / (double)(1ULL << sq);
+        double A1e[MT][2], A2e[MT][2], a[KS];
+#pragma unroll
+        for (int nb = 0; nb < MT; ++nb) {
+            const int c = nb * 8 + 2 * t;
+            A1e[nb][0] = (r < M && c < M) ? scale * __ldg(&Gg[c * M + r]) : 0.0;
+            A1e[nb][1] = (r < M && c + 1 < M) ? scale * __ldg(&Gg[(c + 1) * M + r]) : 0.0;
+        }
+        __syncthreads();                                    // previous member's output pass is done with the planes
+#pragma unroll
+        for (int nb = 0; nb < MT; ++nb) {
+            X[r * LD + nb * 8 + 2 * t] = A1e[nb][0];
+            X[r * LD + nb * 8 + 2 * t + 1] = A1e[nb][1];
+        }
+        __syncthreads();
+        auto load_fragments = [&](const double *W) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) a[ks] = W[r * LD + ks * 4 + t];
+        };
+        auto product = [&](const double *B, int nb, double &v0, double &v1) {
+            double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks += 2) {
+                dmma884r(p0, p1, a[ks], B[(ks * 4 + t) * LD + nb * 8 + g]);
+                if (ks + 1 < KS) dmma884r(q0, q1, a[ks + 1], B[((ks + 1) * 4 + t) * LD + nb * 8 + g]);
+            }
+            v0 = p0 + q0;
+            v1 = p1 + q1;
+        };
+        load_fragments(X);                          // left operand: A
+        // A^2 -> Y (operand of the next product) and the registers
+#pragma unroll
+        for (int nb = 0; nb < MT; ++nb) {
+            product(X, nb, A2e[nb][0], A2e[nb][1]);
+            Y[r * LD + nb * 8 + 2 * t] = A2e[nb][0];
+            Y[r * LD + nb * 8 + 2 * t + 1] = A2e[nb][1];
+        }
+        __syncthreads();
+        // A^3 = A A^2 -> X, and the start of the recursion c9 I + c10 A + c11 A^2 + c12 A^3 -> Z
+#pragma unroll
+        for (int nb = 0; nb < MT; ++nb) {
+            const int c = nb * 8 + 2 * t;
+            double v0, v1;
+            product(Y, nb, v0, v1);
+            X[r * LD + c] = v0;
+            X[r * LD + c + 1] = v1;
+            Z[r * LD + c] = (r == c ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1e[nb][0] + inv_fact_r[11] * A2e[nb][0] + inv_fact_r[12] * v0;
+            Z[r * LD + c + 1] = (r == c + 1 ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1e[nb][1] + inv_fact_r[11] * A2e[nb][1] + inv_fact_r[12] * v1;
+        }
+        __syncthreads();
+        load_fragments(X);                          // left operand from here on: A^3
+        __syncthreads();                            // X may be overwritten from the second Horner product on
+        double *P = Z, *U = Y;
+#pragma unroll 1
+        for (int blk = 2; blk >= 0; --blk) {
+            const double c0 = inv_fact_r[3 * blk], c1 = inv_fact_r[3 * blk + 1], c2 = inv_fact_r[3 * blk + 2];
+#pragma unroll
+            for (int nb = 0; nb < MT; ++nb) {
+                const int c = nb * 8 + 2 * t;
+                double v0, v1;
+                product(P, nb, v0, v1);
+                U[r * LD + c] = v0 + c1 * A1e[nb][0] + c2 * A2e[nb][0] + (r == c ? c0 : 0.0);
+                U[r * LD + c + 1] = v1 + c1 * A1e[nb][1] + c2 * A2e[nb][1] + (r == c + 1 ? c0 : 0.0);
+            }
+            __syncthreads();
+            { double *x = P; P = U; U = x; }
+        }
+        for (int q = 0; q < sq; ++q) {
+            load_fragments(P);
+#pragma unroll
+            for (int nb = 0; nb < MT; ++nb) {
+                double v0, v1;
+                product(P, nb, v0, v1);
+                U[r * LD + nb * 8 + 2 * t] = v0;
+                U[r * LD + nb * 8 + 2 * t + 1] = v1;
+            }
+            __syncthreads();
+            { double *x = P; P = U; U = x; }
+        }
+        double *Pg = P_out + (size_t)gen * M * M;           // row-major: P[r*M + c]
+        for (int i = threadIdx.x; i < M * M; i += blockDim.x) Pg[i] = P[(i / M) * LD + i % M];
+        gemms += 5 + sq;
+    }
+    if (threadIdx.x == 0) atomicAdd(&status[0], gemms);
+}
+
+template <int MT, int KS>
+static cudaError_t launch_real_expm3_ks(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
+                                        unsigned long long *status, cudaStream_t stream) {
+    constexpr int MP = 8 * MT;
+    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
+    const size_t smem = (size_t)3 * MP * LD * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(real_expm3_kernel<MT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, real_expm3_kernel<MT, KS>, 32 * MT, smem);
+    if (e != cudaSuccess) return e;
+    const int grid = std::min(n_gen, sms * std::max(1, per_sm));
+    real_expm3_kernel<MT, KS><<<grid, 32 * MT, smem, stream>>>(Gt, gnorm, M, dt, n_gen, P, status);
+    return cudaGetLastError();
+}
+
 template <int MT, int KS, int NBLK>
 static cudaError_t launch_real_expm_ks(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
                                        unsigned long long *status, cudaStream_t stream) {
@@ -212,9 +344,13 @@ template <int MT>
 static cudaError_t launch_real_expm(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
                                     unsigned long long *status, cudaStream_t stream) {
     // the contraction dimension is padded to a multiple of 4 only (M = 49: 13 k-steps, not 14)
-    // QSX_REXPM_BLOCKS: register cap for 2 / 3 / 4 resident CTAs per SM (A/B runs; default 3)
+    // QSX_REXPM_BLOCKS = 2 / 3 / 4: the scratch-tile kernel with that many resident CTAs per SM (A/B runs)
     const char *sw = getenv("QSX_REXPM_BLOCKS");
-    const int nblk = sw ? atoi(sw) : 3;
+    if (!sw) {
+        if ((M + 3) / 4 == 2 * MT - 1) return launch_real_expm3_ks<MT, 2 * MT - 1>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+        return launch_real_expm3_ks<MT, 2 * MT>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+    }
+    const int nblk = atoi(sw);
     if ((M + 3) / 4 == 2 * MT - 1) {
         if (nblk == 2) return launch_real_expm_ks<MT, 2 * MT - 1, 2>(Gt, gnorm, M, dt, n_gen, P, status, stream);
         if (nblk == 4) return launch_real_expm_ks<MT, 2 * MT - 1, 4>(Gt, gnorm, M, dt, n_gen, P, status, stream);

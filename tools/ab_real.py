@@ -28,8 +28,8 @@ def main():
         return engine.reduce_members(out, 1.0 / E)
 
     ref = None
-    variants = [('complex', {'QSX_NO_HERMITIAN_FORM': '1'})] + \
-        [('real, expm %s CTAs/SM' % b, {'QSX_REXPM_BLOCKS': b}) for b in (sys.argv[2:] or ['2', '3', '4'])]
+    variants = [('complex', {'QSX_NO_HERMITIAN_FORM': '1'}), ('real, register-resident expm', {})] + \
+        [('real, scratch expm %s CTAs/SM' % b, {'QSX_REXPM_BLOCKS': b}) for b in (sys.argv[2:] or ['4'])]
     for name, env in variants:
         for k in ('QSX_NO_HERMITIAN_FORM', 'QSX_REXPM_BLOCKS', 'QSX_RMAP_ONE_WARP', 'QSX_RMAP_BLOCKS'):
             os.environ.pop(k, None)
