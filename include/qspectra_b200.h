@@ -174,6 +174,12 @@ void qsx_dense_destroy(qsx_dense_t h);
  * gnorm_dev [n_generators] inf-norms of G. */
 int qsx_dense_hermitian_form(qsx_dense_t h, const int32_t *perm_host, void *Gt_dev, void *gnorm_dev,
                              void *defect_dev, void *stream);
+/* Both steps in one kernel (the default of the Python layer): every CTA forms the real generator
+ * of its member from the handle's complex one in shared memory and goes straight into the series;
+ * G never exists in global memory.  P_dev, gemm_count_dev as for qsx_real_expm; defect_dev [0..1]
+ * as for qsx_dense_hermitian_form. */
+int qsx_dense_hermitian_expm(qsx_dense_t h, const int32_t *perm_host, double dt, void *P_dev,
+                             void *defect_dev, void *gemm_count_dev, void *stream);
 /* P_dev [n_generators][M][M] float64 row-major = exp(G_g dt), the series of qsx_dense_expm on real
  * DMMA; gemm_count_dev: one uint64 counter (incremented by the number of M x M real products). */
 int qsx_real_expm(const void *Gt_dev, const void *gnorm_dev, int32_t M, int32_t n_generators, double dt,

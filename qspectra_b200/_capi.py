@@ -82,7 +82,7 @@ EXPORTS = ['qsx_last_error', 'qsx_version', 'qsx_kernel_launches', 'qsx_transfer
            'qsx_device_info', 'qsx_dense_create', 'qsx_dense_apply',
            'qsx_dense_propagate', 'qsx_dense_expm', 'qsx_dense_wrap', 'qsx_dense_build_stats',
            'qsx_dense_last_kernel_ms', 'qsx_dense_events_ready',
-           'qsx_dense_destroy', 'qsx_dense_hermitian_form', 'qsx_real_expm', 'qsx_real_map',
+           'qsx_dense_destroy', 'qsx_dense_hermitian_form', 'qsx_dense_hermitian_expm', 'qsx_real_expm', 'qsx_real_map',
            'qsx_hermitian_pack', 'qsx_hermitian_unpack', 'qsx_heom_create',
            'qsx_heom_ado_count', 'qsx_heom_index_maps', 'qsx_heom_apply',
            'qsx_heom_propagate', 'qsx_heom_destroy', 'qsx_ado_count',
@@ -127,6 +127,8 @@ def lib():
     L.qsx_dense_expm.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_void_p), C.c_void_p]
     L.qsx_dense_hermitian_form.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+    L.qsx_dense_hermitian_expm.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_double, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     L.qsx_real_expm.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double,
                                 C.c_void_p, C.c_void_p, C.c_void_p]

@@ -120,6 +120,9 @@ int qsx_dense_map_gemm(const cplx *Lt, int M, int n_runs, int R, const int *run_
 int qsx_real_form_launch(const cplx *Lt, int M, int n_gen, const int32_t *perm_host, double *Gt, double *gnorm,
                          double *defect, cudaStream_t stream);
 
+int qsx_fused_expm_launch(const cplx *Lt, int M, int n_gen, const int32_t *perm_host, double dt, double *P,
+                          double *defect, unsigned long long *gemm_count, cudaStream_t stream);
+
 // Device scratch comes from a small caching pool (power-of-two size classes, blocks up
 // to 64 MB are kept for reuse; larger ones go straight to cudaMalloc/cudaFree): the
 // per-call metadata buffers of the propagate entry points must not cost a

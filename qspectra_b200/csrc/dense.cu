@@ -483,6 +483,14 @@ extern "C" int qsx_dense_create(qsx_dense_t *out, int32_t M, int32_t n_generator
 
 extern "C" void qsx_dense_destroy(qsx_dense_t h) { delete h; }
 
+extern "C" int qsx_dense_hermitian_expm(qsx_dense_t h, const int32_t *perm_host, double dt, void *P_dev,
+                                        void *defect_dev, void *gemm_count_dev, void *stream_) {
+    QSX_REQUIRE(h, "qsx_dense_hermitian_expm: null handle");
+    QSX_REQUIRE(!h->is_propagator, "qsx_dense_hermitian_expm: the handle holds propagators, not generators");
+    return qsx_fused_expm_launch(h->Lt.p, h->M, h->n_gen, perm_host, dt, (double *)P_dev, (double *)defect_dev,
+                                 (unsigned long long *)gemm_count_dev, (cudaStream_t)stream_);
+}
+
 extern "C" int qsx_dense_hermitian_form(qsx_dense_t h, const int32_t *perm_host, void *Gt_dev, void *gnorm_dev,
                                         void *defect_dev, void *stream_) {
     QSX_REQUIRE(h, "qsx_dense_hermitian_form: null handle");

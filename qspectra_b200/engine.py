@@ -306,20 +306,27 @@ class HermitianPropagators(object):
         n, M = eom.n_generators, eom.dim
         self.perm = np.ascontiguousarray(eom.hermitian_perm, dtype=np.int32)
         self.dim, self.n_generators = M, n
-        self.G = torch.empty((n, M, M), dtype=torch.float64, device='cuda')
-        self.gnorm = torch.empty(n, dtype=torch.float64, device='cuda')
         self.P = torch.empty((n, M, M), dtype=torch.float64, device='cuda')
         self.defect = torch.zeros(4, dtype=torch.float64, device='cuda')
         self.counter = torch.zeros(1, dtype=torch.int64, device='cuda')
         self.host = torch.zeros(5, dtype=torch.float64).pin_memory()
         self.events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        pptr = self.perm.ctypes.data_as(C.POINTER(C.c_int32))
         self.events[0].record()
-        _capi.check(lib.qsx_dense_hermitian_form(
-            eom._h, self.perm.ctypes.data_as(C.POINTER(C.c_int32)), self.G.data_ptr(),
-            self.gnorm.data_ptr(), self.defect.data_ptr(), stream))
-        self.events[3].record()
-        _capi.check(lib.qsx_real_expm(self.G.data_ptr(), self.gnorm.data_ptr(), M, n, float(dt),
-                                      self.P.data_ptr(), self.counter.data_ptr(), stream))
+        if os.environ.get('QSX_HERMITIAN_TWO_KERNELS'):
+            # A/B runs: change of coordinates and series as separate launches, G through global memory
+            G = torch.empty((n, M, M), dtype=torch.float64, device='cuda')
+            gnorm = torch.empty(n, dtype=torch.float64, device='cuda')
+            _capi.check(lib.qsx_dense_hermitian_form(eom._h, pptr, G.data_ptr(), gnorm.data_ptr(),
+                                                     self.defect.data_ptr(), stream))
+            self.events[3].record()
+            _capi.check(lib.qsx_real_expm(G.data_ptr(), gnorm.data_ptr(), M, n, float(dt),
+                                          self.P.data_ptr(), self.counter.data_ptr(), stream))
+        else:
+            self.events[3].record()
+            _capi.check(lib.qsx_dense_hermitian_expm(eom._h, pptr, float(dt), self.P.data_ptr(),
+                                                     self.defect.data_ptr(), self.counter.data_ptr(),
+                                                     stream))
         self.events[1].record()
         self.last_event = self.events[1]
         PropagationStats.expm_builds += 1

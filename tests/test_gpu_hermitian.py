@@ -44,8 +44,13 @@ def _hermitian_state(n_states, rng):
     return (rho + rho.conj().T).reshape(-1, order='F')
 
 
+@pytest.mark.parametrize('two_kernels', [False, True])
 @pytest.mark.parametrize('n_states', [2, 3, 4, 5, 6, 7])
-def test_real_form_matches_expm(n_states):
+def test_real_form_matches_expm(n_states, two_kernels, monkeypatch):
+    """default: change of coordinates fused into the propagator kernel (qsx_dense_hermitian_expm);
+    QSX_HERMITIAN_TWO_KERNELS=1: qsx_dense_hermitian_form + qsx_real_expm"""
+    if two_kernels:
+        monkeypatch.setenv('QSX_HERMITIAN_TWO_KERNELS', '1')
     rng = np.random.RandomState(n_states)
     gens = [_compatible_generator(n_states, rng) for _ in range(3)]
     perm = gens[0][1]

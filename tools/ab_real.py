@@ -28,10 +28,10 @@ def main():
         return engine.reduce_members(out, 1.0 / E)
 
     ref = None
-    variants = [('complex', {'QSX_NO_HERMITIAN_FORM': '1'}), ('real, register-resident expm', {})] + \
-        [('real, scratch expm %s CTAs/SM' % b, {'QSX_REXPM_BLOCKS': b}) for b in (sys.argv[2:] or ['4'])]
+    variants = [('complex', {'QSX_NO_HERMITIAN_FORM': '1'}), ('real, fused form + expm', {}),
+                ('real, two kernels', {'QSX_HERMITIAN_TWO_KERNELS': '1'})]
     for name, env in variants:
-        for k in ('QSX_NO_HERMITIAN_FORM', 'QSX_REXPM_BLOCKS', 'QSX_RMAP_ONE_WARP', 'QSX_RMAP_BLOCKS'):
+        for k in ('QSX_NO_HERMITIAN_FORM', 'QSX_REXPM_BLOCKS', 'QSX_HERMITIAN_TWO_KERNELS'):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3):
