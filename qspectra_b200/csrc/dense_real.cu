@@ -10,9 +10,11 @@
 // a stepping y <- P y one DFMA per matrix element (instead of four).  The imaginary residual of
 // G and of the packed state is measured on the device (defect[0..3]) and checked by the caller.
 //
-//   hermitian_form_kernel   Lt (complex, transposed) -> Gt (real, transposed), inf-norms, defect
-//   real_expm_kernel        exp(G dt): the degree-12 Paterson-Stockmeyer series of dense.cu on one plane
-//   real_map_kernel         u <- P u per output step, one warp per column, P in registers
+//   real_expm3_kernel       exp(G dt): the degree-12 Paterson-Stockmeyer series of dense.cu on real DMMA;
+//                           FUSED: forms G from the complex generator in shared memory first
+//   hermitian_form_kernel   Lt (complex, transposed) -> Gt (real, transposed), inf-norms, defect (two-kernel path)
+//   real_map_rows_kernel    u <- P u per output step, one warp per column, two whole rows of P per lane (32 < M <= 50)
+//   real_map_kernel         the same with four lanes per row and a shuffle reduction (other M)
 //   hermitian_pack/unpack   complex state vectors <-> real coordinates
 #include "common.cuh"
 #include <algorithm>
@@ -82,107 +84,14 @@ hermitian_form_kernel(const cplx *__restrict__ Lt, int M, HermPerm perm, double 
 }
 
 // ------------------------------------------------------------------ exp(G dt), real DMMA
-template <int MT, int KS, int NBLK>      // matrix padded to 8*MT rows/cols (4*KS along the contraction); MT warps per CTA, NBLK CTAs per SM
-__global__ void __launch_bounds__(32 * MT, NBLK)
-real_expm_kernel(const double *__restrict__ Gt, const double *__restrict__ gnorm, int M, double dt, int n_gen,
-                 double *__restrict__ P_out, double *__restrict__ A2_scratch, unsigned long long *__restrict__ status) {
-    constexpr int MP = 8 * MT;
-    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *planes = reinterpret_cast<double *>(smem_raw);
-    const int lane = threadIdx.x & 31, rb = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    double *A2g = A2_scratch + (size_t)blockIdx.x * M * M;       // transposed storage like Gt: [c*M + r]
-    unsigned long long gemms = 0;
-
-    for (int gen = blockIdx.x; gen < n_gen; gen += gridDim.x) {
-        double *X = planes, *Y = X + MP * LD;
-        const double *Gg = Gt + (size_t)gen * M * M;
-        int sq = 0;
-        {
-            double nrm = fabs(dt) * gnorm[gen];
-            while (nrm > 0.5 && sq < 40) { nrm *= 0.5; ++sq; }
-        }
-        const double scale = dt / (double)(1ULL << sq);
-        auto A1 = [&](int r, int c) -> double { return (r < M && c < M) ? scale * __ldg(&Gg[c * M + r]) : 0.0; };
-        auto A2 = [&](int r, int c) -> double { return (r < M && c < M) ? __ldcg(&A2g[c * M + r]) : 0.0; };
-        double a[KS];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) a[ks] = A1(rb * 8 + g, ks * 4 + t);
-        __syncthreads();                                    // previous member's output pass is done with the planes
-        for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) X[i] = A1(i / LD, i % LD);
-        __syncthreads();
-        auto row_block_gemm = [&](const double *B, auto &&epi) {
-#pragma unroll
-            for (int nb = 0; nb < MT; ++nb) {
-                // all B fragments of the column block first (one dependent load -> DMMA pair after the
-                // other leaves the tensor pipe idle for a shared-memory round trip per instruction), then
-                // two independent accumulator chains over the even and odd k-steps
-                double b[KS];
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) b[ks] = B[(ks * 4 + t) * LD + nb * 8 + g];
-                double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
-#pragma unroll
-                for (int ks = 0; ks < KS; ks += 2) {
-                    dmma884r(p0, p1, a[ks], b[ks]);
-                    if (ks + 1 < KS) dmma884r(q0, q1, a[ks + 1], b[ks + 1]);
-                }
-                epi(rb * 8 + g, nb * 8 + 2 * t, p0 + q0, p1 + q1);
-            }
-        };
-        auto load_fragments = [&](const double *Z) {
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) a[ks] = Z[(rb * 8 + g) * LD + ks * 4 + t];
-        };
-        // A^2 -> Y (operand of the next product) and the scratch tile (Horner operand)
-        row_block_gemm(X, [&](int r, int c, double v0, double v1) {
-            Y[r * LD + c] = v0; Y[r * LD + c + 1] = v1;
-            if (r < M && c < M) A2g[c * M + r] = v0;
-            if (r < M && c + 1 < M) A2g[(c + 1) * M + r] = v1;
-        });
-        __syncthreads();
-        // A^3 = A A^2 -> X
-        row_block_gemm(Y, [&](int r, int c, double v0, double v1) { X[r * LD + c] = v0; X[r * LD + c + 1] = v1; });
-        __syncthreads();
-        load_fragments(X);                          // left operand from here on: A^3
-        __syncthreads();
-        // Horner start: P = c9 I + c10 A + c11 A^2 + c12 A^3 -> X, in place (A^3 in X, A^2 in Y)
-        for (int i = threadIdx.x; i < MP * LD; i += blockDim.x) {
-            const int r = i / LD, c = i % LD;
-            X[i] = (r == c ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1(r, c) + inv_fact_r[11] * Y[i] + inv_fact_r[12] * X[i];
-        }
-        __syncthreads();
-        double *P = X, *U = Y;
-#pragma unroll 1
-        for (int blk = 2; blk >= 0; --blk) {
-            const double c0 = inv_fact_r[3 * blk], c1 = inv_fact_r[3 * blk + 1], c2 = inv_fact_r[3 * blk + 2];
-            row_block_gemm(P, [&](int r, int c, double v0, double v1) {
-                U[r * LD + c] = v0 + c1 * A1(r, c) + c2 * A2(r, c) + (r == c ? c0 : 0.0);
-                U[r * LD + c + 1] = v1 + c1 * A1(r, c + 1) + c2 * A2(r, c + 1) + (r == c + 1 ? c0 : 0.0);
-            });
-            __syncthreads();
-            { double *x = P; P = U; U = x; }
-        }
-        for (int q = 0; q < sq; ++q) {
-            load_fragments(P);
-            row_block_gemm(P, [&](int r, int c, double v0, double v1) { U[r * LD + c] = v0; U[r * LD + c + 1] = v1; });
-            __syncthreads();
-            { double *x = P; P = U; U = x; }
-        }
-        double *Pg = P_out + (size_t)gen * M * M;           // row-major: P[r*M + c]
-        for (int i = threadIdx.x; i < M * M; i += blockDim.x) Pg[i] = P[(i / M) * LD + i % M];
-        gemms += 5 + sq;
-    }
-    if (threadIdx.x == 0) atomicAdd(&status[0], gemms);
-}
-
-// Register-resident form of the kernel above (default): the element-wise Horner operands A and A^2
+// exp(G dt) by the degree-12 Paterson-Stockmeyer series of dense.cu on real DMMA: the element-wise Horner operands A and A^2
 // stay in the registers of the thread that owns the matching accumulator fragment (A is loaded once
 // per member in that ownership, A^2 is the thread's own result of the first product), the planes
 // are filled from those registers, and the start of the Horner recursion is written by the epilogue
 // of the A^3 product into a third plane.  One global read of the generator per member and no
-// scratch tile: the epilogues of the kernel above re-read A and A^2 from global memory / L2 for
-// every product, which was 45 % of its stall samples.  Three planes, two CTAs per SM.
+// scratch tile (a first version re-read A and A^2 from global memory / L2 in every epilogue, like
+// dense_expm2_kernel does: 45 % of its stall samples, 0.98 instead of 0.81 ms per 1e4 FMO members).
+// Three planes, two CTAs per SM.
 // FUSED: the change of coordinates happens here as well -- the member's complex generator is staged
 // in shared memory (aliasing two of the planes), every thread forms its fragment of G = T L T^-1 from
 // it, the inf-norm and the Hermiticity defect are reduced in the CTA; hermitian_form_kernel and its
@@ -387,59 +296,14 @@ static cudaError_t launch_fused_expm(const cplx *Lt, const HermPerm &perm, doubl
     return launch_real_expm3_ks<MT, 2 * MT, true>(nullptr, nullptr, Lt, perm, defect, M, dt, n_gen, P, status, stream);
 }
 
-template <int MT, int KS, int NBLK>
-static cudaError_t launch_real_expm_ks(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
-                                       unsigned long long *status, cudaStream_t stream) {
-    constexpr int MP = 8 * MT;
-    constexpr int LD = (MP % 16 == 12) ? MP : ((MP + 3) / 16 * 16 + 12 >= MP ? (MP + 3) / 16 * 16 + 12 : (MP + 3) / 16 * 16 + 28);
-    const size_t smem = (size_t)2 * MP * LD * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(real_expm_kernel<MT, KS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, real_expm_kernel<MT, KS, NBLK>, 32 * MT, smem);
-    if (e != cudaSuccess) return e;
-    const int grid = std::min(n_gen, sms * std::max(1, per_sm));
-    // A^2 tiles, one per resident CTA: a process-lifetime buffer (one process per GPU) that only grows
-    static double *scratch = nullptr;
-    static size_t scratch_elems = 0;
-    const size_t need = (size_t)grid * M * M;
-    if (need > scratch_elems) {
-        if (scratch) {
-            cudaDeviceSynchronize();
-            cudaFree(scratch);
-            scratch = nullptr; scratch_elems = 0;
-        }
-        e = cudaMalloc(reinterpret_cast<void **>(&scratch), need * sizeof(double));
-        if (e != cudaSuccess) return e;
-        scratch_elems = need;
-    }
-    real_expm_kernel<MT, KS, NBLK><<<grid, 32 * MT, smem, stream>>>(Gt, gnorm, M, dt, n_gen, P, scratch, status);
-    return cudaGetLastError();
-}
-
 template <int MT>
 static cudaError_t launch_real_expm(const double *Gt, const double *gnorm, int M, double dt, int n_gen, double *P,
                                     unsigned long long *status, cudaStream_t stream) {
     // the contraction dimension is padded to a multiple of 4 only (M = 49: 13 k-steps, not 14)
-    // QSX_REXPM_BLOCKS = 2 / 3 / 4: the scratch-tile kernel with that many resident CTAs per SM (A/B runs)
-    const char *sw = getenv("QSX_REXPM_BLOCKS");
-    if (!sw) {
-        const HermPerm none = {};
-        if ((M + 3) / 4 == 2 * MT - 1)
-            return launch_real_expm3_ks<MT, 2 * MT - 1, false>(Gt, gnorm, nullptr, none, nullptr, M, dt, n_gen, P, status, stream);
-        return launch_real_expm3_ks<MT, 2 * MT, false>(Gt, gnorm, nullptr, none, nullptr, M, dt, n_gen, P, status, stream);
-    }
-    const int nblk = atoi(sw);
-    if ((M + 3) / 4 == 2 * MT - 1) {
-        if (nblk == 2) return launch_real_expm_ks<MT, 2 * MT - 1, 2>(Gt, gnorm, M, dt, n_gen, P, status, stream);
-        if (nblk == 4) return launch_real_expm_ks<MT, 2 * MT - 1, 4>(Gt, gnorm, M, dt, n_gen, P, status, stream);
-        return launch_real_expm_ks<MT, 2 * MT - 1, 3>(Gt, gnorm, M, dt, n_gen, P, status, stream);
-    }
-    if (nblk == 2) return launch_real_expm_ks<MT, 2 * MT, 2>(Gt, gnorm, M, dt, n_gen, P, status, stream);
-    if (nblk == 4) return launch_real_expm_ks<MT, 2 * MT, 4>(Gt, gnorm, M, dt, n_gen, P, status, stream);
-    return launch_real_expm_ks<MT, 2 * MT, 3>(Gt, gnorm, M, dt, n_gen, P, status, stream);
+    const HermPerm none = {};
+    if ((M + 3) / 4 == 2 * MT - 1)
+        return launch_real_expm3_ks<MT, 2 * MT - 1, false>(Gt, gnorm, nullptr, none, nullptr, M, dt, n_gen, P, status, stream);
+    return launch_real_expm3_ks<MT, 2 * MT, false>(Gt, gnorm, nullptr, none, nullptr, M, dt, n_gen, P, status, stream);
 }
 
 // ------------------------------------------------------------------ u <- P u
@@ -520,6 +384,83 @@ real_map_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen
         og += MS;
         step(ld_a, st_b);
     }
+}
+
+// Wide states (32 < M <= 56): one warp per column, lane l keeps the WHOLE rows l and l + 32 of P in
+// registers, so a step needs no cross-lane reduction at all -- the shuffle/DADD tree and the
+// predicated stores of the kernel above were almost half of its issue slots (91 DFMA at two issue
+// cycles each against ~160 other instructions per step; the FP64 pipe cannot be busier than the
+// issue slots left to it).  The state is read as 16-byte broadcast loads; four accumulator chains
+// per row.  CP = column pairs (zero padded).
+template <int CP>
+__global__ void __launch_bounds__(64)
+real_map_rows_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen_of, int identity, int n_col,
+                     const double *__restrict__ u0, int nt, int MS, double *__restrict__ out) {
+    __shared__ __align__(16) double xs[2][2][64];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 2 + w;
+    if (col >= n_col) return;
+    const int gen = gen_of ? gen_of[col] : (identity ? col : 0);
+    const double *Pg = P + (size_t)gen * M * M;
+    const int r0 = lane, r1 = lane + 32;
+    double p0[2 * CP], p1[2 * CP];
+#pragma unroll
+    for (int c = 0; c < 2 * CP; ++c) {
+        p0[c] = (r0 < M && c < M) ? Pg[r0 * M + c] : 0.0;
+        p1[c] = (r1 < M && c < M) ? Pg[r1 * M + c] : 0.0;
+    }
+    double *orow = out + (size_t)col * nt * MS;
+    for (int i = lane; i < 64; i += 32) {
+        const double v = i < M ? u0[(size_t)col * MS + i] : 0.0;
+        xs[w][0][i] = v;
+        xs[w][1][i] = 0.0;
+        if (i < MS) __stcs(&orow[i], v);
+    }
+    for (int k = M; k < MS; ++k)
+        for (int it = 1 + lane; it < nt; it += 32) __stcs(&orow[(size_t)it * MS + k], 0.0);
+    __syncwarp();
+    const bool has0 = r0 < M, has1 = r1 < M;
+    double *og = orow;
+    auto step = [&](const double *__restrict__ ld, double *__restrict__ st) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+            const double2 v = *reinterpret_cast<const double2 *>(ld + 2 * cp);
+            const int k = (cp & 1) * 2;
+            a[k] = fma(p0[2 * cp], v.x, a[k]);
+            b[k] = fma(p1[2 * cp], v.x, b[k]);
+            a[k + 1] = fma(p0[2 * cp + 1], v.y, a[k + 1]);
+            b[k + 1] = fma(p1[2 * cp + 1], v.y, b[k + 1]);
+        }
+        const double s0 = (a[0] + a[1]) + (a[2] + a[3]), s1 = (b[0] + b[1]) + (b[2] + b[3]);
+        if (has0) {
+            st[r0] = s0;
+            __stcs(og + r0, s0);
+        }
+        if (has1) {
+            st[r1] = s1;
+            __stcs(og + r1, s1);
+        }
+        __syncwarp();
+    };
+    int it = 1;
+    for (; it + 1 < nt; it += 2) {
+        og += MS;
+        step(xs[w][0], xs[w][1]);
+        og += MS;
+        step(xs[w][1], xs[w][0]);
+    }
+    if (it < nt) {
+        og += MS;
+        step(xs[w][0], xs[w][1]);
+    }
+}
+
+template <int CP>
+static cudaError_t launch_real_map_rows(const double *P, int M, const int *gen_of, int identity, int n_col, const double *u0,
+                                        int nt, int MS, double *out, cudaStream_t stream) {
+    real_map_rows_kernel<CP><<<(n_col + 1) / 2, 64, 0, stream>>>(P, M, gen_of, identity, n_col, u0, nt, MS, out);
+    return cudaGetLastError();
 }
 
 template <int RW, int CQ>
@@ -671,13 +612,26 @@ extern "C" int qsx_real_map(const void *P_dev, int32_t M, int32_t n_generators, 
         case 2: QSX_RMAP(2, 4); break;
         case 3: QSX_RMAP(3, 6); break;
         case 4: QSX_RMAP(4, 8); break;
-        case 5: QSX_RMAP(5, 10); break;
-        case 6: QSX_RMAP(6, 12); break;
+        case 5:
+            if (getenv("QSX_RMAP_SHUFFLE")) QSX_RMAP(5, 10);
+            else e = launch_real_map_rows<20>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
+            break;
+        case 6:
+            if (getenv("QSX_RMAP_SHUFFLE")) QSX_RMAP(6, 12);
+            else e = launch_real_map_rows<24>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
+            break;
         default:
             // (two warps per column -- half the registers, twice the resident warps -- measured slower:
             // 1.0-1.2 vs 0.8 ms per 1e4 FMO members; the per-step overhead doubles)
-            if (M <= 52) QSX_RMAP(7, 13);
-            else QSX_RMAP(7, 14);
+            // QSX_RMAP_SHUFFLE=1: the four-lanes-per-row kernel for wide states too (A/B runs)
+            // (M > 50: two whole rows per lane do not fit the register file without spills)
+            if (M <= 50 && !getenv("QSX_RMAP_SHUFFLE")) {
+                e = launch_real_map_rows<25>(P, M, gen.p, identity, n_columns, u0, n_times, row_stride, out, stream);
+            } else if (M <= 52) {
+                QSX_RMAP(7, 13);
+            } else {
+                QSX_RMAP(7, 14);
+            }
             break;
     }
 #undef QSX_RMAP

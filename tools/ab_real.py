@@ -28,10 +28,11 @@ def main():
         return engine.reduce_members(out, 1.0 / E)
 
     ref = None
-    variants = [('complex', {'QSX_NO_HERMITIAN_FORM': '1'}), ('real, fused form + expm', {}),
-                ('real, two kernels', {'QSX_HERMITIAN_TWO_KERNELS': '1'})]
+    variants = [('complex', {'QSX_NO_HERMITIAN_FORM': '1'}), ('real (default)', {}),
+                ('real, two kernels', {'QSX_HERMITIAN_TWO_KERNELS': '1'}),
+                ('real, shuffle stepping', {'QSX_RMAP_SHUFFLE': '1'})]
     for name, env in variants:
-        for k in ('QSX_NO_HERMITIAN_FORM', 'QSX_REXPM_BLOCKS', 'QSX_HERMITIAN_TWO_KERNELS'):
+        for k in ('QSX_NO_HERMITIAN_FORM', 'QSX_REXPM_BLOCKS', 'QSX_HERMITIAN_TWO_KERNELS', 'QSX_RMAP_SHUFFLE', 'QSX_RMAP_ROWS'):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3):
