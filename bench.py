@@ -810,12 +810,12 @@ def run_ours(args):
     peak_note = ('cuBLAS FP64 GEMM 6144^3 measured in this run (cutlass d884 DMMA kernel; '
                  'FP64 is not in MEASURED_PEAKS.json)')
     map_tf = map_flops / (kernel_ms * 1e-3) / 1e12
-    expm_name = ('real_expm_kernel<7,13,3> (FP64 DMMA m8n8k4 on the real generators in Hermitian coordinates: '
-                 'exp(G dt) per member, Paterson-Stockmeyer degree 12 + squarings)' if real_form else
+    expm_name = ('real_expm3_kernel<7,13,fused> (change of coordinates L -> G in shared memory, then FP64 DMMA m8n8k4 on '
+                 'the real generators: exp(G dt) per member, Paterson-Stockmeyer degree 12 + squarings)' if real_form else
                  'dense_expm2_kernel<7,13> (FP64 DMMA m8n8k4, three real products per complex one: exp(L dt) per member, '
                  'Paterson-Stockmeyer degree 12 + squarings)')
-    map_name = ('real_map_kernel<7,13> (u <- P u stepping in Hermitian coordinates, one warp per member with P in '
-                'registers; DFMA on the FP64 pipe, measured against the same FP64 ceiling)' if real_form else
+    map_name = ('real_map_rows_kernel<25> (u <- P u stepping in Hermitian coordinates, one warp per member, two whole '
+                'rows of P per lane in registers; DFMA on the FP64 pipe, measured against the same FP64 ceiling)' if real_form else
                 'dense_map_split_kernel<5,10,25,2> (y <- P y stepping with P in registers; DFMA on '
                 'the FP64 pipe, measured against the same FP64 ceiling as SURVEY 8d asks '
                 'for the dense L.Y contraction)')
@@ -834,7 +834,7 @@ def run_ours(args):
     first_k, second_k = (k_map, k_expm) if kernel_ms >= expm_ms else (k_expm, k_map)
     line['roofline'] = first_k
     line['other_kernels'] = {second_k['kernel']: second_k,
-                             'hermitian_form_kernel_ms': form_ms if real_form else None,
+                             'hermitian_form_kernel_ms': (form_ms if form_ms > 1e-3 else 'fused into the propagator kernel') if real_form else None,
                              'share_note': 'per step: propagator build + stepping + member '
                                            'reduction; see profiles/ for the ncu launch list'}
     if extra is not None:

@@ -128,6 +128,13 @@ real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnor
             const cplx *Lg = Lt + (size_t)gen * M * M;
             __syncthreads();                                // previous member's output pass is done with the planes
             for (int i = threadIdx.x; i < M * M; i += blockDim.x) Ls[i] = Lg[i];
+            // the CTA's next member: pull its generator into L2 while this one is being exponentiated
+            // (the staging loads above are the only DRAM round trip of a member)
+            if (gen + (int)gridDim.x < n_gen) {
+                const cplx *Ln = Lg + (size_t)gridDim.x * M * M;
+                for (int i = threadIdx.x * 8; i < M * M; i += blockDim.x * 8)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Ln + i));
+            }
             __syncthreads();
             double rsum = 0.0, dmax = 0.0, amax = 0.0;
             const int sR = r < M ? sperm[r] : 0;
