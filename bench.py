@@ -834,7 +834,7 @@ def run_ours(args):
     first_k, second_k = (k_map, k_expm) if kernel_ms >= expm_ms else (k_expm, k_map)
     line['roofline'] = first_k
     line['other_kernels'] = {second_k['kernel']: second_k,
-                             'hermitian_form_kernel_ms': (form_ms if form_ms > 1e-3 else 'fused into the propagator kernel') if real_form else None,
+                             'hermitian_form_kernel_ms': (form_ms if form_ms > 0.02 else 'fused into the propagator kernel') if real_form else None,
                              'share_note': 'per step: propagator build + stepping + member '
                                            'reduction; see profiles/ for the ncu launch list'}
     if extra is not None:
