@@ -141,7 +141,7 @@ int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnorm_dev,
 /* Handle over caller-owned device storage: Lt_dev [n_generators][M][M] in the engine's
  * transposed storage (Lt[g][c][r] = L_g[r][c]; what qsx_redfield_build* write with
  * transposed_out = 1 and qsx_dense_expm writes to Pt_dev) and lnorm_dev [n_generators]
- * float64 scratch that receives the inf-norms.  No copy is made; the caller keeps the
+ * float64 scratch that receives the inf-norms (formed by the first call that needs them).  No copy is made; the caller keeps the
  * buffers alive for the lifetime of the handle. */
 int qsx_dense_wrap(qsx_dense_t *out, int32_t M, int32_t n_generators, void *Lt_dev,
                    void *lnorm_dev, void *stream);

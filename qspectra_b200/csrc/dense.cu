@@ -26,6 +26,9 @@ struct qsx_dense_s {
     unsigned long long build_gemms = 0;
     // the handle holds propagators exp(L dt): only QSX_METHOD_MAP applies, no norms are kept
     bool is_propagator = false;
+    // inf-norms of wrapped generators are formed when a kernel first needs them (the Hermitian-
+    // coordinate path computes its own norm of the real generator and never does)
+    bool norms_ready = true;
     // Deferred completion: qsx_dense_expm and QSX_METHOD_MAP propagations return as soon as
     // their kernel is queued (neither can fail at run time); the device time and counters are
     // collected when qsx_dense_build_stats / qsx_dense_last_kernel_ms ask for them.
@@ -440,6 +443,13 @@ static cudaError_t launch_map_cq(const DenseKernelArgs &a, int groups, cudaStrea
 }
 
 // --------------------------------------------------------------------- host
+static void ensure_norms(qsx_dense_s *h, cudaStream_t stream) {
+    if (h->norms_ready) return;
+    dense_norm_kernel<<<h->n_gen, 64, 0, stream>>>(h->Lt.p, h->lnorm.p, h->M);
+    qsx_launch_counter += 1;
+    h->norms_ready = true;
+}
+
 static int n_vectors_for(int method) {
     return method == QSX_METHOD_TAYLOR ? 3 : method == QSX_METHOD_RK4 ? 4 : method == QSX_METHOD_MAP ? 2 : 10;
 }
@@ -679,6 +689,7 @@ extern "C" int qsx_dense_propagate(qsx_dense_t h, qsx_propagate_args *args, void
     QSX_CUDA(d_stats.alloc(3));
     QSX_CUDA(cudaMemsetAsync(d_stats.p, 0, 3 * sizeof(unsigned long long), stream));
 
+    if (args->method != QSX_METHOD_MAP) ensure_norms(h, stream);
     DenseKernelArgs a;
     a.M = M; a.nt = nt; a.Lt = h->Lt.p; a.lnorm = h->lnorm.p;
     a.y0 = (const cplx *)args->y0_dev; a.t = d_t.p; a.t0 = args->t0;
@@ -1158,10 +1169,7 @@ static int dense_wrap_impl(qsx_dense_t *out, int32_t M, int32_t n_generators, vo
     h->is_propagator = propagator;
     // generators: inf-norms for sub-step sizes and the propagator scaling; propagators are
     // only ever stepped (y <- P y), which needs none
-    if (!propagator) {
-        dense_norm_kernel<<<n_generators, 64, 0, stream>>>(h->Lt.p, h->lnorm.p, M);
-        qsx_launch_counter += 1;
-    }
+    if (!propagator) h->norms_ready = false;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         delete h;
@@ -1182,6 +1190,7 @@ extern "C" int qsx_dense_expm(qsx_dense_t h, double dt, void *Pt_dev, void *lnor
     cudaStream_t stream = (cudaStream_t)stream_;
     QSX_REQUIRE(h && out && Pt_dev && lnorm_dev, "qsx_dense_expm: null argument");
     const int M = h->M;
+    ensure_norms(h, stream);
     if (M > 56) {
         // wide states: the same series, one tiled tensor-core GEMM launch per product (dense_wide.cu)
         QSX_REQUIRE(M <= 1024, "qsx_dense_expm: state dimension above 1024");

@@ -225,3 +225,46 @@ def test_depth8_ado_table_matches_reference(golden):
     assert np.array_equal(idx[rows], g['ado8_index'])
     assert np.array_equal(up[rows], g['ado8_up'])
     assert np.array_equal(down[rows], g['ado8_down'])
+
+
+def test_transposition_permutation_and_hermitian_coordinates(golden):
+    """host logic of the Hermitian-coordinate path (engine.DenseEOM.hermitian_perm): the
+    transposition permutation of a Liouville subspace, and the fact it rests on -- the reference's
+    FMO generator commutes with Hermitian conjugation, so it is real in the coordinates
+    (populations, Re, Im of the coherences)."""
+    from qspectra_b200.dynamics.liouville_space import (transposition_permutation,
+                                                        liouville_subspace_index)
+    idx = liouville_subspace_index('ee', 'e', 7)
+    perm = transposition_permutation(idx, 7)
+    assert perm.dtype == np.int32 and np.array_equal(perm[perm], np.arange(49))
+    a, b = idx % 7, idx // 7
+    assert np.array_equal(idx[perm], b + 7 * a)
+    assert np.array_equal(np.flatnonzero(perm == np.arange(49)), np.arange(7) * 8)     # populations
+    idx_ge = liouville_subspace_index('gg,ee', 'ge', 7)
+    assert transposition_permutation(idx_ge, 8).size == 50
+    for open_block in ('eg', 'ge', 'gg,eg'):
+        assert transposition_permutation(liouville_subspace_index(open_block, 'ge', 7), 8) is None
+    # the reference generator (fixture recorded from qspectra) in Hermitian coordinates
+    L = golden('redfield')['fmo_L_ee']
+    assert np.abs(L[np.ix_(perm, perm)] - L.conj()).max() < 1e-15 * np.abs(L).max() * 10
+    T = np.zeros((49, 49), complex)
+    for k in range(49):
+        s = perm[k]
+        if s == k:
+            T[k, k] = 1
+        elif k < s:
+            T[k, k] = T[k, s] = 0.5
+        else:
+            T[k, s], T[k, k] = 1 / 2j, -1 / 2j
+    G = T @ L @ np.linalg.inv(T)
+    assert np.abs(G.imag).max() < 1e-15 and np.abs(G.real).max() > 1e-2
+    # a density matrix is a real vector there, and exp(G dt) steps it like exp(L dt)
+    import scipy.linalg
+    rho = (np.diag(np.arange(1.0, 8.0)) / 28 + 0.01 * (np.ones((7, 7)) - np.eye(7))).astype(complex)
+    rho[0, 1] += 0.02j
+    rho[1, 0] -= 0.02j
+    y = rho.reshape(-1, order='F')
+    u = T @ y
+    assert np.abs(u.imag).max() == 0.0
+    stepped = np.linalg.solve(T, scipy.linalg.expm(5.0 * G.real) @ u.real)
+    assert np.abs(stepped - scipy.linalg.expm(5.0 * L) @ y).max() < 1e-14
