@@ -147,12 +147,23 @@ __device__ __forceinline__ cplx corr_complex_finish(const qsx_bath &b, double x,
     cplx drude = cdiv(cmake(1.0 / tan(g / (2.0 * T)), -1.0), cmake(g, -x));
     return cmake(lam * g * (drude.x + 4.0 * T * sr), lam * g * (drude.y + 4.0 * T * si));
 }
+// Terms beyond `split` are summed as a power series in x^2 whose coefficients do not depend on x,
+//   sum_{m >= split} pre_m (nu_m + i x) / (nu_m^2 + x^2) = sum_k (-x^2)^k (A_k + i x B_k),
+//   A_k = sum_m pre_m nu_m^(-1-2k),  B_k = sum_m pre_m nu_m^(-2-2k)        (tail[k], tail[8 + k]),
+// tabulated once per CTA: for x^2 <= x2_max = nu_split^2 / 100 eight coefficients leave a relative
+// remainder of 1e-16, and a pair of eigenstates costs `split` divisions instead of `cutoff`
+// (the 21 x 1000 divisions per FMO member were a quarter of the build kernel).  split = 0 or a larger
+// |x|: the plain sum.
+#define QSX_MATS_TAIL 8
 __device__ __forceinline__ void matsubara_sum(const double *m_nu, const double *m_pre, int cutoff, double x,
+                                              const double *tail, int split, double x2_max,
                                               double &sr, double &si) {
     const int lane = threadIdx.x & 31;
     double ar = 0.0, ai = 0.0;
     const double x2 = x * x;
-    for (int mth = lane; mth < cutoff; mth += 32) {
+    const bool series = split > 0 && x2 <= x2_max;
+    const int stop = series ? split : cutoff;
+    for (int mth = lane; mth < stop; mth += 32) {
         const double nu = m_nu[mth], pre = m_pre[mth];
         const double q = pre / (nu * nu + x2);
         ar = fma(q, nu, ar);
@@ -160,6 +171,16 @@ __device__ __forceinline__ void matsubara_sum(const double *m_nu, const double *
     }
     sr = warp_sum(ar);
     si = warp_sum(ai);
+    if (series) {
+        double pa = 0.0, pb = 0.0;
+#pragma unroll
+        for (int k = QSX_MATS_TAIL - 1; k >= 0; --k) {
+            pa = fma(pa, -x2, tail[k]);
+            pb = fma(pb, -x2, tail[QSX_MATS_TAIL + k]);
+        }
+        sr += pa;
+        si = fma(x, pb, si);
+    }
 }
 
 // Eigensystems of small member Hamiltonians, one WARP per member (N <= 16): the cyclic Jacobi
@@ -224,6 +245,27 @@ __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArg
         m_nu[mth] = nu;
         m_pre[mth] = mth < a.bath.matsubara_cutoff ? nu / (nu * nu - g * g) : 0.0;
     }
+    // tail coefficients of the Matsubara sums (see matsubara_sum)
+    __shared__ double m_tail[2 * QSX_MATS_TAIL];
+    const int m_split = (a.n_mats > 128 && nwarp >= QSX_MATS_TAIL) ? 64 : 0;
+    double x2_max = 0.0;
+    if (m_split) {
+        __syncthreads();
+        if (warp < QSX_MATS_TAIL) {
+            double sa = 0.0, sb = 0.0;
+            for (int mth = m_split + (tid & 31); mth < a.n_mats; mth += 32) {
+                const double inv = 1.0 / m_nu[mth], inv2 = inv * inv;
+                double pw = m_pre[mth] * inv;
+                for (int j = 0; j < warp; ++j) pw *= inv2;
+                sa += pw;
+                sb = fma(pw, inv, sb);
+            }
+            sa = warp_sum(sa);
+            sb = warp_sum(sb);
+            if ((tid & 31) == 0) { m_tail[warp] = sa; m_tail[QSX_MATS_TAIL + warp] = sb; }
+        }
+        x2_max = 0.01 * m_nu[m_split] * m_nu[m_split];
+    }
     for (int mem = blockIdx.x; mem < a.m; mem += gridDim.x) {
         __syncthreads();
         if (a.jacobi) {
@@ -262,7 +304,7 @@ __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArg
                 const int j = i + 1 + rem;
                 const double x = Es[i] - Es[j];
                 double sr, si;
-                matsubara_sum(m_nu, m_pre, a.n_mats, x, sr, si);
+                matsubara_sum(m_nu, m_pre, a.n_mats, x, m_tail, m_split, x2_max, sr, si);
                 if ((tid & 31) == 0) {
                     Cs[i * N + j] = corr_complex_finish(a.bath, x, sr, si);
                     Cs[j * N + i] = corr_complex_finish(a.bath, -x, sr, -si);
@@ -282,15 +324,33 @@ __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArg
         }
         __syncthreads();
         // Gs[a][c] = sum_b sum_n K_n[a][b] K_n[b][c] C[c][b]
-        for (int p = tid; p < N2; p += nthr) {
-            int aa = p / N, cc = p % N;
-            cplx acc = cmake(0, 0);
-            for (int bb = 0; bb < N; ++bb) {
+        if ((size_t)N2 * N <= N4) {
+            // one thread per (a, c, b) term, staged in the (still unused) tensor buffer: with one
+            // thread per (a, c) only N^2 of the CTA's threads worked here (FMO: 49 of 256 on a
+            // chain of ~1500 dependent FMAs -- 17 % of the kernel's stall samples)
+            for (int p = tid; p < N2 * N; p += nthr) {
+                const int bb = p % N, ac = p / N, aa = ac / N, cc = ac % N;
                 cplx kk = cmake(0, 0);
                 for (int n = 0; n < nb; ++n) cfma(kk, Ks[n * N2 + aa * N + bb], Ks[n * N2 + bb * N + cc]);
-                cfma(acc, kk, Cs[cc * N + bb]);
+                TA[p] = cmul(kk, Cs[cc * N + bb]);
             }
-            Gs[p] = acc;
+            __syncthreads();
+            for (int p = tid; p < N2; p += nthr) {
+                cplx acc = cmake(0, 0);
+                for (int bb = 0; bb < N; ++bb) acc = cadd(acc, TA[p * N + bb]);
+                Gs[p] = acc;
+            }
+        } else {
+            for (int p = tid; p < N2; p += nthr) {
+                int aa = p / N, cc = p % N;
+                cplx acc = cmake(0, 0);
+                for (int bb = 0; bb < N; ++bb) {
+                    cplx kk = cmake(0, 0);
+                    for (int n = 0; n < nb; ++n) cfma(kk, Ks[n * N2 + aa * N + bb], Ks[n * N2 + bb * N + cc]);
+                    cfma(acc, kk, Cs[cc * N + bb]);
+                }
+                Gs[p] = acc;
+            }
         }
         __syncthreads();
         // eigenbasis generator as a 4-index tensor T[a][b][c][d] = L[a + N b, c + N d],
