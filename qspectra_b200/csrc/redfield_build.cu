@@ -216,8 +216,10 @@ __global__ void __launch_bounds__(256) redfield_eig_kernel(int m, int N, int nb,
 // NC > 0: compile-time state count for full blocks (N = na = nbb = nb = NC, e.g. FMO 'ee'):
 // the index arithmetic of the tensor loops -- a fifth of the kernel's instructions with
 // run-time divisors -- becomes multiplications by constants and the state loops unroll.
+// (NC = 7: 352 threads -- the 343 lines of a transform pass are one round instead of one full and one
+// quarter-full round of 256 threads, the 21 eigenstate pairs two rounds of 11 warps instead of three of 8)
 template <int NC>
-__global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArgs a) {
+__global__ void __launch_bounds__(NC == 7 ? 352 : 256, NC == 7 ? 2 : 3) redfield_build_kernel(RedfieldBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = NC ? NC : a.N, nb = NC ? NC : a.nb, N2 = N * N;
     const int na = NC ? NC : a.na, nbb = NC ? NC : a.nbb;
@@ -357,8 +359,10 @@ __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArg
         // a, c over the ket states ra[], b, d over the bra states rb[]
         const int n4 = (int)N4;                  // N <= 64: fits 32 bits (cheap index arithmetic)
         for (int p = tid; p < n4; p += nthr) {
-            int dd = a.rb[p % nbb], cc = a.ra[(p / nbb) % na];
-            int bb = a.rb[(p / (nbb * na)) % nbb], aa = a.ra[p / (nbb * na * nbb)];
+            // full blocks (NC > 0): the ket / bra state lists are the identity
+            const int dd = NC ? p % NC : a.rb[p % nbb], cc = NC ? (p / NC) % NC : a.ra[(p / nbb) % na];
+            const int bb = NC ? (p / (NC * NC)) % NC : a.rb[(p / (nbb * na)) % nbb];
+            const int aa = NC ? p / (NC * NC * NC) : a.ra[p / (nbb * na * nbb)];
             cplx g1 = cmake(0, 0), g2 = cmake(0, 0);       // G[c,a,b,d], G[d,b,a,c]
             for (int n = 0; n < nb; ++n) {
                 cfma(g1, Ks[n * N2 + cc * N + aa], Ks[n * N2 + bb * N + dd]);
@@ -392,12 +396,12 @@ __global__ void __launch_bounds__(256, 3) redfield_build_kernel(RedfieldBuildArg
 #pragma unroll
                         for (int q = 0; q < 8; ++q) v[q] = q < n ? src[base + q * stride] : cmake(0, 0);
                         for (int i = 0; i < n; ++i) {
-                            const cplx *urow = Us + states[i] * N;
+                            const cplx *urow = Us + (NC ? i : states[i]) * N;
                             cplx acc = cmake(0, 0);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 if (q < n) {
-                                    cplx u = urow[states[q]];
+                                    cplx u = urow[NC ? q : states[q]];
                                     if (pos >= 2) u.y = -u.y;
                                     cfma(acc, u, v[q]);
                                 }
@@ -524,8 +528,19 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     int tensors_in_smem = with_t <= (size_t)smem_limit;
     size_t smem = tensors_in_smem ? with_t : base;
     int grid;
+    const bool fmo7 = N == 7 && na == 7 && nbb == 7 && n_baths == 7;
+    const int threads = fmo7 ? 352 : 256;
     if (tensors_in_smem) {
-        grid = std::min(n_members, sms * std::max(1, (int)((size_t)smem_limit / smem)));
+        // resident CTAs only: every CTA loops over its share of the members
+        int per_sm = 1;
+        if (fmo7) {
+            QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, redfield_build_kernel<7>, threads, smem));
+        } else {
+            QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, redfield_build_kernel<0>, threads, smem));
+        }
+        grid = std::min(n_members, sms * std::max(1, per_sm));
     } else {
         grid = std::min(n_members, sms * 2);
         QSX_CUDA(scratch.alloc((size_t)grid * 2 * N4));
@@ -555,12 +570,12 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
         QSX_CUDA(cudaGetLastError());
         a.jacobi = 0; a.E = d_E.p; a.U = d_U.p;
     }
-    if (N == 7 && na == 7 && nbb == 7 && n_baths == 7) {
+    if (fmo7) {
         QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        redfield_build_kernel<7><<<grid, 256, smem, stream>>>(a);
+        redfield_build_kernel<7><<<grid, threads, smem, stream>>>(a);
     } else {
         QSX_CUDA(cudaFuncSetAttribute(redfield_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        redfield_build_kernel<0><<<grid, 256, smem, stream>>>(a);
+        redfield_build_kernel<0><<<grid, threads, smem, stream>>>(a);
     }
     qsx_launch_counter += 1;
     QSX_CUDA(cudaGetLastError());
