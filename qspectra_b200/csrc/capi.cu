@@ -364,6 +364,15 @@ extern "C" int qsx_sample_streams(const uint32_t *seed_prefix, int32_t n_prefix,
 // transform uses the device log/sqrt (<= 1 ulp from the host libm).  Writes
 // out[m][i] = scale * randn_i of member member0 + m.  Removes the host replay and the
 // H2D copy from the end-to-end path of a disorder ensemble.
+// The serial part of the seeding (init_by_array: 1247 dependent steps after the member-independent
+// init_genrand(19650218), whose 624 words come from a table) carries the previous word in a register
+// and loads the words it mixes in eight at a time ahead of the chain, so a step is a handful of
+// integer operations instead of a store -> load round trip through local memory (0.33 -> see
+// profiles/README.md ms per 1e4 members); the first outputs are generated straight from the seeded
+// state (word k of the first twist needs words k, k + 1 and k + 397 of it), the full twist only
+// runs if a member needs more than 227 words.
+__device__ uint32_t qsx_mt_seed_table[624];
+
 __global__ void __launch_bounds__(64) sample_streams_kernel(const uint32_t *prefix, int n_prefix, long long member0,
                                                             int n_members, int n_gauss, double scale, double *out) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,8 +380,78 @@ __global__ void __launch_bounds__(64) sample_streams_kernel(const uint32_t *pref
     uint32_t key[16];
     for (int i = 0; i < n_prefix; ++i) key[i] = prefix[i];
     key[n_prefix] = (uint32_t)(member0 + m);
-    MT19937 g;
-    g.init_by_array(key, n_prefix + 1);
+    const int len = n_prefix + 1;
+    uint32_t mt[624];
+    // ---- init_by_array, first loop: i = 1 .. 623, then the wrapped step at i = 1
+    uint32_t prev = qsx_mt_seed_table[0];
+    int j = 0;
+    for (int i = 1; i < 624; i += 8) {
+        uint32_t old[8], add[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            old[u] = i + u < 624 ? qsx_mt_seed_table[i + u] : 0U;
+            add[u] = key[j] + (uint32_t)j;
+            if (++j >= len) j = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i + u < 624) {
+                prev = (old[u] ^ ((prev ^ (prev >> 30)) * 1664525U)) + add[u];
+                mt[i + u] = prev;
+            }
+        }
+    }
+    // 623 steps done, j advanced 624 times (one too many: the last group is padded): realign
+    j = 623 % len;
+    prev = (mt[1] ^ ((prev ^ (prev >> 30)) * 1664525U)) + key[j] + (uint32_t)j;      // mt[0] = mt[623]; i = 1
+    mt[1] = prev;
+    // ---- second loop: i = 2 .. 623, then the wrapped step at i = 1
+    for (int i = 2; i < 624; i += 8) {
+        uint32_t old[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) old[u] = i + u < 624 ? mt[i + u] : 0U;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i + u < 624) {
+                prev = (old[u] ^ ((prev ^ (prev >> 30)) * 1566083941U)) - (uint32_t)(i + u);
+                mt[i + u] = prev;
+            }
+        }
+    }
+    prev = (mt[1] ^ ((prev ^ (prev >> 30)) * 1566083941U)) - 1U;                        // mt[0] = mt[623]; i = 1
+    mt[1] = prev;
+    mt[0] = 0x80000000U;
+    // ---- outputs
+    int pos = 0;
+    bool twisted = false;
+    auto next32 = [&]() -> uint32_t {
+        uint32_t y;
+        if (!twisted && pos < 227) {
+            const uint32_t w = (mt[pos] & 0x80000000U) | (mt[pos + 1] & 0x7fffffffU);
+            y = mt[pos + 397] ^ (w >> 1) ^ ((w & 1U) ? 0x9908b0dfU : 0U);
+            ++pos;
+        } else {
+            if (!twisted || pos >= 624) {
+                // full twist of the current state (the direct outputs above did not modify it)
+                for (int k = 0; k < 624; ++k) {
+                    const uint32_t w = (mt[k] & 0x80000000U) | (mt[(k + 1) % 624] & 0x7fffffffU);
+                    mt[k] = mt[(k + 397) % 624] ^ (w >> 1) ^ ((w & 1U) ? 0x9908b0dfU : 0U);
+                }
+                if (twisted) pos = 0;
+                twisted = true;
+            }
+            y = mt[pos++];
+        }
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680U;
+        y ^= (y << 15) & 0xefc60000U;
+        y ^= (y >> 18);
+        return y;
+    };
+    auto next_double = [&]() -> double {
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    };
     bool has = false;
     double cached = 0.0;
     for (int i = 0; i < n_gauss; ++i) {
@@ -383,8 +462,8 @@ __global__ void __launch_bounds__(64) sample_streams_kernel(const uint32_t *pref
         } else {
             double x1, x2, r2;
             do {
-                x1 = 2.0 * g.next_double() - 1.0;
-                x2 = 2.0 * g.next_double() - 1.0;
+                x1 = 2.0 * next_double() - 1.0;
+                x2 = 2.0 * next_double() - 1.0;
                 r2 = x1 * x1 + x2 * x2;
             } while (r2 >= 1.0 || r2 == 0.0);
             double f = sqrt(-2.0 * log(r2) / r2);
@@ -403,6 +482,14 @@ extern "C" int qsx_sample_gauss_device(const uint32_t *seed_prefix, int32_t n_pr
     QSX_REQUIRE(n_prefix >= 0 && n_prefix < 15 && n_members > 0 && n_gauss > 0 && out_dev,
                 "qsx_sample_gauss_device: bad arguments");
     QSX_REQUIRE(member0 >= 0 && member0 + n_members <= (int64_t)0xffffffffLL, "member index out of range");
+    static std::once_flag seed_once;
+    static cudaError_t seed_err = cudaSuccess;
+    std::call_once(seed_once, [] {
+        MT19937 g;
+        g.init_genrand(19650218U);
+        seed_err = cudaMemcpyToSymbol(qsx_mt_seed_table, g.mt, sizeof(g.mt));
+    });
+    QSX_CUDA(seed_err);
     DevBuf<uint32_t> prefix;
     if (n_prefix > 0) QSX_CUDA(prefix.upload(seed_prefix, (size_t)n_prefix, stream));
     sample_streams_kernel<<<(n_members + 63) / 64, 64, 0, stream>>>(prefix.p, n_prefix, member0, n_members, n_gauss,

@@ -831,6 +831,19 @@ def test_device_disorder_streams_match_numpy():
     assert (dev == host).mean() > 0.5
 
 
+@pytest.mark.parametrize('prefix,member0,n_gauss', [([7, 11], 0, 7), ([7, 11], 0, 130), ([3], 5, 400)])
+def test_device_gauss_streams_long(prefix, member0, n_gauss):
+    """the device replay of RandomState(prefix + [n]).randn(n_gauss): outputs taken straight from
+    the seeded state (first 227 words), after the first full twist (130 Gaussians need ~330
+    words) and after the second (400 need ~1000)"""
+    from qspectra_b200 import _capi
+    n = 257
+    dev = _capi.sample_gauss_device(prefix, member0, n, n_gauss).cpu().numpy()
+    ref = np.array([np.random.RandomState(list(prefix) + [member0 + k]).randn(n_gauss) for k in range(n)])
+    assert np.abs(dev - ref).max() <= 16 * np.finfo(float).eps * np.abs(ref).max()
+    assert (dev == ref).mean() > 0.5
+
+
 def test_wide_state_propagator_stepping():
     """state dimensions above the single-CTA propagator kernel's 56 (FMO 'fe', M = 147): tiled
     tensor-core propagator build + streamed propagator stepping against Taylor"""
