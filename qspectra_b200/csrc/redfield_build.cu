@@ -363,13 +363,13 @@ __global__ void __launch_bounds__(NC == 7 ? 352 : 256, NC == 7 ? 2 : 3) redfield
             const int dd = NC ? p % NC : a.rb[p % nbb], cc = NC ? (p / NC) % NC : a.ra[(p / nbb) % na];
             const int bb = NC ? (p / (NC * NC)) % NC : a.rb[(p / (nbb * na)) % nbb];
             const int aa = NC ? p / (NC * NC * NC) : a.ra[p / (nbb * na * nbb)];
-            cplx g1 = cmake(0, 0), g2 = cmake(0, 0);       // G[c,a,b,d], G[d,b,a,c]
-            for (int n = 0; n < nb; ++n) {
-                cfma(g1, Ks[n * N2 + cc * N + aa], Ks[n * N2 + bb * N + dd]);
-                cfma(g2, Ks[n * N2 + dd * N + bb], Ks[n * N2 + aa * N + cc]);
-            }
+            // G[c,a,b,d] = sum_n K_n[c][a] K_n[b][d] and G[d,b,a,c] = sum_n K_n[d][b] K_n[a][c]: the
+            // couplings are Hermitian in the eigenbasis (real diagonal system-bath operators), so the
+            // second sum is the complex conjugate of the first
+            cplx g1 = cmake(0, 0);
+            for (int n = 0; n < nb; ++n) cfma(g1, Ks[n * N2 + cc * N + aa], Ks[n * N2 + bb * N + dd]);
+            cplx g2 = cmul(cmake(g1.x, -g1.y), Cs[cc * N + aa]);
             g1 = cmul(g1, Cs[dd * N + bb]);
-            g2 = cmul(g2, Cs[cc * N + aa]);
             cplx R = cmake(-g1.x - g2.x, g1.y - g2.y);     // - conj(g1) - g2
             if (aa == cc) { cplx s = Gs[bb * N + dd]; R.x += s.x; R.y -= s.y; }
             if (bb == dd) { cplx s = Gs[aa * N + cc]; R.x += s.x; R.y += s.y; }
