@@ -45,6 +45,7 @@ struct RedfieldBuildArgs {
     // on-device eigensystems (jacobi != 0): H_m = H0 + diag(sum_j shift[m][j] v[j][.]), lab frame
     int transposed_out;     // write Lt[m][c][r] (storage of qsx_dense_wrap) instead of L[m][r][c]
     int jacobi;
+    int u_real;             // the eigenvectors are real (device eigensystems of a real symmetric H)
     const double *H0;       // [N][N] real symmetric
     const double *shifts;   // [m][nb]
     const double *quanta;   // [N] excitation number of each basis state (rotating-frame shift)
@@ -402,8 +403,12 @@ __global__ void __launch_bounds__(NC == 7 ? 352 : 256, NC == 7 ? 2 : 3) redfield
                             for (int q = 0; q < 8; ++q) {
                                 if (q < n) {
                                     cplx u = urow[NC ? q : states[q]];
-                                    if (pos >= 2) u.y = -u.y;
-                                    cfma(acc, u, v[q]);
+                                    if (a.u_real) {         // half the multiply-adds
+                                        rfma(acc, u.x, v[q]);
+                                    } else {
+                                        if (pos >= 2) u.y = -u.y;
+                                        cfma(acc, u, v[q]);
+                                    }
                                 }
                             }
                             src[base + i * stride] = acc;
@@ -555,7 +560,7 @@ static int redfield_build_impl(int32_t n_members, int32_t N, const void *E_dev, 
     a.secular = secular; a.eigen_basis = eigen_basis; a.unit_convert = unit_convert;
     a.L = (cplx *)L_out_dev; a.scratch = scratch.p; a.tensors_in_smem = tensors_in_smem; a.in_place = in_place;
     a.transposed_out = transposed_out;
-    a.jacobi = jacobi; a.H0 = d_H0.p; a.shifts = shifts_dev; a.quanta = d_quanta.p; a.rw_freq = rw_freq;
+    a.jacobi = jacobi; a.u_real = jacobi ? 1 : 0; a.H0 = d_H0.p; a.shifts = shifts_dev; a.quanta = d_quanta.p; a.rw_freq = rw_freq;
     DevBuf<double> d_E;
     DevBuf<cplx> d_U;
     if (jacobi && N <= 16) {
