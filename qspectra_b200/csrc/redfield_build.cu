@@ -435,10 +435,16 @@ __global__ void __launch_bounds__(NC == 7 ? 352 : 256, NC == 7 ? 2 : 3) redfield
         }
         // restricted, scaled output
         cplx *Lout = a.L + (size_t)mem * a.M * a.M;
+        // p runs over the OUTPUT positions (coalesced stores whichever storage order is asked for);
+        // the whole operator space of a full block needs no slot tables: element i = ket i % N, bra i / N
+        const bool whole = NC && a.M == NC * NC;
         for (int p = tid; p < a.M * a.M; p += nthr) {
-            int r = p / a.M, c = p % a.M;
-            cplx val = src[(((size_t)a.oa[r] * nbb + a.ob[r]) * na + a.oa[c]) * nbb + a.ob[c]];
-            Lout[a.transposed_out ? c * a.M + r : p] = cscale(a.unit_convert, val);
+            const int hi = p / a.M, lo = p % a.M;
+            const int r = a.transposed_out ? lo : hi, c = a.transposed_out ? hi : lo;
+            const int ar = whole ? r % (NC ? NC : 1) : a.oa[r], br = whole ? r / (NC ? NC : 1) : a.ob[r];
+            const int ac = whole ? c % (NC ? NC : 1) : a.oa[c], bc = whole ? c / (NC ? NC : 1) : a.ob[c];
+            const cplx val = src[(((size_t)ar * nbb + br) * na + ac) * nbb + bc];
+            Lout[p] = cscale(a.unit_convert, val);
         }
     }
 }
