@@ -309,7 +309,7 @@ class HermitianPropagators(object):
         self.P = torch.empty((n, M, M), dtype=torch.float64, device='cuda')
         self.defect = torch.zeros(4, dtype=torch.float64, device='cuda')
         self.counter = torch.zeros(1, dtype=torch.int64, device='cuda')
-        self.host = torch.zeros(5, dtype=torch.float64).pin_memory()
+        self.host = self._pinned_slot(torch)
         self.events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         pptr = self.perm.ctypes.data_as(C.POINTER(C.c_int32))
         self.events[0].record()
@@ -332,6 +332,19 @@ class HermitianPropagators(object):
         PropagationStats.expm_builds += 1
         PropagationStats.hermitian_builds += 1
         PropagationStats.defer(self, '_resolve_build')
+
+    _ring, _ring_next = None, 0
+
+    @classmethod
+    def _pinned_slot(cls, torch):
+        """five pinned doubles from a process-lifetime ring (cudaHostAlloc per build would cost
+        more host time than the build's launches); a slot is reused after 256 further builds"""
+        if cls._ring is None:
+            cls._ring = torch.zeros((256, 5), dtype=torch.float64).pin_memory()
+        slot = cls._ring[cls._ring_next % 256]
+        cls._ring_next += 1
+        slot.zero_()
+        return slot
 
     def snapshot(self):
         """queue the copy of the device-side check values to pinned host memory"""
