@@ -164,3 +164,34 @@ def test_gg_ee_subspace_real_form(golden):
     assert rho.shape == (len(t), 50)
     assert rel_l2(rho, rho_c) < 1e-12
     engine.PropagationStats.flush()
+
+
+def test_headline_size_properties(monkeypatch):
+    """BASELINE configs[1] at a quarter of its size (2500 members x 197 points, enough for several
+    rounds of every persistent CTA): the Hermitian-coordinate path against the complex path on the
+    same resident generators, and the size-independent properties of the mean -- unit trace,
+    Hermiticity, positivity of the populations, member linearity (mean of two halves)."""
+    model = qb.RedfieldModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS, secular=False)
+    E = 2500
+    t = np.arange(0, 1000.0, model.time_step)
+    psi0 = np.eye(7)[0]
+    y0 = model.density_matrix_to_state_vector(np.outer(psi0, psi0).astype(complex), 'ee')
+    eom = model.ensemble_eom(E, False, 'ee', member0=0)
+    y0_dev = _capi.to_device(y0).reshape(1, -1).expand(E, -1).contiguous()
+    gens = np.arange(E)
+    out = eom.propagate(y0_dev, t, generators=gens, return_device=True, hermitian_state=True, packed=True)
+    assert isinstance(out, engine.HermitianTrajectory)
+    mean = _capi.to_host(engine.reduce_members(out, 1.0 / E))
+    per_member = _capi.to_host(out.to_complex())
+    monkeypatch.setenv('QSX_NO_HERMITIAN_FORM', '1')
+    eom.__dict__.pop('_propagators', None)
+    ref = _capi.to_host(eom.propagate(y0_dev, t, generators=gens, return_device=True))
+    assert rel_l2(per_member, ref) < 1e-12
+    assert rel_l2(mean, ref.mean(axis=0)) < 1e-12
+    rho = mean.reshape(len(t), 7, 7, order='F')
+    assert np.abs(np.einsum('tii->t', rho) - 1).max() < 1e-13
+    assert np.abs(rho - rho.conj().transpose(0, 2, 1)).max() < 1e-15
+    assert np.einsum('tii->ti', rho).real.min() > -1e-12
+    halves = 0.5 * (per_member[:E // 2].mean(axis=0) + per_member[E // 2:].mean(axis=0))
+    assert rel_l2(mean, halves) < 1e-13
+    engine.PropagationStats.flush()
