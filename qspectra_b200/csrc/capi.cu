@@ -482,14 +482,21 @@ extern "C" int qsx_sample_gauss_device(const uint32_t *seed_prefix, int32_t n_pr
     QSX_REQUIRE(n_prefix >= 0 && n_prefix < 15 && n_members > 0 && n_gauss > 0 && out_dev,
                 "qsx_sample_gauss_device: bad arguments");
     QSX_REQUIRE(member0 >= 0 && member0 + n_members <= (int64_t)0xffffffffLL, "member index out of range");
-    static std::once_flag seed_once;
-    static cudaError_t seed_err = cudaSuccess;
-    std::call_once(seed_once, [] {
-        MT19937 g;
-        g.init_genrand(19650218U);
-        seed_err = cudaMemcpyToSymbol(qsx_mt_seed_table, g.mt, sizeof(g.mt));
-    });
-    QSX_CUDA(seed_err);
+    {
+        // the table is a per-device symbol: upload it once for every device this process uses
+        static std::mutex seed_mu;
+        static bool seeded[64] = {false};
+        int dev = 0;
+        QSX_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(seed_mu);
+        if (dev < 0 || dev >= 64 || !seeded[dev]) {
+            MT19937 g;
+            g.init_genrand(19650218U);
+            QSX_CUDA(cudaMemcpyToSymbolAsync(qsx_mt_seed_table, g.mt, sizeof(g.mt), 0, cudaMemcpyHostToDevice, stream));
+            QSX_CUDA(cudaStreamSynchronize(stream));        // g.mt lives on this stack frame
+            if (dev >= 0 && dev < 64) seeded[dev] = true;
+        }
+    }
     DevBuf<uint32_t> prefix;
     if (n_prefix > 0) QSX_CUDA(prefix.upload(seed_prefix, (size_t)n_prefix, stream));
     sample_streams_kernel<<<(n_members + 63) / 64, 64, 0, stream>>>(prefix.p, n_prefix, member0, n_members, n_gauss,
