@@ -201,8 +201,7 @@ real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnor
         }
 #pragma unroll
         for (int nb = 0; nb < MT; ++nb) {
-            X[r * LD + nb * 8 + 2 * t] = A1e[nb][0];
-            X[r * LD + nb * 8 + 2 * t + 1] = A1e[nb][1];
+            *reinterpret_cast<double2 *>(&X[r * LD + nb * 8 + 2 * t]) = make_double2(A1e[nb][0], A1e[nb][1]);
         }
         __syncthreads();
         auto load_fragments = [&](const double *W) {
@@ -224,8 +223,7 @@ real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnor
 #pragma unroll
         for (int nb = 0; nb < MT; ++nb) {
             product(X, nb, A2e[nb][0], A2e[nb][1]);
-            Y[r * LD + nb * 8 + 2 * t] = A2e[nb][0];
-            Y[r * LD + nb * 8 + 2 * t + 1] = A2e[nb][1];
+            *reinterpret_cast<double2 *>(&Y[r * LD + nb * 8 + 2 * t]) = make_double2(A2e[nb][0], A2e[nb][1]);
         }
         __syncthreads();
         // A^3 = A A^2 -> X, and the start of the recursion c9 I + c10 A + c11 A^2 + c12 A^3 -> Z
@@ -234,10 +232,10 @@ real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnor
             const int c = nb * 8 + 2 * t;
             double v0, v1;
             product(Y, nb, v0, v1);
-            X[r * LD + c] = v0;
-            X[r * LD + c + 1] = v1;
-            Z[r * LD + c] = (r == c ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1e[nb][0] + inv_fact_r[11] * A2e[nb][0] + inv_fact_r[12] * v0;
-            Z[r * LD + c + 1] = (r == c + 1 ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1e[nb][1] + inv_fact_r[11] * A2e[nb][1] + inv_fact_r[12] * v1;
+            *reinterpret_cast<double2 *>(&X[r * LD + c]) = make_double2(v0, v1);
+            *reinterpret_cast<double2 *>(&Z[r * LD + c]) = make_double2(
+                (r == c ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1e[nb][0] + inv_fact_r[11] * A2e[nb][0] + inv_fact_r[12] * v0,
+                (r == c + 1 ? inv_fact_r[9] : 0.0) + inv_fact_r[10] * A1e[nb][1] + inv_fact_r[11] * A2e[nb][1] + inv_fact_r[12] * v1);
         }
         __syncthreads();
         load_fragments(X);                          // left operand from here on: A^3
@@ -251,8 +249,9 @@ real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnor
                 const int c = nb * 8 + 2 * t;
                 double v0, v1;
                 product(P, nb, v0, v1);
-                U[r * LD + c] = v0 + c1 * A1e[nb][0] + c2 * A2e[nb][0] + (r == c ? c0 : 0.0);
-                U[r * LD + c + 1] = v1 + c1 * A1e[nb][1] + c2 * A2e[nb][1] + (r == c + 1 ? c0 : 0.0);
+                *reinterpret_cast<double2 *>(&U[r * LD + c]) = make_double2(
+                    v0 + c1 * A1e[nb][0] + c2 * A2e[nb][0] + (r == c ? c0 : 0.0),
+                    v1 + c1 * A1e[nb][1] + c2 * A2e[nb][1] + (r == c + 1 ? c0 : 0.0));
             }
             __syncthreads();
             { double *x = P; P = U; U = x; }
@@ -263,8 +262,7 @@ real_expm3_kernel(const double *__restrict__ Gt, const double *__restrict__ gnor
             for (int nb = 0; nb < MT; ++nb) {
                 double v0, v1;
                 product(P, nb, v0, v1);
-                U[r * LD + nb * 8 + 2 * t] = v0;
-                U[r * LD + nb * 8 + 2 * t + 1] = v1;
+                *reinterpret_cast<double2 *>(&U[r * LD + nb * 8 + 2 * t]) = make_double2(v0, v1);
             }
             __syncthreads();
             { double *x = P; P = U; U = x; }
@@ -397,7 +395,7 @@ real_map_kernel(const double *__restrict__ P, int M, const int *__restrict__ gen
 // registers, so a step needs no cross-lane reduction at all -- the shuffle/DADD tree and the
 // predicated stores of the kernel above were almost half of its issue slots (91 DFMA at two issue
 // cycles each against ~160 other instructions per step; the FP64 pipe cannot be busier than the
-// issue slots left to it).  The state is read as 16-byte broadcast loads; four accumulator chains
+// issue slots left to it).  The state is read as 16-byte broadcast loads; two accumulator chains
 // per row.  CP = column pairs (zero padded).
 template <int CP>
 __global__ void __launch_bounds__(64)
@@ -426,40 +424,43 @@ real_map_rows_kernel(const double *__restrict__ P, int M, const int *__restrict_
     for (int k = M; k < MS; ++k)
         for (int it = 1 + lane; it < nt; it += 32) __stcs(&orow[(size_t)it * MS + k], 0.0);
     __syncwarp();
-    const bool has0 = r0 < M, has1 = r1 < M;
+    const bool has1 = r1 < M;
     double *og = orow;
     auto step = [&](const double *__restrict__ ld, double *__restrict__ st) {
-        double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+        // two accumulator chains per row (four chains per lane cover the 8.4-cycle DFMA latency at
+        // ~2.9 issue cycles each); more chains only add DADDs to the issue stream
+        double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
 #pragma unroll
         for (int cp = 0; cp < CP; ++cp) {
             const double2 v = *reinterpret_cast<const double2 *>(ld + 2 * cp);
-            const int k = (cp & 1) * 2;
-            a[k] = fma(p0[2 * cp], v.x, a[k]);
-            b[k] = fma(p1[2 * cp], v.x, b[k]);
-            a[k + 1] = fma(p0[2 * cp + 1], v.y, a[k + 1]);
-            b[k + 1] = fma(p1[2 * cp + 1], v.y, b[k + 1]);
+            a[0] = fma(p0[2 * cp], v.x, a[0]);
+            b[0] = fma(p1[2 * cp], v.x, b[0]);
+            a[1] = fma(p0[2 * cp + 1], v.y, a[1]);
+            b[1] = fma(p1[2 * cp + 1], v.y, b[1]);
         }
-        const double s0 = (a[0] + a[1]) + (a[2] + a[3]), s1 = (b[0] + b[1]) + (b[2] + b[3]);
-        if (has0) {
-            st[r0] = s0;
-            __stcs(og + r0, s0);
-        }
-        if (has1) {
-            st[r1] = s1;
-            __stcs(og + r1, s1);
-        }
+        const double s0 = a[0] + a[1], s1 = b[0] + b[1];
+        // row l always exists (M > 32); lanes without a second row park it in the unused slot 63
+        st[r0] = s0;
+        __stcs(og + r0, s0);
+        st[has1 ? r1 : 63] = s1;
+        if (has1) __stcs(og + r1, s1);
         __syncwarp();
     };
     int it = 1;
-    for (; it + 1 < nt; it += 2) {
+    for (; it + 3 < nt; it += 4) {
+        og += MS;
+        step(xs[w][0], xs[w][1]);
+        og += MS;
+        step(xs[w][1], xs[w][0]);
         og += MS;
         step(xs[w][0], xs[w][1]);
         og += MS;
         step(xs[w][1], xs[w][0]);
     }
-    if (it < nt) {
+    for (; it < nt; ++it) {
         og += MS;
-        step(xs[w][0], xs[w][1]);
+        if (it & 1) step(xs[w][0], xs[w][1]);
+        else step(xs[w][1], xs[w][0]);
     }
 }
 
