@@ -87,6 +87,9 @@ def workload_config(members, n_gpus):
                           'every timed step (QSX_NO_HERMITIAN_FORM=1: the complex path)',
             'parallelism': 'ensemble members sharded over %d GPU(s), one NCCL '
                            'reduce' % n_gpus,
+            'launch': 'the six kernels of a step are replayed as one CUDA graph (engine.CapturedEnsembleStep); '
+                      'kernel times for the roofline come from an untimed pass through the eager calls '
+                      '(QSX_BENCH_NO_GRAPH=1: eager launches in the timed region too)',
             'l2_policy': 'inputs larger than L2 (1e4 generators = 384 MB vs 126 MB L2)'}
 
 
@@ -629,8 +632,23 @@ def run_ours(args):
                                 hermitian_state=True, packed=True)
             return engine.reduce_members(out, 1.0 / total_members)
 
+        # The same step as one CUDA graph (engine.CapturedEnsembleStep: change of coordinates + real
+        # propagators rebuilt by every replay, packing, stepping, member mean, conversion of the mean);
+        # the eager form above is kept for the instrumented pass that times the kernels one by one.
+        captured = None
+        if not os.environ.get('QSX_BENCH_NO_GRAPH'):
+            try:
+                captured = engine.CapturedEnsembleStep(eom, y0_dev, t, 1.0 / total_members)
+                ref_mean = local_step()
+                if float((captured.run() - ref_mean).abs().max()) > 1e-14:
+                    raise RuntimeError('captured step differs from the eager step')
+                captured.verify()
+            except Exception as exc:                 # keep the bench alive on the eager path
+                sys.stderr.write('bench: CUDA-graph step unavailable (%r), eager launches\n' % (exc,))
+                captured = None
+
         def step():
-            return reduce_across(local_step())
+            return reduce_across(captured.run() if captured is not None else local_step())
         for _ in range(warmup):
             step()
         # untimed rehearsal of the timed block with the same object lifetimes (the propagators of all
@@ -662,15 +680,27 @@ def run_ours(args):
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             ms = float(tmax.item())
         st = engine.PropagationStats
-        st.flush()          # collect the deferred device times of the timed steps
+        launches = _capi.kernel_launches() - l0
+        if captured is not None:
+            # graph replays carry no per-kernel events: the kernels are timed one by one in an
+            # untimed pass of the same step through the eager calls
+            launches = captured.launches_per_run * steps
+            captured.verify()
+            st.reset()
+            st.keep_alive = True
+            for _ in range(steps):
+                local_step()
+            torch.cuda.synchronize()
+        st.flush()          # collect the deferred device times of the (instrumented) steps
         st.keep_alive = False
         stats = dict(expm_ms=st.expm_ms, expm_gemms=st.expm_gemms, expm_builds=st.expm_builds,
                      form_ms=st.form_ms, hermitian_builds=st.hermitian_builds,
                      kernel_ms=st.kernel_ms / max(1, st.propagations),
                      rhs=st.rhs_evaluations / max(1, st.propagations),
                      steps=st.accepted_steps / max(1, st.propagations),
-                     launches=_capi.kernel_launches() - l0, window=(t_a, t_b))
-        return ms / steps, stats, result, eom, local_step
+                     launches=launches, window=(t_a, t_b), graph=captured is not None)
+        rank_local = (lambda: captured.run()) if captured is not None else local_step
+        return ms / steps, stats, result, eom, rank_local
 
     # nvidia-smi needs ~0.1-0.2 s before its first sample: start it ahead of the warm-up and keep
     # only the samples that arrive inside the timed window

@@ -381,6 +381,80 @@ class HermitianPropagators(object):
         return self.__dict__['_build']
 
 
+class CapturedEnsembleStep(object):
+    """One ensemble step in Hermitian coordinates as a CUDA graph: change of coordinates and real
+    tensor-core propagators of every generator (rebuilt by every replay), packing of the initial
+    states, stepping, member mean and the conversion of the mean to the complex vectorisation --
+    six kernels behind one ``cudaGraphLaunch``.  For small ensembles (a strongly sharded job) the
+    host-side launch path of the eager calls (~0.6 ms of Python / ctypes per step) is longer than
+    the kernels; a replay costs ~10 us.  Buffers are owned by the object; ``run()`` returns the
+    (n_times, dim) complex128 CUDA tensor that the next replay overwrites."""
+
+    def __init__(self, eom, y0_dev, t, scale):
+        torch = _capi.torch_cuda()
+        if eom.hermitian_perm is None or eom.dim > DenseEOM.HERMITIAN_MAX_DIM or eom.heisenberg_picture:
+            raise ValueError('generator has no Hermitian-coordinate form')
+        dt = eom._uniform_step(t, None)
+        if dt is None:
+            raise ValueError('propagator stepping needs a uniform output grid')
+        self.eom, self.dt, self.scale = eom, float(dt), float(scale)
+        M, n = eom.dim, eom.n_generators
+        self.M, self.MS, self.nt = M, M + (M & 1), len(t)
+        self.perm = np.ascontiguousarray(eom.hermitian_perm, dtype=np.int32)
+        self.y0 = _capi.to_device(y0_dev).reshape(-1, M).contiguous()
+        self.B = self.y0.shape[0]
+        if self.B != n:
+            raise ValueError('one column per generator expected')
+        f64 = dict(dtype=torch.float64, device=self.y0.device)
+        self.P = torch.empty((n, M, M), **f64)
+        self.check = torch.zeros(5, **f64)           # defect[0..3] + the product counter (as int64 bits)
+        self.u0 = torch.empty((self.B, self.MS), **f64)
+        self.out = torch.empty((self.B, self.nt, self.MS), **f64)
+        self.mean_real = torch.empty((self.nt, self.MS), **f64)
+        self.mean = torch.empty((self.nt, M), dtype=torch.complex128, device=self.y0.device)
+        # warm-up on a side stream (scratch pools and kernel attributes settle outside the capture)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._enqueue()
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        self.launches_per_run = 7
+
+    def _enqueue(self):
+        lib, stream = _capi.lib(), _capi.current_stream_ptr()
+        pptr = self.perm.ctypes.data_as(C.POINTER(C.c_int32))
+        M, MS, B, nt = self.M, self.MS, self.B, self.nt
+        self.check.zero_()
+        _capi.check(lib.qsx_dense_hermitian_expm(self.eom._h, pptr, self.dt, self.P.data_ptr(),
+                                                 self.check.data_ptr(), self.check[4:].data_ptr(), stream))
+        _capi.check(lib.qsx_hermitian_pack(self.y0.data_ptr(), M, B, pptr, MS, self.u0.data_ptr(),
+                                           self.check.data_ptr(), stream))
+        _capi.check(lib.qsx_real_map(self.P.data_ptr(), M, B, None, B, self.u0.data_ptr(), nt, MS,
+                                     self.out.data_ptr(), stream))
+        _capi.check(lib.qsx_reduce_members(self.out.data_ptr(), B, nt * MS // 2, self.scale,
+                                           self.mean_real.data_ptr(), stream))
+        _capi.check(lib.qsx_hermitian_unpack(self.mean_real.data_ptr(), M, nt, MS, pptr,
+                                             self.mean.data_ptr(), stream))
+
+    def run(self):
+        self.graph.replay()
+        return self.mean
+
+    def verify(self):
+        """synchronises; raises if generators or states failed the device-side Hermiticity check"""
+        d = self.check.cpu().numpy()
+        tol = HermitianPropagators.TOLERANCE
+        if not (d[0] <= tol * d[1] and d[2] <= tol * max(d[3], 1e-300)):
+            raise RuntimeError('generator or state is not compatible with Hermitian conjugation '
+                               '(|Im G| %.3e of %.3e, |Im u0| %.3e of %.3e)' % tuple(d[:4]))
+        return int(d[4:].view(np.int64)[0])          # real M x M products of the last replay
+
+
 class _MapTiming(object):
     """deferred device time of one stepping call in Hermitian coordinates"""
     _h = True

@@ -195,3 +195,25 @@ def test_headline_size_properties(monkeypatch):
     halves = 0.5 * (per_member[:E // 2].mean(axis=0) + per_member[E // 2:].mean(axis=0))
     assert rel_l2(mean, halves) < 1e-13
     engine.PropagationStats.flush()
+
+
+def test_captured_ensemble_step_matches_eager_path():
+    """the resident ensemble step as a CUDA graph (engine.CapturedEnsembleStep) against the eager
+    calls it captures; replays rebuild the propagators and return the same mean"""
+    model = qb.RedfieldModel(systems.fmo(), hilbert_subspace='e', unit_convert=CM_FS, secular=False)
+    E = 300
+    t = np.arange(0, 1000.0, model.time_step)
+    psi0 = np.eye(7)[0]
+    y0 = model.density_matrix_to_state_vector(np.outer(psi0, psi0).astype(complex), 'ee')
+    eom = model.ensemble_eom(E, False, 'ee', member0=0)
+    y0_dev = _capi.to_device(y0).reshape(1, -1).expand(E, -1).contiguous()
+    out = eom.propagate(y0_dev, t, generators=np.arange(E), return_device=True, hermitian_state=True, packed=True)
+    eager = _capi.to_host(engine.reduce_members(out, 1.0 / E))
+    step = engine.CapturedEnsembleStep(eom, y0_dev, t, 1.0 / E)
+    first = _capi.to_host(step.run()).copy()
+    assert step.verify() == 6 * E or step.verify() >= 5 * E      # 5 products + squarings per member
+    assert np.abs(first - eager).max() <= 1e-15
+    step.P.zero_()                                                  # a replay rebuilds the propagators
+    second = _capi.to_host(step.run())
+    assert np.array_equal(first, second)
+    engine.PropagationStats.flush()
